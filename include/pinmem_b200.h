@@ -1,0 +1,166 @@
+/*
+ * pinmem_b200.h -- C ABI of the B200 (sm_100a) categorical-memory kernels.
+ *
+ * This is the drop-in boundary of the hot path named by BASELINE.json: the reference's
+ * `network/memory.py::Memory_sup` (read, get_score, write, diversityloss, classification_loss).
+ * The reference is pure PyTorch, so there is no FFI to replace; each entry point below is what a
+ * maintainer's binding (ctypes) calls instead of the cited eager torch lines.
+ * Paths are relative to the reference tree.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a NEGATIVE pm_status on a rejected argument and a POSITIVE
+ *     cudaError_t if the launch failed; nothing throws, nothing allocates, nothing synchronises.
+ *   - all pointers are DEVICE pointers owned by the caller (PyTorch's caching allocator in the shipped
+ *     host side); `stream` is a cudaStream_t passed as void*.
+ *   - feature-sized tensors (x, u, f, du, dx, df) are NCHW-contiguous in `dtype` (PM_F32 or PM_BF16);
+ *     memory, scores, sums, losses and every accumulation are fp32; labels are int64 [B,Hm,Wm] with
+ *     255 = ignore (transforms/transforms.py:95-97).
+ *   - C (mem_dim) must be one of 32, 64, 128, 256; K (mem_slot) must be 1..31.
+ *   - N = B*h*w. "Score buffers" internal to the path (s, ds_rl, ds) have a padded row stride
+ *     pm_score_stride(K) floats so rows are 16-byte aligned; user-visible scores are dense [N,K].
+ */
+#ifndef PINMEM_B200_H
+#define PINMEM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum pm_dtype { PM_F32 = 0, PM_BF16 = 1 };
+
+enum pm_status {
+    PM_OK = 0,
+    PM_ERR_NULL = -1,      /* a required pointer is NULL */
+    PM_ERR_DTYPE = -2,     /* dtype not PM_F32 / PM_BF16 */
+    PM_ERR_CHANNELS = -3,  /* C not in {32,64,128,256} */
+    PM_ERR_SLOTS = -4,     /* K not in 1..31 */
+    PM_ERR_SHAPE = -5,     /* a dimension is <= 0 or too large */
+    PM_ERR_ALIGN = -6      /* a pointer is not aligned as documented */
+};
+
+/* 64-bit words of the read-loss workspace (`ws`, zero it before pm_readloss_fwd). */
+enum pm_readloss_ws_layout {
+    PM_WS_LOSS_SUM = 0, /* double: sum over valid label pixels of (LSE - logit[y])            */
+    PM_WS_COUNTER = 1,  /* uint64: CTA arrival counter                                         */
+    PM_WS_BAD = 2,      /* int64: label values outside [0,K) u {255} (counted as ignore)       */
+    PM_WS_HIST = 4,     /* int64[K+1]: label histogram, bin K = ignore; sum(bins<K) = V        */
+    PM_WS_WORDS = 40
+};
+
+int pm_version(void);
+const char* pm_status_string(int code);
+/* Row stride (floats) of the internal score buffers for K slots: 20 for K<=19, else 32. */
+int pm_score_stride(int K);
+/* Floats of scratch pm_colsoftmax needs. */
+int pm_colsoftmax_workspace_floats(int K);
+
+/*
+ * Memory read, forward. Replaces memory.py:319-320 (normalise + NCHW->NHWC), :171 (q.M^T),
+ * :181-187 dim=1 [gumbel-]softmax, :328 (p.M), :330-332 (cat + NHWC->NCHW).
+ *   x        [B,C,h,w] dtype          M         [K,C] fp32
+ *   gumbel_m [N,K] fp32 or NULL       (the noise of F.gumbel_softmax(score, dim=1), memory.py:184)
+ *   u        [B,2C,h,w] dtype out     = [x/|x| ; softmax_k(s+g).M]
+ *   s        [N,stride] fp32 out      raw similarities (internal score buffer)
+ *   score_m  [N,K] fp32 out           softmax over slots (score_memory)
+ */
+int pm_read_fwd(const void* x, const float* M, const float* gumbel_m, void* u, float* s, float* score_m,
+                int B, int C, int h, int w, int K, int dtype, void* stream);
+
+/*
+ * score_query = softmax over ALL N pixels (dim 0) of s (+ gumbel_q). memory.py:183/186.
+ *   s [N,stride] fp32, gumbel_q [N,K] fp32 or NULL, score_q [N,K] fp32 out,
+ *   workspace: pm_colsoftmax_workspace_floats(K) floats of scratch.
+ */
+int pm_colsoftmax(const float* s, const float* gumbel_q, float* score_q, float* workspace, int N, int K,
+                  void* stream);
+
+/*
+ * Feature-cohesion (read) loss, forward, plus everything its backward needs. Replaces
+ * memory.py:173-176: s/T -> bilinear up-sample (align_corners=True) to [Hm,Wm] -> CrossEntropy
+ * (ignore 255, mean over valid pixels) WITHOUT materialising the [B,K,Hm,Wm] logits.
+ *   s      [N,stride] fp32          labels [B,Hm,Wm] int64
+ *   ds_rl  [N,stride] fp32, ZEROED by the caller; receives sum over label pixels of
+ *          bilinear^T (softmax(logits) - onehot(y)) (i.e. d loss_sum / d (s/T))
+ *   ws     PM_WS_WORDS 64-bit words, ZEROED by the caller (layout above)
+ *   out    float[2] out: out[0] = readloss = loss_sum / V (NaN when V == 0, like torch),
+ *                        out[1] = 1 / (V*T)  (scale of ds_rl in the backward)
+ */
+int pm_readloss_fwd(const float* s, const int64_t* labels, float temperature, int B, int h, int w, int Hm,
+                    int Wm, int K, float* ds_rl, void* ws, float* out, void* stream);
+
+/*
+ * Memory read, backward (autograd of the lines pm_read_fwd + pm_readloss_fwd replace).
+ *   du       [B,2C,h,w] dtype     upstream gradient of u
+ *   x, M, score_m                  as in the forward (score_m carries the gumbel noise implicitly)
+ *   ds_rl    [N,stride] fp32 or NULL; g_loss: device float* (upstream grad of readloss) or NULL;
+ *   rl_out   the `out` array of pm_readloss_fwd (its [1] is the scale) or NULL
+ *   dx       [B,C,h,w] dtype out
+ *   ds       [N,stride] fp32 out or NULL: total gradient w.r.t. the similarities (input of pm_read_bwd_dM)
+ */
+int pm_read_bwd(const void* du, const void* x, const float* M, const float* score_m, const float* ds_rl,
+                const float* g_loss, const float* rl_out, void* dx, float* ds, int B, int C, int h, int w,
+                int K, int dtype, void* stream);
+
+/*
+ * Gradient w.r.t. the memory when m_items carries graph (meta-test read, train.py:558,570):
+ * dM = sum_n score_m[n]^T dc[n] + ds[n]^T q[n].  dM [K,C] fp32 must be ZEROED by the caller.
+ */
+int pm_read_bwd_dM(const void* du, const void* x, const float* score_m, const float* ds, float* dM, int B,
+                   int C, int h, int w, int K, int dtype, void* stream);
+
+/*
+ * get_score on an already normalised NHWC query (external call at train.py:894): s = q.M^T.
+ *   q [N,C] fp32 (channels contiguous), M [K,C] fp32, s [N,stride] fp32 out.
+ */
+int pm_score_nhwc(const float* q, const float* M, float* s, int N, int C, int K, void* stream);
+
+/*
+ * score_memory for that external get_score path: dense [N,K] row softmax of s (+ gumbel_m), memory.py:184/187.
+ */
+int pm_rowsoftmax(const float* s, const float* gumbel_m, float* score_m, int N, int K, void* stream);
+
+/*
+ * Memory write, class sums. Replaces memory.py:215 (normalise), :220-223 (255->K, one_hot(K+1),
+ * float, bilinear down-sample to [h,w], align_corners=True), :226-231 (per-class sums and counts).
+ *   f   [B,C,h,w] dtype (output of the writing net)      labels [B,Hm,Wm] int64
+ *   SD  [K+1, C+4] fp32, ZEROED by the caller; rows = classes (row K = ignore), columns 0..C-1 =
+ *       sum_n omega[n,k] f[n]/|f[n]|, column C = soft count sum_n omega[n,k], columns C+1..C+3 unused.
+ *   This [K+1,C+4] buffer is what a sharded run all-reduces.
+ */
+int pm_write_reduce_fwd(const void* f, const int64_t* labels, float* SD, int B, int C, int h, int w, int Hm,
+                        int Wm, int K, int dtype, void* stream);
+
+/*
+ * Momentum update + re-normalisation + both write losses. Replaces memory.py:233-239 (branch-free:
+ * no host sync per slot), :264-272 (diversityloss), :259-262 (classification_loss).
+ *   SD [K+1,C+4], M_old [K,C], W_cls [K,C], b_cls [K] fp32
+ *   M_new [K,C] out (unit rows), losses float[2] out = {div, cls},
+ *   saved float[2K] out = {|M'_k| (pre-normalisation norms), D_k} for the backward.
+ */
+int pm_update_fwd(const float* SD, const float* M_old, float momentum, const float* W_cls, const float* b_cls,
+                  float* M_new, float* losses, float* saved, int C, int K, void* stream);
+
+/*
+ * Backward of pm_update_fwd.
+ *   dM_new [K,C] or NULL (gradient arriving at the new memory), g_losses: device float[2] = upstream
+ *   grads of {div, cls} (either pointer may be NULL = 0), M_new, saved, W_cls, b_cls as in the forward.
+ *   dS [K,C] out (gradient w.r.t. the class sums; zero rows for absent classes; this is what a sharded
+ *   run all-reduces in the backward), dW_cls [K,C] out, db_cls [K] out.
+ */
+int pm_update_bwd(const float* dM_new, const float* g_div, const float* g_cls, const float* M_new,
+                  const float* saved, const float* W_cls, const float* b_cls, float momentum, float* dS,
+                  float* dW_cls, float* db_cls, int C, int K, void* stream);
+
+/*
+ * Memory write, backward to the write feature: dv[n] = sum_k omega[n,k] dS[k];
+ * df = (dv - v (v.dv)) / |f|.   dS [K,C] fp32, f and labels as in the forward, df [B,C,h,w] dtype out.
+ */
+int pm_write_bwd(const float* dS, const void* f, const int64_t* labels, void* df, int B, int C, int h, int w,
+                 int Hm, int Wm, int K, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PINMEM_B200_H */

@@ -1,0 +1,175 @@
+"""ctypes binding of ``include/pinmem_b200.h`` -- the only way this package reaches the GPU.
+
+There is no fallback: if ``_lib/libpinmem_b200.so`` is missing and cannot be built, or a call returns a
+non-zero status, a ``RuntimeError`` is raised. Nothing here touches ``oracle/``.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+from . import build as _build
+
+PM_F32, PM_BF16 = 0, 1
+WS_WORDS = 40  # PM_WS_WORDS
+WS_HIST = 4    # PM_WS_HIST
+WS_BAD = 2     # PM_WS_BAD
+
+_c_p = ctypes.c_void_p
+_c_i = ctypes.c_int
+_c_f = ctypes.c_float
+
+# name -> argtypes, exactly the prototypes of include/pinmem_b200.h
+PROTOTYPES = {
+    "pm_version": [],
+    "pm_score_stride": [_c_i],
+    "pm_colsoftmax_workspace_floats": [_c_i],
+    "pm_read_fwd": [_c_p] * 6 + [_c_i] * 6 + [_c_p],
+    "pm_colsoftmax": [_c_p] * 4 + [_c_i] * 2 + [_c_p],
+    "pm_readloss_fwd": [_c_p, _c_p, _c_f] + [_c_i] * 6 + [_c_p] * 4,
+    "pm_read_bwd": [_c_p] * 9 + [_c_i] * 6 + [_c_p],
+    "pm_read_bwd_dM": [_c_p] * 5 + [_c_i] * 6 + [_c_p],
+    "pm_score_nhwc": [_c_p] * 3 + [_c_i] * 3 + [_c_p],
+    "pm_rowsoftmax": [_c_p] * 3 + [_c_i] * 2 + [_c_p],
+    "pm_write_reduce_fwd": [_c_p] * 3 + [_c_i] * 8 + [_c_p],
+    "pm_update_fwd": [_c_p, _c_p, _c_f] + [_c_p] * 5 + [_c_i] * 2 + [_c_p],
+    "pm_update_bwd": [_c_p] * 7 + [_c_f] + [_c_p] * 3 + [_c_i] * 2 + [_c_p],
+    "pm_write_bwd": [_c_p] * 4 + [_c_i] * 8 + [_c_p],
+}
+EXPORTED_SYMBOLS = sorted(list(PROTOTYPES) + ["pm_status_string"])
+
+_lib = None
+_lock = threading.Lock()
+
+
+def library_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """Load (building first if the tree has no up-to-date library) and return the ctypes handle."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB_PATH
+        if not os.path.exists(path):
+            path = _build.build()
+        lib = ctypes.CDLL(path)
+        for name, argtypes in PROTOTYPES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = _c_i
+        lib.pm_status_string.argtypes = [_c_i]
+        lib.pm_status_string.restype = ctypes.c_char_p
+        _lib = lib
+    return _lib
+
+
+def _check(code, what):
+    if code != 0:
+        msg = load().pm_status_string(code).decode()
+        raise RuntimeError(f"pinmem_b200: {what} failed with status {code}: {msg}")
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dtype_code(t):
+    if t.dtype == torch.float32:
+        return PM_F32
+    if t.dtype == torch.bfloat16:
+        return PM_BF16
+    raise RuntimeError(f"pinmem_b200: feature dtype must be float32 or bfloat16, got {t.dtype}")
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("pinmem_b200 has no CPU path: every tensor must live on a CUDA device")
+
+
+def _f32c(t, what):
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise RuntimeError(f"pinmem_b200: {what} must be a contiguous float32 tensor")
+    return t
+
+
+def score_stride(K):
+    return load().pm_score_stride(int(K))
+
+
+# --------------------------------------------------------------------------------------------- calls
+
+
+def read_fwd(x, M, gumbel_m, u, s, score_m, K):
+    B, C, h, w = x.shape
+    _check(load().pm_read_fwd(_ptr(x), _ptr(M), _ptr(gumbel_m), _ptr(u), _ptr(s), _ptr(score_m), B, C, h, w, K,
+                              dtype_code(x), _stream()), "pm_read_fwd")
+
+
+def colsoftmax(s, gumbel_q, score_q, workspace, N, K):
+    _check(load().pm_colsoftmax(_ptr(s), _ptr(gumbel_q), _ptr(score_q), _ptr(workspace), N, K, _stream()),
+           "pm_colsoftmax")
+
+
+def colsoftmax_workspace_floats(K):
+    return load().pm_colsoftmax_workspace_floats(int(K))
+
+
+def readloss_fwd(s, labels, temperature, B, h, w, K, ds_rl, ws, out):
+    Hm, Wm = labels.shape[1], labels.shape[2]
+    _check(load().pm_readloss_fwd(_ptr(s), _ptr(labels), float(temperature), B, h, w, Hm, Wm, K, _ptr(ds_rl),
+                                  _ptr(ws), _ptr(out), _stream()), "pm_readloss_fwd")
+
+
+def read_bwd(du, x, M, score_m, ds_rl, g_loss, rl_out, dx, ds, K):
+    B, C, h, w = x.shape
+    _check(load().pm_read_bwd(_ptr(du), _ptr(x), _ptr(M), _ptr(score_m), _ptr(ds_rl), _ptr(g_loss), _ptr(rl_out),
+                              _ptr(dx), _ptr(ds), B, C, h, w, K, dtype_code(x), _stream()), "pm_read_bwd")
+
+
+def read_bwd_dM(du, x, score_m, ds, dM, K):
+    B, C, h, w = x.shape
+    _check(load().pm_read_bwd_dM(_ptr(du), _ptr(x), _ptr(score_m), _ptr(ds), _ptr(dM), B, C, h, w, K,
+                                 dtype_code(x), _stream()), "pm_read_bwd_dM")
+
+
+def score_nhwc(q, M, s, N, C, K):
+    _check(load().pm_score_nhwc(_ptr(q), _ptr(M), _ptr(s), N, C, K, _stream()), "pm_score_nhwc")
+
+
+def rowsoftmax(s, gumbel_m, score_m, N, K):
+    _check(load().pm_rowsoftmax(_ptr(s), _ptr(gumbel_m), _ptr(score_m), N, K, _stream()), "pm_rowsoftmax")
+
+
+def write_reduce_fwd(f, labels, SD, K):
+    B, C, h, w = f.shape
+    Hm, Wm = labels.shape[1], labels.shape[2]
+    _check(load().pm_write_reduce_fwd(_ptr(f), _ptr(labels), _ptr(SD), B, C, h, w, Hm, Wm, K, dtype_code(f),
+                                      _stream()), "pm_write_reduce_fwd")
+
+
+def update_fwd(SD, M_old, momentum, W, b, M_new, losses, saved, C, K):
+    _check(load().pm_update_fwd(_ptr(SD), _ptr(M_old), float(momentum), _ptr(W), _ptr(b), _ptr(M_new),
+                                _ptr(losses), _ptr(saved), C, K, _stream()), "pm_update_fwd")
+
+
+def update_bwd(dM_new, g_div, g_cls, M_new, saved, W, b, momentum, dS, dW, db, C, K):
+    _check(load().pm_update_bwd(_ptr(dM_new), _ptr(g_div), _ptr(g_cls), _ptr(M_new), _ptr(saved), _ptr(W), _ptr(b),
+                                float(momentum), _ptr(dS), _ptr(dW), _ptr(db), C, K, _stream()), "pm_update_bwd")
+
+
+def write_bwd(dS, f, labels, df, K):
+    B, C, h, w = f.shape
+    Hm, Wm = labels.shape[1], labels.shape[2]
+    _check(load().pm_write_bwd(_ptr(dS), _ptr(f), _ptr(labels), _ptr(df), B, C, h, w, Hm, Wm, K, dtype_code(f),
+                               _stream()), "pm_write_bwd")

@@ -1,0 +1,102 @@
+// Shared device helpers for the pinmem-b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pinmem_b200.h"
+
+#define PM_IGNORE_LABEL 255
+#define PM_NORM_EPS 1e-12f  // F.normalize eps (reference memory.py:215,239,319)
+
+#define PM_CHECK_LAUNCH()                                   \
+    do {                                                    \
+        cudaError_t e__ = cudaGetLastError();               \
+        if (e__ != cudaSuccess) return (int)e__;            \
+    } while (0)
+
+namespace pm {
+
+template <typename T>
+__device__ __forceinline__ float ldf(const T* p);
+template <>
+__device__ __forceinline__ float ldf<float>(const float* p) {
+    return __ldg(p);
+}
+template <>
+__device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) {
+    return __bfloat162float(__ldg(p));
+}
+template <typename T>
+__device__ __forceinline__ void stf(T* p, float v);
+template <>
+__device__ __forceinline__ void stf<float>(float* p, float v) {
+    *p = v;
+}
+template <>
+__device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) {
+    *p = __float2bfloat16_rn(v);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Bilinear (align_corners=True) source index of output index `dst`: PyTorch computes
+// src = scale * dst in fp32, i0 = floor(src) clamped to in-1, lambda = src - i0.
+__device__ __forceinline__ int src_index(float scale, int dst, int n_in, float* lambda) {
+    float src = scale * (float)dst;
+    int i0 = (int)src;
+    if (i0 > n_in - 1) i0 = n_in - 1;
+    float l = src - (float)i0;
+    *lambda = fminf(fmaxf(l, 0.f), 1.f);
+    return i0;
+}
+
+// The (<=4) label taps a feature pixel samples when the (K+1)-channel one-hot label map is
+// bilinearly down-sampled to the feature grid (reference memory.py:220-223). Equal classes
+// are merged; unused slots get weight 0. Class K is the ignore slot.
+struct LabelTaps {
+    int cls[4];
+    float w[4];
+};
+
+__device__ __forceinline__ int map_label(long long v, int K) {
+    return (v >= 0 && v < K) ? (int)v : K;  // 255 (and anything out of range) -> ignore slot
+}
+
+__device__ __forceinline__ LabelTaps label_taps(const long long* __restrict__ lab, int Hm, int Wm, int fy,
+                                                int fx, float sy, float sx, int K) {
+    float ly, lx;
+    int y0 = src_index(sy, fy, Hm, &ly), x0 = src_index(sx, fx, Wm, &lx);
+    int y1 = y0 + (y0 < Hm - 1 ? 1 : 0), x1 = x0 + (x0 < Wm - 1 ? 1 : 0);
+    LabelTaps t;
+    t.cls[0] = map_label(lab[(size_t)y0 * Wm + x0], K);
+    t.cls[1] = map_label(lab[(size_t)y0 * Wm + x1], K);
+    t.cls[2] = map_label(lab[(size_t)y1 * Wm + x0], K);
+    t.cls[3] = map_label(lab[(size_t)y1 * Wm + x1], K);
+    // PyTorch: out = h0l*(w0l*a + w1l*b) + h1l*(w0l*c + w1l*d)
+    float hy0 = 1.f - ly, hx0 = 1.f - lx;
+    t.w[0] = hy0 * hx0;
+    t.w[1] = hy0 * lx;
+    t.w[2] = ly * hx0;
+    t.w[3] = ly * lx;
+#pragma unroll
+    for (int j = 1; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < j; ++i)
+            if (t.w[j] != 0.f && t.cls[j] == t.cls[i] && t.w[i] != 0.f) {
+                t.w[i] += t.w[j];
+                t.w[j] = 0.f;
+            }
+    return t;
+}
+
+}  // namespace pm

@@ -1,0 +1,527 @@
+// Memory write: label-masked per-class segmented reduction, momentum update (+ both write losses),
+// and their backward kernels.
+#include "pm_common.cuh"
+
+namespace pm {
+
+// ----------------------------------------------------------------------------- class sums (forward)
+// S[k] = sum_n omega[n,k] f[n]/|f[n]|, D[k] = sum_n omega[n,k]; omega = the <=4 bilinear label taps of
+// feature pixel n. A reduction over pixels: a thread owns one CHANNEL and walks the pixels of a
+// transposed [C][32+1] tile in shared memory. Class indices are warp-uniform (broadcast from shared
+// memory), so each thread keeps a register accumulator for the current class (run-length: label maps
+// are piecewise constant) and spills it into its private column of the CTA's [K+1][C+4] tile only when
+// the class changes -- no atomics in the loop. CTAs are persistent; one vector RED per touched class
+// row at the end.
+
+constexpr int WR_P = 32;
+
+template <typename T, int C, int KP>
+__global__ void __launch_bounds__(C) write_reduce_kernel(const T* __restrict__ f, const long long* __restrict__ labels,
+                                                          float* __restrict__ SD, int h, int w, int Hm, int Wm, int K,
+                                                          float sy, float sx, int tiles_per_img, int ntiles) {
+    constexpr int P = WR_P, LD = P + 1, NW = C / 32, CS = C + 4;
+    extern __shared__ __align__(16) float smem[];
+    float* S_tile = smem;                 // [KP][CS]
+    float* ft = S_tile + KP * CS;         // [C][LD]
+    float* pn = ft + C * LD;              // [NW][P]
+    float* invr = pn + NW * P;            // [P]
+    float2* ent = reinterpret_cast<float2*>(invr + P);  // [P][4] (class bits, weight)
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, hw = h * w;
+    for (int i = tid; i < KP * CS; i += C) S_tile[i] = 0.f;
+    int cur = -1;
+    unsigned seen = 0u;
+    float acc = 0.f, accD = 0.f;
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_img, px0 = (tile - b * tiles_per_img) * P;
+        const int nvalid = min(P, hw - px0);
+        const bool v = lane < nvalid;
+        const T* fb = f + (size_t)b * C * hw + px0 + lane;
+        float n2 = 0.f;
+#pragma unroll 8
+        for (int c = wid; c < C; c += NW) {
+            float fv = v ? ldf(fb + (size_t)c * hw) : 0.f;
+            n2 = fmaf(fv, fv, n2);
+            ft[c * LD + lane] = fv;
+        }
+        pn[wid * P + lane] = n2;
+        if (tid < P) {
+            LabelTaps t;
+            if (tid < nvalid) {
+                int px = px0 + tid, fy = px / w, fx = px - fy * w;
+                t = label_taps(labels + (size_t)b * Hm * Wm, Hm, Wm, fy, fx, sy, sx, K);
+            } else {
+                t.cls[0] = t.cls[1] = t.cls[2] = t.cls[3] = K;
+                t.w[0] = t.w[1] = t.w[2] = t.w[3] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ent[tid * 4 + j] = make_float2(__int_as_float(t.cls[j]), t.w[j]);
+        }
+        __syncthreads();
+        if (tid < P) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) s += pn[i * P + tid];
+            invr[tid] = 1.f / fmaxf(sqrtf(s), PM_NORM_EPS);
+        }
+        __syncthreads();
+        for (int px = 0; px < nvalid; ++px) {
+            const float val = ft[tid * LD + px] * invr[px];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 e = ent[px * 4 + j];
+                if (e.y != 0.f) {  // warp-uniform
+                    const int cls = __float_as_int(e.x);
+                    if (cls != cur) {
+                        if (cur >= 0) {
+                            S_tile[cur * CS + tid] += acc;
+                            if (tid == 0) S_tile[cur * CS + C] += accD;
+                        }
+                        acc = 0.f;
+                        accD = 0.f;
+                        cur = cls;
+                        seen |= 1u << cls;
+                    }
+                    acc = fmaf(e.y, val, acc);
+                    accD += e.y;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (cur >= 0) {
+        S_tile[cur * CS + tid] += acc;
+        if (tid == 0) S_tile[cur * CS + C] += accD;
+    }
+    __syncthreads();
+    for (int k = 0; k <= K; ++k) {
+        if (!((seen >> k) & 1u)) continue;
+        for (int i = tid; i < CS / 4; i += C)
+            atomicAdd(reinterpret_cast<float4*>(SD + (size_t)k * CS) + i,
+                      reinterpret_cast<const float4*>(S_tile + k * CS)[i]);
+    }
+}
+
+// ---------------------------------------------------------------------------- write backward (to f)
+// dv[n] = sum_k omega[n,k] dS[k]; df = (dv - v (v.dv)) / |f|. Per-pixel map, so the read kernels' mapping:
+// CTA = 64 pixels x C channels, 8 warps split channels, a lane owns pixels (lane, lane+32). dS sits in
+// shared memory with row stride C+1 so lanes with different classes hit different banks.
+
+constexpr int WB_THREADS = 256, WB_WARPS = 8, WB_P = 64;
+
+template <typename T, int CW, int KP>
+__global__ void __launch_bounds__(WB_THREADS) write_bwd_kernel(const float* __restrict__ dS, const T* __restrict__ f,
+                                                               const long long* __restrict__ labels,
+                                                               T* __restrict__ df, int h, int w, int Hm, int Wm, int K,
+                                                               float sy, float sx, int tiles_per_img) {
+    constexpr int C = CW * WB_WARPS, P = WB_P, LDS_ = C + 1;
+    extern __shared__ __align__(16) float smem[];
+    float* dSs = smem;              // [K+1][C+1]; row K (ignore) is zero
+    float* pn = dSs + KP * LDS_;    // [8][P]
+    float* invr = pn + WB_WARPS * P;
+    float* rnorm = invr + P;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, hw = h * w;
+    const int b = blockIdx.x / tiles_per_img, px0 = (blockIdx.x - b * tiles_per_img) * P;
+    const int nvalid = min(P, hw - px0);
+    const bool v0 = lane < nvalid, v1 = lane + 32 < nvalid;
+
+    const T* fb = f + ((size_t)b * C + wid * CW) * hw + px0 + lane;
+    float a0[CW], a1[CW], d0[CW], d1[CW];
+    float n0 = 0.f, n1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < CW; ++j) {
+        a0[j] = v0 ? ldf(fb + (size_t)j * hw) : 0.f;
+        a1[j] = v1 ? ldf(fb + (size_t)j * hw + 32) : 0.f;
+    }
+    for (int i = tid; i < KP * LDS_; i += WB_THREADS) {
+        int k = i / LDS_, c = i - k * LDS_;
+        dSs[i] = (k < K && c < C) ? __ldg(dS + (size_t)k * C + c) : 0.f;
+    }
+    LabelTaps t0, t1;
+    {
+        const long long* lab_b = labels + (size_t)b * Hm * Wm;
+        int px = px0 + (v0 ? lane : 0), fy = px / w, fx = px - fy * w;
+        t0 = label_taps(lab_b, Hm, Wm, fy, fx, sy, sx, K);
+        px = px0 + (v1 ? lane + 32 : 0), fy = px / w, fx = px - fy * w;
+        t1 = label_taps(lab_b, Hm, Wm, fy, fx, sy, sx, K);
+    }
+#pragma unroll
+    for (int j = 0; j < CW; ++j) {
+        n0 = fmaf(a0[j], a0[j], n0);
+        n1 = fmaf(a1[j], a1[j], n1);
+    }
+    pn[wid * P + lane] = n0;
+    pn[wid * P + lane + 32] = n1;
+    __syncthreads();
+    if (tid < P) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < WB_WARPS; ++i) s += pn[i * P + tid];
+        float n = sqrtf(s);
+        rnorm[tid] = n;
+        invr[tid] = 1.f / fmaxf(n, PM_NORM_EPS);
+    }
+    __syncthreads();
+    const float ir0 = invr[lane], ir1 = invr[lane + 32];
+    float dot0 = 0.f, dot1 = 0.f;
+    const float* r00 = dSs + t0.cls[0] * LDS_ + wid * CW;
+    const float* r01 = dSs + t0.cls[1] * LDS_ + wid * CW;
+    const float* r02 = dSs + t0.cls[2] * LDS_ + wid * CW;
+    const float* r03 = dSs + t0.cls[3] * LDS_ + wid * CW;
+    const float* r10 = dSs + t1.cls[0] * LDS_ + wid * CW;
+    const float* r11 = dSs + t1.cls[1] * LDS_ + wid * CW;
+    const float* r12 = dSs + t1.cls[2] * LDS_ + wid * CW;
+    const float* r13 = dSs + t1.cls[3] * LDS_ + wid * CW;
+#pragma unroll
+    for (int j = 0; j < CW; ++j) {
+        float dv0 = t0.w[0] * r00[j];
+        dv0 = fmaf(t0.w[1], r01[j], dv0);
+        dv0 = fmaf(t0.w[2], r02[j], dv0);
+        dv0 = fmaf(t0.w[3], r03[j], dv0);
+        float dv1 = t1.w[0] * r10[j];
+        dv1 = fmaf(t1.w[1], r11[j], dv1);
+        dv1 = fmaf(t1.w[2], r12[j], dv1);
+        dv1 = fmaf(t1.w[3], r13[j], dv1);
+        a0[j] *= ir0;  // v
+        a1[j] *= ir1;
+        d0[j] = dv0;
+        d1[j] = dv1;
+        dot0 = fmaf(a0[j], dv0, dot0);
+        dot1 = fmaf(a1[j], dv1, dot1);
+    }
+    __syncthreads();  // pn reuse
+    pn[wid * P + lane] = dot0;
+    pn[wid * P + lane + 32] = dot1;
+    __syncthreads();
+    dot0 = dot1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < WB_WARPS; ++i) {
+        dot0 += pn[i * P + lane];
+        dot1 += pn[i * P + lane + 32];
+    }
+    if (rnorm[lane] <= PM_NORM_EPS) dot0 = 0.f;
+    if (rnorm[lane + 32] <= PM_NORM_EPS) dot1 = 0.f;
+    T* dfb = df + ((size_t)b * C + wid * CW) * hw + px0 + lane;
+#pragma unroll
+    for (int j = 0; j < CW; ++j) {
+        if (v0) stf(dfb + (size_t)j * hw, (d0[j] - a0[j] * dot0) * ir0);
+        if (v1) stf(dfb + (size_t)j * hw + 32, (d1[j] - a1[j] * dot1) * ir1);
+    }
+}
+
+// --------------------------------------------------------------------------- momentum update + losses
+// One CTA (K x C is 19 x 256): a warp per memory row. Branch-free replacement of the reference's per-slot
+// python loop with its 19 host syncs (memory.py:233-237).
+
+constexpr int UP_THREADS = 256, UP_WARPS = 8, UP_KMAX = 32;
+
+__global__ void __launch_bounds__(UP_THREADS) update_fwd_kernel(const float* __restrict__ SD, const float* __restrict__ M_old,
+                                                                float momentum, const float* __restrict__ W,
+                                                                const float* __restrict__ bias, float* __restrict__ M_new,
+                                                                float* __restrict__ losses, float* __restrict__ saved,
+                                                                int C, int K) {
+    extern __shared__ __align__(16) float smem[];
+    float* Mn = smem;            // [K][C] new memory
+    float* Ws = Mn + K * C;      // [K][C] classifier weight
+    float* zs = Ws + K * C;      // [K][UP_KMAX] logits
+    float* red = zs + K * UP_KMAX;  // [UP_WARPS] + [K]
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, CS = C + 4;
+
+    for (int i = tid; i < K * C; i += UP_THREADS) Ws[i] = __ldg(W + i);
+    for (int k = wid; k < K; k += UP_WARPS) {
+        const float D = __ldg(SD + (size_t)k * CS + C);
+        const bool present = D != 0.f;
+        const float coef = present ? (1.f - momentum) / D : 0.f;
+        float n2 = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float old = __ldg(M_old + (size_t)k * C + c);
+            const float v = present ? fmaf(coef, __ldg(SD + (size_t)k * CS + c), momentum * old) : old;
+            Mn[k * C + c] = v;
+            n2 = fmaf(v, v, n2);
+        }
+        n2 = warp_sum(n2);
+        const float n = sqrtf(n2), inv = 1.f / fmaxf(n, PM_NORM_EPS);
+        for (int c = lane; c < C; c += 32) {
+            const float v = Mn[k * C + c] * inv;
+            Mn[k * C + c] = v;
+            M_new[(size_t)k * C + c] = v;
+        }
+        if (lane == 0) {
+            saved[k] = n;
+            saved[K + k] = D;
+        }
+    }
+    __syncthreads();
+    // divergence loss: sum over i != j of relu(M_i . M_j) / (K (K-1))
+    float dsum = 0.f;
+    for (int pair = wid; pair < K * K; pair += UP_WARPS) {
+        const int i = pair / K, j = pair - i * K;
+        // logits z[i][j] = M_i . W_j + b_j for every pair; Gram only for i < j
+        float zz = 0.f, gg = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float mi = Mn[i * C + c];
+            zz = fmaf(mi, Ws[j * C + c], zz);
+            gg = fmaf(mi, Mn[j * C + c], gg);
+        }
+        zz = warp_sum(zz);
+        gg = warp_sum(gg);
+        if (lane == 0) {
+            zs[i * UP_KMAX + j] = zz + __ldg(bias + j);
+            if (i != j) dsum += fmaxf(gg, 0.f);
+        }
+    }
+    if (lane == 0) red[wid] = dsum;
+    __syncthreads();
+    // classification loss: mean over rows of LSE(z_i) - z_ii
+    if (tid < K) {
+        float mx = -INFINITY;
+        for (int j = 0; j < K; ++j) mx = fmaxf(mx, zs[tid * UP_KMAX + j]);
+        float sum = 0.f;
+        for (int j = 0; j < K; ++j) sum += expf(zs[tid * UP_KMAX + j] - mx);
+        red[UP_WARPS + tid] = mx + logf(sum) - zs[tid * UP_KMAX + tid];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float d = 0.f;
+        for (int i = 0; i < UP_WARPS; ++i) d += red[i];
+        float c = 0.f;
+        for (int i = 0; i < K; ++i) c += red[UP_WARPS + i];
+        losses[0] = d / (float)(K * (K - 1));
+        losses[1] = c / (float)K;
+    }
+}
+
+__global__ void __launch_bounds__(UP_THREADS) update_bwd_kernel(const float* __restrict__ dM_new, const float* __restrict__ g_div,
+                                                                const float* __restrict__ g_cls, const float* __restrict__ M_new,
+                                                                const float* __restrict__ saved, const float* __restrict__ W,
+                                                                const float* __restrict__ bias, float momentum,
+                                                                float* __restrict__ dS, float* __restrict__ dW,
+                                                                float* __restrict__ db, int C, int K) {
+    extern __shared__ __align__(16) float smem[];
+    float* Mn = smem;               // [K][C]
+    float* Ws = Mn + K * C;         // [K][C]
+    float* zs = Ws + K * C;         // [K][UP_KMAX] logits -> dz
+    float* gs = zs + K * UP_KMAX;   // [K][UP_KMAX] Gram indicator
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const float gd = g_div ? __ldg(g_div) : 0.f, gc = g_cls ? __ldg(g_cls) : 0.f;
+
+    for (int i = tid; i < K * C; i += UP_THREADS) {
+        Mn[i] = __ldg(M_new + i);
+        Ws[i] = __ldg(W + i);
+    }
+    __syncthreads();
+    for (int pair = wid; pair < K * K; pair += UP_WARPS) {
+        const int i = pair / K, j = pair - i * K;
+        float zz = 0.f, gg = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float mi = Mn[i * C + c];
+            zz = fmaf(mi, Ws[j * C + c], zz);
+            gg = fmaf(mi, Mn[j * C + c], gg);
+        }
+        zz = warp_sum(zz);
+        gg = warp_sum(gg);
+        if (lane == 0) {
+            zs[i * UP_KMAX + j] = zz + __ldg(bias + j);
+            gs[i * UP_KMAX + j] = (i != j && gg >= 0.f) ? 1.f : 0.f;  // reference zeroes only cos < 0
+        }
+    }
+    __syncthreads();
+    if (tid < K) {  // dz_i = g_cls * (softmax(z_i) - e_i) / K
+        float mx = -INFINITY;
+        for (int j = 0; j < K; ++j) mx = fmaxf(mx, zs[tid * UP_KMAX + j]);
+        float sum = 0.f;
+        for (int j = 0; j < K; ++j) sum += expf(zs[tid * UP_KMAX + j] - mx);
+        const float inv = 1.f / sum, sc = gc / (float)K;
+        for (int j = 0; j < K; ++j) {
+            float p = expf(zs[tid * UP_KMAX + j] - mx) * inv;
+            zs[tid * UP_KMAX + j] = sc * (p - (j == tid ? 1.f : 0.f));
+        }
+    }
+    __syncthreads();
+    const float cdiv = gd * 2.f / (float)(K * (K - 1));
+    for (int i = wid; i < K; i += UP_WARPS) {
+        const float n = saved[i], D = saved[K + i];
+        float g[8];  // C <= 256 -> <= 8 channels per lane
+        float dot = 0.f;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int c = lane + 32 * t;
+            g[t] = 0.f;
+            if (c < C) {
+                float a = dM_new ? __ldg(dM_new + (size_t)i * C + c) : 0.f;
+                float dv = 0.f, cl = 0.f;
+                for (int j = 0; j < K; ++j) {
+                    dv = fmaf(gs[i * UP_KMAX + j], Mn[j * C + c], dv);
+                    cl = fmaf(zs[i * UP_KMAX + j], Ws[j * C + c], cl);
+                }
+                a = fmaf(cdiv, dv, a) + cl;
+                g[t] = a;
+                dot = fmaf(a, Mn[i * C + c], dot);
+            }
+        }
+        dot = warp_sum(dot);
+        const bool clamped = n <= PM_NORM_EPS;
+        const float inv = 1.f / fmaxf(n, PM_NORM_EPS);
+        const float coef = (D != 0.f) ? (1.f - momentum) / D : 0.f;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int c = lane + 32 * t;
+            if (c < C) {
+                float dmp = clamped ? g[t] * inv : (g[t] - Mn[i * C + c] * dot) * inv;
+                dS[(size_t)i * C + c] = coef * dmp;
+            }
+        }
+    }
+    // dW_j = sum_i dz[i][j] M_i ; db_j = sum_i dz[i][j]
+    for (int idx = tid; idx < K * C; idx += UP_THREADS) {
+        const int j = idx / C, c = idx - j * C;
+        float a = 0.f;
+        for (int i = 0; i < K; ++i) a = fmaf(zs[i * UP_KMAX + j], Mn[i * C + c], a);
+        dW[idx] = a;
+    }
+    if (tid < K) {
+        float a = 0.f;
+        for (int i = 0; i < K; ++i) a += zs[i * UP_KMAX + tid];
+        db[tid] = a;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ dispatch
+
+template <typename T, int C, int KP>
+int launch_write_reduce(const void* f, const int64_t* labels, float* SD, int B, int h, int w, int Hm, int Wm, int K,
+                        cudaStream_t st) {
+    constexpr int LD = WR_P + 1, CS = C + 4;
+    const size_t smem = sizeof(float) * ((size_t)KP * CS + (size_t)C * LD + (C / 32) * WR_P + WR_P + 8 * WR_P);
+    auto kern = write_reduce_kernel<T, C, KP>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int hw = h * w, tiles = (hw + WR_P - 1) / WR_P, ntiles = B * tiles;
+    int grid = 148 * 2;
+    if (grid > ntiles) grid = ntiles;
+    // down-sampling the label map to the feature grid: scale = (Hm-1)/(h-1)  (in = labels, out = features)
+    const float sy = h > 1 ? (float)(Hm - 1) / (float)(h - 1) : 0.f;
+    const float sx = w > 1 ? (float)(Wm - 1) / (float)(w - 1) : 0.f;
+    kern<<<grid, C, smem, st>>>((const T*)f, (const long long*)labels, SD, h, w, Hm, Wm, K, sy, sx, tiles, ntiles);
+    PM_CHECK_LAUNCH();
+    return 0;
+}
+
+template <typename T, int CW, int KP>
+int launch_write_bwd(const float* dS, const void* f, const int64_t* labels, void* df, int B, int h, int w, int Hm,
+                     int Wm, int K, cudaStream_t st) {
+    constexpr int C = CW * WB_WARPS;
+    const size_t smem = sizeof(float) * ((size_t)KP * (C + 1) + WB_WARPS * WB_P + 2 * WB_P);
+    auto kern = write_bwd_kernel<T, CW, KP>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int hw = h * w, tiles = (hw + WB_P - 1) / WB_P;
+    const float sy = h > 1 ? (float)(Hm - 1) / (float)(h - 1) : 0.f;
+    const float sx = w > 1 ? (float)(Wm - 1) / (float)(w - 1) : 0.f;
+    kern<<<B * tiles, WB_THREADS, smem, st>>>(dS, (const T*)f, (const long long*)labels, (T*)df, h, w, Hm, Wm, K, sy,
+                                               sx, tiles);
+    PM_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace pm
+
+#define PMW_DISPATCH_CW(T, KP, FN, ...)                  \
+    switch (C) {                                         \
+        case 32: return pm::FN<T, 4, KP>(__VA_ARGS__);   \
+        case 64: return pm::FN<T, 8, KP>(__VA_ARGS__);   \
+        case 128: return pm::FN<T, 16, KP>(__VA_ARGS__); \
+        case 256: return pm::FN<T, 32, KP>(__VA_ARGS__); \
+        default: return PM_ERR_CHANNELS;                 \
+    }
+#define PMW_DISPATCH_C(T, KP, FN, ...)                    \
+    switch (C) {                                          \
+        case 32: return pm::FN<T, 32, KP>(__VA_ARGS__);   \
+        case 64: return pm::FN<T, 64, KP>(__VA_ARGS__);   \
+        case 128: return pm::FN<T, 128, KP>(__VA_ARGS__); \
+        case 256: return pm::FN<T, 256, KP>(__VA_ARGS__); \
+        default: return PM_ERR_CHANNELS;                  \
+    }
+#define PMW_DISPATCH(MACRO, FN, ...)                                   \
+    do {                                                               \
+        if (dtype == PM_F32) {                                         \
+            if (K <= 19) { MACRO(float, 20, FN, __VA_ARGS__) }         \
+            else { MACRO(float, 32, FN, __VA_ARGS__) }                 \
+        } else if (dtype == PM_BF16) {                                 \
+            if (K <= 19) { MACRO(__nv_bfloat16, 20, FN, __VA_ARGS__) } \
+            else { MACRO(__nv_bfloat16, 32, FN, __VA_ARGS__) }         \
+        }                                                              \
+        return PM_ERR_DTYPE;                                           \
+    } while (0)
+
+static int check_write(int B, int C, int h, int w, int Hm, int Wm, int K, int dtype) {
+    if (dtype != PM_F32 && dtype != PM_BF16) return PM_ERR_DTYPE;
+    if (C != 32 && C != 64 && C != 128 && C != 256) return PM_ERR_CHANNELS;
+    if (K < 1 || K > 31) return PM_ERR_SLOTS;
+    if (B <= 0 || h <= 0 || w <= 0 || Hm <= 0 || Wm <= 0 || (long long)B * h * w > 0x7fffffffLL / 64)
+        return PM_ERR_SHAPE;
+    return 0;
+}
+
+extern "C" int pm_write_reduce_fwd(const void* f, const int64_t* labels, float* SD, int B, int C, int h, int w, int Hm,
+                                   int Wm, int K, int dtype, void* stream) {
+    if (!f || !labels || !SD) return PM_ERR_NULL;
+    if (int e = check_write(B, C, h, w, Hm, Wm, K, dtype)) return e;
+    if ((uintptr_t)SD & 15) return PM_ERR_ALIGN;
+    PMW_DISPATCH(PMW_DISPATCH_C, launch_write_reduce, f, labels, SD, B, h, w, Hm, Wm, K, (cudaStream_t)stream);
+}
+
+extern "C" int pm_write_bwd(const float* dS, const void* f, const int64_t* labels, void* df, int B, int C, int h, int w,
+                            int Hm, int Wm, int K, int dtype, void* stream) {
+    if (!dS || !f || !labels || !df) return PM_ERR_NULL;
+    if (int e = check_write(B, C, h, w, Hm, Wm, K, dtype)) return e;
+    PMW_DISPATCH(PMW_DISPATCH_CW, launch_write_bwd, dS, f, labels, df, B, h, w, Hm, Wm, K, (cudaStream_t)stream);
+}
+
+extern "C" int pm_update_fwd(const float* SD, const float* M_old, float momentum, const float* W_cls,
+                             const float* b_cls, float* M_new, float* losses, float* saved, int C, int K,
+                             void* stream) {
+    if (!SD || !M_old || !W_cls || !b_cls || !M_new || !losses || !saved) return PM_ERR_NULL;
+    if (C != 32 && C != 64 && C != 128 && C != 256) return PM_ERR_CHANNELS;
+    if (K < 1 || K > 31) return PM_ERR_SLOTS;
+    const size_t smem = sizeof(float) * ((size_t)2 * K * C + K * pm::UP_KMAX + pm::UP_WARPS + K);
+    cudaError_t e = cudaFuncSetAttribute(pm::update_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    pm::update_fwd_kernel<<<1, pm::UP_THREADS, smem, (cudaStream_t)stream>>>(SD, M_old, momentum, W_cls, b_cls, M_new,
+                                                                              losses, saved, C, K);
+    PM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int pm_update_bwd(const float* dM_new, const float* g_div, const float* g_cls, const float* M_new,
+                             const float* saved, const float* W_cls, const float* b_cls, float momentum, float* dS,
+                             float* dW_cls, float* db_cls, int C, int K, void* stream) {
+    if (!M_new || !saved || !W_cls || !b_cls || !dS || !dW_cls || !db_cls) return PM_ERR_NULL;
+    if (C != 32 && C != 64 && C != 128 && C != 256) return PM_ERR_CHANNELS;
+    if (K < 1 || K > 31) return PM_ERR_SLOTS;
+    const size_t smem = sizeof(float) * ((size_t)2 * K * C + 2 * K * pm::UP_KMAX);
+    cudaError_t e = cudaFuncSetAttribute(pm::update_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    pm::update_bwd_kernel<<<1, pm::UP_THREADS, smem, (cudaStream_t)stream>>>(dM_new, g_div, g_cls, M_new, saved, W_cls,
+                                                                              b_cls, momentum, dS, dW_cls, db_cls, C, K);
+    PM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int pm_version(void) { return 100; }
+
+extern "C" const char* pm_status_string(int code) {
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    switch (code) {
+        case PM_OK: return "ok";
+        case PM_ERR_NULL: return "a required pointer is NULL";
+        case PM_ERR_DTYPE: return "dtype must be PM_F32 (0) or PM_BF16 (1)";
+        case PM_ERR_CHANNELS: return "C (mem_dim) must be one of 32, 64, 128, 256";
+        case PM_ERR_SLOTS: return "K (mem_slot) must be in 1..31";
+        case PM_ERR_SHAPE: return "a dimension is <= 0 or too large";
+        case PM_ERR_ALIGN: return "a pointer is not aligned as documented";
+        default: return "unknown pinmem_b200 status";
+    }
+}

@@ -1,0 +1,316 @@
+"""B200-native drop-in for the reference's ``network/memory.py`` (``Memory_sup``, ``Writingnet``).
+
+Same constructor, attributes, sub-module names (``output``, ``writenet.writefeat``, ``clsfier`` -- so
+``state_dict`` keys, ``SyncBatchNorm`` conversion and the meta-learning ``put_theta`` of train.py:246-277
+keep working), same 5-tuple from ``forward`` and the same ``m_items`` aliasing rules as the reference
+(memory.py:94-122, 167-257, 317-336); the arithmetic between the two 1x1-conv blocks runs in the
+hand-written sm_100a kernels of ``csrc/`` reached through the C ABI of ``include/pinmem_b200.h``.
+There is no CPU path and no torch fallback: tensors off the GPU raise.
+
+Install under the reference's module name with ``pinthememory_b200.install()``.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import capi
+from . import sharding
+
+IGNORE_LABEL = 255
+
+
+def initialize_weights(*models):
+    """memory.py:9-19: conv kaiming-normal, BN weight 1 / bias 1e-4, Linear N(0, 1e-4) / bias 0."""
+    for model in models:
+        for module in model.modules():
+            if isinstance(module, nn.Conv2d):
+                nn.init.kaiming_normal_(module.weight, nonlinearity="relu")
+            elif isinstance(module, nn.BatchNorm2d):
+                module.weight.data.fill_(1.0)
+                module.bias.data.fill_(1e-4)
+            elif isinstance(module, nn.Linear):
+                module.weight.data.normal_(0.0, 0.0001)
+                module.bias.data.zero_()
+
+
+def _check_labels(mask, B):
+    if mask.dtype != torch.int64:
+        raise RuntimeError(f"pinmem_b200: labels must be int64 (got {mask.dtype}); the reference one-hots them")
+    if mask.dim() != 3 or mask.shape[0] != B:
+        raise RuntimeError(f"pinmem_b200: labels must be [B,Hm,Wm] with B={B}, got {tuple(mask.shape)}")
+    capi.require_cuda(mask)
+    return mask.contiguous()
+
+
+def _check_features(x, what):
+    capi.require_cuda(x)
+    if x.dim() != 4:
+        raise RuntimeError(f"pinmem_b200: {what} must be [B,C,h,w], got {tuple(x.shape)}")
+    capi.dtype_code(x)
+    return x.contiguous()
+
+
+def draw_gumbel_pair(N, K, device):
+    """The two noise tensors of ``F.gumbel_softmax`` in the reference's order (memory.py:183-184):
+    the dim-0 (score_query) draw first, then the dim-1 (score_memory) draw, each
+    ``-empty_like(score).exponential_().log()`` on an fp32 [N,K] tensor, so the device generator stays
+    aligned with the reference module."""
+    probe = torch.empty(N, K, dtype=torch.float32, device=device)
+    g_query = -torch.empty_like(probe, memory_format=torch.legacy_contiguous_format).exponential_().log()
+    g_memory = -torch.empty_like(probe, memory_format=torch.legacy_contiguous_format).exponential_().log()
+    return g_query, g_memory
+
+
+class _ReadFn(torch.autograd.Function):
+    """x, M (, labels, noise) -> u = [q ; p.M], score_query, score_memory, readloss, label histogram."""
+
+    @staticmethod
+    def forward(ctx, x, M, labels, g_query, g_memory, temperature, K):
+        B, C, h, w = x.shape
+        N = B * h * w
+        dev = x.device
+        KP = capi.score_stride(K)
+        u = torch.empty(B, 2 * C, h, w, dtype=x.dtype, device=dev)
+        s = torch.empty(N, KP, dtype=torch.float32, device=dev)
+        score_m = torch.empty(N, K, dtype=torch.float32, device=dev)
+        score_q = torch.empty(N, K, dtype=torch.float32, device=dev)
+        M = M.contiguous()
+        capi.read_fwd(x, M, g_memory, u, s, score_m, K)
+        cs_ws = torch.empty(capi.colsoftmax_workspace_floats(K), dtype=torch.float32, device=dev)
+        capi.colsoftmax(s, g_query, score_q, cs_ws, N, K)
+        if labels is not None:
+            # one zeroed allocation: [ds_rl (N*KP floats) | workspace (40 x 8 bytes) | out (2 floats)]
+            buf = torch.zeros(N * KP + 2 * capi.WS_WORDS + 4, dtype=torch.float32, device=dev)
+            ds_rl = buf[: N * KP]
+            ws = buf[N * KP: N * KP + 2 * capi.WS_WORDS]
+            rl_out = buf[N * KP + 2 * capi.WS_WORDS:]
+            capi.readloss_fwd(s, labels, temperature, B, h, w, K, ds_rl, ws, rl_out)
+            readloss = rl_out[0]
+            hist = ws.view(torch.int64)[capi.WS_HIST: capi.WS_HIST + K + 1]
+        else:
+            ds_rl = rl_out = None
+            readloss = torch.zeros((), dtype=torch.float32, device=dev)
+            hist = torch.zeros(K + 1, dtype=torch.int64, device=dev)
+        ctx.K = K
+        ctx.has_loss = labels is not None
+        ctx.save_for_backward(x, M, score_m, ds_rl, rl_out)
+        ctx.mark_non_differentiable(score_q, score_m, hist)
+        return u, score_q.view(B, h, w, K), score_m.view(B, h, w, K), readloss, hist
+
+    @staticmethod
+    def backward(ctx, du, _g_sq, _g_sm, g_loss, _g_hist):
+        x, M, score_m, ds_rl, rl_out = ctx.saved_tensors
+        B, C, h, w = x.shape
+        K = ctx.K
+        need_dM = ctx.needs_input_grad[1]
+        if du is None:
+            du = torch.zeros(B, 2 * C, h, w, dtype=x.dtype, device=x.device)
+        du = du.to(x.dtype).contiguous()
+        if ctx.has_loss and g_loss is not None:
+            g_loss = g_loss.to(torch.float32).contiguous()
+        else:
+            g_loss = None
+        dx = torch.empty_like(x)
+        ds = torch.empty(B * h * w, capi.score_stride(K), dtype=torch.float32, device=x.device) if need_dM else None
+        capi.read_bwd(du, x, M, score_m, ds_rl if g_loss is not None else None, g_loss,
+                      rl_out if g_loss is not None else None, dx, ds, K)
+        dM = None
+        if need_dM:
+            dM = torch.zeros_like(M)
+            capi.read_bwd_dM(du, x, score_m, ds, dM, K)
+        return dx, dM, None, None, None, None, None
+
+
+class _WriteFn(torch.autograd.Function):
+    """f, labels, M_old, classifier -> new memory, divergence loss, classification loss.
+
+    With a shard group the packed class sums|counts are all-reduced before the update and the gradient
+    w.r.t. the sums is all-reduced in the backward, so every rank computes the update of
+    the concatenated global batch.
+    """
+
+    @staticmethod
+    def forward(ctx, f, labels, M_old, W, b, momentum, K, group):
+        B, C, h, w = f.shape
+        dev = f.device
+        SD = torch.zeros(K + 1, C + 4, dtype=torch.float32, device=dev)
+        capi.write_reduce_fwd(f, labels, SD, K)
+        if group is not None:
+            sharding.all_reduce_sum_(SD, group)
+        M_old = M_old.detach().contiguous()
+        W = W.detach().to(torch.float32).contiguous()
+        b = b.detach().to(torch.float32).contiguous()
+        M_new = torch.empty(K, C, dtype=torch.float32, device=dev)
+        losses = torch.empty(2, dtype=torch.float32, device=dev)
+        saved = torch.empty(2 * K, dtype=torch.float32, device=dev)
+        capi.update_fwd(SD, M_old, momentum, W, b, M_new, losses, saved, C, K)
+        ctx.K, ctx.momentum, ctx.group = K, momentum, group
+        ctx.save_for_backward(f, labels, M_new, saved, W, b)
+        ctx.mark_non_differentiable(SD)
+        return M_new, losses[0], losses[1], SD
+
+    @staticmethod
+    def backward(ctx, dM_new, g_div, g_cls, _g_sd):
+        f, labels, M_new, saved, W, b = ctx.saved_tensors
+        K, C = ctx.K, f.shape[1]
+        dev = f.device
+        as32 = lambda t: None if t is None else t.to(torch.float32).contiguous()
+        dS = torch.empty(K, C, dtype=torch.float32, device=dev)
+        dW = torch.empty(K, C, dtype=torch.float32, device=dev)
+        db = torch.empty(K, dtype=torch.float32, device=dev)
+        capi.update_bwd(as32(dM_new), as32(g_div), as32(g_cls), M_new, saved, W, b, ctx.momentum, dS, dW, db, C, K)
+        if ctx.group is not None:
+            sharding.all_reduce_sum_(dS, ctx.group)
+        df = None
+        if ctx.needs_input_grad[0]:
+            df = torch.empty_like(f)
+            capi.write_bwd(dS, f, labels, df, K)
+        return df, None, None, dW, db, None, None, None
+
+
+class Writingnet(nn.Module):
+    """relu(x + BN(conv1x1(x))) -- memory.py:67-87 (stays a cuDNN/cuBLAS block)."""
+
+    def __init__(self, input_feature_dim, feature_dim):
+        super().__init__()
+        assert input_feature_dim == feature_dim, \
+            "Should match when residual mode is on ({} != {})".format(input_feature_dim, feature_dim)
+        self.writefeat = nn.Sequential(
+            nn.Conv2d(input_feature_dim, feature_dim, kernel_size=1, stride=1, bias=False),
+            nn.BatchNorm2d(feature_dim),
+        )
+        self.relu = nn.ReLU(inplace=True)
+        initialize_weights(self)
+
+    def forward(self, x):
+        return self.relu(x + self.writefeat(x))
+
+
+class Memory_sup(nn.Module):
+    """Categorical class memory with the reference's interface (memory.py:93-257, 317-336)."""
+
+    def __init__(self, memory_size, input_feature_dim, feature_dim, momentum, temperature, gumbel_read,
+                 device=None):
+        super().__init__()
+        self.memory_size = memory_size
+        self.feature_dim = feature_dim
+        self.momentum = momentum
+        self.initial_momentum = momentum
+        self.temperature = temperature
+        self.output = nn.Sequential(
+            nn.Conv2d(feature_dim * 2, input_feature_dim, kernel_size=1, stride=1, bias=False),
+            nn.BatchNorm2d(input_feature_dim),
+            nn.ReLU(inplace=True),
+        )
+        self.writenet = Writingnet(input_feature_dim, feature_dim)
+        # the reference puts its state on the GPU unconditionally (memory.py:111,121); ``device`` exists
+        # only so host-side logic can be unit-tested without one -- forward() still refuses CPU tensors.
+        dev = torch.device("cuda") if device is None else torch.device(device)
+        self.mem_cls = torch.arange(self.memory_size, device=dev)
+        self.clsfier = nn.Linear(in_features=self.feature_dim, out_features=self.memory_size, bias=True)
+        self.celoss = nn.CrossEntropyLoss(ignore_index=IGNORE_LABEL)
+        self.gumbel_read = gumbel_read
+        self.writeTF = lambda x: x.clone()
+        self.m_items = F.normalize(torch.rand((memory_size, feature_dim), dtype=torch.float), dim=1).to(dev)
+        initialize_weights(self)
+        # extras (not in the reference)
+        self.shard_group = None        # set by sharding.enable_sharded_update()
+        self.last_label_hist = None    # int64 [K+1] label histogram of the last read with labels
+        self.last_class_sums = None    # fp32 [K+1, C+4] sums|counts of the last write (after all-reduce)
+
+    # ------------------------------------------------------------------------------------- forward
+
+    def forward(self, query, mask=None, memory_writing=True, writing_detach=True):
+        updated_query, score_query, score_memory, readloss = self.read(query, mask, memory_writing)
+        if memory_writing:
+            writeloss = self.write(query, mask, writing_detach)
+        else:
+            writeloss = [0, 0]
+        return updated_query, score_query, score_memory, readloss, writeloss
+
+    def _memory_for_kernels(self, device):
+        M = self.m_items
+        if not M.is_cuda:
+            raise RuntimeError("pinmem_b200 has no CPU path: m_items must live on a CUDA device")
+        if M.dtype != torch.float32:
+            raise RuntimeError("pinmem_b200: m_items must be float32")
+        if M.shape != (self.memory_size, self.feature_dim):
+            raise RuntimeError(f"pinmem_b200: m_items must be [{self.memory_size},{self.feature_dim}]")
+        return M
+
+    def read(self, query, mask, memory_writing):
+        """memory.py:317-336. Returns (updated_query, score_query, score_memory, readloss)."""
+        query = _check_features(query, "query")
+        B, C, h, w = query.shape
+        if C != self.feature_dim:
+            raise RuntimeError(f"pinmem_b200: query has {C} channels, memory has {self.feature_dim}")
+        if memory_writing:  # memory.py:323-324: cut the gradient into the memory when it is about to be rewritten
+            self.m_items = self.m_items.detach()
+        M = self._memory_for_kernels(query.device)
+        labels = _check_labels(mask, B) if mask is not None else None
+        g_query = g_memory = None
+        if self.gumbel_read:
+            g_query, g_memory = draw_gumbel_pair(B * h * w, self.memory_size, query.device)
+        u, score_query, score_memory, readloss, hist = _ReadFn.apply(
+            query, M, labels, g_query, g_memory, float(self.temperature), self.memory_size)
+        if labels is None:
+            readloss = 0  # memory.py:178
+        else:
+            self.last_label_hist = hist
+        updated_query = self.output(u)
+        return updated_query, score_query, score_memory, readloss
+
+    def write(self, input, mask, writing_detach=True):
+        """memory.py:206-257. Rebinds ``m_items`` to a fresh tensor; returns [div_loss, cls_loss]."""
+        query = _check_features(input, "input")
+        B = query.shape[0]
+        if mask is None:
+            raise RuntimeError("pinmem_b200: memory_writing=True needs labels (the reference crashes at memory.py:208)")
+        labels = _check_labels(mask, B)
+        f = self.writenet(query)
+        f = _check_features(f, "write feature")
+        M_old = self._memory_for_kernels(query.device)
+        M_new, div_loss, cls_loss, SD = _WriteFn.apply(f, labels, M_old, self.clsfier.weight, self.clsfier.bias,
+                                                       float(self.momentum), self.memory_size, self.shard_group)
+        self.last_class_sums = SD
+        self.m_items = M_new.detach() if writing_detach else M_new
+        return [div_loss, cls_loss]
+
+    # ----------------------------------------------------------------------- external entry points
+
+    def get_score(self, query, mask, mem):
+        """memory.py:167-189 on an already normalised NHWC query (validation, train.py:891-896).
+
+        Forward only (the reference calls it under ``no_grad``): returns
+        (score_query [N,K], score_memory [N,K], readloss).
+        """
+        capi.require_cuda(query, mem)
+        Bq, h, w, C = query.shape
+        K = mem.shape[0]
+        N = Bq * h * w
+        dev = query.device
+        with torch.no_grad():
+            q = query.detach().to(torch.float32).contiguous()
+            M = mem.detach().to(torch.float32).contiguous()
+            KP = capi.score_stride(K)
+            s = torch.empty(N, KP, dtype=torch.float32, device=dev)
+            capi.score_nhwc(q, M, s, N, C, K)
+            if mask is not None:
+                labels = _check_labels(mask, Bq)
+                buf = torch.zeros(N * KP + 2 * capi.WS_WORDS + 4, dtype=torch.float32, device=dev)
+                ws = buf[N * KP: N * KP + 2 * capi.WS_WORDS]
+                rl_out = buf[N * KP + 2 * capi.WS_WORDS:]
+                capi.readloss_fwd(s, labels, float(self.temperature), Bq, h, w, K, buf[: N * KP], ws, rl_out)
+                readloss = rl_out[0]
+                self.last_label_hist = ws.view(torch.int64)[capi.WS_HIST: capi.WS_HIST + K + 1]
+            else:
+                readloss = 0
+            g_query = g_memory = None
+            if self.gumbel_read:
+                g_query, g_memory = draw_gumbel_pair(N, K, dev)
+            score_query = torch.empty(N, K, dtype=torch.float32, device=dev)
+            score_memory = torch.empty(N, K, dtype=torch.float32, device=dev)
+            cs_ws = torch.empty(capi.colsoftmax_workspace_floats(K), dtype=torch.float32, device=dev)
+            capi.colsoftmax(s, g_query, score_query, cs_ws, N, K)
+            capi.rowsoftmax(s, g_memory, score_memory, N, K)
+        return score_query, score_memory, readloss

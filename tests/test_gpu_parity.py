@@ -1,0 +1,208 @@
+"""GPU parity: the CUDA path (through the C ABI) against the reference's committed outputs and the oracle.
+
+Tolerances (BASELINE.json north_star): fp32 1e-5 relative (rel-L2 and max-abs/scale per tensor), bf16 2e-2,
+integer results (label histogram, 0/1-weight counts) bit-exact.
+"""
+import pytest
+import torch
+
+from golden_util import LOSS_WEIGHTS, assert_close, golden_names, load_golden, load_state
+
+pytestmark = pytest.mark.gpu
+
+TOL32 = 1e-5
+TOL16 = 2e-2
+
+
+@pytest.fixture(autouse=True)
+def _exact_fp32_convs():
+    # the two 1x1-conv blocks stay torch/cuDNN: keep them in true fp32 for the 1e-5 comparison
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _new_module(K, C, momentum, temperature, gumbel):
+    from pinthememory_b200.memory import Memory_sup
+
+    return Memory_sup(K, C, C, momentum, temperature, gumbel).cuda()
+
+
+def _total(uq, rl, wl, G, has_labels, writing):
+    total = (uq * G).sum()
+    if has_labels:
+        total = total + LOSS_WEIGHTS["read"] * rl
+    if writing:
+        total = total + LOSS_WEIGHTS["div"] * wl[0] + LOSS_WEIGHTS["cls"] * wl[1]
+    return total
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_module_reproduces_reference_fixture(name, monkeypatch):
+    """Whole module (our kernels + the two torch conv blocks) vs. outputs of the unmodified reference."""
+    from pinthememory_b200 import memory as pm_memory
+
+    meta, fx = load_golden(name, "cuda")
+    mem = _new_module(meta["K"], meta["C"], meta["momentum"], meta["temperature"], bool(meta.get("gumbel")))
+    load_state(mem, fx)
+    mem.train(meta["train"])
+    if meta.get("gumbel"):  # replay the noise the reference drew on its CPU generator
+        monkeypatch.setattr(pm_memory, "draw_gumbel_pair", lambda N, K, dev: (fx["g_query"], fx["g_memory"]))
+    if meta.get("mem_grad"):
+        mem.m_items = mem.m_items.clone().requires_grad_(True)
+    mem_in = mem.m_items
+    m_in_copy = mem_in.detach().clone()
+    x = fx["x"].clone().requires_grad_(meta["backward"])
+    labels = fx.get("labels")
+    uq, sq, sm, rl, wl = mem(x, labels, meta["writing"], meta["detach"])
+
+    assert torch.equal(mem_in.detach(), m_in_copy), "m_items must never be updated in place"
+    assert_close(uq.detach(), fx["updated_query"], TOL32, "updated_query")
+    assert_close(sq.detach(), fx["score_query"], TOL32, "score_query")
+    assert_close(sm.detach(), fx["score_memory"], TOL32, "score_memory")
+    assert_close(mem.m_items.detach(), fx["m_items_out"], TOL32, "m_items")
+    if labels is None:
+        assert rl == 0 and isinstance(rl, int)
+    else:
+        assert_close(torch.as_tensor(rl).detach().reshape(()), fx["readloss"].reshape(()), TOL32, "readloss")
+    if meta["writing"]:
+        assert_close(wl[0].detach().reshape(()), fx["div_loss"].reshape(()), TOL32, "div_loss")
+        assert_close(wl[1].detach().reshape(()), fx["cls_loss"].reshape(()), TOL32, "cls_loss")
+        assert mem.m_items.requires_grad == (not meta["detach"] and meta["backward"])
+    else:
+        assert wl == [0, 0]
+    if meta["backward"]:
+        total = _total(uq, rl, wl, fx["G"], labels is not None, meta["writing"])
+        total.backward(retain_graph=True)
+        assert_close(x.grad, fx["grad_x"], TOL32, "grad_x")
+        if meta.get("mem_grad"):
+            assert_close(mem_in.grad, fx["grad_m_items"], TOL32, "grad_m_items")
+        for n, p in mem.named_parameters():
+            key = "grad_param." + n
+            if key in fx:
+                assert p.grad is not None, n
+                assert_close(p.grad, fx[key], 2e-5 if "output" in n else TOL32, n)
+        # train.py:541 backpropagates with retain_graph=True and walks the graph again later
+        g1 = x.grad.clone()
+        x.grad = None
+        total.backward()
+        assert_close(x.grad, g1, 1e-6, "second backward")
+
+
+def _oracle_case(B, C, h, w, Hm, Wm, K, kind, seed, dtype=torch.float32, gumbel=False, temperature=1.0,
+                 momentum=0.8):
+    """Inputs on the GPU + the oracle's answers (fp32 torch ops on the same device) for the core path."""
+    from oracle import memory_oracle as mo
+    from pinthememory_b200 import synth
+
+    dev = "cuda"
+    x = synth.make_features(B, C, h, w, seed=seed, device=dev)
+    f = synth.make_features(B, C, h, w, seed=seed + 1, device=dev).relu_() + 0.01
+    M = synth.make_memory(K, C, seed=seed + 2, device=dev)
+    labels = synth.make_labels(B, Hm, Wm, K, kind, seed=seed + 3, device=dev) if kind else None
+    G = synth.make_upstream_grad((B, 2 * C, h, w), seed=seed + 4, device=dev)
+    Wc = 0.2 * synth.make_features(1, 1, K, C, seed=seed + 5, device=dev).view(K, C)
+    bc = 0.1 * synth.make_features(1, 1, 1, K, seed=seed + 6, device=dev).view(K)
+    noise = synth.make_gumbel_noise(B * h * w, K, seed=seed + 7, device=dev) if gumbel else None
+    if dtype == torch.bfloat16:  # bf16 oracle = fp32 math on bf16-rounded feature tensors
+        x, f, G = (t.to(torch.bfloat16).float() for t in (x, f, G))
+    xo, fo, Mo = x.clone().requires_grad_(True), f.clone().requires_grad_(True), M.clone().requires_grad_(True)
+    Wo, bo = Wc.clone().requires_grad_(True), bc.clone().requires_grad_(True)
+    r = mo.read(xo, Mo, labels, temperature, noise)
+    out = dict(x=x, f=f, M=M, labels=labels, G=G, Wc=Wc, bc=bc, noise=noise, u=r["u"].detach(),
+               score_query=r["score_query"].detach(), score_memory=r["score_memory"].detach(), s=r["s"].detach())
+    total = (r["u"] * G).sum()
+    if labels is not None:
+        out["readloss"] = r["readloss"].detach()
+        total = total + LOSS_WEIGHTS["read"] * r["readloss"]
+        wr = mo.write(fo, labels, M, momentum, Wo, bo)
+        total = total + LOSS_WEIGHTS["div"] * wr["div_loss"] + LOSS_WEIGHTS["cls"] * wr["cls_loss"]
+        # a later read of the new memory (meta-test, train.py:570) sends a gradient into M_new
+        Gm = synth.make_upstream_grad((K, C), seed=seed + 8, device=dev)
+        total = total + (wr["memory_new"] * Gm).sum()
+        out.update(S=wr["S"].detach(), D=wr["D"].detach(), M_new=wr["memory_new"].detach(),
+                   div=wr["div_loss"].detach(), cls=wr["cls_loss"].detach(), Gm=Gm)
+    total.backward()
+    out.update(dx=xo.grad, dM=Mo.grad)
+    if labels is not None:
+        out.update(df=fo.grad, dW=Wo.grad, db=bo.grad)
+    return out
+
+
+def _run_core(o, K, temperature=1.0, momentum=0.8, dtype=torch.float32):
+    """The same computation through the autograd Functions that wrap the C ABI."""
+    from pinthememory_b200.memory import _ReadFn, _WriteFn
+
+    x = o["x"].to(dtype).requires_grad_(True)
+    M = o["M"].clone().requires_grad_(True)
+    gq, gm = o["noise"] if o["noise"] is not None else (None, None)
+    u, sq, sm, rl, hist = _ReadFn.apply(x, M, o["labels"], gq, gm, temperature, K)
+    res = dict(u=u.detach().float(), score_query=sq.detach(), score_memory=sm.detach(), hist=hist)
+    total = (u.float() * o["G"]).sum()
+    if o["labels"] is not None:
+        res["readloss"] = rl.detach()
+        total = total + LOSS_WEIGHTS["read"] * rl
+        f = o["f"].to(dtype).requires_grad_(True)
+        Wc, bc = o["Wc"].clone().requires_grad_(True), o["bc"].clone().requires_grad_(True)
+        M_new, div, cls, SD = _WriteFn.apply(f, o["labels"], o["M"], Wc, bc, momentum, K, None)
+        total = total + LOSS_WEIGHTS["div"] * div + LOSS_WEIGHTS["cls"] * cls + (M_new * o["Gm"]).sum()
+        res.update(S=SD[:, :-4].detach(), D=SD[:, -4].detach(), M_new=M_new.detach(), div=div.detach(),
+                   cls=cls.detach())
+    total.backward()
+    res.update(dx=x.grad.float(), dM=M.grad)
+    if o["labels"] is not None:
+        res.update(df=f.grad.float(), dW=Wc.grad, db=bc.grad)
+    return res
+
+
+CORE_CASES = [
+    # B, C, h, w, Hm, Wm, K, kind, gumbel
+    (2, 256, 48, 48, 768, 768, 19, "blocky", False),   # BASELINE cfg 1 shape
+    (2, 256, 48, 48, 768, 768, 19, "iid", True),
+    (1, 256, 96, 96, 768, 768, 19, "blocky", False),   # OS8 (cfg 2 per-image shape)
+    (2, 256, 33, 65, 129, 257, 19, "iid", False),      # pixel count not a multiple of the tile
+    (1, 64, 7, 9, 29, 41, 19, "iid", False),           # ragged, non-integer scale
+    (2, 128, 12, 20, 12, 20, 19, "iid", False),        # labels at feature resolution (0/1 weights)
+    (2, 32, 16, 16, 64, 64, 7, "blocky", False),       # K != 19 (oracle only; the reference hard-codes 19)
+    (1, 64, 16, 16, 64, 64, 25, "iid", False),         # K > 19 -> 32-wide score rows
+    (1, 256, 128, 256, 0, 0, 19, None, False),         # cfg 5: eval read, no labels
+    (3, 64, 5, 40, 7, 300, 19, "iid", False),          # one tile row, labels coarser than features in y
+]
+
+
+@pytest.mark.parametrize("case", CORE_CASES, ids=lambda c: "B%d_C%d_%dx%d_L%dx%d_K%d_%s_%s" % c[:8] + str(c[8]))
+def test_core_fp32_matches_oracle(case):
+    B, C, h, w, Hm, Wm, K, kind, gumbel = case
+    o = _oracle_case(B, C, h, w, Hm, Wm, K, kind, seed=500 + C + h, gumbel=gumbel)
+    r = _run_core(o, K)
+    for key in ("u", "score_query", "score_memory", "dx", "dM"):
+        assert_close(r[key], o[key], TOL32, key)
+    if kind is not None:
+        for key in ("readloss", "S", "M_new", "div", "cls", "df", "dW", "db"):
+            assert_close(r[key].reshape(o[key].shape), o[key], TOL32, key)
+        assert_close(r["D"], o["D"], 1e-6, "soft counts")
+        lab = o["labels"].reshape(-1).clone()
+        lab[lab == 255] = K
+        assert torch.equal(r["hist"], torch.bincount(lab, minlength=K + 1)), "label histogram must be bit-exact"
+        if (Hm, Wm) == (h, w):  # resample is the identity: counts are integers and must be exact
+            assert torch.equal(r["D"], r["hist"].float())
+
+
+@pytest.mark.parametrize("case", CORE_CASES[:3] + CORE_CASES[4:6], ids=lambda c: "C%d_%dx%d_%s" % (c[1], c[2], c[3], c[7]))
+def test_core_bf16_matches_oracle(case):
+    B, C, h, w, Hm, Wm, K, kind, gumbel = case
+    o = _oracle_case(B, C, h, w, Hm, Wm, K, kind, seed=900 + C + h, dtype=torch.bfloat16, gumbel=gumbel)
+    r = _run_core(o, K, dtype=torch.bfloat16)
+    for key in ("u", "score_query", "score_memory", "dx", "dM", "readloss", "S", "M_new", "div", "cls", "df", "dW",
+                "db"):
+        assert_close(r[key].reshape(o[key].shape), o[key], TOL16, key)
+    assert_close(r["D"], o["D"], 1e-6, "soft counts")  # counts never depend on the feature dtype
+
+
+def test_temperature_and_momentum():
+    o = _oracle_case(2, 64, 12, 12, 48, 48, 19, "iid", seed=77, temperature=0.37, momentum=0.25)
+    r = _run_core(o, 19, temperature=0.37, momentum=0.25)
+    for key in ("readloss", "dx", "M_new", "df", "dM"):
+        assert_close(r[key].reshape(o[key].shape), o[key], TOL32, key)
