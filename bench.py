@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""Benchmark of the categorical-memory hot path (BASELINE.json metric) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dtype f32|bf16]
+                    [--workload cfg2_module_os8_b8] [--labels blocky|iid]
+
+One "step" = one pass of the hot path over one batch of synthetic input: ``Memory_sup.forward(query, labels,
+memory_writing=True, writing_detach=False)`` + backward of ``<G, updated_query> + 0.02*readloss + 0.4*div +
+0.2*cls`` (loss weights train.py:1213-1215), i.e. memory read + update, forward + backward, BN in train mode.
+The metric is feature-map Mpixels/s. Prints ONE JSON line (rank 0).
+
+* ``value``      whole module (our kernels + the two torch 1x1-conv blocks), inputs resident in HBM
+* ``e2e``        the same call with HOST (pinned) inputs: H2D of features+labels and D2H of losses+memory per step
+* ``core``       only the hand-written kernels (write feature f and upstream du given), with the aggregate
+                 fraction of the HBM roofline for A_train bytes/pixel
+* ``roofline``   the dominant kernel: algorithmic bytes / its CUDA-event duration measured inside the timed region
+* ``cpu_baseline`` the CPU port of the reference (oracle/) timed on this host's cores on a bounded sample
+``--impl reference`` times that CPU port instead (all host threads) and prints the same line shape.
+Under torchrun (N>1) every rank runs its own batch (weak scaling); the write path all-reduces the class sums.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from pinthememory_b200 import synth  # noqa: E402
+
+METRIC = "memory read+update fwd+bwd Mpixels/s"
+UNIT = "Mpixels/s"
+K, C = 19, 256
+LOSS_W = dict(read=0.02, div=0.4, cls=0.2)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
+    ap.add_argument("--workload", default="cfg2_module_os8_b8", choices=sorted(synth.WORKLOADS))
+    ap.add_argument("--labels", default="blocky", choices=["blocky", "iid"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------- clock sampler
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                 "hw_power_brake": 0x80, "sw_power_cap": 0x4, "sync_boost": 0x10, "applications_clocks": 0x2}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for n, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------ CPU reference
+
+
+def cpu_reference_run(wl, kind, steps, warmup, sample_B):
+    """The CPU port of the reference module (oracle/) on a bounded sample of the workload, all host threads."""
+    from oracle import memory_oracle as mo
+
+    torch.manual_seed(synth.SEED)
+    B = min(sample_B, wl["B"])
+    mem = mo.OracleMemorySup(K, C, C, 0.8, 1.0, False)
+    mem.train()
+    x = synth.make_features(B, C, wl["h"], wl["w"]).requires_grad_(True)
+    labels = synth.make_labels(B, wl["Hm"], wl["Wm"], K, kind)
+    G = synth.make_upstream_grad((B, C, wl["h"], wl["w"]))
+    M0 = mem.m_items.clone()
+    times = []
+    for i in range(warmup + steps):
+        mem.m_items = M0
+        x.grad = None
+        mem.zero_grad(set_to_none=True)
+        t0 = time.perf_counter()
+        uq, _, _, rl, wlss = mem(x, labels, True, False)
+        torch.autograd.backward([uq, rl, wlss[0], wlss[1]],
+                                [G, torch.tensor(LOSS_W["read"]), torch.tensor(LOSS_W["div"]),
+                                 torch.tensor(LOSS_W["cls"])])
+        t1 = time.perf_counter()
+        if i >= warmup:
+            times.append(t1 - t0)
+    px = B * wl["h"] * wl["w"]
+    total = sum(times)
+    return dict(value=px * len(times) / total / 1e6, ms_per_step=1e3 * total / len(times), cores=torch.get_num_threads(),
+                sample="B=%d of the workload's %d images per step (%dx%d features, %dx%d labels), %d timed steps" %
+                       (B, wl["B"], wl["h"], wl["w"], wl["Hm"], wl["Wm"], len(times)))
+
+
+# -------------------------------------------------------------------------------------------- main
+
+
+def main():
+    args = parse()
+    wl = synth.WORKLOADS[args.workload]
+    if wl["Hm"] == 0:
+        raise SystemExit("bench.py measures the training path; pick a workload with labels")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload_desc = ("%s: per-GPU batch %d, %dx%d feature map, C=%d, K=%d, labels %dx%d int64 (%s), gumbel off, "
+                     "momentum 0.8, T=1" % (args.workload, wl["B"], wl["h"], wl["w"], C, K, wl["Hm"], wl["Wm"],
+                                            args.labels))
+    base = {"metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic",
+            "dtype": args.dtype,
+            "config": {"workload": workload_desc,
+                       "l2": "no flush: per-step working set (x,f,u,du,dx,df + labels ~ %d MB in fp32) exceeds the 126 MB L2"
+                             % round((10 * C * 4 + 8 * wl["Hm"] * wl["Wm"] / (wl["h"] * wl["w"])) * wl["B"] * wl["h"] * wl["w"] / 1e6)}}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sample_B = 2
+        r = cpu_reference_run(wl, args.labels, args.steps, min(args.warmup, 2), sample_B)
+        line = dict(base)
+        line.update({"impl": "reference", "value": r["value"], "ms_per_step": r["ms_per_step"], "n_gpus": args.gpus,
+                     "dtype": "f32", "gpu_launches": 0,
+                     "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                      "sample": r["sample"]},
+                     "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                     "note": "reference's own CPU path = oracle/ port of network/memory.py (the reference is Python and "
+                             "/root/reference is not on this box); torch %s, %d threads" %
+                             (torch.__version__, r["cores"])})
+        print(json.dumps(line))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    import torch.distributed as dist
+
+    from pinthememory_b200 import capi, sharding
+    from pinthememory_b200.memory import Memory_sup, _ReadFn, _WriteFn
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dt = torch.float32 if args.dtype == "f32" else torch.bfloat16
+    B, h, w, Hm, Wm = wl["B"], wl["h"], wl["w"], wl["Hm"], wl["Wm"]
+    N = B * h * w
+    esz = 4 if dt == torch.float32 else 2
+
+    torch.manual_seed(synth.SEED)
+    mem = Memory_sup(K, C, C, 0.8, 1.0, False).to(dev)
+    mem.train()
+    if world > 1:
+        for p in mem.parameters():
+            dist.broadcast(p.data, 0)
+        sharding.broadcast_memory(mem)
+        sharding.enable_sharded_update(mem)
+    seed = synth.SEED + 100 * rank
+    x_host = synth.make_features(B, C, h, w, seed=seed, dtype=dt).pin_memory()
+    lab_host = synth.make_labels(B, Hm, Wm, K, args.labels, seed=seed + 2).pin_memory()
+    x = x_host.to(dev).requires_grad_(True)
+    labels = lab_host.to(dev)
+    G = synth.make_upstream_grad((B, C, h, w), seed=seed + 3, dtype=dt, device=dev)
+    f_core = synth.make_features(B, C, h, w, seed=seed + 5, dtype=dt, device=dev).abs_().requires_grad_(True)
+    Gu = synth.make_upstream_grad((B, 2 * C, h, w), seed=seed + 6, dtype=dt, device=dev)
+    M0 = mem.m_items.clone()
+    gw = [torch.tensor(LOSS_W[k], device=dev) for k in ("read", "div", "cls")]
+    autocast = torch.autocast("cuda", dtype=torch.bfloat16, enabled=(dt == torch.bfloat16))
+
+    def module_step(xin, lab):
+        mem.m_items = M0
+        xin.grad = None
+        mem.zero_grad(set_to_none=True)
+        with autocast:
+            uq, _, _, rl, wlss = mem(xin, lab, True, False)
+        torch.autograd.backward([uq, rl, wlss[0], wlss[1]], [G.to(uq.dtype), gw[0], gw[1], gw[2]])
+        return rl, wlss
+
+    Wc, bc = mem.clsfier.weight, mem.clsfier.bias
+
+    def core_step():
+        x.grad = None
+        f_core.grad = None
+        u, _, _, rl, _ = _ReadFn.apply(x, M0, labels, None, None, 1.0, K)
+        M_new, div, cls, _ = _WriteFn.apply(f_core, labels, M0, Wc, bc, 0.8, K, mem.shard_group)
+        torch.autograd.backward([u, rl, div, cls], [Gu, gw[0], gw[1], gw[2]])
+
+    res_host = torch.empty(3 + K * C, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        xin = x_host.to(dev, non_blocking=True).requires_grad_(True)
+        lab = lab_host.to(dev, non_blocking=True)
+        rl, wlss = module_step(xin, lab)
+        res = torch.cat([rl.detach().reshape(1), wlss[0].detach().reshape(1), wlss[1].detach().reshape(1),
+                         mem.m_items.detach().reshape(-1)])
+        res_host.copy_(res, non_blocking=True)
+
+    def timed(fn, steps, warmup, sample_clocks=False, kernel_timing=False):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        capi.enable_kernel_timing(kernel_timing)
+        capi.reset_counters()
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler:
+            sampler.__enter__()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.__exit__()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        launches = capi.LAUNCHES
+        ktimes = capi.kernel_timings_ms() if kernel_timing else {}
+        capi.enable_kernel_timing(False)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, ktimes, (sampler.summary() if sampler else None)
+
+    # headline: whole module, device-resident inputs
+    ms, launches, _, clocks = timed(lambda: module_step(x, labels), args.steps, args.warmup, sample_clocks=True)
+    ms_per_step = ms / args.steps
+    value = world * N / (ms_per_step * 1e-3) / 1e6
+
+    # per-kernel durations measured live (events around every C-ABI launch) in a second timed region
+    ms_k, _, ktimes, _ = timed(lambda: module_step(x, labels), args.steps, 2, kernel_timing=True)
+    kavg = {k: sum(v) / len(v) for k, v in ktimes.items()}  # ms per call
+    r = Hm * Wm / float(h * w)
+    KP = 20
+    alg_bytes = {  # ALGORITHMIC bytes per launch
+        "pm_read_fwd": N * (3 * C * esz + 4 * KP + 4 * K),
+        "pm_read_bwd": N * (4 * C * esz + 4 * KP + 4 * K),
+        "pm_readloss_fwd": N * (8 * r + 2 * 4 * KP),
+        "pm_write_reduce_fwd": N * (C * esz),
+        "pm_write_bwd": N * (2 * C * esz),
+        "pm_colsoftmax": N * (2 * 4 * KP + 4 * K),
+    }
+    peak, peak_src = measured_peaks()
+    kernels = {}
+    for k, t_ms in kavg.items():
+        ent = {"ms": round(t_ms, 5)}
+        if k in alg_bytes:
+            ent["alg_MB"] = round(alg_bytes[k] / 1e6, 3)
+            ent["GBps"] = round(alg_bytes[k] / (t_ms * 1e-3) / 1e9, 1)
+            ent["frac"] = round(ent["GBps"] / peak, 4)
+        kernels[k] = ent
+    dom = max((k for k in kavg if k in alg_bytes), key=lambda k: kavg[k])
+    ncu_traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            ncu_traffic = json.load(fh).get(args.dtype, {}).get(dom)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[dom]["frac"], "traffic": ncu_traffic, "peak_source": peak_src,
+                "alg_bytes_per_launch": alg_bytes[dom], "launch_ms": kernels[dom]["ms"]}
+
+    # core: hand-written kernels only
+    ms_c, launches_c, _, _ = timed(core_step, args.steps, args.warmup)
+    ms_core = ms_c / args.steps
+    a_train = 10 * C * esz + 8 * r + 8 * K
+    core_gbps = N * a_train / (ms_core * 1e-3) / 1e9
+    core = {"value": world * N / (ms_core * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_core,
+            "a_train_bytes_per_pixel": a_train, "GBps": core_gbps, "frac_of_peak": core_gbps / peak,
+            "gpu_launches_per_step": launches_c / args.steps,
+            "what": "read_fwd+colsoftmax+readloss+write_reduce+update fwd, update+write+read bwd; f and du given"}
+
+    # e2e: host (pinned) inputs through the public module API
+    ms_e, _, _, _ = timed(e2e_step, max(args.steps // 2, 5), 3)
+    ms_e2e = ms_e / max(args.steps // 2, 5)
+    e2e = {"value": world * N / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_e2e,
+           "h2d_bytes_per_step": x_host.numel() * x_host.element_size() + lab_host.numel() * 8,
+           "d2h_bytes_per_step": res_host.numel() * 4,
+           "what": "Memory_sup.forward+backward with pinned-host features and int64 labels copied in, losses + new memory copied out"}
+
+    line = dict(base)
+    line.update({"value": value, "ms_per_step": ms_per_step, "gpu_launches": launches, "clocks": clocks,
+                 "e2e": e2e, "roofline": roofline, "core": core, "kernels": kernels})
+
+    if rank == 0 and world == 1:
+        # like-for-like GPU comparison: the oracle restatement (eager torch ops) on the same B200
+        try:
+            from oracle import memory_oracle as mo
+
+            ora = mo.OracleMemorySup(K, C, C, 0.8, 1.0, False).to(dev)
+            ora.load_state_dict(mem.state_dict())
+            ora.train()
+
+            def eager_step():
+                ora.m_items = M0
+                x.grad = None
+                ora.zero_grad(set_to_none=True)
+                with autocast:
+                    uq, _, _, rl, wlss = ora(x, labels, True, False)
+                torch.autograd.backward([uq, rl, wlss[0], wlss[1]], [G.to(uq.dtype), gw[0], gw[1], gw[2]])
+
+            ms_o, _, _, _ = timed(eager_step, 10, 3)
+            line["torch_eager_same_gpu"] = {"value": N / (ms_o / 10 * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_o / 10,
+                                            "what": "oracle restatement of the reference module, eager PyTorch ops, fp32"
+                                            if dt == torch.float32 else "oracle restatement under bf16 autocast (speed only)"}
+        except Exception as e:  # the comparison is informative only
+            line["torch_eager_same_gpu"] = {"error": str(e)[:200]}
+        if not args.no_cpu_baseline:
+            cb = cpu_reference_run(wl, args.labels, 8, 2, 2)
+            line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "port",
+                                    "sample": cb["sample"], "ms_per_step": cb["ms_per_step"]}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

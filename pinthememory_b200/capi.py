@@ -107,18 +107,61 @@ def score_stride(K):
     return load().pm_score_stride(int(K))
 
 
+# ------------------------------------------------------------------------------- launch accounting
+# bench.py counts the kernels launched inside its timed region and (optionally) brackets every C-ABI call
+# with CUDA events on the launching stream to get per-kernel durations live.
+
+LAUNCHES = 0
+_KERNELS_PER_CALL = {"pm_colsoftmax": 2}
+_timing = None  # name -> list of (start_event, end_event) when enabled
+
+
+def enable_kernel_timing(on=True):
+    global _timing
+    _timing = {} if on else None
+
+
+def kernel_timings_ms():
+    """name -> list of per-call durations (ms). Synchronises."""
+    if _timing is None:
+        return {}
+    torch.cuda.synchronize()
+    return {k: [a.elapsed_time(b) for a, b in v] for k, v in _timing.items()}
+
+
+def reset_counters():
+    global LAUNCHES
+    LAUNCHES = 0
+    if _timing is not None:
+        _timing.clear()
+
+
+def _call(name, *args):
+    global LAUNCHES
+    fn = getattr(load(), name)
+    if _timing is None:
+        code = fn(*args)
+    else:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        code = fn(*args)
+        b.record()
+        _timing.setdefault(name, []).append((a, b))
+    LAUNCHES += _KERNELS_PER_CALL.get(name, 1)
+    _check(code, name)
+
+
 # --------------------------------------------------------------------------------------------- calls
 
 
 def read_fwd(x, M, gumbel_m, u, s, score_m, K):
     B, C, h, w = x.shape
-    _check(load().pm_read_fwd(_ptr(x), _ptr(M), _ptr(gumbel_m), _ptr(u), _ptr(s), _ptr(score_m), B, C, h, w, K,
-                              dtype_code(x), _stream()), "pm_read_fwd")
+    _call("pm_read_fwd", _ptr(x), _ptr(M), _ptr(gumbel_m), _ptr(u), _ptr(s), _ptr(score_m), B, C, h, w, K,
+                              dtype_code(x), _stream())
 
 
 def colsoftmax(s, gumbel_q, score_q, workspace, N, K):
-    _check(load().pm_colsoftmax(_ptr(s), _ptr(gumbel_q), _ptr(score_q), _ptr(workspace), N, K, _stream()),
-           "pm_colsoftmax")
+    _call("pm_colsoftmax", _ptr(s), _ptr(gumbel_q), _ptr(score_q), _ptr(workspace), N, K, _stream())
 
 
 def colsoftmax_workspace_floats(K):
@@ -127,49 +170,49 @@ def colsoftmax_workspace_floats(K):
 
 def readloss_fwd(s, labels, temperature, B, h, w, K, ds_rl, ws, out):
     Hm, Wm = labels.shape[1], labels.shape[2]
-    _check(load().pm_readloss_fwd(_ptr(s), _ptr(labels), float(temperature), B, h, w, Hm, Wm, K, _ptr(ds_rl),
-                                  _ptr(ws), _ptr(out), _stream()), "pm_readloss_fwd")
+    _call("pm_readloss_fwd", _ptr(s), _ptr(labels), float(temperature), B, h, w, Hm, Wm, K, _ptr(ds_rl),
+                                  _ptr(ws), _ptr(out), _stream())
 
 
 def read_bwd(du, x, M, score_m, ds_rl, g_loss, rl_out, dx, ds, K):
     B, C, h, w = x.shape
-    _check(load().pm_read_bwd(_ptr(du), _ptr(x), _ptr(M), _ptr(score_m), _ptr(ds_rl), _ptr(g_loss), _ptr(rl_out),
-                              _ptr(dx), _ptr(ds), B, C, h, w, K, dtype_code(x), _stream()), "pm_read_bwd")
+    _call("pm_read_bwd", _ptr(du), _ptr(x), _ptr(M), _ptr(score_m), _ptr(ds_rl), _ptr(g_loss), _ptr(rl_out),
+                              _ptr(dx), _ptr(ds), B, C, h, w, K, dtype_code(x), _stream())
 
 
 def read_bwd_dM(du, x, score_m, ds, dM, K):
     B, C, h, w = x.shape
-    _check(load().pm_read_bwd_dM(_ptr(du), _ptr(x), _ptr(score_m), _ptr(ds), _ptr(dM), B, C, h, w, K,
-                                 dtype_code(x), _stream()), "pm_read_bwd_dM")
+    _call("pm_read_bwd_dM", _ptr(du), _ptr(x), _ptr(score_m), _ptr(ds), _ptr(dM), B, C, h, w, K,
+                                 dtype_code(x), _stream())
 
 
 def score_nhwc(q, M, s, N, C, K):
-    _check(load().pm_score_nhwc(_ptr(q), _ptr(M), _ptr(s), N, C, K, _stream()), "pm_score_nhwc")
+    _call("pm_score_nhwc", _ptr(q), _ptr(M), _ptr(s), N, C, K, _stream())
 
 
 def rowsoftmax(s, gumbel_m, score_m, N, K):
-    _check(load().pm_rowsoftmax(_ptr(s), _ptr(gumbel_m), _ptr(score_m), N, K, _stream()), "pm_rowsoftmax")
+    _call("pm_rowsoftmax", _ptr(s), _ptr(gumbel_m), _ptr(score_m), N, K, _stream())
 
 
 def write_reduce_fwd(f, labels, SD, K):
     B, C, h, w = f.shape
     Hm, Wm = labels.shape[1], labels.shape[2]
-    _check(load().pm_write_reduce_fwd(_ptr(f), _ptr(labels), _ptr(SD), B, C, h, w, Hm, Wm, K, dtype_code(f),
-                                      _stream()), "pm_write_reduce_fwd")
+    _call("pm_write_reduce_fwd", _ptr(f), _ptr(labels), _ptr(SD), B, C, h, w, Hm, Wm, K, dtype_code(f),
+                                      _stream())
 
 
 def update_fwd(SD, M_old, momentum, W, b, M_new, losses, saved, C, K):
-    _check(load().pm_update_fwd(_ptr(SD), _ptr(M_old), float(momentum), _ptr(W), _ptr(b), _ptr(M_new),
-                                _ptr(losses), _ptr(saved), C, K, _stream()), "pm_update_fwd")
+    _call("pm_update_fwd", _ptr(SD), _ptr(M_old), float(momentum), _ptr(W), _ptr(b), _ptr(M_new),
+                                _ptr(losses), _ptr(saved), C, K, _stream())
 
 
 def update_bwd(dM_new, g_div, g_cls, M_new, saved, W, b, momentum, dS, dW, db, C, K):
-    _check(load().pm_update_bwd(_ptr(dM_new), _ptr(g_div), _ptr(g_cls), _ptr(M_new), _ptr(saved), _ptr(W), _ptr(b),
-                                float(momentum), _ptr(dS), _ptr(dW), _ptr(db), C, K, _stream()), "pm_update_bwd")
+    _call("pm_update_bwd", _ptr(dM_new), _ptr(g_div), _ptr(g_cls), _ptr(M_new), _ptr(saved), _ptr(W), _ptr(b),
+                                float(momentum), _ptr(dS), _ptr(dW), _ptr(db), C, K, _stream())
 
 
 def write_bwd(dS, f, labels, df, K):
     B, C, h, w = f.shape
     Hm, Wm = labels.shape[1], labels.shape[2]
-    _check(load().pm_write_bwd(_ptr(dS), _ptr(f), _ptr(labels), _ptr(df), B, C, h, w, Hm, Wm, K, dtype_code(f),
-                               _stream()), "pm_write_bwd")
+    _call("pm_write_bwd", _ptr(dS), _ptr(f), _ptr(labels), _ptr(df), B, C, h, w, Hm, Wm, K, dtype_code(f),
+                               _stream())

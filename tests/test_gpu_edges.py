@@ -1,0 +1,273 @@
+"""GPU edge cases and full-size properties of the CUDA path (reference semantics)."""
+import math
+
+import pytest
+import torch
+
+from golden_util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _module(K=19, C=64, gumbel=False, momentum=0.8, temperature=1.0):
+    from pinthememory_b200.memory import Memory_sup
+
+    torch.manual_seed(5)
+    m = Memory_sup(K, C, C, momentum, temperature, gumbel).cuda()
+    with torch.no_grad():
+        m.clsfier.weight.normal_(0, 0.2)
+    return m
+
+
+def _oracle_like(mem):
+    from oracle import memory_oracle as mo
+
+    o = mo.OracleMemorySup(mem.memory_size, mem.feature_dim, mem.feature_dim, mem.momentum, mem.temperature,
+                           mem.gumbel_read).cuda()
+    o.load_state_dict(mem.state_dict())
+    o.m_items = mem.m_items.clone()
+    return o
+
+
+@pytest.fixture(autouse=True)
+def _exact_fp32_convs():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def test_native_library_is_loaded():
+    """The .so of this tree is what runs (no silent fallback)."""
+    from pinthememory_b200 import capi
+
+    lib = capi.load()
+    assert lib.pm_version() >= 100
+    with open("/proc/self/maps") as fh:
+        assert "libpinmem_b200.so" in fh.read()
+
+
+def test_cpu_tensors_are_rejected():
+    mem = _module()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        mem(torch.randn(1, 64, 4, 4), None, False)
+
+
+def test_bad_arguments_return_status_codes():
+    from pinthememory_b200 import capi
+
+    x = torch.randn(1, 48, 4, 4, device="cuda")  # C=48 unsupported
+    M = torch.randn(19, 48, device="cuda")
+    u = torch.empty(1, 96, 4, 4, device="cuda")
+    s = torch.empty(16, 20, device="cuda")
+    p = torch.empty(16, 19, device="cuda")
+    with pytest.raises(RuntimeError, match="status -3"):
+        capi.read_fwd(x, M, None, u, s, p, 19)
+    x = torch.randn(1, 64, 4, 4, device="cuda")
+    with pytest.raises(RuntimeError, match="status -4"):
+        capi.read_fwd(x, M, None, u, s, p, 40)
+    with pytest.raises(RuntimeError, match="int64"):
+        _module()(x, torch.zeros(1, 8, 8, dtype=torch.int32, device="cuda"), True)
+
+
+def test_no_labels_and_no_writing_return_python_zeros():
+    mem = _module()
+    x = torch.randn(2, 64, 6, 10, device="cuda")
+    uq, sq, sm, rl, wl = mem(x, None, False)
+    assert isinstance(rl, int) and rl == 0 and wl == [0, 0]
+    assert sq.shape == (2, 6, 10, 19) and sm.shape == (2, 6, 10, 19) and uq.shape == (2, 64, 6, 10)
+    assert_close(sm.sum(-1), torch.ones(2, 6, 10, device="cuda"), 1e-6, "score_memory rows")
+    assert_close(sq.view(-1, 19).sum(0), torch.ones(19, device="cuda"), 1e-5, "score_query columns")
+
+
+def test_all_labels_ignored_gives_nan_readloss_and_untouched_memory():
+    """V == 0: torch's CE returns NaN; every class absent -> memory only re-normalised (memory.py:235)."""
+    mem = _module()
+    ora = _oracle_like(mem)
+    x = torch.randn(2, 64, 8, 8, device="cuda")
+    labels = torch.full((2, 32, 32), 255, dtype=torch.int64, device="cuda")
+    m0 = mem.m_items.clone()
+    with torch.no_grad():
+        _, _, _, rl, wl = mem(x, labels, True, True)
+        _, _, _, rl_o, wl_o = ora(x, labels, True, True)
+    assert math.isnan(float(rl)) and math.isnan(float(rl_o))
+    assert_close(mem.m_items, m0, 1e-6, "memory with no class present")
+    assert_close(mem.m_items, ora.m_items, 1e-6, "vs oracle")
+    assert_close(wl[0], wl_o[0], 1e-5, "div")
+    assert int(mem.last_label_hist[19]) == labels.numel() and int(mem.last_label_hist[:19].sum()) == 0
+
+
+def test_zero_feature_vector_hits_eps_clamp():
+    from oracle import memory_oracle as mo
+    from pinthememory_b200.memory import _ReadFn
+
+    x = torch.randn(1, 64, 4, 8, device="cuda")
+    x[0, :, 1, 3] = 0.0
+    M = torch.nn.functional.normalize(torch.rand(19, 64, device="cuda"), dim=1)
+    G = torch.randn(1, 128, 4, 8, device="cuda")
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    u = _ReadFn.apply(xa, M, None, None, None, 1.0, 19)[0]
+    (u * G).sum().backward()
+    r = mo.read(xb, M)
+    (r["u"] * G).sum().backward()
+    assert torch.isfinite(u).all() and torch.isfinite(xa.grad).all()
+    assert_close(u, r["u"].detach(), 1e-5, "u")
+    # away from the zero pixel the gradients agree; at the zero pixel both are dq/eps (huge but finite)
+    mask = torch.ones_like(x, dtype=torch.bool)
+    mask[0, :, 1, 3] = False
+    assert_close(xa.grad[mask], xb.grad[mask], 1e-5, "dx")
+    assert_close(xa.grad[~mask], xb.grad[~mask], 1e-4, "dx at the clamped pixel")
+
+
+def test_m_items_aliasing_rules():
+    """mem_t is assigned (not copied) across module instances in train.py:530,547,580."""
+    a, b = _module(), _module()
+    mem_t = a.m_items.clone().detach()
+    keep = mem_t.clone()
+    b.m_items = mem_t
+    x = torch.randn(2, 64, 8, 8, device="cuda", requires_grad=True)
+    labels = torch.randint(0, 19, (2, 32, 32), device="cuda")
+    b(x, labels, True, False)
+    assert torch.equal(mem_t, keep)
+    assert b.m_items is not mem_t and b.m_items.requires_grad
+    # writing_detach=True -> detached result
+    b.m_items = mem_t
+    b(x, labels, True, True)
+    assert not b.m_items.requires_grad and torch.equal(mem_t, keep)
+    # memory_writing=False keeps the very same object (and its graph)
+    mg = mem_t.clone().requires_grad_(True)
+    b.m_items = mg
+    b(x, labels, False)
+    assert b.m_items is mg
+
+
+def test_metatest_gradient_reaches_writenet_through_memory():
+    """train.py:555-575: write with graph (B), read the new memory on other data (C), backprop into writenet."""
+    mem = _module()
+    ora = _oracle_like(mem)
+    xa = torch.randn(2, 64, 8, 8, device="cuda")
+    xb = torch.randn(2, 64, 8, 8, device="cuda")
+    la = torch.randint(0, 19, (2, 32, 32), device="cuda")
+    lb = torch.randint(0, 19, (2, 32, 32), device="cuda")
+    G = torch.randn(2, 64, 8, 8, device="cuda")
+    grads = []
+    for m in (mem, ora):
+        m.zero_grad()
+        m(xa, la, True, False)
+        uq, _, _, rl, _ = m(xb, lb, False)
+        ((uq * G).sum() + 0.02 * rl).backward()
+        grads.append({n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None})
+    assert "writenet.writefeat.0.weight" in grads[0]
+    for n in grads[1]:
+        # these gradients pass through BatchNorm's batch statistics twice (sums with cancellation over
+        # all pixels), which amplifies fp32 rounding of either implementation to a few 1e-5
+        assert_close(grads[0][n], grads[1][n], 1e-4, n)
+
+
+def test_gumbel_rng_alignment_with_torch():
+    """Same seed -> same noise as F.gumbel_softmax draws in the reference's order (dim 0 first)."""
+    mem = _module(gumbel=True)
+    ora = _oracle_like(mem)
+    x = torch.randn(2, 64, 8, 8, device="cuda")
+    torch.manual_seed(11)
+    with torch.no_grad():
+        _, sq, sm, _, _ = mem(x, None, False)
+    torch.manual_seed(11)
+    with torch.no_grad():
+        _, sq_o, sm_o, _, _ = ora(x, None, False)
+    assert_close(sq, sq_o, 1e-5, "score_query")
+    assert_close(sm, sm_o, 1e-5, "score_memory")
+
+
+def test_get_score_external_entry_point():
+    """train.py:891-896 calls get_score(normalised NHWC query, gt, m_items)."""
+    mem = _module()
+    ora = _oracle_like(mem)
+    q = torch.nn.functional.normalize(torch.randn(2, 9, 7, 64, device="cuda"), dim=3)
+    labels = torch.randint(0, 19, (2, 36, 28), device="cuda")
+    labels[0, :5] = 255
+    with torch.no_grad():
+        a = mem.get_score(q, labels, mem.m_items)
+        b = ora.get_score(q, labels, ora.m_items)
+    for x, y, n in zip(a, b, ("score_query", "score_memory", "readloss")):
+        assert_close(torch.as_tensor(x).reshape(torch.as_tensor(y).shape), torch.as_tensor(y), 1e-5, n)
+    assert mem.get_score(q, None, mem.m_items)[2] == 0
+
+
+def test_state_dict_round_trip_with_oracle_names():
+    mem = _module()
+    ora = _oracle_like(mem)
+    assert list(mem.state_dict().keys()) == list(ora.state_dict().keys())
+    assert "m_items" not in mem.state_dict()
+    mem.load_state_dict(ora.state_dict())
+
+
+# ------------------------------------------------------------------- full-size (BASELINE cfg 2) checks
+
+
+def test_full_size_cfg2_against_oracle_on_device_and_properties():
+    """B=8, 96x96, C=256, K=19, 768x768 labels: oracle evaluated with torch ops on the same GPU."""
+    from test_gpu_parity import _oracle_case, _run_core
+
+    K = 19
+    o = _oracle_case(8, 256, 96, 96, 768, 768, K, "blocky", seed=304)
+    r = _run_core(o, K)
+    for key in ("u", "score_query", "score_memory", "readloss", "dx", "dM", "S", "M_new", "div", "cls", "df", "dW",
+                "db"):
+        assert_close(r[key].reshape(o[key].shape), o[key], 1e-5, key)
+    N = 8 * 96 * 96
+    # size-independent properties
+    lab = o["labels"].reshape(-1).clone()
+    lab[lab == 255] = K
+    assert torch.equal(r["hist"], torch.bincount(lab, minlength=K + 1))
+    assert abs(float(r["D"].double().sum()) - N) < 1e-3 * N ** 0.5, "soft counts sum to the pixel count"
+    q = r["u"][:, :256]
+    assert_close(q.square().sum(1), torch.ones(8, 96, 96, device="cuda"), 1e-5, "|q| = 1")
+    assert_close(r["M_new"].square().sum(1), torch.ones(K, device="cuda"), 1e-5, "|M_new| = 1")
+    assert_close(r["score_memory"].sum(-1), torch.ones(8, 96, 96, device="cuda"), 1e-5, "rows of score_memory")
+    assert_close(r["score_query"].reshape(-1, K).sum(0), torch.ones(K, device="cuda"), 1e-4, "cols of score_query")
+    # dx is orthogonal to x (gradient of a function of x/|x|)
+    dots = (r["dx"] * o["x"]).sum(1)
+    assert float(dots.detach().abs().max()) < 1e-3 * float(r["dx"].abs().max()) * float(o["x"].norm(dim=1).max())
+
+
+def test_read_backward_is_linear_in_upstream_gradient():
+    from pinthememory_b200 import capi, synth
+
+    B, C, h, w, K = 4, 256, 48, 48, 19
+    x = synth.make_features(B, C, h, w, device="cuda")
+    M = synth.make_memory(K, C, device="cuda")
+    N = B * h * w
+    u = torch.empty(B, 2 * C, h, w, device="cuda")
+    s = torch.empty(N, 20, device="cuda")
+    p = torch.empty(N, K, device="cuda")
+    capi.read_fwd(x, M, None, u, s, p, K)
+    g1 = synth.make_upstream_grad((B, 2 * C, h, w), seed=1, device="cuda")
+    g2 = synth.make_upstream_grad((B, 2 * C, h, w), seed=2, device="cuda")
+    outs = []
+    for g in (g1, g2, 2.0 * g1 - 3.0 * g2):
+        dx = torch.empty_like(x)
+        capi.read_bwd(g.contiguous(), x, M, p, None, None, None, dx, None, K)
+        outs.append(dx)
+    assert_close(outs[2], 2.0 * outs[0] - 3.0 * outs[1], 1e-5, "linearity")
+
+
+def test_write_is_permutation_invariant_over_images():
+    """Class sums do not depend on image order (the reduction that a sharded run splits across ranks)."""
+    from pinthememory_b200 import capi, synth
+
+    B, C, h, w, K = 6, 256, 48, 48, 19
+    f = synth.make_features(B, C, h, w, device="cuda").abs_()
+    labels = synth.make_labels(B, 768, 768, K, "blocky", device="cuda")
+    perm = torch.tensor([3, 0, 5, 1, 4, 2], device="cuda")
+    SD1 = torch.zeros(K + 1, C + 4, device="cuda")
+    SD2 = torch.zeros(K + 1, C + 4, device="cuda")
+    capi.write_reduce_fwd(f, labels, SD1, K)
+    capi.write_reduce_fwd(f[perm].contiguous(), labels[perm].contiguous(), SD2, K)
+    assert_close(SD1, SD2, 1e-5, "class sums")
+    # ...and splitting the batch in two and adding (what the all-reduce does) gives the same sums
+    SD3 = torch.zeros(K + 1, C + 4, device="cuda")
+    capi.write_reduce_fwd(f[:2].contiguous(), labels[:2].contiguous(), SD3, K)
+    capi.write_reduce_fwd(f[2:].contiguous(), labels[2:].contiguous(), SD3, K)
+    assert_close(SD1, SD3, 1e-5, "split + add")

@@ -172,7 +172,7 @@ CORE_CASES = [
 ]
 
 
-@pytest.mark.parametrize("case", CORE_CASES, ids=lambda c: "B%d_C%d_%dx%d_L%dx%d_K%d_%s_%s" % c[:8] + str(c[8]))
+@pytest.mark.parametrize("case", CORE_CASES, ids=lambda c: "B%d_C%d_%dx%d_L%dx%d_K%d_%s_g%d" % tuple(c))
 def test_core_fp32_matches_oracle(case):
     B, C, h, w, Hm, Wm, K, kind, gumbel = case
     o = _oracle_case(B, C, h, w, Hm, Wm, K, kind, seed=500 + C + h, gumbel=gumbel)
@@ -190,7 +190,7 @@ def test_core_fp32_matches_oracle(case):
             assert torch.equal(r["D"], r["hist"].float())
 
 
-@pytest.mark.parametrize("case", CORE_CASES[:3] + CORE_CASES[4:6], ids=lambda c: "C%d_%dx%d_%s" % (c[1], c[2], c[3], c[7]))
+@pytest.mark.parametrize("case", CORE_CASES[:3] + CORE_CASES[4:6], ids=lambda c: "C%d_%dx%d_%s_g%d" % (c[1], c[2], c[3], c[7], c[8]))
 def test_core_bf16_matches_oracle(case):
     B, C, h, w, Hm, Wm, K, kind, gumbel = case
     o = _oracle_case(B, C, h, w, Hm, Wm, K, kind, seed=900 + C + h, dtype=torch.bfloat16, gumbel=gumbel)
