@@ -49,11 +49,14 @@ enum pm_readloss_ws_layout {
     PM_WS_WORDS = 40
 };
 
+/* Rows of the per-CTA column-softmax partials buffer ([PM_COLPART_ROWS][64] floats). */
+#define PM_COLPART_ROWS 296
+
 int pm_version(void);
 const char* pm_status_string(int code);
 /* Row stride (floats) of the internal score buffers for K slots: 20 for K<=19, else 32. */
 int pm_score_stride(int K);
-/* Floats of scratch pm_colsoftmax needs. */
+/* Floats of the column-softmax partials buffer (PM_COLPART_ROWS * 64). */
 int pm_colsoftmax_workspace_floats(int K);
 
 /*
@@ -61,12 +64,16 @@ int pm_colsoftmax_workspace_floats(int K);
  * :181-187 dim=1 [gumbel-]softmax, :328 (p.M), :330-332 (cat + NHWC->NCHW).
  *   x        [B,C,h,w] dtype          M         [K,C] fp32
  *   gumbel_m [N,K] fp32 or NULL       (the noise of F.gumbel_softmax(score, dim=1), memory.py:184)
+ *   gumbel_q [N,K] fp32 or NULL       (the noise of the dim=0 call, memory.py:183; only used for col_partials)
  *   u        [B,2C,h,w] dtype out     = [x/|x| ; softmax_k(s+g).M]
  *   s        [N,stride] fp32 out      raw similarities (internal score buffer)
  *   score_m  [N,K] fp32 out           softmax over slots (score_memory)
+ *   col_partials  NULL, or pm_colsoftmax_workspace_floats(K) floats out: per-CTA (max,sum) of every column of
+ *                 s + gumbel_q, the first pass of the dim-0 softmax fused into this kernel; feed it to
+ *                 pm_colsoftmax_apply.
  */
-int pm_read_fwd(const void* x, const float* M, const float* gumbel_m, void* u, float* s, float* score_m,
-                int B, int C, int h, int w, int K, int dtype, void* stream);
+int pm_read_fwd(const void* x, const float* M, const float* gumbel_m, const float* gumbel_q, void* u, float* s,
+                float* score_m, float* col_partials, int B, int C, int h, int w, int K, int dtype, void* stream);
 
 /*
  * score_query = softmax over ALL N pixels (dim 0) of s (+ gumbel_q). memory.py:183/186.
@@ -75,6 +82,9 @@ int pm_read_fwd(const void* x, const float* M, const float* gumbel_m, void* u, f
  */
 int pm_colsoftmax(const float* s, const float* gumbel_q, float* score_q, float* workspace, int N, int K,
                   void* stream);
+/* Second pass only: normalise with the column partials produced by pm_read_fwd. */
+int pm_colsoftmax_apply(const float* s, const float* gumbel_q, const float* col_partials, float* score_q, int N,
+                        int K, void* stream);
 
 /*
  * Feature-cohesion (read) loss, forward, plus everything its backward needs. Replaces

@@ -25,8 +25,9 @@ PROTOTYPES = {
     "pm_version": [],
     "pm_score_stride": [_c_i],
     "pm_colsoftmax_workspace_floats": [_c_i],
-    "pm_read_fwd": [_c_p] * 6 + [_c_i] * 6 + [_c_p],
+    "pm_read_fwd": [_c_p] * 8 + [_c_i] * 6 + [_c_p],
     "pm_colsoftmax": [_c_p] * 4 + [_c_i] * 2 + [_c_p],
+    "pm_colsoftmax_apply": [_c_p] * 4 + [_c_i] * 2 + [_c_p],
     "pm_readloss_fwd": [_c_p, _c_p, _c_f] + [_c_i] * 6 + [_c_p] * 4,
     "pm_read_bwd": [_c_p] * 9 + [_c_i] * 6 + [_c_p],
     "pm_read_bwd_dM": [_c_p] * 5 + [_c_i] * 6 + [_c_p],
@@ -154,10 +155,14 @@ def _call(name, *args):
 # --------------------------------------------------------------------------------------------- calls
 
 
-def read_fwd(x, M, gumbel_m, u, s, score_m, K):
+def read_fwd(x, M, gumbel_m, u, s, score_m, K, gumbel_q=None, col_partials=None):
     B, C, h, w = x.shape
-    _call("pm_read_fwd", _ptr(x), _ptr(M), _ptr(gumbel_m), _ptr(u), _ptr(s), _ptr(score_m), B, C, h, w, K,
-                              dtype_code(x), _stream())
+    _call("pm_read_fwd", _ptr(x), _ptr(M), _ptr(gumbel_m), _ptr(gumbel_q), _ptr(u), _ptr(s), _ptr(score_m),
+          _ptr(col_partials), B, C, h, w, K, dtype_code(x), _stream())
+
+
+def colsoftmax_apply(s, gumbel_q, col_partials, score_q, N, K):
+    _call("pm_colsoftmax_apply", _ptr(s), _ptr(gumbel_q), _ptr(col_partials), _ptr(score_q), N, K, _stream())
 
 
 def colsoftmax(s, gumbel_q, score_q, workspace, N, K):

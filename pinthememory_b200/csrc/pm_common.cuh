@@ -49,6 +49,41 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// ---- Ampere-style async copies (LDGSTS): 16-byte global -> shared, zero-filled when !valid ----------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    int bytes = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gmem_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// Load one [ROWS x 32 pixel] tile of an NCHW map into shared memory (dense rows of 32 elements) with
+// 16-byte async copies. `base` points at element (row 0, pixel 0 of the image); rows are `hw` apart.
+// Requires hw % (16/sizeof(T)) == 0 and 16-byte aligned base (checked by the host dispatcher).
+template <typename T, int ROWS, int NTHREADS>
+__device__ __forceinline__ void tile_load_async(T* smem_tile, const T* __restrict__ base, int hw, int px0) {
+    constexpr int EPC = 16 / (int)sizeof(T);  // elements per 16-byte chunk
+    constexpr int CPR = 32 / EPC;             // chunks per tile row
+    for (int i = threadIdx.x; i < ROWS * CPR; i += NTHREADS) {
+        const int row = i / CPR, ch = i - row * CPR;
+        const int px = px0 + ch * EPC;
+        const bool valid = px < hw;
+        const T* src = base + (size_t)row * hw + (valid ? px : 0);
+        cp_async16(smem_tile + row * 32 + ch * EPC, src, valid);
+    }
+}
+
+__device__ __forceinline__ float to_float(float v) { return v; }
+__device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float tile_get(const float* t, int row, int px) { return t[row * 32 + px]; }
+__device__ __forceinline__ float tile_get(const __nv_bfloat16* t, int row, int px) {
+    return __bfloat162float(t[row * 32 + px]);
+}
+
 // Bilinear (align_corners=True) source index of output index `dst`: PyTorch computes
 // src = scale * dst in fp32, i0 = floor(src) clamped to in-1, lambda = src - i0.
 __device__ __forceinline__ int src_index(float scale, int dst, int n_in, float* lambda) {

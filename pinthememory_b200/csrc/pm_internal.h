@@ -1,0 +1,16 @@
+// Internal cross-file declarations (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace pm {
+
+// true when the pipelined (16-byte async copy) kernels can be used for these feature pointers
+bool tiled_ok(const void* p0, const void* p1, const void* p2, int hw, int dtype);
+
+int read_fwd_tiled(const void* x, const float* M, const float* gum_m, const float* gum_q, void* u, float* s, float* p,
+                   float* colpart, int B, int C, int hw, int K, int dtype, cudaStream_t st);
+
+// fills `partial` ([PM_COLPART_ROWS][64]: max at [k], sum at [32+k]) from s (+ gumbel_q)
+int colsoftmax_stats(const float* s, const float* gumbel_q, float* partial, int N, int K, cudaStream_t st);
+
+}  // namespace pm

@@ -9,6 +9,7 @@
 // Per-pixel quantities that need all channels (|x|^2 and the K similarities) are reduced across the
 // 8 warps through shared memory.
 #include "pm_common.cuh"
+#include "pm_internal.h"
 
 namespace pm {
 
@@ -537,12 +538,24 @@ static int check_common(int B, int C, int h, int w, int K, int dtype) {
     return 0;
 }
 
-extern "C" int pm_read_fwd(const void* x, const float* M, const float* gumbel_m, void* u, float* s, float* score_m,
-                           int B, int C, int h, int w, int K, int dtype, void* stream) {
+static int read_fwd_generic(const void* x, const float* M, const float* gumbel_m, void* u, float* s, float* score_m,
+                            int B, int C, int h, int w, int K, int dtype, void* stream) {
+    PM_DISPATCH(PM_DISPATCH_CW, launch_read_fwd, x, M, gumbel_m, u, s, score_m, B, h * w, K, (cudaStream_t)stream);
+}
+
+extern "C" int pm_read_fwd(const void* x, const float* M, const float* gumbel_m, const float* gumbel_q, void* u,
+                           float* s, float* score_m, float* col_partials, int B, int C, int h, int w, int K, int dtype,
+                           void* stream) {
     if (!x || !M || !u || !s || !score_m) return PM_ERR_NULL;
     if (int e = check_common(B, C, h, w, K, dtype)) return e;
     if (((uintptr_t)s & 15) != 0) return PM_ERR_ALIGN;
-    PM_DISPATCH(PM_DISPATCH_CW, launch_read_fwd, x, M, gumbel_m, u, s, score_m, B, h * w, K, (cudaStream_t)stream);
+    if (pm::tiled_ok(x, u, s, h * w, dtype))
+        return pm::read_fwd_tiled(x, M, gumbel_m, gumbel_q, u, s, score_m, col_partials, B, C, h * w, K, dtype,
+                                  (cudaStream_t)stream);
+    // generic path (any hw / alignment): un-pipelined kernel, column statistics in a separate launch
+    if (int e = read_fwd_generic(x, M, gumbel_m, u, s, score_m, B, C, h, w, K, dtype, stream)) return e;
+    if (col_partials) return pm::colsoftmax_stats(s, gumbel_q, col_partials, B * h * w, K, (cudaStream_t)stream);
+    return 0;
 }
 
 extern "C" int pm_read_bwd(const void* du, const void* x, const float* M, const float* score_m, const float* ds_rl,

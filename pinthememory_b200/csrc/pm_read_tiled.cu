@@ -1,0 +1,294 @@
+// Memory read, pipelined variants (the fast path when hw is a multiple of the 16-byte chunk).
+//
+// Persistent CTAs (2 per SM) walk tiles of 32 consecutive pixels x all C channels. Each tile is brought
+// into shared memory with 16-byte async copies (LDGSTS) into a 2-stage ring, so the next tile streams
+// from HBM while the current one is consumed and the feature values never occupy registers. The 8 warps
+// split the channels, a lane owns one pixel (conflict-free column reads of the dense [C][32] tile), the
+// K x C memory sits transposed in shared memory (Mt[c][KP]: a channel's K values are five broadcast
+// 128-bit loads) and all multiply-adds are packed FFMA2 (fp32x2), which is what reaches the fp32 peak
+// on sm_100 (profiles/microbench/ffma2.cu: 65.9 vs 46.8 TFLOP/s for scalar FFMA).
+#include "pm_common.cuh"
+#include "pm_internal.h"
+
+namespace pm {
+
+constexpr int TP = 32;        // pixels per tile (= lanes)
+constexpr int TL_THREADS = 256;
+constexpr int TL_WARPS = 8;
+
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+
+template <int C, int KP>
+__device__ __forceinline__ void load_Mt(float* Mt, const float* __restrict__ M, int K) {
+    constexpr int PER = (C * KP + TL_THREADS - 1) / TL_THREADS;
+    float v[PER];
+#pragma unroll
+    for (int r = 0; r < PER; ++r) {  // all loads in flight before the first store
+        const int i = threadIdx.x + r * TL_THREADS;
+        const int c = i / KP, k = i - c * KP;
+        v[r] = (i < C * KP && k < K) ? __ldg(M + (size_t)k * C + c) : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < PER; ++r) {
+        const int i = threadIdx.x + r * TL_THREADS;
+        if (i < C * KP) Mt[i] = v[r];
+    }
+}
+
+// dots of this warp's CW channels of tile `xt` (column `lane`) with the memory: a2[k/2] += x * Mt[c][k]
+template <typename T, int CW, int KP>
+__device__ __forceinline__ void tile_dots(const T* xt, const float* Mt, int c0, int lane, float2 (&a2)[KP / 2],
+                                          float& n2) {
+    const T* xcol = xt + c0 * 32 + lane;
+    const float4* mbase = reinterpret_cast<const float4*>(Mt + c0 * KP);
+#pragma unroll
+    for (int j = 0; j < CW; ++j) {
+        const float xv = to_float(xcol[j * 32]);
+        const float2 x2 = f2(xv, xv);
+        n2 = fmaf(xv, xv, n2);
+        const float4* mrow = mbase + j * (KP / 4);
+#pragma unroll
+        for (int q = 0; q < KP / 4; ++q) {
+            const float4 m = mrow[q];
+            a2[2 * q] = __ffma2_rn(x2, f2(m.x, m.y), a2[2 * q]);
+            a2[2 * q + 1] = __ffma2_rn(x2, f2(m.z, m.w), a2[2 * q + 1]);
+        }
+    }
+}
+
+template <int KP>
+__device__ __forceinline__ void store_partial(float* part, int wid, int lane, const float2 (&a2)[KP / 2]) {
+    float4* d = reinterpret_cast<float4*>(part + ((size_t)wid * TP + lane) * KP);
+#pragma unroll
+    for (int q = 0; q < KP / 4; ++q) d[q] = make_float4(a2[2 * q].x, a2[2 * q].y, a2[2 * q + 1].x, a2[2 * q + 1].y);
+}
+
+// --------------------------------------------------------------------------------------------- forward
+
+template <typename T, int C, int KP, int NSTAGE>
+__global__ void __launch_bounds__(TL_THREADS, 2)
+    read_fwd_tiled_kernel(const T* __restrict__ x, const float* __restrict__ M, const float* __restrict__ gum_m,
+                          const float* __restrict__ gum_q, T* __restrict__ u, float* __restrict__ s_out,
+                          float* __restrict__ p_out, float* __restrict__ colpart, int hw, int K, int tiles_per_img,
+                          int ntiles) {
+    constexpr int CW = C / TL_WARPS, NI = (KP + 7) / 8;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    float* Mt = reinterpret_cast<float*>(smraw);  // [C][KP]
+    float* part = Mt + C * KP;                    // [8][TP][KP]
+    float* pn = part + TL_WARPS * TP * KP;        // [8][TP]
+    float* s_sm = pn + TL_WARPS * TP;             // [TP][KP]
+    float* p_sm = s_sm + TP * KP;                 // [TP][KP]
+    float* invr = p_sm + TP * KP;                 // [TP]
+    T* xs = reinterpret_cast<T*>(invr + TP);      // [NSTAGE][C][TP]
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int tile = blockIdx.x;
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) {
+        const int t = tile + s * gridDim.x;
+        if (t < ntiles) {
+            const int b = t / tiles_per_img, px0 = (t - b * tiles_per_img) * TP;
+            tile_load_async<T, C, TL_THREADS>(xs + s * C * TP, x + (size_t)b * C * hw, hw, px0);
+        }
+        cp_async_commit();
+    }
+    load_Mt<C, KP>(Mt, M, K);
+    float cm[NI], cl[NI];  // running column (max, sum) of this thread's slots for score_query
+#pragma unroll
+    for (int i = 0; i < NI; ++i) cm[i] = -INFINITY, cl[i] = 0.f;
+
+    int stage = 0;
+    for (; tile < ntiles; tile += gridDim.x) {
+        cp_async_wait<NSTAGE - 1>();
+        __syncthreads();
+        const T* xt = xs + stage * C * TP;
+        const int b = tile / tiles_per_img, px0 = (tile - b * tiles_per_img) * TP;
+        const int nvalid = min(TP, hw - px0);
+        const size_t n0g = (size_t)b * hw + px0;
+        {
+            float2 a2[KP / 2];
+#pragma unroll
+            for (int i = 0; i < KP / 2; ++i) a2[i] = f2(0.f, 0.f);
+            float n2 = 0.f;
+            tile_dots<T, CW, KP>(xt, Mt, wid * CW, lane, a2, n2);
+            store_partial<KP>(part, wid, lane, a2);
+            pn[wid * TP + lane] = n2;
+        }
+        __syncthreads();
+        {  // cross-warp reduction + softmax over slots: 8 threads per pixel, slots j, j+8, j+16(, j+24)
+            const int px = tid >> 3, j = tid & 7;
+            float n2 = 0.f;
+#pragma unroll
+            for (int w = 0; w < TL_WARPS; ++w) n2 += pn[w * TP + px];
+            const float ir = 1.f / fmaxf(sqrtf(n2), PM_NORM_EPS);
+            const bool valid = px < nvalid;
+            float sv[NI], z[NI], mx = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+                const int k = j + 8 * i;
+                float acc = 0.f;
+                if (k < KP) {
+#pragma unroll
+                    for (int w = 0; w < TL_WARPS; ++w) acc += part[((size_t)w * TP + px) * KP + k];
+                }
+                sv[i] = acc * ir;
+                float g = 0.f;
+                if (gum_m != nullptr && valid && k < K) g = __ldg(gum_m + (n0g + px) * K + k);
+                z[i] = (k < K) ? sv[i] + g : -INFINITY;
+                mx = fmaxf(mx, z[i]);
+            }
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+            float sum = 0.f;
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+                z[i] = (j + 8 * i < K) ? expf(z[i] - mx) : 0.f;
+                sum += z[i];
+            }
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+            const float inv = 1.f / sum;
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+                const int k = j + 8 * i;
+                if (k < KP) {
+                    s_sm[px * KP + k] = (k < K) ? sv[i] : 0.f;
+                    p_sm[px * KP + k] = z[i] * inv;
+                }
+                if (colpart != nullptr && valid && k < K) {
+                    float zq = sv[i];
+                    if (gum_q != nullptr) zq += __ldg(gum_q + (n0g + px) * K + k);
+                    if (zq > cm[i]) {
+                        cl[i] = cl[i] * expf(cm[i] - zq) + 1.f;
+                        cm[i] = zq;
+                    } else {
+                        cl[i] += expf(zq - cm[i]);
+                    }
+                }
+            }
+            if (j == 0) invr[px] = ir;
+        }
+        __syncthreads();
+        for (int o = tid; o < nvalid * (KP / 4); o += TL_THREADS)
+            reinterpret_cast<float4*>(s_out + n0g * KP)[o] = reinterpret_cast<const float4*>(s_sm)[o];
+        for (int o = tid; o < nvalid * K; o += TL_THREADS) {
+            const int px = o / K, k = o - px * K;
+            p_out[n0g * K + o] = p_sm[px * KP + k];
+        }
+        {  // u = [q ; p.M]
+            float2 p2[KP / 2];
+            const float4* pr = reinterpret_cast<const float4*>(p_sm + lane * KP);
+#pragma unroll
+            for (int q = 0; q < KP / 4; ++q) {
+                const float4 v = pr[q];
+                p2[2 * q] = f2(v.x, v.y);
+                p2[2 * q + 1] = f2(v.z, v.w);
+            }
+            const float ir = invr[lane];
+            const bool v = lane < nvalid;
+            T* uq = u + ((size_t)b * 2 * C + wid * CW) * hw + px0 + lane;
+            const size_t chw = (size_t)C * hw;
+            const T* xcol = xt + wid * CW * 32 + lane;
+            const float4* mbase = reinterpret_cast<const float4*>(Mt + wid * CW * KP);
+#pragma unroll
+            for (int j = 0; j < CW; ++j) {
+                const float4* mrow = mbase + j * (KP / 4);
+                float2 acc = f2(0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < KP / 4; ++q) {
+                    const float4 m = mrow[q];
+                    acc = __ffma2_rn(p2[2 * q], f2(m.x, m.y), acc);
+                    acc = __ffma2_rn(p2[2 * q + 1], f2(m.z, m.w), acc);
+                }
+                const float xq = to_float(xcol[j * 32]) * ir;
+                if (v) {
+                    stf(uq, xq);
+                    stf(uq + chw, acc.x + acc.y);
+                }
+                uq += hw;
+            }
+        }
+        __syncthreads();  // every read of this stage is done: refill it
+        const int next = tile + NSTAGE * gridDim.x;
+        if (next < ntiles) {
+            const int nb = next / tiles_per_img, npx0 = (next - nb * tiles_per_img) * TP;
+            tile_load_async<T, C, TL_THREADS>(xs + stage * C * TP, x + (size_t)nb * C * hw, hw, npx0);
+        }
+        cp_async_commit();
+        stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
+    }
+    cp_async_wait<0>();
+
+    if (colpart != nullptr) {  // per-CTA column (max,sum) partials, same layout as colsoftmax_stats_kernel
+        __syncthreads();
+        float* scr = part;  // [NI][2][256]
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            scr[(i * 2 + 0) * TL_THREADS + tid] = cm[i];
+            scr[(i * 2 + 1) * TL_THREADS + tid] = cl[i];
+        }
+        __syncthreads();
+        if (tid < K) {
+            const int j = tid & 7, i = tid >> 3;
+            float Mx = -INFINITY;
+            for (int px = 0; px < TP; ++px) Mx = fmaxf(Mx, scr[(i * 2 + 0) * TL_THREADS + px * 8 + j]);
+            float L = 0.f;
+            for (int px = 0; px < TP; ++px) {
+                const float mi = scr[(i * 2 + 0) * TL_THREADS + px * 8 + j];
+                if (mi > -INFINITY) L += scr[(i * 2 + 1) * TL_THREADS + px * 8 + j] * expf(mi - Mx);
+            }
+            colpart[(size_t)blockIdx.x * 64 + tid] = Mx;
+            colpart[(size_t)blockIdx.x * 64 + 32 + tid] = L;
+        }
+        if (blockIdx.x == 0) {  // rows of CTAs that do not exist
+            for (int i = gridDim.x * 64 + tid; i < PM_COLPART_ROWS * 64; i += TL_THREADS)
+                colpart[i] = ((i & 63) < 32) ? -INFINITY : 0.f;
+        }
+    }
+}
+
+template <typename T, int C, int KP>
+int launch_read_fwd_tiled(const void* x, const float* M, const float* gum_m, const float* gum_q, void* u, float* s,
+                          float* p, float* colpart, int B, int hw, int K, cudaStream_t st) {
+    constexpr int NSTAGE = 2;
+    const size_t smem = sizeof(float) * ((size_t)C * KP + TL_WARPS * TP * KP + TL_WARPS * TP + 2 * TP * KP + TP) +
+                        sizeof(T) * (size_t)NSTAGE * C * TP;
+    auto kern = read_fwd_tiled_kernel<T, C, KP, NSTAGE>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int tiles = (hw + TP - 1) / TP, ntiles = B * tiles;
+    int grid = 2 * 148;
+    if (grid > ntiles) grid = ntiles;
+    kern<<<grid, TL_THREADS, smem, st>>>((const T*)x, M, gum_m, gum_q, (T*)u, s, p, colpart, hw, K, tiles, ntiles);
+    cudaError_t le = cudaGetLastError();
+    return le == cudaSuccess ? 0 : (int)le;
+}
+
+#define PM_TILED_SWITCH_C(T, KP, FN, ...)                   \
+    switch (C) {                                            \
+        case 32: return FN<T, 32, KP>(__VA_ARGS__);         \
+        case 64: return FN<T, 64, KP>(__VA_ARGS__);         \
+        case 128: return FN<T, 128, KP>(__VA_ARGS__);       \
+        case 256: return FN<T, 256, KP>(__VA_ARGS__);       \
+        default: return PM_ERR_CHANNELS;                    \
+    }
+
+bool tiled_ok(const void* p0, const void* p1, const void* p2, int hw, int dtype) {
+    const int epc = dtype == PM_F32 ? 4 : 8;
+    return (hw % epc) == 0 && (((uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)p2) & 15) == 0;
+}
+
+int read_fwd_tiled(const void* x, const float* M, const float* gum_m, const float* gum_q, void* u, float* s, float* p,
+                   float* colpart, int B, int C, int hw, int K, int dtype, cudaStream_t st) {
+    if (dtype == PM_F32) {
+        if (K <= 19) { PM_TILED_SWITCH_C(float, 20, launch_read_fwd_tiled, x, M, gum_m, gum_q, u, s, p, colpart, B, hw, K, st) }
+        else { PM_TILED_SWITCH_C(float, 32, launch_read_fwd_tiled, x, M, gum_m, gum_q, u, s, p, colpart, B, hw, K, st) }
+    } else {
+        if (K <= 19) { PM_TILED_SWITCH_C(__nv_bfloat16, 20, launch_read_fwd_tiled, x, M, gum_m, gum_q, u, s, p, colpart, B, hw, K, st) }
+        else { PM_TILED_SWITCH_C(__nv_bfloat16, 32, launch_read_fwd_tiled, x, M, gum_m, gum_q, u, s, p, colpart, B, hw, K, st) }
+    }
+}
+
+}  // namespace pm

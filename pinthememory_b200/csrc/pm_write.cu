@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(WB_THREADS) write_bwd_kernel(const float* __re
 // One CTA (K x C is 19 x 256): a warp per memory row. Branch-free replacement of the reference's per-slot
 // python loop with its 19 host syncs (memory.py:233-237).
 
-constexpr int UP_THREADS = 256, UP_WARPS = 8, UP_KMAX = 32;
+constexpr int UP_THREADS = 1024, UP_WARPS = 32, UP_KMAX = 32;
 
 __global__ void __launch_bounds__(UP_THREADS) update_fwd_kernel(const float* __restrict__ SD, const float* __restrict__ M_old,
                                                                 float momentum, const float* __restrict__ W,

@@ -75,9 +75,9 @@ class _ReadFn(torch.autograd.Function):
         score_m = torch.empty(N, K, dtype=torch.float32, device=dev)
         score_q = torch.empty(N, K, dtype=torch.float32, device=dev)
         M = M.contiguous()
-        capi.read_fwd(x, M, g_memory, u, s, score_m, K)
-        cs_ws = torch.empty(capi.colsoftmax_workspace_floats(K), dtype=torch.float32, device=dev)
-        capi.colsoftmax(s, g_query, score_q, cs_ws, N, K)
+        col_partials = torch.empty(capi.colsoftmax_workspace_floats(K), dtype=torch.float32, device=dev)
+        capi.read_fwd(x, M, g_memory, u, s, score_m, K, gumbel_q=g_query, col_partials=col_partials)
+        capi.colsoftmax_apply(s, g_query, col_partials, score_q, N, K)
         if labels is not None:
             # one zeroed allocation: [ds_rl (N*KP floats) | workspace (40 x 8 bytes) | out (2 floats)]
             buf = torch.zeros(N * KP + 2 * capi.WS_WORDS + 4, dtype=torch.float32, device=dev)

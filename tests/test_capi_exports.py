@@ -22,7 +22,7 @@ def test_header_declares_the_documented_entry_points():
     d = _declared()
     for name in ("pm_read_fwd", "pm_read_bwd", "pm_read_bwd_dM", "pm_colsoftmax", "pm_readloss_fwd",
                  "pm_write_reduce_fwd", "pm_update_fwd", "pm_update_bwd", "pm_write_bwd", "pm_score_nhwc",
-                 "pm_rowsoftmax", "pm_status_string", "pm_version"):
+                 "pm_rowsoftmax", "pm_colsoftmax_apply", "pm_status_string", "pm_version"):
         assert name in d, name
 
 
@@ -54,9 +54,9 @@ def test_argument_checks_run_without_a_gpu():
 
     lib = capi.load()
     one = ctypes.c_void_p(16)
-    assert lib.pm_read_fwd(None, one, None, one, one, one, 1, 256, 4, 4, 19, 0, None) == -1
-    assert lib.pm_read_fwd(one, one, None, one, one, one, 1, 48, 4, 4, 19, 0, None) == -3
-    assert lib.pm_read_fwd(one, one, None, one, one, one, 1, 256, 4, 4, 0, 0, None) == -4
-    assert lib.pm_read_fwd(one, one, None, one, one, one, 1, 256, 4, 4, 19, 7, None) == -2
-    assert lib.pm_read_fwd(one, one, None, one, one, one, 0, 256, 4, 4, 19, 0, None) == -5
+    assert lib.pm_read_fwd(None, one, None, None, one, one, one, None, 1, 256, 4, 4, 19, 0, None) == -1
+    assert lib.pm_read_fwd(one, one, None, None, one, one, one, None, 1, 48, 4, 4, 19, 0, None) == -3
+    assert lib.pm_read_fwd(one, one, None, None, one, one, one, None, 1, 256, 4, 4, 0, 0, None) == -4
+    assert lib.pm_read_fwd(one, one, None, None, one, one, one, None, 1, 256, 4, 4, 19, 7, None) == -2
+    assert lib.pm_read_fwd(one, one, None, None, one, one, one, None, 0, 256, 4, 4, 19, 0, None) == -5
     assert lib.pm_write_reduce_fwd(one, one, ctypes.c_void_p(4), 1, 256, 4, 4, 8, 8, 19, 0, None) == -6
