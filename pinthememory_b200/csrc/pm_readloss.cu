@@ -9,10 +9,11 @@
 // Two threads (lane pair) own a cell, each half of the K slots (keeps the 4 x K/2 gradient accumulators in
 // registers at 2 CTAs/SM); a thread walks the cell's label rows (optionally 1/RS of them), per row forms
 // z_k(lambda_x) = A_k + lambda_x * B_k, and per pixel spends K/2 FFMA (packed FFMA2), K/2 ex2, one shuffle
-// for the softmax denominator and 4 x K/4 FFMA2 for the tap gradients. Labels are fetched a chunk of 8
-// pixels ahead. The one-hot part of the gradient and the label histogram need a dynamic class index: they
-// are run-length accumulated in registers and flushed to thread-private shared-memory columns (no
-// atomics). Cells merge into the CTA's tap tile in conflict-free phases; the tile is flushed to ds_rl
+// for the softmax denominator and 4 x K/4 FFMA2 for the tap gradients. Loop bounds are warp-uniform
+// (out-of-range pixels are predicated off) so the warp never diverges around the shuffles. Labels are
+// fetched a chunk of 8 pixels ahead. The one-hot part of the gradient, the label histogram and the
+// "- logit[label]" term of the loss need a dynamic class index: they are run-length accumulated in
+// registers and flushed to thread-private shared-memory columns (no atomics). Cells merge into the CTA's tap tile in conflict-free phases; the tile is flushed to ds_rl
 // with 16-byte vector REDs (only tile borders are shared between CTAs). The last CTA divides by V.
 //
 // Softmax stabiliser: the maximum over the cell's 4 taps x K slots bounds every logit in the cell, so it
@@ -109,139 +110,168 @@ __global__ void __launch_bounds__(RL_THREADS, 2)
     float* pv = priv + tid;        // element (tap, kk) at pv[(tap*KH + kk)*NT]
     int* pc = pcnt + pair;         // element k at pc[k*(NT/2)]
 
+    // Loop bounds are made warp-uniform (max over the lanes, out-of-range pixels predicated off) so the
+    // whole warp stays converged and the pair shuffles can use the full mask.
+    int Ya = 0, Yb = 0, Xa = 0, Xb = 0;
     if (active) {
-        const int Ya = first_ge(cy, sy, Hm, h), Yb = first_ge(cy + 1, sy, Hm, h);
-        const int Xa = first_ge(cx, sx, Wm, w), Xb = first_ge(cx + 1, sx, Wm, w);
-        const float c2 = inv_T * 1.4426950408889634f;
-        const float* t00 = s_tile + (ly0 * RL_LDX + lx0) * KP;
-        const float* t01 = s_tile + (ly0 * RL_LDX + lx1) * KP;
-        const float* t10 = s_tile + (ly1 * RL_LDX + lx0) * KP;
-        const float* t11 = s_tile + (ly1 * RL_LDX + lx1) * KP;
-        const unsigned pairmask = 3u << (lane & ~1);  // the two lanes of a cell always run in lock step
-        float shift, lo;  // softmax stabiliser (log2 units): max / min over the cell's taps and slots
-        {
-            float m = -INFINITY, n = INFINITY;
+        Ya = first_ge(cy, sy, Hm, h), Yb = first_ge(cy + 1, sy, Hm, h);
+        Xa = first_ge(cx, sx, Wm, w), Xb = first_ge(cx + 1, sx, Wm, w);
+    }
+    const int nr_lane = (Yb - Ya - split + RS - 1) / RS;  // rows this thread owns (<= 0: none)
+    const int nr_max = __reduce_max_sync(0xffffffffu, max(nr_lane, 0));
+    const int nc_max = __reduce_max_sync(0xffffffffu, Xb - Xa);
+    const float c2 = inv_T * 1.4426950408889634f;
+    // taps of this cell (inactive lanes read tap (0,0): finite values, results never merged)
+    const int tl0 = active ? ly0 : 0, tl1 = active ? ly1 : 0, tx0 = active ? lx0 : 0, tx1 = active ? lx1 : 0;
+    const float* t00 = s_tile + (tl0 * RL_LDX + tx0) * KP + k0;
+    const float* t01 = s_tile + (tl0 * RL_LDX + tx1) * KP + k0;
+    const float* t10 = s_tile + (tl1 * RL_LDX + tx0) * KP + k0;
+    const float* t11 = s_tile + (tl1 * RL_LDX + tx1) * KP + k0;
+    float shift;  // softmax stabiliser (log2 units): max over the cell's taps and slots
+    bool pxmax;
+    {
+        float m = -INFINITY, n = INFINITY;
 #pragma unroll
-            for (int i = 0; i < KH; ++i) {
-                if (k0 + i < K) {
-                    m = fmaxf(m, fmaxf(fmaxf(t00[k0 + i], t01[k0 + i]), fmaxf(t10[k0 + i], t11[k0 + i])));
-                    n = fminf(n, fminf(fminf(t00[k0 + i], t01[k0 + i]), fminf(t10[k0 + i], t11[k0 + i])));
-                }
+        for (int i = 0; i < KH; ++i) {
+            if (k0 + i < K) {
+                m = fmaxf(m, fmaxf(fmaxf(t00[i], t01[i]), fmaxf(t10[i], t11[i])));
+                n = fminf(n, fminf(fminf(t00[i], t01[i]), fminf(t10[i], t11[i])));
             }
-            shift = fmaxf(m, __shfl_xor_sync(pairmask, m, 1)) * c2;
-            lo = fminf(n, __shfl_xor_sync(pairmask, n, 1)) * c2;
         }
-        const bool pxmax = !(shift - lo < 60.f);  // also true for NaN/inf inputs
-        // run-length state of the one-hot / histogram part
-        int cur = -1, cnt = 0;
-        float o00 = 0.f, o01 = 0.f, o10 = 0.f, o11 = 0.f;
-        auto flush = [&]() {
-            if (cur >= 0) {
-                if (half == 0) pc[cur * (NT / 2)] += cnt;
-                const int kk = cur - k0;
-                if (kk >= 0 && kk < KH && cur < K) {
-                    pv[(0 * KH + kk) * NT] += o00;
-                    pv[(1 * KH + kk) * NT] += o01;
-                    pv[(2 * KH + kk) * NT] += o10;
-                    pv[(3 * KH + kk) * NT] += o11;
+        shift = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1)) * c2;
+        const float lo = fminf(n, __shfl_xor_sync(0xffffffffu, n, 1)) * c2;
+        // spread too large for the per-cell stabiliser (tiny T / un-normalised queries; also NaN/inf)
+        pxmax = __any_sync(0xffffffffu, !(shift - lo < 60.f));
+    }
+    // run-length state of the one-hot / histogram part
+    int cur = -1, cnt = 0;
+    float o00 = 0.f, o01 = 0.f, o10 = 0.f, o11 = 0.f;
+    const long long* lab_b = labels + (size_t)b * Hm * Wm;
+    const float cxf = (float)cx, cyf = (float)cy;
+
+    for (int r = 0; r < nr_max; ++r) {
+        const int Y = Ya + split + r * RS;
+        const bool rowok = active && Y < Yb;
+        const float lamy = fminf(fmaxf(sy * (float)Y - cyf, 0.f), 1.f);
+        const float hy = 1.f - lamy;
+        float2 A[NH2], Bc[NH2];
+#pragma unroll
+        for (int i = 0; i < NH2; ++i) {
+            const float2 v00 = reinterpret_cast<const float2*>(t00)[i], v01 = reinterpret_cast<const float2*>(t01)[i];
+            const float2 v10 = reinterpret_cast<const float2*>(t10)[i], v11 = reinterpret_cast<const float2*>(t11)[i];
+            float l0 = fmaf(lamy, v10.x - v00.x, v00.x), l1 = fmaf(lamy, v11.x - v01.x, v01.x);
+            A[i].x = fmaf(l0, c2, -shift), Bc[i].x = (l1 - l0) * c2;
+            l0 = fmaf(lamy, v10.y - v00.y, v00.y), l1 = fmaf(lamy, v11.y - v01.y, v01.y);
+            A[i].y = fmaf(l0, c2, -shift), Bc[i].y = (l1 - l0) * c2;
+            if (k0 + 2 * i >= K) A[i].x = -INFINITY, Bc[i].x = 0.f;
+            if (k0 + 2 * i + 1 >= K) A[i].y = -INFINITY, Bc[i].y = 0.f;
+        }
+        const long long* lrow = lab_b + (size_t)(rowok ? Y : 0) * Wm + Xa;
+        const int ncols = rowok ? Xb - Xa : 0;
+        for (int X0 = 0; X0 < nc_max; X0 += RL_CHUNK) {
+            long long lab[RL_CHUNK];
+#pragma unroll
+            for (int i = 0; i < RL_CHUNK; ++i) lab[i] = (X0 + i < ncols) ? __ldg(lrow + X0 + i) : PM_IGNORE_LABEL;
+#pragma unroll
+            for (int i = 0; i < RL_CHUNK; ++i) {
+                if (X0 + i >= nc_max) break;  // warp-uniform
+                const bool ok = X0 + i < ncols;
+                const long long lv = lab[i];
+                const int cls = map_label(lv, K);
+                const bool valid = ok && cls < K;
+                const float lamx = fminf(fmaxf(sx * (float)(Xa + X0 + i) - cxf, 0.f), 1.f);
+                float2 e[NH2];
+#pragma unroll
+                for (int q = 0; q < NH2; ++q) e[q] = __ffma2_rn(make_float2(lamx, lamx), Bc[q], A[q]);
+                float pshift = shift;
+                if (pxmax) {  // warp-uniform
+                    float m = -INFINITY;
+#pragma unroll
+                    for (int q = 0; q < NH2; ++q) m = fmaxf(m, fmaxf(e[q].x, e[q].y));
+                    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                    pshift += m;
+#pragma unroll
+                    for (int q = 0; q < NH2; ++q) e[q].x -= m, e[q].y -= m;
                 }
-            }
-            cnt = 0;
-            o00 = o01 = o10 = o11 = 0.f;
-        };
-        const long long* lab_b = labels + (size_t)b * Hm * Wm;
-        for (int Y = Ya + split; Y < Yb; Y += RS) {
-            const float lamy = fminf(fmaxf(sy * (float)Y - (float)cy, 0.f), 1.f);
-            float2 A[NH2], Bc[NH2];
+                float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int i = 0; i < NH2; ++i) {
-                const float2 v00 = reinterpret_cast<const float2*>(t00 + k0)[i], v01 = reinterpret_cast<const float2*>(t01 + k0)[i];
-                const float2 v10 = reinterpret_cast<const float2*>(t10 + k0)[i], v11 = reinterpret_cast<const float2*>(t11 + k0)[i];
-                float l0 = fmaf(lamy, v10.x - v00.x, v00.x), l1 = fmaf(lamy, v11.x - v01.x, v01.x);
-                A[i].x = fmaf(l0, c2, -shift), Bc[i].x = (l1 - l0) * c2;
-                l0 = fmaf(lamy, v10.y - v00.y, v00.y), l1 = fmaf(lamy, v11.y - v01.y, v01.y);
-                A[i].y = fmaf(l0, c2, -shift), Bc[i].y = (l1 - l0) * c2;
-                if (k0 + 2 * i >= K) A[i].x = -INFINITY, Bc[i].x = 0.f;
-                if (k0 + 2 * i + 1 >= K) A[i].y = -INFINITY, Bc[i].y = 0.f;
-            }
-            const long long* lrow = lab_b + (size_t)Y * Wm;
-            for (int X0 = Xa; X0 < Xb; X0 += RL_CHUNK) {
-                long long lab[RL_CHUNK];
+                for (int q = 0; q < NH2; ++q) {
+                    e[q].x = ex2_approx(e[q].x);
+                    e[q].y = ex2_approx(e[q].y);
+                    sum2 = __fadd2_rn(sum2, e[q]);
+                }
+                float sum = sum2.x + sum2.y;
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                const float vmask = valid ? 1.f : 0.f;
+                if (half == 0) lossacc = fmaf(vmask, pshift + lg2_approx(sum), lossacc);
+                const float inv = rcp_approx(sum) * vmask;
+                const float hx = 1.f - lamx;
+                const float w00 = hy * hx * vmask, w01 = hy * lamx * vmask, w10 = lamy * hx * vmask,
+                            w11 = lamy * lamx * vmask;
+                const float hyi = hy * inv, lyi = lamy * inv;
+                const float i00 = hyi * hx, i01 = hyi * lamx, i10 = lyi * hx, i11 = lyi * lamx;
 #pragma unroll
-                for (int i = 0; i < RL_CHUNK; ++i) lab[i] = (X0 + i < Xb) ? __ldg(lrow + X0 + i) : -1;
-#pragma unroll
-                for (int i = 0; i < RL_CHUNK; ++i) {
-                    if (X0 + i >= Xb) break;
-                    const int X = X0 + i;
-                    const long long lv = lab[i];
-                    const int cls = map_label(lv, K);
+                for (int q = 0; q < NH2; ++q) {
+                    G00[q] = __ffma2_rn(e[q], make_float2(i00, i00), G00[q]);
+                    G01[q] = __ffma2_rn(e[q], make_float2(i01, i01), G01[q]);
+                    G10[q] = __ffma2_rn(e[q], make_float2(i10, i10), G10[q]);
+                    G11[q] = __ffma2_rn(e[q], make_float2(i11, i11), G11[q]);
+                }
+                // one-hot part + histogram: run-length accumulate, flush to the private columns on a change
+                if (ok) {
                     if (cls != cur) {
-                        flush();
+                        if (cur >= 0) {
+                            if (half == 0) pc[cur * (NT / 2)] += cnt;
+                            const int kk = cur - k0;
+                            if (kk >= 0 && kk < KH && cur < K) {
+                                pv[(0 * KH + kk) * NT] += o00;
+                                pv[(1 * KH + kk) * NT] += o01;
+                                pv[(2 * KH + kk) * NT] += o10;
+                                pv[(3 * KH + kk) * NT] += o11;
+                            }
+                        }
+                        cnt = 0;
+                        o00 = o01 = o10 = o11 = 0.f;
                         cur = cls;
                     }
                     cnt += 1;
-                    if (cls == K) {
-                        if (lv != PM_IGNORE_LABEL && half == 0) atomicAdd(ws + PM_WS_BAD, 1ULL);
-                        continue;
-                    }
-                    const float lamx = fminf(fmaxf(sx * (float)X - (float)cx, 0.f), 1.f);
-                    const float2 lx2 = make_float2(lamx, lamx);
-                    float2 e[NH2];
-#pragma unroll
-                    for (int q = 0; q < NH2; ++q) e[q] = __ffma2_rn(lx2, Bc[q], A[q]);
-                    float pshift = shift;
-                    if (pxmax) {
-                        float m = -INFINITY;
-#pragma unroll
-                        for (int q = 0; q < NH2; ++q) m = fmaxf(m, fmaxf(e[q].x, e[q].y));
-                        m = fmaxf(m, __shfl_xor_sync(pairmask, m, 1));
-                        pshift += m;
-#pragma unroll
-                        for (int q = 0; q < NH2; ++q) e[q].x -= m, e[q].y -= m;
-                    }
-                    float2 sum2 = make_float2(0.f, 0.f);
-#pragma unroll
-                    for (int q = 0; q < NH2; ++q) {
-                        e[q].x = ex2_approx(e[q].x);
-                        e[q].y = ex2_approx(e[q].y);
-                        sum2 = __fadd2_rn(sum2, e[q]);
-                    }
-                    float sum = sum2.x + sum2.y;
-                    sum += __shfl_xor_sync(pairmask, sum, 1);
-                    if (half == 0) lossacc += pshift + lg2_approx(sum);
-                    {  // minus the (unshifted) logit of the labelled class, by the half that owns it
-                        const int kk = cls - k0;
-                        if (kk >= 0 && kk < KH) {
-                            const float a = t00[cls], bq = t01[cls], c = t10[cls], d = t11[cls];
-                            const float l0 = fmaf(lamy, c - a, a), l1 = fmaf(lamy, d - bq, bq);
-                            lossacc -= fmaf(lamx, (l1 - l0) * c2, l0 * c2);
-                        }
-                    }
-                    const float inv = rcp_approx(sum);
-                    const float hy = 1.f - lamy, hx = 1.f - lamx;
-                    const float w00 = hy * hx, w01 = hy * lamx, w10 = lamy * hx, w11 = lamy * lamx;
-                    const float2 i00 = make_float2(w00 * inv, w00 * inv), i01 = make_float2(w01 * inv, w01 * inv);
-                    const float2 i10 = make_float2(w10 * inv, w10 * inv), i11 = make_float2(w11 * inv, w11 * inv);
-#pragma unroll
-                    for (int q = 0; q < NH2; ++q) {
-                        G00[q] = __ffma2_rn(e[q], i00, G00[q]);
-                        G01[q] = __ffma2_rn(e[q], i01, G01[q]);
-                        G10[q] = __ffma2_rn(e[q], i10, G10[q]);
-                        G11[q] = __ffma2_rn(e[q], i11, G11[q]);
-                    }
                     o00 += w00, o01 += w01, o10 += w10, o11 += w11;
+                    if (cls == K && lv != PM_IGNORE_LABEL && half == 0) atomicAdd(ws + PM_WS_BAD, 1ULL);
                 }
             }
         }
-        flush();
-        // subtract the one-hot part; fold degenerate taps (last row / column clamp onto themselves)
+    }
+    if (active) {
+        if (cur >= 0) {
+            if (half == 0) pc[cur * (NT / 2)] += cnt;
+            const int kk = cur - k0;
+            if (kk >= 0 && kk < KH && cur < K) {
+                pv[(0 * KH + kk) * NT] += o00;
+                pv[(1 * KH + kk) * NT] += o01;
+                pv[(2 * KH + kk) * NT] += o10;
+                pv[(3 * KH + kk) * NT] += o11;
+            }
+        }
+        // minus the logit of the labelled class: sum_px z_y = c2 * sum_{tap,k} onehot_weight[tap][k] * tap[k];
+        // then subtract the one-hot part from the tap gradients
+        float zy = 0.f;
 #pragma unroll
         for (int q = 0; q < NH2; ++q) {
-            G00[q].x -= pv[(0 * KH + 2 * q) * NT], G00[q].y -= pv[(0 * KH + 2 * q + 1) * NT];
-            G01[q].x -= pv[(1 * KH + 2 * q) * NT], G01[q].y -= pv[(1 * KH + 2 * q + 1) * NT];
-            G10[q].x -= pv[(2 * KH + 2 * q) * NT], G10[q].y -= pv[(2 * KH + 2 * q + 1) * NT];
-            G11[q].x -= pv[(3 * KH + 2 * q) * NT], G11[q].y -= pv[(3 * KH + 2 * q + 1) * NT];
+            const float a0 = pv[(0 * KH + 2 * q) * NT], a1 = pv[(0 * KH + 2 * q + 1) * NT];
+            const float b0 = pv[(1 * KH + 2 * q) * NT], b1 = pv[(1 * KH + 2 * q + 1) * NT];
+            const float c0 = pv[(2 * KH + 2 * q) * NT], c1 = pv[(2 * KH + 2 * q + 1) * NT];
+            const float d0 = pv[(3 * KH + 2 * q) * NT], d1 = pv[(3 * KH + 2 * q + 1) * NT];
+            zy = fmaf(a0, t00[2 * q], fmaf(a1, t00[2 * q + 1], zy));
+            zy = fmaf(b0, t01[2 * q], fmaf(b1, t01[2 * q + 1], zy));
+            zy = fmaf(c0, t10[2 * q], fmaf(c1, t10[2 * q + 1], zy));
+            zy = fmaf(d0, t11[2 * q], fmaf(d1, t11[2 * q + 1], zy));
+            G00[q].x -= a0, G00[q].y -= a1;
+            G01[q].x -= b0, G01[q].y -= b1;
+            G10[q].x -= c0, G10[q].y -= c1;
+            G11[q].x -= d0, G11[q].y -= d1;
         }
+        lossacc = fmaf(-c2, zy, lossacc);
+        // fold degenerate taps (last row / column clamp onto themselves)
         if (ly1 == ly0) {
 #pragma unroll
             for (int q = 0; q < NH2; ++q) {
@@ -256,6 +286,8 @@ __global__ void __launch_bounds__(RL_THREADS, 2)
                 G01[q] = G11[q] = make_float2(0.f, 0.f);
             }
         }
+    } else {
+        lossacc = 0.f;
     }
 
     // merge into the tap tile: within one (tap, split) phase every active thread owns distinct addresses
