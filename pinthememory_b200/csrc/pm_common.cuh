@@ -68,12 +68,42 @@ template <typename T, int ROWS, int NTHREADS>
 __device__ __forceinline__ void tile_load_async(T* smem_tile, const T* __restrict__ base, int hw, int px0) {
     constexpr int EPC = 16 / (int)sizeof(T);  // elements per 16-byte chunk
     constexpr int CPR = 32 / EPC;             // chunks per tile row
-    for (int i = threadIdx.x; i < ROWS * CPR; i += NTHREADS) {
-        const int row = i / CPR, ch = i - row * CPR;
-        const int px = px0 + ch * EPC;
-        const bool valid = px < hw;
-        const T* src = base + (size_t)row * hw + (valid ? px : 0);
-        cp_async16(smem_tile + row * 32 + ch * EPC, src, valid);
+    static_assert(NTHREADS % CPR == 0, "thread count must be a multiple of the chunks per row");
+    const int ch = threadIdx.x % CPR;
+    const int px = px0 + ch * EPC;
+    const bool valid = px < hw;
+    const T* src = base + (size_t)(threadIdx.x / CPR) * hw + (valid ? px : 0);
+    const size_t step = (size_t)(NTHREADS / CPR) * hw;
+    T* dst = smem_tile + (threadIdx.x / CPR) * 32 + ch * EPC;
+    for (int row = threadIdx.x / CPR; row < ROWS; row += NTHREADS / CPR) {
+        cp_async16(dst, src, valid);
+        src += step;
+        dst += (NTHREADS / CPR) * 32;
+    }
+}
+
+// Same tile, but the 16-byte chunks of every row are XOR-swizzled so that a warp whose lanes are CHANNELS
+// (32 consecutive rows) can read one chunk per lane with LDS.128 without bank conflicts:
+// physical chunk = chunk ^ swz(row), swz(row) = (row / (128 / row_bytes)) & (chunks_per_row - 1).
+template <typename T>
+__device__ __forceinline__ int tile_swz(int row) {
+    constexpr int CPR = 32 * (int)sizeof(T) / 16;
+    constexpr int RPL = 128 / (32 * (int)sizeof(T));  // rows per 128-byte bank window
+    return (row / RPL) & (CPR - 1);
+}
+template <typename T, int ROWS, int NTHREADS>
+__device__ __forceinline__ void tile_load_async_swz(T* smem_tile, const T* __restrict__ base, int hw, int px0) {
+    constexpr int EPC = 16 / (int)sizeof(T);
+    constexpr int CPR = 32 / EPC;
+    static_assert(NTHREADS % CPR == 0, "thread count must be a multiple of the chunks per row");
+    const int ch = threadIdx.x % CPR;
+    const int px = px0 + ch * EPC;
+    const bool valid = px < hw;
+    const T* src = base + (size_t)(threadIdx.x / CPR) * hw + (valid ? px : 0);
+    const size_t step = (size_t)(NTHREADS / CPR) * hw;
+    for (int row = threadIdx.x / CPR; row < ROWS; row += NTHREADS / CPR) {
+        cp_async16(smem_tile + row * 32 + (ch ^ tile_swz<T>(row)) * EPC, src, valid);
+        src += step;
     }
 }
 
@@ -132,6 +162,24 @@ __device__ __forceinline__ LabelTaps label_taps(const long long* __restrict__ la
                 t.w[j] = 0.f;
             }
     return t;
+}
+
+// Move the non-zero taps to the front (entry 0 is non-zero for every real pixel: the weights sum to 1);
+// returns how many are non-zero. Static indices only (a 3-pass bubble), so it stays in registers.
+__device__ __forceinline__ int compact_taps(LabelTaps& t) {
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass)
+#pragma unroll
+        for (int j = 0; j < 3 - pass; ++j)
+            if (t.w[j] == 0.f && t.w[j + 1] != 0.f) {
+                t.w[j] = t.w[j + 1];
+                t.cls[j] = t.cls[j + 1];
+                t.w[j + 1] = 0.f;
+            }
+    int n = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) n += (t.w[j] != 0.f) ? 1 : 0;
+    return n;
 }
 
 }  // namespace pm

@@ -1,6 +1,7 @@
 // Internal cross-file declarations (not part of the C ABI).
 #pragma once
 #include <cuda_runtime.h>
+#include <stdint.h>
 
 namespace pm {
 
@@ -9,6 +10,9 @@ bool tiled_ok(const void* p0, const void* p1, const void* p2, int hw, int dtype)
 
 int read_fwd_tiled(const void* x, const float* M, const float* gum_m, const float* gum_q, void* u, float* s, float* p,
                    float* colpart, int B, int C, int hw, int K, int dtype, cudaStream_t st);
+
+int write_reduce_tiled(const void* f, const int64_t* labels, float* SD, int B, int C, int h, int w, int Hm, int Wm,
+                       int K, int dtype, cudaStream_t st);
 
 // fills `partial` ([PM_COLPART_ROWS][64]: max at [k], sum at [32+k]) from s (+ gumbel_q)
 int colsoftmax_stats(const float* s, const float* gumbel_q, float* partial, int N, int K, cudaStream_t st);

@@ -166,19 +166,20 @@ __global__ void __launch_bounds__(RL_THREADS, 2)
             if (k0 + 2 * i >= K) A[i].x = -INFINITY, Bc[i].x = 0.f;
             if (k0 + 2 * i + 1 >= K) A[i].y = -INFINITY, Bc[i].y = 0.f;
         }
-        const long long* lrow = lab_b + (size_t)(rowok ? Y : 0) * Wm + Xa;
+        // labels are interpreted by their low 32 bits (little endian int64)
+        const int* lrow = reinterpret_cast<const int*>(lab_b + (size_t)(rowok ? Y : 0) * Wm + Xa);
         const int ncols = rowok ? Xb - Xa : 0;
         for (int X0 = 0; X0 < nc_max; X0 += RL_CHUNK) {
-            long long lab[RL_CHUNK];
+            int lab[RL_CHUNK];
 #pragma unroll
-            for (int i = 0; i < RL_CHUNK; ++i) lab[i] = (X0 + i < ncols) ? __ldg(lrow + X0 + i) : PM_IGNORE_LABEL;
+            for (int i = 0; i < RL_CHUNK; ++i) lab[i] = (X0 + i < ncols) ? __ldg(lrow + 2 * (X0 + i)) : -1;
 #pragma unroll
             for (int i = 0; i < RL_CHUNK; ++i) {
                 if (X0 + i >= nc_max) break;  // warp-uniform
                 const bool ok = X0 + i < ncols;
-                const long long lv = lab[i];
-                const int cls = map_label(lv, K);
-                const bool valid = ok && cls < K;
+                const unsigned ucls = (unsigned)lab[i];
+                const bool valid = ok && ucls < (unsigned)K;
+                const int cls = (int)min(ucls, (unsigned)K);
                 const float lamx = fminf(fmaxf(sx * (float)(Xa + X0 + i) - cxf, 0.f), 1.f);
                 float2 e[NH2];
 #pragma unroll
@@ -202,12 +203,9 @@ __global__ void __launch_bounds__(RL_THREADS, 2)
                 }
                 float sum = sum2.x + sum2.y;
                 sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-                const float vmask = valid ? 1.f : 0.f;
-                if (half == 0) lossacc = fmaf(vmask, pshift + lg2_approx(sum), lossacc);
-                const float inv = rcp_approx(sum) * vmask;
+                if (valid && half == 0) lossacc += pshift + lg2_approx(sum);
+                const float inv = valid ? rcp_approx(sum) : 0.f;
                 const float hx = 1.f - lamx;
-                const float w00 = hy * hx * vmask, w01 = hy * lamx * vmask, w10 = lamy * hx * vmask,
-                            w11 = lamy * lamx * vmask;
                 const float hyi = hy * inv, lyi = lamy * inv;
                 const float i00 = hyi * hx, i01 = hyi * lamx, i10 = lyi * hx, i11 = lyi * lamx;
 #pragma unroll
@@ -218,26 +216,27 @@ __global__ void __launch_bounds__(RL_THREADS, 2)
                     G11[q] = __ffma2_rn(e[q], make_float2(i11, i11), G11[q]);
                 }
                 // one-hot part + histogram: run-length accumulate, flush to the private columns on a change
-                if (ok) {
-                    if (cls != cur) {
-                        if (cur >= 0) {
-                            if (half == 0) pc[cur * (NT / 2)] += cnt;
-                            const int kk = cur - k0;
-                            if (kk >= 0 && kk < KH && cur < K) {
-                                pv[(0 * KH + kk) * NT] += o00;
-                                pv[(1 * KH + kk) * NT] += o01;
-                                pv[(2 * KH + kk) * NT] += o10;
-                                pv[(3 * KH + kk) * NT] += o11;
-                            }
+                if (ok && cls != cur) {
+                    if (cur >= 0) {
+                        if (half == 0) pc[cur * (NT / 2)] += cnt;
+                        const int kk = cur - k0;
+                        if (kk >= 0 && kk < KH && cur < K) {
+                            pv[(0 * KH + kk) * NT] += o00;
+                            pv[(1 * KH + kk) * NT] += o01;
+                            pv[(2 * KH + kk) * NT] += o10;
+                            pv[(3 * KH + kk) * NT] += o11;
                         }
-                        cnt = 0;
-                        o00 = o01 = o10 = o11 = 0.f;
-                        cur = cls;
                     }
-                    cnt += 1;
-                    o00 += w00, o01 += w01, o10 += w10, o11 += w11;
-                    if (cls == K && lv != PM_IGNORE_LABEL && half == 0) atomicAdd(ws + PM_WS_BAD, 1ULL);
+                    cnt = 0;
+                    o00 = o01 = o10 = o11 = 0.f;
+                    cur = cls;
                 }
+                if (ok && !valid && lab[i] != PM_IGNORE_LABEL && half == 0) atomicAdd(ws + PM_WS_BAD, 1ULL);
+                const float okf = ok ? 1.f : 0.f;
+                cnt += ok ? 1 : 0;
+                const float hyo = hy * okf, lyo = lamy * okf;
+                o00 = fmaf(hyo, hx, o00), o01 = fmaf(hyo, lamx, o01);
+                o10 = fmaf(lyo, hx, o10), o11 = fmaf(lyo, lamx, o11);
             }
         }
     }

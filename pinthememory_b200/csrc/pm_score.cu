@@ -49,17 +49,23 @@ __global__ void __launch_bounds__(256) colsoftmax_apply_kernel(const float* __re
                                                                int rows_per_cta) {
     __shared__ float sm_m[256], sm_l[256], col_m[32], col_il[32];
     const int t = threadIdx.x, k = t % K, r0 = t / K, rstep = blockDim.x / K;
-    {  // combine the PM_COLPART_ROWS per-CTA partials of column k: rstep threads per column, then one
-        float M = -INFINITY, L = 0.f;
-        for (int i = r0; i < CS_MAXG; i += rstep) {
-            const float mi = __ldg(partial + (size_t)i * 64 + k), li = __ldg(partial + (size_t)i * 64 + 32 + k);
-            if (mi > M) {
-                L = L * expf(M - mi) + li;
-                M = mi;
-            } else if (mi > -INFINITY) {
-                L += li * expf(mi - M);
-            }
+    {  // combine the PM_COLPART_ROWS per-CTA partials of column k: rstep threads per column, then one.
+        // All loads are issued before the first use (they are independent L2 hits).
+        constexpr int MAXJ = (CS_MAXG + 7) / 8;  // rstep >= 8 for K <= 31
+        float pm_[MAXJ], pl_[MAXJ];
+#pragma unroll
+        for (int j = 0; j < MAXJ; ++j) {
+            const int i = r0 + j * rstep;
+            const bool ok = i < CS_MAXG;
+            pm_[j] = ok ? __ldg(partial + (size_t)i * 64 + k) : -INFINITY;
+            pl_[j] = ok ? __ldg(partial + (size_t)i * 64 + 32 + k) : 0.f;
         }
+        float M = -INFINITY, L = 0.f;
+#pragma unroll
+        for (int j = 0; j < MAXJ; ++j) M = fmaxf(M, pm_[j]);
+#pragma unroll
+        for (int j = 0; j < MAXJ; ++j)
+            if (pm_[j] > -INFINITY) L += pl_[j] * expf(pm_[j] - M);
         sm_m[t] = M;
         sm_l[t] = L;
     }
@@ -132,7 +138,7 @@ extern "C" int pm_colsoftmax_apply(const float* s, const float* gumbel_q, const 
     if (N <= 0) return PM_ERR_SHAPE;
     const int KP = pm_score_stride(K), tpb = K * (256 / K), rstep = tpb / K;
     int G = (N + rstep * 8 - 1) / (rstep * 8);  // >= 8 rows per thread
-    if (G > 4 * 148) G = 4 * 148;
+    if (G > 2 * 148) G = 2 * 148;                // every CTA re-combines the partials: keep them few
     const int rows_per_cta = (N + G - 1) / G;
     G = (N + rows_per_cta - 1) / rows_per_cta;
     pm::colsoftmax_apply_kernel<<<G, tpb, 0, (cudaStream_t)stream>>>(s, gumbel_q, col_partials, score_q, N, K, KP,

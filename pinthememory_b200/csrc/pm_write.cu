@@ -1,6 +1,7 @@
 // Memory write: label-masked per-class segmented reduction, momentum update (+ both write losses),
 // and their backward kernels.
 #include "pm_common.cuh"
+#include "pm_internal.h"
 
 namespace pm {
 
@@ -212,10 +213,55 @@ __global__ void __launch_bounds__(WB_THREADS) write_bwd_kernel(const float* __re
 }
 
 // --------------------------------------------------------------------------- momentum update + losses
-// One CTA (K x C is 19 x 256): a warp per memory row. Branch-free replacement of the reference's per-slot
-// python loop with its 19 host syncs (memory.py:233-237).
+// One CTA of 1024 threads (K x C is 19 x 256): pure latency work, so every phase issues all of its loads
+// up front and uses as many threads as the phase has independent items. Branch-free replacement of the
+// reference's per-slot python loop with its 19 host syncs (memory.py:233-237).
+// Shared rows have stride C+1 so threads that differ in the ROW index hit different banks.
 
-constexpr int UP_THREADS = 1024, UP_WARPS = 32, UP_KMAX = 32;
+constexpr int UP_THREADS = 1024, UP_WARPS = 32, UP_KMAX = 32, UP_CMAX = 256;
+
+// zs[i][j] = M_i . W_j + b_j and gs[i][j] = M_i . M_j for all K*K pairs; `parts` threads share a pair.
+__device__ __forceinline__ void pair_dots(const float* Mn, const float* Ws, const float* __restrict__ bias, float* zs,
+                                          float* gs, float* scratch, int C, int K) {
+    const int tid = threadIdx.x, CP = C + 1, KK = K * K;
+    const int parts = UP_THREADS / KK >= 4 ? 4 : (UP_THREADS / KK >= 2 ? 2 : 1);
+    const int pair = tid / parts, part = tid - pair * parts;
+    float zz = 0.f, gg = 0.f;
+    if (pair < KK) {
+        const int i = pair / K, j = pair - i * K;
+        const int clen = C / parts, c0 = part * clen;
+        const float* mi = Mn + i * CP + c0;
+        const float* mj = Mn + j * CP + c0;
+        const float* wj = Ws + j * CP + c0;
+        float z0 = 0.f, z1 = 0.f, g0 = 0.f, g1 = 0.f;
+#pragma unroll 4
+        for (int c = 0; c < clen; c += 2) {
+            const float a0 = mi[c], a1 = mi[c + 1];
+            z0 = fmaf(a0, wj[c], z0);
+            z1 = fmaf(a1, wj[c + 1], z1);
+            g0 = fmaf(a0, mj[c], g0);
+            g1 = fmaf(a1, mj[c + 1], g1);
+        }
+        zz = z0 + z1;
+        gg = g0 + g1;
+    }
+    if (parts > 1) {
+        scratch[tid] = zz;
+        scratch[UP_THREADS + tid] = gg;
+        __syncthreads();
+        if (pair < KK && part == 0) {
+            for (int q = 1; q < parts; ++q) {
+                zz += scratch[tid + q];
+                gg += scratch[UP_THREADS + tid + q];
+            }
+        }
+    }
+    if (pair < KK && part == 0) {
+        const int i = pair / K, j = pair - i * K;
+        zs[i * UP_KMAX + j] = zz + __ldg(bias + j);
+        gs[i * UP_KMAX + j] = gg;
+    }
+}
 
 __global__ void __launch_bounds__(UP_THREADS) update_fwd_kernel(const float* __restrict__ SD, const float* __restrict__ M_old,
                                                                 float momentum, const float* __restrict__ W,
@@ -223,30 +269,57 @@ __global__ void __launch_bounds__(UP_THREADS) update_fwd_kernel(const float* __r
                                                                 float* __restrict__ losses, float* __restrict__ saved,
                                                                 int C, int K) {
     extern __shared__ __align__(16) float smem[];
-    float* Mn = smem;            // [K][C] new memory
-    float* Ws = Mn + K * C;      // [K][C] classifier weight
-    float* zs = Ws + K * C;      // [K][UP_KMAX] logits
-    float* red = zs + K * UP_KMAX;  // [UP_WARPS] + [K]
+    const int CP = C + 1;
+    float* Mn = smem;                  // [K][C+1] new memory
+    float* Ws = Mn + K * CP;           // [K][C+1] classifier weight
+    float* zs = Ws + K * CP;           // [K][UP_KMAX] logits
+    float* gs = zs + K * UP_KMAX;      // [K][UP_KMAX] Gram
+    float* red = gs + K * UP_KMAX;     // [2][UP_KMAX]
+    float* scratch = red + 2 * UP_KMAX;  // [2][UP_THREADS]
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, CS = C + 4;
 
-    for (int i = tid; i < K * C; i += UP_THREADS) Ws[i] = __ldg(W + i);
-    for (int k = wid; k < K; k += UP_WARPS) {
+    {  // classifier weight -> shared, all loads in flight first
+        constexpr int PER = (UP_KMAX * UP_CMAX) / UP_THREADS;
+        float v[PER];
+#pragma unroll
+        for (int r = 0; r < PER; ++r) {
+            const int i = tid + r * UP_THREADS;
+            v[r] = (i < K * C) ? __ldg(W + i) : 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < PER; ++r) {
+            const int i = tid + r * UP_THREADS;
+            if (i < K * C) Ws[(i / C) * CP + (i % C)] = v[r];
+        }
+    }
+    if (wid < K) {  // one warp per memory row
+        const int k = wid;
         const float D = __ldg(SD + (size_t)k * CS + C);
+        float old[UP_CMAX / 32], sd[UP_CMAX / 32];
+#pragma unroll
+        for (int t = 0; t < UP_CMAX / 32; ++t) {
+            const int c = lane + 32 * t;
+            old[t] = (c < C) ? __ldg(M_old + (size_t)k * C + c) : 0.f;
+            sd[t] = (c < C) ? __ldg(SD + (size_t)k * CS + c) : 0.f;
+        }
         const bool present = D != 0.f;
         const float coef = present ? (1.f - momentum) / D : 0.f;
         float n2 = 0.f;
-        for (int c = lane; c < C; c += 32) {
-            const float old = __ldg(M_old + (size_t)k * C + c);
-            const float v = present ? fmaf(coef, __ldg(SD + (size_t)k * CS + c), momentum * old) : old;
-            Mn[k * C + c] = v;
-            n2 = fmaf(v, v, n2);
+#pragma unroll
+        for (int t = 0; t < UP_CMAX / 32; ++t) {
+            old[t] = present ? fmaf(coef, sd[t], momentum * old[t]) : old[t];
+            n2 = fmaf(old[t], old[t], n2);
         }
         n2 = warp_sum(n2);
         const float n = sqrtf(n2), inv = 1.f / fmaxf(n, PM_NORM_EPS);
-        for (int c = lane; c < C; c += 32) {
-            const float v = Mn[k * C + c] * inv;
-            Mn[k * C + c] = v;
-            M_new[(size_t)k * C + c] = v;
+#pragma unroll
+        for (int t = 0; t < UP_CMAX / 32; ++t) {
+            const int c = lane + 32 * t;
+            if (c < C) {
+                const float v = old[t] * inv;
+                Mn[k * CP + c] = v;
+                M_new[(size_t)k * C + c] = v;
+            }
         }
         if (lane == 0) {
             saved[k] = n;
@@ -254,42 +327,28 @@ __global__ void __launch_bounds__(UP_THREADS) update_fwd_kernel(const float* __r
         }
     }
     __syncthreads();
-    // divergence loss: sum over i != j of relu(M_i . M_j) / (K (K-1))
-    float dsum = 0.f;
-    for (int pair = wid; pair < K * K; pair += UP_WARPS) {
-        const int i = pair / K, j = pair - i * K;
-        // logits z[i][j] = M_i . W_j + b_j for every pair; Gram only for i < j
-        float zz = 0.f, gg = 0.f;
-        for (int c = lane; c < C; c += 32) {
-            const float mi = Mn[i * C + c];
-            zz = fmaf(mi, Ws[j * C + c], zz);
-            gg = fmaf(mi, Mn[j * C + c], gg);
-        }
-        zz = warp_sum(zz);
-        gg = warp_sum(gg);
+    pair_dots(Mn, Ws, bias, zs, gs, scratch, C, K);
+    __syncthreads();
+    if (wid < K) {  // per row: classification CE term and the positive off-diagonal Gram sum
+        const int i = wid;
+        const float z = lane < K ? zs[i * UP_KMAX + lane] : -INFINITY;
+        const float mx = warp_max(z);
+        const float sum = warp_sum(lane < K ? expf(z - mx) : 0.f);
+        const float g = (lane < K && lane != i) ? fmaxf(gs[i * UP_KMAX + lane], 0.f) : 0.f;
+        const float gsum = warp_sum(g);
         if (lane == 0) {
-            zs[i * UP_KMAX + j] = zz + __ldg(bias + j);
-            if (i != j) dsum += fmaxf(gg, 0.f);
+            red[i] = mx + logf(sum) - zs[i * UP_KMAX + i];
+            red[UP_KMAX + i] = gsum;
         }
     }
-    if (lane == 0) red[wid] = dsum;
     __syncthreads();
-    // classification loss: mean over rows of LSE(z_i) - z_ii
-    if (tid < K) {
-        float mx = -INFINITY;
-        for (int j = 0; j < K; ++j) mx = fmaxf(mx, zs[tid * UP_KMAX + j]);
-        float sum = 0.f;
-        for (int j = 0; j < K; ++j) sum += expf(zs[tid * UP_KMAX + j] - mx);
-        red[UP_WARPS + tid] = mx + logf(sum) - zs[tid * UP_KMAX + tid];
-    }
-    __syncthreads();
-    if (tid == 0) {
-        float d = 0.f;
-        for (int i = 0; i < UP_WARPS; ++i) d += red[i];
-        float c = 0.f;
-        for (int i = 0; i < K; ++i) c += red[UP_WARPS + i];
-        losses[0] = d / (float)(K * (K - 1));
-        losses[1] = c / (float)K;
+    if (wid == 0) {
+        const float c = warp_sum(lane < K ? red[lane] : 0.f);
+        const float d = warp_sum(lane < K ? red[UP_KMAX + lane] : 0.f);
+        if (lane == 0) {
+            losses[0] = d / (float)(K * (K - 1));
+            losses[1] = c / (float)K;
+        }
     }
 }
 
@@ -300,65 +359,71 @@ __global__ void __launch_bounds__(UP_THREADS) update_bwd_kernel(const float* __r
                                                                 float* __restrict__ dS, float* __restrict__ dW,
                                                                 float* __restrict__ db, int C, int K) {
     extern __shared__ __align__(16) float smem[];
-    float* Mn = smem;               // [K][C]
-    float* Ws = Mn + K * C;         // [K][C]
-    float* zs = Ws + K * C;         // [K][UP_KMAX] logits -> dz
-    float* gs = zs + K * UP_KMAX;   // [K][UP_KMAX] Gram indicator
+    const int CP = C + 1;
+    float* Mn = smem;               // [K][C+1]
+    float* Ws = Mn + K * CP;        // [K][C+1]
+    float* zs = Ws + K * CP;        // [K][UP_KMAX] logits -> dz
+    float* gs = zs + K * UP_KMAX;   // [K][UP_KMAX] Gram -> indicator * g_div * 2/(K(K-1))
+    float* scratch = gs + K * UP_KMAX;  // [2][UP_THREADS]
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const float gd = g_div ? __ldg(g_div) : 0.f, gc = g_cls ? __ldg(g_cls) : 0.f;
-
-    for (int i = tid; i < K * C; i += UP_THREADS) {
-        Mn[i] = __ldg(M_new + i);
-        Ws[i] = __ldg(W + i);
+    // upstream gradient rows are needed last: fetch them first
+    float up[UP_CMAX / 32];
+#pragma unroll
+    for (int t = 0; t < UP_CMAX / 32; ++t) {
+        const int c = lane + 32 * t;
+        up[t] = (dM_new != nullptr && wid < K && c < C) ? __ldg(dM_new + (size_t)wid * C + c) : 0.f;
     }
-    __syncthreads();
-    for (int pair = wid; pair < K * K; pair += UP_WARPS) {
-        const int i = pair / K, j = pair - i * K;
-        float zz = 0.f, gg = 0.f;
-        for (int c = lane; c < C; c += 32) {
-            const float mi = Mn[i * C + c];
-            zz = fmaf(mi, Ws[j * C + c], zz);
-            gg = fmaf(mi, Mn[j * C + c], gg);
+    {
+        constexpr int PER = (UP_KMAX * UP_CMAX) / UP_THREADS;
+        float v[PER], u[PER];
+#pragma unroll
+        for (int r = 0; r < PER; ++r) {
+            const int i = tid + r * UP_THREADS;
+            v[r] = (i < K * C) ? __ldg(M_new + i) : 0.f;
+            u[r] = (i < K * C) ? __ldg(W + i) : 0.f;
         }
-        zz = warp_sum(zz);
-        gg = warp_sum(gg);
-        if (lane == 0) {
-            zs[i * UP_KMAX + j] = zz + __ldg(bias + j);
-            gs[i * UP_KMAX + j] = (i != j && gg >= 0.f) ? 1.f : 0.f;  // reference zeroes only cos < 0
-        }
-    }
-    __syncthreads();
-    if (tid < K) {  // dz_i = g_cls * (softmax(z_i) - e_i) / K
-        float mx = -INFINITY;
-        for (int j = 0; j < K; ++j) mx = fmaxf(mx, zs[tid * UP_KMAX + j]);
-        float sum = 0.f;
-        for (int j = 0; j < K; ++j) sum += expf(zs[tid * UP_KMAX + j] - mx);
-        const float inv = 1.f / sum, sc = gc / (float)K;
-        for (int j = 0; j < K; ++j) {
-            float p = expf(zs[tid * UP_KMAX + j] - mx) * inv;
-            zs[tid * UP_KMAX + j] = sc * (p - (j == tid ? 1.f : 0.f));
+#pragma unroll
+        for (int r = 0; r < PER; ++r) {
+            const int i = tid + r * UP_THREADS;
+            if (i < K * C) {
+                Mn[(i / C) * CP + (i % C)] = v[r];
+                Ws[(i / C) * CP + (i % C)] = u[r];
+            }
         }
     }
     __syncthreads();
-    const float cdiv = gd * 2.f / (float)(K * (K - 1));
-    for (int i = wid; i < K; i += UP_WARPS) {
+    pair_dots(Mn, Ws, bias, zs, gs, scratch, C, K);
+    __syncthreads();
+    if (wid < K) {  // dz_i = g_cls (softmax(z_i) - e_i) / K ; Gram indicator scaled by g_div 2/(K(K-1))
+        const int i = wid;
+        const float z = lane < K ? zs[i * UP_KMAX + lane] : -INFINITY;
+        const float mx = warp_max(z);
+        const float e = lane < K ? expf(z - mx) : 0.f;
+        const float sum = warp_sum(e);
+        if (lane < K) {
+            zs[i * UP_KMAX + lane] = (gc / (float)K) * (e / sum - (lane == i ? 1.f : 0.f));
+            const float g = gs[i * UP_KMAX + lane];
+            // the reference zeroes only cos < 0 (memory.py:269-271)
+            gs[i * UP_KMAX + lane] = (lane != i && g >= 0.f) ? gd * 2.f / (float)(K * (K - 1)) : 0.f;
+        }
+    }
+    __syncthreads();
+    if (wid < K) {  // row i: dM''_i, projection through the normalisation, scale into dS_i
+        const int i = wid;
         const float n = saved[i], D = saved[K + i];
-        float g[8];  // C <= 256 -> <= 8 channels per lane
         float dot = 0.f;
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
+        for (int t = 0; t < UP_CMAX / 32; ++t) {
             const int c = lane + 32 * t;
-            g[t] = 0.f;
             if (c < C) {
-                float a = dM_new ? __ldg(dM_new + (size_t)i * C + c) : 0.f;
-                float dv = 0.f, cl = 0.f;
+                float a = up[t];
                 for (int j = 0; j < K; ++j) {
-                    dv = fmaf(gs[i * UP_KMAX + j], Mn[j * C + c], dv);
-                    cl = fmaf(zs[i * UP_KMAX + j], Ws[j * C + c], cl);
+                    a = fmaf(gs[i * UP_KMAX + j], Mn[j * CP + c], a);
+                    a = fmaf(zs[i * UP_KMAX + j], Ws[j * CP + c], a);
                 }
-                a = fmaf(cdiv, dv, a) + cl;
-                g[t] = a;
-                dot = fmaf(a, Mn[i * C + c], dot);
+                up[t] = a;
+                dot = fmaf(a, Mn[i * CP + c], dot);
             }
         }
         dot = warp_sum(dot);
@@ -366,10 +431,10 @@ __global__ void __launch_bounds__(UP_THREADS) update_bwd_kernel(const float* __r
         const float inv = 1.f / fmaxf(n, PM_NORM_EPS);
         const float coef = (D != 0.f) ? (1.f - momentum) / D : 0.f;
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
+        for (int t = 0; t < UP_CMAX / 32; ++t) {
             const int c = lane + 32 * t;
             if (c < C) {
-                float dmp = clamped ? g[t] * inv : (g[t] - Mn[i * C + c] * dot) * inv;
+                const float dmp = clamped ? up[t] * inv : (up[t] - Mn[i * CP + c] * dot) * inv;
                 dS[(size_t)i * C + c] = coef * dmp;
             }
         }
@@ -378,7 +443,7 @@ __global__ void __launch_bounds__(UP_THREADS) update_bwd_kernel(const float* __r
     for (int idx = tid; idx < K * C; idx += UP_THREADS) {
         const int j = idx / C, c = idx - j * C;
         float a = 0.f;
-        for (int i = 0; i < K; ++i) a = fmaf(zs[i * UP_KMAX + j], Mn[i * C + c], a);
+        for (int i = 0; i < K; ++i) a = fmaf(zs[i * UP_KMAX + j], Mn[i * CP + c], a);
         dW[idx] = a;
     }
     if (tid < K) {
@@ -470,6 +535,8 @@ extern "C" int pm_write_reduce_fwd(const void* f, const int64_t* labels, float* 
     if (!f || !labels || !SD) return PM_ERR_NULL;
     if (int e = check_write(B, C, h, w, Hm, Wm, K, dtype)) return e;
     if ((uintptr_t)SD & 15) return PM_ERR_ALIGN;
+    if (pm::tiled_ok(f, nullptr, nullptr, h * w, dtype))
+        return pm::write_reduce_tiled(f, labels, SD, B, C, h, w, Hm, Wm, K, dtype, (cudaStream_t)stream);
     PMW_DISPATCH(PMW_DISPATCH_C, launch_write_reduce, f, labels, SD, B, h, w, Hm, Wm, K, (cudaStream_t)stream);
 }
 
@@ -486,7 +553,7 @@ extern "C" int pm_update_fwd(const float* SD, const float* M_old, float momentum
     if (!SD || !M_old || !W_cls || !b_cls || !M_new || !losses || !saved) return PM_ERR_NULL;
     if (C != 32 && C != 64 && C != 128 && C != 256) return PM_ERR_CHANNELS;
     if (K < 1 || K > 31) return PM_ERR_SLOTS;
-    const size_t smem = sizeof(float) * ((size_t)2 * K * C + K * pm::UP_KMAX + pm::UP_WARPS + K);
+    const size_t smem = sizeof(float) * ((size_t)2 * K * (C + 1) + 2 * K * pm::UP_KMAX + 2 * pm::UP_KMAX + 2 * pm::UP_THREADS);
     cudaError_t e = cudaFuncSetAttribute(pm::update_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     pm::update_fwd_kernel<<<1, pm::UP_THREADS, smem, (cudaStream_t)stream>>>(SD, M_old, momentum, W_cls, b_cls, M_new,
@@ -501,7 +568,7 @@ extern "C" int pm_update_bwd(const float* dM_new, const float* g_div, const floa
     if (!M_new || !saved || !W_cls || !b_cls || !dS || !dW_cls || !db_cls) return PM_ERR_NULL;
     if (C != 32 && C != 64 && C != 128 && C != 256) return PM_ERR_CHANNELS;
     if (K < 1 || K > 31) return PM_ERR_SLOTS;
-    const size_t smem = sizeof(float) * ((size_t)2 * K * C + 2 * K * pm::UP_KMAX);
+    const size_t smem = sizeof(float) * ((size_t)2 * K * (C + 1) + 2 * K * pm::UP_KMAX + 2 * pm::UP_THREADS);
     cudaError_t e = cudaFuncSetAttribute(pm::update_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     pm::update_bwd_kernel<<<1, pm::UP_THREADS, smem, (cudaStream_t)stream>>>(dM_new, g_div, g_cls, M_new, saved, W_cls,

@@ -1,0 +1,226 @@
+// Memory write, pipelined variants (fast path when hw is a multiple of the 16-byte chunk).
+#include "pm_common.cuh"
+#include "pm_internal.h"
+
+namespace pm {
+
+// ----------------------------------------------------------------------------- class sums (forward)
+// Same algorithm as write_reduce_kernel (thread = channel, warp-uniform class index, run-length register
+// accumulator, private column of a CTA-resident [K+1][C+4] tile, one vector RED per touched class row),
+// but the [C][32] feature tile arrives through a 2-stage ring of 16-byte async copies and is stored with
+// XOR-swizzled chunks, so a thread reads 4 (fp32) / 8 (bf16) pixels of its channel per conflict-free
+// LDS.128; the label taps of the NEXT tile are fetched while the current one is reduced.
+
+template <typename T, int C, int KP>
+__global__ void __launch_bounds__(C) write_reduce_tiled_kernel(const T* __restrict__ f, const long long* __restrict__ labels,
+                                                                float* __restrict__ SD, int h, int w, int Hm, int Wm,
+                                                                int K, float sy, float sx, int tiles_per_img,
+                                                                int ntiles) {
+    constexpr int NSTAGE = 2, EPC = 16 / (int)sizeof(T), CPR = 32 / EPC, NW = C / 32, CS = C + 4;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    float* S_tile = reinterpret_cast<float*>(smraw);               // [KP][CS]
+    float* pn = S_tile + KP * CS;                                   // [NW][32]
+    float* invr = pn + NW * 32;                                     // [32]
+    float4* ent = reinterpret_cast<float4*>(invr + 32);             // [2][32][4] (class bits, w/|f|, w, -)
+    unsigned* multi = reinterpret_cast<unsigned*>(ent + 2 * 32 * 4);  // [2] + pad
+    T* ft = reinterpret_cast<T*>(multi + 4);                        // [NSTAGE][C][32], swizzled chunks
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, hw = h * w;
+    for (int i = tid; i < KP * CS; i += C) S_tile[i] = 0.f;
+    int cur = -1;
+    unsigned seen = 0u;
+    float acc = 0.f, accD = 0.f;
+
+    auto tile_coords = [&](int t, int& b, int& px0) {
+        b = t / tiles_per_img;
+        px0 = (t - b * tiles_per_img) * 32;
+    };
+    auto store_entries = [&](int buf, const LabelTaps& t, int n) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            ent[(buf * 32 + lane) * 4 + j] = make_float4(__int_as_float(t.cls[j]), 0.f, t.w[j], 0.f);
+        const unsigned m = __ballot_sync(0xffffffffu, n > 1);
+        if (lane == 0) multi[buf] = m;
+    };
+    auto taps_for = [&](int t) {
+        LabelTaps r;
+        int b, px0;
+        tile_coords(t, b, px0);
+        const int px = px0 + lane;
+        if (t < ntiles && px < hw) {
+            const int fy = px / w, fx = px - fy * w;
+            r = label_taps(labels + (size_t)b * Hm * Wm, Hm, Wm, fy, fx, sy, sx, K);
+        } else {
+            r.cls[0] = r.cls[1] = r.cls[2] = r.cls[3] = K;
+            r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0.f;
+        }
+        return r;
+    };
+
+    int tile = blockIdx.x;
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) {
+        const int t = tile + s * gridDim.x;
+        if (t < ntiles) {
+            int b, px0;
+            tile_coords(t, b, px0);
+            tile_load_async_swz<T, C, C>(ft + s * C * 32, f + (size_t)b * C * hw, hw, px0);
+        }
+        cp_async_commit();
+    }
+    if (wid == 0) {
+        LabelTaps t0 = taps_for(tile);
+        const int n = compact_taps(t0);
+        store_entries(0, t0, n);
+    }
+
+    int stage = 0, ebuf = 0;
+    for (; tile < ntiles; tile += gridDim.x) {
+        // raw taps of the next tile: loads are issued now, consumed at the end of this iteration
+        LabelTaps tn;
+        if (wid == 0) tn = taps_for(tile + gridDim.x);
+        cp_async_wait<NSTAGE - 1>();
+        __syncthreads();
+        const T* xt = ft + stage * C * 32;
+        int b, px0;
+        tile_coords(tile, b, px0);
+        const int nvalid = min(32, hw - px0);
+        {  // |f|^2 per pixel: lanes = pixels, each warp sums 32 of the C rows
+            float n2 = 0.f;
+#pragma unroll 8
+            for (int c = wid; c < C; c += NW) {
+                const int pc = ((lane / EPC) ^ tile_swz<T>(c)) * EPC + (lane % EPC);
+                const float v = to_float(xt[c * 32 + pc]);
+                n2 = fmaf(v, v, n2);
+            }
+            pn[wid * 32 + lane] = n2;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            float sacc = 0.f;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) sacc += pn[i * 32 + tid];
+            const float ir = 1.f / fmaxf(sqrtf(sacc), PM_NORM_EPS);
+            float4* e4 = ent + (ebuf * 32 + tid) * 4;  // fold 1/|f| into the tap weights of this pixel
+#pragma unroll
+            for (int j = 0; j < 4; ++j) e4[j].y = e4[j].z * ir;
+        }
+        __syncthreads();
+        {
+            const unsigned mm = multi[ebuf];
+            const float4* eb = ent + ebuf * 32 * 4;
+            const int swz = tile_swz<T>(tid);
+            auto add_entry = [&](const float4 en, float val) {
+                if (en.z != 0.f) {  // warp-uniform (pixels past the end of the image carry zero weights)
+                    const int cls = __float_as_int(en.x);
+                    if (cls != cur) {
+                        if (cur >= 0) {
+                            S_tile[cur * CS + tid] += acc;
+                            if (tid == 0) S_tile[cur * CS + C] += accD;
+                        }
+                        acc = 0.f;
+                        accD = 0.f;
+                        cur = cls;
+                        seen |= 1u << cls;
+                    }
+                    acc = fmaf(en.y, val, acc);
+                    accD += en.z;
+                }
+            };
+#pragma unroll 1
+            for (int q = 0; q < CPR; ++q) {
+                float v[EPC];
+                if (sizeof(T) == 4) {
+                    const float4 r = reinterpret_cast<const float4*>(xt + tid * 32)[q ^ swz];
+                    v[0] = r.x, v[1] = r.y, v[2] = r.z, v[3] = r.w;
+                } else {
+                    const uint4 r = reinterpret_cast<const uint4*>(xt + tid * 32)[q ^ swz];
+                    const unsigned rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        v[(2 * i) % EPC] = __uint_as_float(rr[i] << 16);
+                        v[(2 * i + 1) % EPC] = __uint_as_float(rr[i] & 0xffff0000u);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < EPC; ++j) {
+                    const int px = q * EPC + j;
+                    add_entry(eb[px * 4], v[j]);
+                    if ((mm >> px) & 1u) {  // warp-uniform: this pixel straddles classes
+#pragma unroll 1
+                        for (int e = 1; e < 4; ++e) add_entry(eb[px * 4 + e], v[j]);
+                    }
+                }
+            }
+        }
+        __syncthreads();  // stage and entry buffer consumed
+        const int next = tile + NSTAGE * gridDim.x;
+        if (next < ntiles) {
+            int nb, npx0;
+            tile_coords(next, nb, npx0);
+            tile_load_async_swz<T, C, C>(ft + stage * C * 32, f + (size_t)nb * C * hw, hw, npx0);
+        }
+        cp_async_commit();
+        if (wid == 0) {
+            const int n = compact_taps(tn);
+            store_entries(ebuf ^ 1, tn, n);
+        }
+        stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
+        ebuf ^= 1;
+    }
+    cp_async_wait<0>();
+    if (cur >= 0) {
+        S_tile[cur * CS + tid] += acc;
+        if (tid == 0) S_tile[cur * CS + C] += accD;
+    }
+    __syncthreads();
+    for (int k = 0; k <= K; ++k) {
+        if (!((seen >> k) & 1u)) continue;
+        for (int i = tid; i < CS / 4; i += C)
+            atomicAdd(reinterpret_cast<float4*>(SD + (size_t)k * CS) + i,
+                      reinterpret_cast<const float4*>(S_tile + k * CS)[i]);
+    }
+}
+
+template <typename T, int C, int KP>
+int launch_write_reduce_tiled(const void* f, const int64_t* labels, float* SD, int B, int h, int w, int Hm, int Wm,
+                              int K, cudaStream_t st) {
+    const size_t smem = sizeof(float) * ((size_t)KP * (C + 4) + (C / 32) * 32 + 32) + sizeof(float4) * 2 * 32 * 4 + 16 +
+                        sizeof(T) * (size_t)2 * C * 32;
+    auto kern = write_reduce_tiled_kernel<T, C, KP>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int hw = h * w, tiles = (hw + 31) / 32, ntiles = B * tiles;
+    int per_sm = (int)(220 * 1024 / (smem + 1024));
+    if (per_sm > 2048 / C) per_sm = 2048 / C;
+    if (per_sm < 1) per_sm = 1;
+    int grid = 148 * per_sm;
+    if (grid > ntiles) grid = ntiles;
+    const float sy = h > 1 ? (float)(Hm - 1) / (float)(h - 1) : 0.f;
+    const float sx = w > 1 ? (float)(Wm - 1) / (float)(w - 1) : 0.f;
+    kern<<<grid, C, smem, st>>>((const T*)f, (const long long*)labels, SD, h, w, Hm, Wm, K, sy, sx, tiles, ntiles);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+#define PM_WT_SWITCH_C(T, KP, FN, ...)                \
+    switch (C) {                                      \
+        case 32: return FN<T, 32, KP>(__VA_ARGS__);   \
+        case 64: return FN<T, 64, KP>(__VA_ARGS__);   \
+        case 128: return FN<T, 128, KP>(__VA_ARGS__); \
+        case 256: return FN<T, 256, KP>(__VA_ARGS__); \
+        default: return PM_ERR_CHANNELS;              \
+    }
+
+int write_reduce_tiled(const void* f, const int64_t* labels, float* SD, int B, int C, int h, int w, int Hm, int Wm,
+                       int K, int dtype, cudaStream_t st) {
+    if (dtype == PM_F32) {
+        if (K <= 19) { PM_WT_SWITCH_C(float, 20, launch_write_reduce_tiled, f, labels, SD, B, h, w, Hm, Wm, K, st) }
+        else { PM_WT_SWITCH_C(float, 32, launch_write_reduce_tiled, f, labels, SD, B, h, w, Hm, Wm, K, st) }
+    } else {
+        if (K <= 19) { PM_WT_SWITCH_C(__nv_bfloat16, 20, launch_write_reduce_tiled, f, labels, SD, B, h, w, Hm, Wm, K, st) }
+        else { PM_WT_SWITCH_C(__nv_bfloat16, 32, launch_write_reduce_tiled, f, labels, SD, B, h, w, Hm, Wm, K, st) }
+    }
+}
+
+}  // namespace pm
