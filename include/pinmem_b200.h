@@ -107,7 +107,9 @@ int pm_readloss_fwd(const float* s, const int64_t* labels, float temperature, in
  *   ds_rl    [N,stride] fp32 or NULL; g_loss: device float* (upstream grad of readloss) or NULL;
  *   rl_out   the `out` array of pm_readloss_fwd (its [1] is the scale) or NULL
  *   dx       [B,C,h,w] dtype out
- *   ds       [N,stride] fp32 out or NULL: total gradient w.r.t. the similarities (input of pm_read_bwd_dM)
+ *   ds       [N,stride] fp32 out or NULL: total gradient w.r.t. the similarities (input of pm_read_bwd_dM).
+ *            Pass a buffer: the pipelined two-kernel path (score gradients, then dx) needs it as scratch;
+ *            with NULL the slower single-kernel generic path runs.
  */
 int pm_read_bwd(const void* du, const void* x, const float* M, const float* score_m, const float* ds_rl,
                 const float* g_loss, const float* rl_out, void* dx, float* ds, int B, int C, int h, int w,

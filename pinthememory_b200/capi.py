@@ -113,7 +113,7 @@ def score_stride(K):
 # with CUDA events on the launching stream to get per-kernel durations live.
 
 LAUNCHES = 0
-_KERNELS_PER_CALL = {"pm_colsoftmax": 2}
+_KERNELS_PER_CALL = {"pm_colsoftmax": 2, "pm_read_bwd": 2}
 _timing = None  # name -> list of (start_event, end_event) when enabled
 
 

@@ -564,6 +564,9 @@ extern "C" int pm_read_bwd(const void* du, const void* x, const float* M, const 
     if (!du || !x || !M || !score_m || !dx) return PM_ERR_NULL;
     if (int e = check_common(B, C, h, w, K, dtype)) return e;
     if (((uintptr_t)ds & 15) != 0 || ((uintptr_t)ds_rl & 15) != 0) return PM_ERR_ALIGN;
+    if (ds != nullptr && pm::tiled_ok(du, x, dx, h * w, dtype))
+        return pm::read_bwd_tiled(du, x, M, score_m, ds_rl, g_loss, rl_out, dx, ds, B, C, h * w, K, dtype,
+                                  (cudaStream_t)stream);
     PM_DISPATCH(PM_DISPATCH_CW, launch_read_bwd, du, x, M, score_m, ds_rl, g_loss, rl_out, dx, ds, B, h * w, K,
                 (cudaStream_t)stream);
 }

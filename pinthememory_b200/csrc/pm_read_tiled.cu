@@ -266,6 +266,253 @@ int launch_read_fwd_tiled(const void* x, const float* M, const float* gum_m, con
     return le == cudaSuccess ? 0 : (int)le;
 }
 
+// -------------------------------------------------------------------------------- backward, part A: ds
+// ds = p * (M.dc - p.(M.dc)) + g_loss/(V*T) * ds_rl  per pixel: the forward's first phase applied to the
+// dc half of du, then the softmax backward by 8 threads per pixel. Writes the [N][KP] score-gradient
+// buffer that part B (and the dM kernel) consume.
+
+template <typename T, int C, int KP, int NSTAGE>
+__global__ void __launch_bounds__(TL_THREADS, 2)
+    read_bwd_ds_tiled_kernel(const T* __restrict__ du, const float* __restrict__ M, const float* __restrict__ p_in,
+                             const float* __restrict__ ds_rl, const float* __restrict__ g_loss,
+                             const float* __restrict__ rl_out, float* __restrict__ ds_out, int hw, int K,
+                             int tiles_per_img, int ntiles) {
+    constexpr int CW = C / TL_WARPS, NI = (KP + 7) / 8;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    float* Mt = reinterpret_cast<float*>(smraw);  // [C][KP]
+    float* part = Mt + C * KP;                    // [8][TP][KP]
+    float* ds_sm = part + TL_WARPS * TP * KP;     // [TP][KP]
+    T* xs = reinterpret_cast<T*>(ds_sm + TP * KP);  // [NSTAGE][C][TP]  (dc tiles)
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int tile = blockIdx.x;
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) {
+        const int t = tile + s * gridDim.x;
+        if (t < ntiles) {
+            const int b = t / tiles_per_img, px0 = (t - b * tiles_per_img) * TP;
+            tile_load_async<T, C, TL_THREADS>(xs + s * C * TP, du + ((size_t)b * 2 * C + C) * hw, hw, px0);
+        }
+        cp_async_commit();
+    }
+    load_Mt<C, KP>(Mt, M, K);
+    float scale = 0.f;
+    if (ds_rl != nullptr && g_loss != nullptr && rl_out != nullptr) scale = __ldg(g_loss) * __ldg(rl_out + 1);
+
+    int stage = 0;
+    for (; tile < ntiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_img, px0 = (tile - b * tiles_per_img) * TP;
+        const int nvalid = min(TP, hw - px0);
+        const size_t n0g = (size_t)b * hw + px0;
+        // this thread's share of p and ds_rl (pixel tid>>3, slots j, j+8, ..): fetched before the dots
+        const int px = tid >> 3, j = tid & 7;
+        const bool valid = px < nvalid;
+        float pk[NI], rl[NI];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const int k = j + 8 * i;
+            pk[i] = (valid && k < K) ? __ldg(p_in + (n0g + px) * K + k) : 0.f;
+            rl[i] = (valid && k < K && scale != 0.f) ? __ldg(ds_rl + (n0g + px) * KP + k) : 0.f;
+        }
+        cp_async_wait<NSTAGE - 1>();
+        __syncthreads();
+        const T* xt = xs + stage * C * TP;
+        {
+            float2 a2[KP / 2];
+#pragma unroll
+            for (int i = 0; i < KP / 2; ++i) a2[i] = f2(0.f, 0.f);
+            float n2 = 0.f;
+            tile_dots<T, CW, KP>(xt, Mt, wid * CW, lane, a2, n2);
+            store_partial<KP>(part, wid, lane, a2);
+        }
+        __syncthreads();
+        {
+            float dp[NI], dot = 0.f;
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+                const int k = j + 8 * i;
+                float acc = 0.f;
+                if (k < KP) {
+#pragma unroll
+                    for (int w = 0; w < TL_WARPS; ++w) acc += part[((size_t)w * TP + px) * KP + k];
+                }
+                dp[i] = acc;
+                dot = fmaf(pk[i], acc, dot);
+            }
+            dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+                const int k = j + 8 * i;
+                if (k < KP) ds_sm[px * KP + k] = fmaf(scale, rl[i], pk[i] * (dp[i] - dot));
+            }
+        }
+        __syncthreads();  // ds_sm complete; every read of this stage and of `part` is done
+        for (int o = tid; o < nvalid * (KP / 4); o += TL_THREADS)
+            reinterpret_cast<float4*>(ds_out + n0g * KP)[o] = reinterpret_cast<const float4*>(ds_sm)[o];
+        const int next = tile + NSTAGE * gridDim.x;
+        if (next < ntiles) {
+            const int nb = next / tiles_per_img, npx0 = (next - nb * tiles_per_img) * TP;
+            tile_load_async<T, C, TL_THREADS>(xs + stage * C * TP, du + ((size_t)nb * 2 * C + C) * hw, hw, npx0);
+        }
+        cp_async_commit();
+        stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
+        // ds_sm is rewritten only after the next iteration's two barriers
+    }
+    cp_async_wait<0>();
+}
+
+// -------------------------------------------------------------------------------- backward, part B: dx
+// dq = dq0 + ds.M ; q = x/|x| ; dx = (dq - q (q.dq)) / |x|. One CTA per SM, 16 warps x (C/16) channels,
+// lanes = pixels; x, dq0 and the ds rows of a tile arrive through a 2-stage async-copy ring.
+
+constexpr int DX_THREADS = 512, DX_WARPS = 16;
+
+template <typename T, int C, int KP, int NSTAGE>
+__global__ void __launch_bounds__(DX_THREADS, 1)
+    read_bwd_dx_tiled_kernel(const T* __restrict__ du, const T* __restrict__ x, const float* __restrict__ M,
+                             const float* __restrict__ ds, T* __restrict__ dx, int hw, int K, int tiles_per_img,
+                             int ntiles) {
+    constexpr int CW = C / DX_WARPS;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    float* Mt = reinterpret_cast<float*>(smraw);        // [C][KP]
+    float* pn = Mt + C * KP;                            // [16][TP]
+    float* pd = pn + DX_WARPS * TP;                     // [16][TP]
+    float* dss = pd + DX_WARPS * TP;                    // [NSTAGE][TP][KP]
+    T* xs = reinterpret_cast<T*>(dss + NSTAGE * TP * KP);  // [NSTAGE][2][C][TP]: x tile, dq0 tile
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    auto issue = [&](int t, int s) {
+        const int b = t / tiles_per_img, px0 = (t - b * tiles_per_img) * TP;
+        T* base = xs + (size_t)s * 2 * C * TP;
+        tile_load_async<T, C, DX_THREADS>(base, x + (size_t)b * C * hw, hw, px0);
+        tile_load_async<T, C, DX_THREADS>(base + C * TP, du + (size_t)b * 2 * C * hw, hw, px0);
+        const size_t n0g = (size_t)b * hw + px0;
+        const int nvalid = min(TP, hw - px0);
+        for (int i = tid; i < TP * KP / 4; i += DX_THREADS)
+            cp_async16(dss + s * TP * KP + i * 4, ds + n0g * KP + (i * 4 < nvalid * KP ? i * 4 : 0), i * 4 < nvalid * KP);
+    };
+    int tile = blockIdx.x;
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) {
+        const int t = tile + s * gridDim.x;
+        if (t < ntiles) issue(t, s);
+        cp_async_commit();
+    }
+    for (int i = tid; i < C * KP; i += DX_THREADS) {
+        const int c = i / KP, k = i - c * KP;
+        Mt[i] = (k < K) ? __ldg(M + (size_t)k * C + c) : 0.f;
+    }
+
+    int stage = 0;
+    for (; tile < ntiles; tile += gridDim.x) {
+        cp_async_wait<NSTAGE - 1>();
+        __syncthreads();
+        const T* xt = xs + (size_t)stage * 2 * C * TP;
+        const T* qt = xt + C * TP;
+        const int b = tile / tiles_per_img, px0 = (tile - b * tiles_per_img) * TP;
+        const int nvalid = min(TP, hw - px0);
+        const T* xcol = xt + wid * CW * 32 + lane;
+        const T* qcol = qt + wid * CW * 32 + lane;
+        float xv[CW], n2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+            xv[j] = to_float(xcol[j * 32]);
+            n2 = fmaf(xv[j], xv[j], n2);
+        }
+        pn[wid * TP + lane] = n2;
+        // dq = dq0 + ds . M for this warp's channels
+        float2 s2[KP / 2];
+        {
+            const float4* sr = reinterpret_cast<const float4*>(dss + stage * TP * KP + lane * KP);
+#pragma unroll
+            for (int q = 0; q < KP / 4; ++q) {
+                const float4 v = sr[q];
+                s2[2 * q] = f2(v.x, v.y);
+                s2[2 * q + 1] = f2(v.z, v.w);
+            }
+        }
+        float dq[CW];
+        const float4* mbase = reinterpret_cast<const float4*>(Mt + wid * CW * KP);
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+            const float4* mrow = mbase + j * (KP / 4);
+            float2 acc = f2(to_float(qcol[j * 32]), 0.f);
+#pragma unroll
+            for (int q = 0; q < KP / 4; ++q) {
+                const float4 m = mrow[q];
+                acc = __ffma2_rn(s2[2 * q], f2(m.x, m.y), acc);
+                acc = __ffma2_rn(s2[2 * q + 1], f2(m.z, m.w), acc);
+            }
+            dq[j] = acc.x + acc.y;
+        }
+        __syncthreads();
+        float nn = 0.f;
+#pragma unroll
+        for (int w = 0; w < DX_WARPS; ++w) nn += pn[w * TP + lane];
+        const float nrm = sqrtf(nn), ir = 1.f / fmaxf(nrm, PM_NORM_EPS);
+        float dot = 0.f;
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+            xv[j] *= ir;  // q
+            dot = fmaf(xv[j], dq[j], dot);
+        }
+        pd[wid * TP + lane] = dot;
+        __syncthreads();  // also: every read of this stage's tiles is done
+        const int next = tile + NSTAGE * gridDim.x;
+        if (next < ntiles) issue(next, stage);
+        cp_async_commit();
+        dot = 0.f;
+#pragma unroll
+        for (int w = 0; w < DX_WARPS; ++w) dot += pd[w * TP + lane];
+        if (nrm <= PM_NORM_EPS) dot = 0.f;  // F.normalize clamps the norm: no projection gradient below eps
+        if (lane < nvalid) {
+            T* dxp = dx + ((size_t)b * C + wid * CW) * hw + px0 + lane;
+#pragma unroll
+            for (int j = 0; j < CW; ++j) {
+                stf(dxp, (dq[j] - xv[j] * dot) * ir);
+                dxp += hw;
+            }
+        }
+        stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
+    }
+    cp_async_wait<0>();
+}
+
+template <typename T, int C, int KP>
+int launch_read_bwd_tiled(const void* du, const void* x, const float* M, const float* p, const float* ds_rl,
+                          const float* g_loss, const float* rl_out, void* dx, float* ds, int B, int hw, int K,
+                          cudaStream_t st) {
+    constexpr int NSTAGE = 2;
+    const int tiles = (hw + TP - 1) / TP, ntiles = B * tiles;
+    {
+        const size_t smem = sizeof(float) * ((size_t)C * KP + TL_WARPS * TP * KP + TP * KP) +
+                            sizeof(T) * (size_t)NSTAGE * C * TP;
+        auto kern = read_bwd_ds_tiled_kernel<T, C, KP, NSTAGE>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        int grid = 2 * 148;
+        if (grid > ntiles) grid = ntiles;
+        kern<<<grid, TL_THREADS, smem, st>>>((const T*)du, M, p, ds_rl, g_loss, rl_out, ds, hw, K, tiles, ntiles);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+    }
+    {
+        const size_t smem = sizeof(float) * ((size_t)C * KP + 2 * DX_WARPS * TP + (size_t)NSTAGE * TP * KP) +
+                            sizeof(T) * (size_t)NSTAGE * 2 * C * TP;
+        auto kern = read_bwd_dx_tiled_kernel<T, C, KP, NSTAGE>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        int grid = 148;
+        if (grid > ntiles) grid = ntiles;
+        kern<<<grid, DX_THREADS, smem, st>>>((const T*)du, (const T*)x, M, ds, (T*)dx, hw, K, tiles, ntiles);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+    }
+    return 0;
+}
+
 #define PM_TILED_SWITCH_C(T, KP, FN, ...)                   \
     switch (C) {                                            \
         case 32: return FN<T, 32, KP>(__VA_ARGS__);         \
@@ -288,6 +535,18 @@ int read_fwd_tiled(const void* x, const float* M, const float* gum_m, const floa
     } else {
         if (K <= 19) { PM_TILED_SWITCH_C(__nv_bfloat16, 20, launch_read_fwd_tiled, x, M, gum_m, gum_q, u, s, p, colpart, B, hw, K, st) }
         else { PM_TILED_SWITCH_C(__nv_bfloat16, 32, launch_read_fwd_tiled, x, M, gum_m, gum_q, u, s, p, colpart, B, hw, K, st) }
+    }
+}
+
+int read_bwd_tiled(const void* du, const void* x, const float* M, const float* p, const float* ds_rl,
+                   const float* g_loss, const float* rl_out, void* dx, float* ds, int B, int C, int hw, int K, int dtype,
+                   cudaStream_t st) {
+    if (dtype == PM_F32) {
+        if (K <= 19) { PM_TILED_SWITCH_C(float, 20, launch_read_bwd_tiled, du, x, M, p, ds_rl, g_loss, rl_out, dx, ds, B, hw, K, st) }
+        else { PM_TILED_SWITCH_C(float, 32, launch_read_bwd_tiled, du, x, M, p, ds_rl, g_loss, rl_out, dx, ds, B, hw, K, st) }
+    } else {
+        if (K <= 19) { PM_TILED_SWITCH_C(__nv_bfloat16, 20, launch_read_bwd_tiled, du, x, M, p, ds_rl, g_loss, rl_out, dx, ds, B, hw, K, st) }
+        else { PM_TILED_SWITCH_C(__nv_bfloat16, 32, launch_read_bwd_tiled, du, x, M, p, ds_rl, g_loss, rl_out, dx, ds, B, hw, K, st) }
     }
 }
 

@@ -111,7 +111,7 @@ class _ReadFn(torch.autograd.Function):
         else:
             g_loss = None
         dx = torch.empty_like(x)
-        ds = torch.empty(B * h * w, capi.score_stride(K), dtype=torch.float32, device=x.device) if need_dM else None
+        ds = torch.empty(B * h * w, capi.score_stride(K), dtype=torch.float32, device=x.device)
         capi.read_bwd(du, x, M, score_m, ds_rl if g_loss is not None else None, g_loss,
                       rl_out if g_loss is not None else None, dx, ds, K)
         dM = None
