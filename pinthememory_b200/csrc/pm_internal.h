@@ -19,6 +19,9 @@ int read_bwd_tiled(const void* du, const void* x, const float* M, const float* p
 int write_reduce_tiled(const void* f, const int64_t* labels, float* SD, int B, int C, int h, int w, int Hm, int Wm,
                        int K, int dtype, cudaStream_t st);
 
+int write_bwd_tiled(const float* dS, const void* f, const int64_t* labels, void* df, int B, int C, int h, int w, int Hm,
+                    int Wm, int K, int dtype, cudaStream_t st);
+
 // fills `partial` ([PM_COLPART_ROWS][64]: max at [k], sum at [32+k]) from s (+ gumbel_q)
 int colsoftmax_stats(const float* s, const float* gumbel_q, float* partial, int N, int K, cudaStream_t st);
 

@@ -544,6 +544,8 @@ extern "C" int pm_write_bwd(const float* dS, const void* f, const int64_t* label
                             int Hm, int Wm, int K, int dtype, void* stream) {
     if (!dS || !f || !labels || !df) return PM_ERR_NULL;
     if (int e = check_write(B, C, h, w, Hm, Wm, K, dtype)) return e;
+    if (pm::tiled_ok(f, df, nullptr, h * w, dtype))
+        return pm::write_bwd_tiled(dS, f, labels, df, B, C, h, w, Hm, Wm, K, dtype, (cudaStream_t)stream);
     PMW_DISPATCH(PMW_DISPATCH_CW, launch_write_bwd, dS, f, labels, df, B, h, w, Hm, Wm, K, (cudaStream_t)stream);
 }
 

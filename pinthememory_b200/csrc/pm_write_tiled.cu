@@ -203,6 +203,167 @@ int launch_write_reduce_tiled(const void* f, const int64_t* labels, float* SD, i
     return e == cudaSuccess ? 0 : (int)e;
 }
 
+// ---------------------------------------------------------------------------- write backward (to f)
+// dv[n] = sum_taps w * dS[class]; df = (dv - v (v.dv)) / |f|, v = f/|f|. Persistent CTAs (2 per SM), the
+// [C][32] tile of f arrives through a 2-stage async-copy ring, lanes = pixels, 8 warps split the channels,
+// dS sits in shared memory with row stride C+1 (lanes with different classes hit different banks). The
+// label taps of the next tile are fetched by warp 0 while the current tile is processed.
+
+constexpr int WBT_THREADS = 256, WBT_WARPS = 8;
+
+template <typename T, int C, int KP>
+__global__ void __launch_bounds__(WBT_THREADS, 2)
+    write_bwd_tiled_kernel(const float* __restrict__ dS, const T* __restrict__ f, const long long* __restrict__ labels,
+                           T* __restrict__ df, int h, int w, int Hm, int Wm, int K, float sy, float sx,
+                           int tiles_per_img, int ntiles) {
+    constexpr int NSTAGE = 2, CW = C / WBT_WARPS, LDS_ = C + 1;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    float* dSs = reinterpret_cast<float*>(smraw);      // [KP][C+1]; rows >= K are zero (ignore class)
+    float* pn = dSs + KP * LDS_;                        // [8][32]
+    float* pd = pn + WBT_WARPS * 32;                    // [8][32]
+    float2* ent = reinterpret_cast<float2*>(pd + WBT_WARPS * 32 + ((KP * LDS_) & 1));  // [2][32][4]
+    T* ft = reinterpret_cast<T*>(ent + 2 * 32 * 4);     // [NSTAGE][C][32]
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, hw = h * w;
+    auto tile_coords = [&](int t, int& b, int& px0) {
+        b = t / tiles_per_img;
+        px0 = (t - b * tiles_per_img) * 32;
+    };
+    auto taps_for = [&](int t) {
+        LabelTaps r;
+        int b, px0;
+        tile_coords(t, b, px0);
+        const int px = px0 + lane;
+        if (t < ntiles && px < hw) {
+            const int fy = px / w, fx = px - fy * w;
+            r = label_taps(labels + (size_t)b * Hm * Wm, Hm, Wm, fy, fx, sy, sx, K);
+        } else {
+            r.cls[0] = r.cls[1] = r.cls[2] = r.cls[3] = K;
+            r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0.f;
+        }
+        return r;
+    };
+    auto store_entries = [&](int buf, const LabelTaps& t) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ent[(buf * 32 + lane) * 4 + j] = make_float2(__int_as_float(t.cls[j]), t.w[j]);
+    };
+
+    int tile = blockIdx.x;
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) {
+        const int t = tile + s * gridDim.x;
+        if (t < ntiles) {
+            int b, px0;
+            tile_coords(t, b, px0);
+            tile_load_async<T, C, WBT_THREADS>(ft + s * C * 32, f + (size_t)b * C * hw, hw, px0);
+        }
+        cp_async_commit();
+    }
+    for (int i = tid; i < KP * LDS_; i += WBT_THREADS) {
+        const int k = i / LDS_, c = i - k * LDS_;
+        dSs[i] = (k < K && c < C) ? __ldg(dS + (size_t)k * C + c) : 0.f;
+    }
+    if (wid == 0) {
+        LabelTaps t0 = taps_for(tile);
+        compact_taps(t0);
+        store_entries(0, t0);
+    }
+
+    int stage = 0, ebuf = 0;
+    for (; tile < ntiles; tile += gridDim.x) {
+        LabelTaps tn;
+        if (wid == 0) tn = taps_for(tile + gridDim.x);  // loads in flight across this tile
+        cp_async_wait<NSTAGE - 1>();
+        __syncthreads();
+        const T* xt = ft + stage * C * 32;
+        int b, px0;
+        tile_coords(tile, b, px0);
+        const int nvalid = min(32, hw - px0);
+        // this pixel's taps
+        int cls[4];
+        float wt[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 e = ent[(ebuf * 32 + lane) * 4 + j];
+            cls[j] = __float_as_int(e.x);
+            wt[j] = e.y;
+        }
+        const bool multi = wt[1] != 0.f;
+        const T* fcol = xt + wid * CW * 32 + lane;
+        const float* r0 = dSs + cls[0] * LDS_ + wid * CW;
+        float dv[CW], n2 = 0.f, dotf = 0.f;
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+            const float fv = to_float(fcol[j * 32]);
+            n2 = fmaf(fv, fv, n2);
+            dv[j] = wt[0] * r0[j];
+        }
+        if (multi) {  // pixel straddles classes (rare for real label maps)
+            const float* r1 = dSs + cls[1] * LDS_ + wid * CW;
+            const float* r2 = dSs + cls[2] * LDS_ + wid * CW;
+            const float* r3 = dSs + cls[3] * LDS_ + wid * CW;
+#pragma unroll
+            for (int j = 0; j < CW; ++j) dv[j] = fmaf(wt[1], r1[j], fmaf(wt[2], r2[j], fmaf(wt[3], r3[j], dv[j])));
+        }
+#pragma unroll
+        for (int j = 0; j < CW; ++j) dotf = fmaf(to_float(fcol[j * 32]), dv[j], dotf);
+        pn[wid * 32 + lane] = n2;
+        pd[wid * 32 + lane] = dotf;
+        __syncthreads();
+        float nn = 0.f, dd = 0.f;
+#pragma unroll
+        for (int i = 0; i < WBT_WARPS; ++i) {
+            nn += pn[i * 32 + lane];
+            dd += pd[i * 32 + lane];
+        }
+        const float nrm = sqrtf(nn), ir = 1.f / fmaxf(nrm, PM_NORM_EPS);
+        // v.dv = ir * (f.dv); df = (dv - v (v.dv)) * ir = dv*ir - f * (ir^3 * f.dv)
+        const float coef = (nrm <= PM_NORM_EPS) ? 0.f : ir * ir * ir * dd;
+        if (lane < nvalid) {
+            T* dfp = df + ((size_t)b * C + wid * CW) * hw + px0 + lane;
+#pragma unroll
+            for (int j = 0; j < CW; ++j) {
+                stf(dfp, fmaf(-coef, to_float(fcol[j * 32]), dv[j] * ir));
+                dfp += hw;
+            }
+        }
+        __syncthreads();  // stage, entries and pn/pd consumed
+        const int next = tile + NSTAGE * gridDim.x;
+        if (next < ntiles) {
+            int nb, npx0;
+            tile_coords(next, nb, npx0);
+            tile_load_async<T, C, WBT_THREADS>(ft + stage * C * 32, f + (size_t)nb * C * hw, hw, npx0);
+        }
+        cp_async_commit();
+        if (wid == 0) {
+            compact_taps(tn);
+            store_entries(ebuf ^ 1, tn);
+        }
+        stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
+        ebuf ^= 1;
+    }
+    cp_async_wait<0>();
+}
+
+template <typename T, int C, int KP>
+int launch_write_bwd_tiled(const float* dS, const void* f, const int64_t* labels, void* df, int B, int h, int w, int Hm,
+                           int Wm, int K, cudaStream_t st) {
+    const size_t smem = sizeof(float) * ((size_t)KP * (C + 1) + 2 * WBT_WARPS * 32 + 1) + sizeof(float2) * 2 * 32 * 4 +
+                        sizeof(T) * (size_t)2 * C * 32;
+    auto kern = write_bwd_tiled_kernel<T, C, KP>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int hw = h * w, tiles = (hw + 31) / 32, ntiles = B * tiles;
+    int grid = 2 * 148;
+    if (grid > ntiles) grid = ntiles;
+    const float sy = h > 1 ? (float)(Hm - 1) / (float)(h - 1) : 0.f;
+    const float sx = w > 1 ? (float)(Wm - 1) / (float)(w - 1) : 0.f;
+    kern<<<grid, WBT_THREADS, smem, st>>>(dS, (const T*)f, (const long long*)labels, (T*)df, h, w, Hm, Wm, K, sy, sx, tiles,
+                                          ntiles);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
 #define PM_WT_SWITCH_C(T, KP, FN, ...)                \
     switch (C) {                                      \
         case 32: return FN<T, 32, KP>(__VA_ARGS__);   \
@@ -220,6 +381,17 @@ int write_reduce_tiled(const void* f, const int64_t* labels, float* SD, int B, i
     } else {
         if (K <= 19) { PM_WT_SWITCH_C(__nv_bfloat16, 20, launch_write_reduce_tiled, f, labels, SD, B, h, w, Hm, Wm, K, st) }
         else { PM_WT_SWITCH_C(__nv_bfloat16, 32, launch_write_reduce_tiled, f, labels, SD, B, h, w, Hm, Wm, K, st) }
+    }
+}
+
+int write_bwd_tiled(const float* dS, const void* f, const int64_t* labels, void* df, int B, int C, int h, int w, int Hm,
+                    int Wm, int K, int dtype, cudaStream_t st) {
+    if (dtype == PM_F32) {
+        if (K <= 19) { PM_WT_SWITCH_C(float, 20, launch_write_bwd_tiled, dS, f, labels, df, B, h, w, Hm, Wm, K, st) }
+        else { PM_WT_SWITCH_C(float, 32, launch_write_bwd_tiled, dS, f, labels, df, B, h, w, Hm, Wm, K, st) }
+    } else {
+        if (K <= 19) { PM_WT_SWITCH_C(__nv_bfloat16, 20, launch_write_bwd_tiled, dS, f, labels, df, B, h, w, Hm, Wm, K, st) }
+        else { PM_WT_SWITCH_C(__nv_bfloat16, 32, launch_write_bwd_tiled, dS, f, labels, df, B, h, w, Hm, Wm, K, st) }
     }
 }
 
