@@ -27,7 +27,7 @@ namespace pm {
 constexpr int RL_TX = 32;          // cells per CTA along x
 constexpr int RL_LDX = RL_TX + 1;  // taps per tile row
 constexpr int RL_THREADS = 256;    // 128 cells x 2 slot halves
-constexpr int RL_CHUNK = 8;        // label pixels fetched ahead
+constexpr int RL_CHUNK = 3;        // label pixels fetched ahead (cells are 8-9 / 16-17 pixels wide: 3 divides 9 and 18)
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -169,6 +169,11 @@ __global__ void __launch_bounds__(RL_THREADS, 2)
         // labels are interpreted by their low 32 bits (little endian int64)
         const int* lrow = reinterpret_cast<const int*>(lab_b + (size_t)(rowok ? Y : 0) * Wm + Xa);
         const int ncols = rowok ? Xb - Xa : 0;
+        // per-row accumulators of p*(1-lambda_x) and p*lambda_x; split over the two tap rows at row end
+        float2 R0[NH2], R1[NH2];
+#pragma unroll
+        for (int q = 0; q < NH2; ++q) R0[q] = R1[q] = make_float2(0.f, 0.f);
+        float ox0 = 0.f, ox1 = 0.f;  // one-hot counterparts for the current run (this row only)
         for (int X0 = 0; X0 < nc_max; X0 += RL_CHUNK) {
             int lab[RL_CHUNK];
 #pragma unroll
@@ -177,7 +182,8 @@ __global__ void __launch_bounds__(RL_THREADS, 2)
             for (int i = 0; i < RL_CHUNK; ++i) {
                 if (X0 + i >= nc_max) break;  // warp-uniform
                 const bool ok = X0 + i < ncols;
-                const unsigned ucls = (unsigned)lab[i];
+                const int labi = lab[i];
+                const unsigned ucls = (unsigned)labi;
                 const bool valid = ok && ucls < (unsigned)K;
                 const int cls = (int)min(ucls, (unsigned)K);
                 const float lamx = fminf(fmaxf(sx * (float)(Xa + X0 + i) - cxf, 0.f), 1.f);
@@ -206,14 +212,11 @@ __global__ void __launch_bounds__(RL_THREADS, 2)
                 if (valid && half == 0) lossacc += pshift + lg2_approx(sum);
                 const float inv = valid ? rcp_approx(sum) : 0.f;
                 const float hx = 1.f - lamx;
-                const float hyi = hy * inv, lyi = lamy * inv;
-                const float i00 = hyi * hx, i01 = hyi * lamx, i10 = lyi * hx, i11 = lyi * lamx;
+                const float ihx = inv * hx, ilx = inv * lamx;
 #pragma unroll
                 for (int q = 0; q < NH2; ++q) {
-                    G00[q] = __ffma2_rn(e[q], make_float2(i00, i00), G00[q]);
-                    G01[q] = __ffma2_rn(e[q], make_float2(i01, i01), G01[q]);
-                    G10[q] = __ffma2_rn(e[q], make_float2(i10, i10), G10[q]);
-                    G11[q] = __ffma2_rn(e[q], make_float2(i11, i11), G11[q]);
+                    R0[q] = __ffma2_rn(e[q], make_float2(ihx, ihx), R0[q]);
+                    R1[q] = __ffma2_rn(e[q], make_float2(ilx, ilx), R1[q]);
                 }
                 // one-hot part + histogram: run-length accumulate, flush to the private columns on a change
                 if (ok && cls != cur) {
@@ -221,22 +224,34 @@ __global__ void __launch_bounds__(RL_THREADS, 2)
                         if (half == 0) pc[cur * (NT / 2)] += cnt;
                         const int kk = cur - k0;
                         if (kk >= 0 && kk < KH && cur < K) {
-                            pv[(0 * KH + kk) * NT] += o00;
-                            pv[(1 * KH + kk) * NT] += o01;
-                            pv[(2 * KH + kk) * NT] += o10;
-                            pv[(3 * KH + kk) * NT] += o11;
+                            pv[(0 * KH + kk) * NT] += fmaf(hy, ox0, o00);
+                            pv[(1 * KH + kk) * NT] += fmaf(hy, ox1, o01);
+                            pv[(2 * KH + kk) * NT] += fmaf(lamy, ox0, o10);
+                            pv[(3 * KH + kk) * NT] += fmaf(lamy, ox1, o11);
                         }
                     }
                     cnt = 0;
                     o00 = o01 = o10 = o11 = 0.f;
+                    ox0 = ox1 = 0.f;
                     cur = cls;
                 }
-                if (ok && !valid && lab[i] != PM_IGNORE_LABEL && half == 0) atomicAdd(ws + PM_WS_BAD, 1ULL);
-                const float okf = ok ? 1.f : 0.f;
+                if (ok && !valid && labi != PM_IGNORE_LABEL && half == 0) atomicAdd(ws + PM_WS_BAD, 1ULL);
                 cnt += ok ? 1 : 0;
-                const float hyo = hy * okf, lyo = lamy * okf;
-                o00 = fmaf(hyo, hx, o00), o01 = fmaf(hyo, lamx, o01);
-                o10 = fmaf(lyo, hx, o10), o11 = fmaf(lyo, lamx, o11);
+                ox0 += ok ? hx : 0.f;
+                ox1 += ok ? lamx : 0.f;
+            }
+        }
+        // end of row: fold the row accumulators into the four taps
+        o00 = fmaf(hy, ox0, o00), o01 = fmaf(hy, ox1, o01);
+        o10 = fmaf(lamy, ox0, o10), o11 = fmaf(lamy, ox1, o11);
+        {
+            const float2 hy2 = make_float2(hy, hy), ly2 = make_float2(lamy, lamy);
+#pragma unroll
+            for (int q = 0; q < NH2; ++q) {
+                G00[q] = __ffma2_rn(R0[q], hy2, G00[q]);
+                G01[q] = __ffma2_rn(R1[q], hy2, G01[q]);
+                G10[q] = __ffma2_rn(R0[q], ly2, G10[q]);
+                G11[q] = __ffma2_rn(R1[q], ly2, G11[q]);
             }
         }
     }

@@ -204,19 +204,21 @@ int launch_write_reduce_tiled(const void* f, const int64_t* labels, float* SD, i
 }
 
 // ---------------------------------------------------------------------------- write backward (to f)
-// dv[n] = sum_taps w * dS[class]; df = (dv - v (v.dv)) / |f|, v = f/|f|. Persistent CTAs (2 per SM), the
-// [C][32] tile of f arrives through a 2-stage async-copy ring, lanes = pixels, 8 warps split the channels,
+// dv[n] = sum_taps w * dS[class]; df = (dv - v (v.dv)) / |f|, v = f/|f|. Persistent CTAs, 2 per SM (measured:
+// one 16-warp CTA with a 5-stage ring is 45% slower -- the per-tile barriers need a second CTA to hide
+// behind, bytes in flight are not the limit); the [C][32] tiles of f arrive through a 2-stage async-copy
+// ring, lanes = pixels, 8 warps split the channels,
 // dS sits in shared memory with row stride C+1 (lanes with different classes hit different banks). The
 // label taps of the next tile are fetched by warp 0 while the current tile is processed.
 
-constexpr int WBT_THREADS = 256, WBT_WARPS = 8;
+constexpr int WBT_THREADS = 256, WBT_WARPS = 8, WBT_STAGES = 2;
 
 template <typename T, int C, int KP>
 __global__ void __launch_bounds__(WBT_THREADS, 2)
     write_bwd_tiled_kernel(const float* __restrict__ dS, const T* __restrict__ f, const long long* __restrict__ labels,
                            T* __restrict__ df, int h, int w, int Hm, int Wm, int K, float sy, float sx,
                            int tiles_per_img, int ntiles) {
-    constexpr int NSTAGE = 2, CW = C / WBT_WARPS, LDS_ = C + 1;
+    constexpr int NSTAGE = WBT_STAGES, CW = C / WBT_WARPS, LDS_ = C + 1;
     extern __shared__ __align__(16) unsigned char smraw[];
     float* dSs = reinterpret_cast<float*>(smraw);      // [KP][C+1]; rows >= K are zero (ignore class)
     float* pn = dSs + KP * LDS_;                        // [8][32]
@@ -349,7 +351,7 @@ template <typename T, int C, int KP>
 int launch_write_bwd_tiled(const float* dS, const void* f, const int64_t* labels, void* df, int B, int h, int w, int Hm,
                            int Wm, int K, cudaStream_t st) {
     const size_t smem = sizeof(float) * ((size_t)KP * (C + 1) + 2 * WBT_WARPS * 32 + 1) + sizeof(float2) * 2 * 32 * 4 +
-                        sizeof(T) * (size_t)2 * C * 32;
+                        sizeof(T) * (size_t)WBT_STAGES * C * 32;
     auto kern = write_bwd_tiled_kernel<T, C, KP>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
