@@ -85,13 +85,24 @@ __global__ void __launch_bounds__(C) write_reduce_tiled_kernel(const T* __restri
         int b, px0;
         tile_coords(tile, b, px0);
         const int nvalid = min(32, hw - px0);
-        {  // |f|^2 per pixel: lanes = pixels, each warp sums 32 of the C rows
+        {  // |f|^2 per pixel: lanes = pixels, each warp sums C/NW of the C rows
             float n2 = 0.f;
+            if (NW % 8 == 0) {
+                // rows wid, wid+NW, ... share one swizzle phase: the lane's offset inside a row is constant
+                const int pc = ((lane / EPC) ^ tile_swz<T>(wid)) * EPC + (lane % EPC);
+                const T* col = xt + wid * 32 + pc;
 #pragma unroll 8
-            for (int c = wid; c < C; c += NW) {
-                const int pc = ((lane / EPC) ^ tile_swz<T>(c)) * EPC + (lane % EPC);
-                const float v = to_float(xt[c * 32 + pc]);
-                n2 = fmaf(v, v, n2);
+                for (int i = 0; i < C / NW; ++i) {
+                    const float v = to_float(col[i * NW * 32]);
+                    n2 = fmaf(v, v, n2);
+                }
+            } else {
+#pragma unroll 8
+                for (int c = wid; c < C; c += NW) {
+                    const int pc = ((lane / EPC) ^ tile_swz<T>(c)) * EPC + (lane % EPC);
+                    const float v = to_float(xt[c * 32 + pc]);
+                    n2 = fmaf(v, v, n2);
+                }
             }
             pn[wid * 32 + lane] = n2;
         }
@@ -110,22 +121,21 @@ __global__ void __launch_bounds__(C) write_reduce_tiled_kernel(const T* __restri
             const unsigned mm = multi[ebuf];
             const float4* eb = ent + ebuf * 32 * 4;
             const int swz = tile_swz<T>(tid);
+            // entries are warp-uniform; a zero-weight entry (pixel past the end of the image) adds zeros
             auto add_entry = [&](const float4 en, float val) {
-                if (en.z != 0.f) {  // warp-uniform (pixels past the end of the image carry zero weights)
-                    const int cls = __float_as_int(en.x);
-                    if (cls != cur) {
-                        if (cur >= 0) {
-                            S_tile[cur * CS + tid] += acc;
-                            if (tid == 0) S_tile[cur * CS + C] += accD;
-                        }
-                        acc = 0.f;
-                        accD = 0.f;
-                        cur = cls;
-                        seen |= 1u << cls;
+                const int cls = __float_as_int(en.x);
+                if (cls != cur) {
+                    if (cur >= 0) {
+                        S_tile[cur * CS + tid] += acc;
+                        if (tid == 0) S_tile[cur * CS + C] += accD;
                     }
-                    acc = fmaf(en.y, val, acc);
-                    accD += en.z;
+                    acc = 0.f;
+                    accD = 0.f;
+                    cur = cls;
+                    seen |= 1u << cls;
                 }
+                acc = fmaf(en.y, val, acc);
+                accD += en.z;
             };
 #pragma unroll 1
             for (int q = 0; q < CPR; ++q) {
@@ -148,7 +158,10 @@ __global__ void __launch_bounds__(C) write_reduce_tiled_kernel(const T* __restri
                     add_entry(eb[px * 4], v[j]);
                     if ((mm >> px) & 1u) {  // warp-uniform: this pixel straddles classes
 #pragma unroll 1
-                        for (int e = 1; e < 4; ++e) add_entry(eb[px * 4 + e], v[j]);
+                        for (int e = 1; e < 4; ++e) {
+                            const float4 en = eb[px * 4 + e];
+                            if (en.z != 0.f) add_entry(en, v[j]);
+                        }
                     }
                 }
             }
