@@ -301,7 +301,13 @@ def main():
         "pm_readloss_fwd": N * (8 * r + 2 * 4 * KP),
         "pm_write_reduce_fwd": N * (C * esz),
         "pm_write_bwd": N * (2 * C * esz),
-        "pm_colsoftmax": N * (2 * 4 * KP + 4 * K),
+        "pm_colsoftmax_apply": N * (4 * KP + 4 * K),
+    }
+    bound_note = {
+        "pm_readloss_fwd": "not HBM-bound by nature: ~19 ex2 + ~60 FMA per LABEL pixel (64 label pixels per feature "
+                           "pixel) make it FP32/MUFU-issue bound; the HBM fraction is reported because the contract asks "
+                           "for it, see DESIGN.md 4/6",
+        "pm_read_bwd": "one C-ABI call = two kernels (score gradients, then dx); bytes and time are their sums",
     }
     peak, peak_src = measured_peaks()
     kernels = {}
@@ -322,6 +328,8 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["frac"], "traffic": ncu_traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": alg_bytes[dom], "launch_ms": kernels[dom]["ms"]}
+    if dom in bound_note:
+        roofline["note"] = bound_note[dom]
 
     # core: hand-written kernels only
     ms_c, launches_c, _, _ = timed(core_step, args.steps, args.warmup)
