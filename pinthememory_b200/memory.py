@@ -9,6 +9,8 @@ There is no CPU path and no torch fallback: tensors off the GPU raise.
 
 Install under the reference's module name with ``pinthememory_b200.install()``.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -203,9 +205,10 @@ class Memory_sup(nn.Module):
             nn.ReLU(inplace=True),
         )
         self.writenet = Writingnet(input_feature_dim, feature_dim)
-        # the reference puts its state on the GPU unconditionally (memory.py:111,121); ``device`` exists
-        # only so host-side logic can be unit-tested without one -- forward() still refuses CPU tensors.
-        dev = torch.device("cuda") if device is None else torch.device(device)
+        # the reference puts its state on the GPU unconditionally (memory.py:111,121); ``device`` (or the
+        # PINMEM_B200_DEVICE environment variable) exists only so host-side logic can be unit-tested
+        # without one -- forward() still refuses CPU tensors.
+        dev = torch.device(device if device is not None else os.environ.get("PINMEM_B200_DEVICE", "cuda"))
         self.mem_cls = torch.arange(self.memory_size, device=dev)
         self.clsfier = nn.Linear(in_features=self.feature_dim, out_features=self.memory_size, bias=True)
         self.celoss = nn.CrossEntropyLoss(ignore_index=IGNORE_LABEL)
