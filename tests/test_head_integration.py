@@ -75,7 +75,15 @@ def test_reference_head_constructs_and_calls_our_module(monkeypatch):
                 net(torch.randn(1, 3, 64, 64))
     finally:
         sys.path[:] = saved_path
+        # drop only what this test brought in (reference packages and the stubs); never torch's own lazily
+        # imported sub-modules, which must not be imported twice
+        stubs = ("skimage", "imageio", "tensorboardX", "kmeans1d")
         for k in list(sys.modules):
-            if k not in saved:
+            if k in saved:
+                continue
+            f = getattr(sys.modules[k], "__file__", None) or ""
+            if f.startswith(REF) or k.split(".")[0] in stubs or k == "network.memory":
                 del sys.modules[k]
-        sys.modules.update(saved)
+        for k in stubs + ("network", "network.memory", "config", "datasets", "transforms", "transforms.transforms"):
+            if k in saved:
+                sys.modules[k] = saved[k]
