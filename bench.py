@@ -330,6 +330,11 @@ def main():
         "pm_write_reduce_fwd": N * (C * esz),
         "pm_write_bwd": N * (2 * C * esz),
         "pm_colsoftmax_apply": N * (4 * KP + 4 * K),
+        # the fused BatchNorm passes run once per conv block (2 per step); bytes are the mean of the two calls
+        "pm_bn_stats": N * C * esz,
+        "pm_bn_apply": N * C * esz * 2.5,        # x (+ residual in one of the two blocks) -> y
+        "pm_bn_bwd_reduce": N * C * esz * 3,     # dy, y, x
+        "pm_bn_bwd_apply": N * C * esz * 4.5,    # dy, y, x -> dx (+ dres in one of the two blocks)
     }
     bound_note = {
         "pm_readloss_fwd": "not HBM-bound by nature: ~19 ex2 + ~60 FMA per LABEL pixel (64 label pixels per feature "

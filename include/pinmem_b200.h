@@ -172,6 +172,27 @@ int pm_update_bwd(const float* dM_new, const float* g_div, const float* g_cls, c
 int pm_write_bwd(const float* dS, const void* f, const int64_t* labels, void* df, int B, int C, int h, int w,
                  int Hm, int Wm, int K, int dtype, void* stream);
 
+/*
+ * BatchNorm2d (+ residual, + ReLU) of the module's two 1x1-conv blocks, NCHW (x, y, residual, dy, dx, dres are
+ * [B,C,hw] in `dtype`; statistics and affine parameters fp32 [C]). Replaces, for `self.output`
+ * (memory.py:103-107) and `Writingnet` (memory.py:74-87), the BatchNorm2d / add / ReLU modules that follow
+ * the 1x1 convolution (the convolution itself stays a library GEMM).
+ *   pm_bn_stats       batch mean and 1/sqrt(biased var + eps) per channel; if running_mean/var are given they
+ *                     are updated in place with `momentum` (unbiased variance), like nn.BatchNorm2d in training
+ *   pm_bn_apply       y = [relu]((x - mean) * invstd * gamma + beta [+ residual])
+ *   pm_bn_bwd_reduce  g = dy * (y > 0 if relu);  dbeta = sum g,  dgamma = sum g * xhat
+ *   pm_bn_bwd_apply   dx = gamma * invstd * (g - [training](dbeta + xhat * dgamma) / (B*hw));  dres = g (or NULL)
+ */
+int pm_bn_stats(const void* x, int B, int C, int hw, int dtype, float eps, float* mean, float* invstd,
+                float* running_mean, float* running_var, float momentum, void* stream);
+int pm_bn_apply(const void* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                const void* residual, void* y, int relu, int B, int C, int hw, int dtype, void* stream);
+int pm_bn_bwd_reduce(const void* dy, const void* y, const void* x, const float* mean, const float* invstd, int relu,
+                     float* dgamma, float* dbeta, int B, int C, int hw, int dtype, void* stream);
+int pm_bn_bwd_apply(const void* dy, const void* y, const void* x, const float* mean, const float* invstd,
+                    const float* gamma, const float* dgamma, const float* dbeta, int relu, int training, void* dx,
+                    void* dres, int B, int C, int hw, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

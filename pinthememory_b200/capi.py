@@ -37,6 +37,10 @@ PROTOTYPES = {
     "pm_update_fwd": [_c_p, _c_p, _c_f] + [_c_p] * 5 + [_c_i] * 2 + [_c_p],
     "pm_update_bwd": [_c_p] * 7 + [_c_f] + [_c_p] * 3 + [_c_i] * 2 + [_c_p],
     "pm_write_bwd": [_c_p] * 4 + [_c_i] * 8 + [_c_p],
+    "pm_bn_stats": [_c_p] + [_c_i] * 4 + [_c_f] + [_c_p] * 4 + [_c_f, _c_p],
+    "pm_bn_apply": [_c_p] * 7 + [_c_i] * 5 + [_c_p],
+    "pm_bn_bwd_reduce": [_c_p] * 5 + [_c_i] + [_c_p] * 2 + [_c_i] * 4 + [_c_p],
+    "pm_bn_bwd_apply": [_c_p] * 8 + [_c_i] * 2 + [_c_p] * 2 + [_c_i] * 4 + [_c_p],
 }
 EXPORTED_SYMBOLS = sorted(list(PROTOTYPES) + ["pm_status_string"])
 
@@ -221,3 +225,27 @@ def write_bwd(dS, f, labels, df, K):
     Hm, Wm = labels.shape[1], labels.shape[2]
     _call("pm_write_bwd", _ptr(dS), _ptr(f), _ptr(labels), _ptr(df), B, C, h, w, Hm, Wm, K, dtype_code(f),
                                _stream())
+
+
+def bn_stats(x, eps, mean, invstd, running_mean, running_var, momentum):
+    B, C, h, w = x.shape
+    _call("pm_bn_stats", _ptr(x), B, C, h * w, dtype_code(x), float(eps), _ptr(mean), _ptr(invstd), _ptr(running_mean),
+          _ptr(running_var), float(momentum), _stream())
+
+
+def bn_apply(x, mean, invstd, gamma, beta, residual, y, relu):
+    B, C, h, w = x.shape
+    _call("pm_bn_apply", _ptr(x), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(beta), _ptr(residual), _ptr(y), int(relu),
+          B, C, h * w, dtype_code(x), _stream())
+
+
+def bn_bwd_reduce(dy, y, x, mean, invstd, relu, dgamma, dbeta):
+    B, C, h, w = x.shape
+    _call("pm_bn_bwd_reduce", _ptr(dy), _ptr(y), _ptr(x), _ptr(mean), _ptr(invstd), int(relu), _ptr(dgamma), _ptr(dbeta),
+          B, C, h * w, dtype_code(x), _stream())
+
+
+def bn_bwd_apply(dy, y, x, mean, invstd, gamma, dgamma, dbeta, relu, training, dx, dres):
+    B, C, h, w = x.shape
+    _call("pm_bn_bwd_apply", _ptr(dy), _ptr(y), _ptr(x), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(dgamma),
+          _ptr(dbeta), int(relu), int(training), _ptr(dx), _ptr(dres), B, C, h * w, dtype_code(x), _stream())

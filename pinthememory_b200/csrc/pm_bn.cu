@@ -1,0 +1,312 @@
+// BatchNorm (+ residual, + ReLU) of the module's two 1x1-conv blocks, NCHW, training and eval mode.
+//
+// Reference: `self.output = Sequential(Conv2d 1x1, BatchNorm2d, ReLU)` (memory.py:103-107) and
+// `Writingnet: relu(x + BatchNorm2d(Conv2d 1x1(x)))` (memory.py:74-87). The 1x1 convolutions stay library
+// GEMMs; everything after them -- batch statistics, running-stat update, normalise + affine (+ residual)
+// + ReLU, and the whole backward through those -- is done here in four streaming passes instead of
+// cuDNN's BN kernels plus separate add / ReLU / threshold-backward element-wise kernels:
+//   bn_stats      : per channel sum, sum of squares  -> mean, 1/sqrt(var+eps), running stats   (reads x)
+//   bn_apply      : y = relu((x-mean)*invstd*gamma + beta + residual)                          (reads x[,res], writes y)
+//   bn_bwd_reduce : g = dy*(y>0); dbeta = sum g, dgamma = sum g*xhat                           (reads dy,y,x)
+//   bn_bwd_apply  : dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)); dres = g              (reads dy,y,x, writes dx[,dres])
+// A channel's data is B contiguous rows of hw elements; rows are read with 16-byte vectors when hw allows.
+#include "pm_common.cuh"
+
+namespace pm {
+
+constexpr int BN_THREADS = 512;
+
+template <typename T>
+struct Vec4;
+template <>
+struct Vec4<float> {
+    float4 v;
+    __device__ __forceinline__ void load(const float* p) { v = *reinterpret_cast<const float4*>(p); }
+    __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = v; }
+    __device__ __forceinline__ float get(int i) const { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+    __device__ __forceinline__ void set(int i, float f) {
+        if (i == 0) v.x = f;
+        else if (i == 1) v.y = f;
+        else if (i == 2) v.z = f;
+        else v.w = f;
+    }
+};
+template <>
+struct Vec4<__nv_bfloat16> {
+    uint2 v;
+    __device__ __forceinline__ void load(const __nv_bfloat16* p) { v = *reinterpret_cast<const uint2*>(p); }
+    __device__ __forceinline__ void store(__nv_bfloat16* p) const { *reinterpret_cast<uint2*>(p) = v; }
+    __device__ __forceinline__ float get(int i) const {
+        const unsigned w = i < 2 ? v.x : v.y;
+        return __uint_as_float((i & 1) ? (w & 0xffff0000u) : (w << 16));
+    }
+    __device__ __forceinline__ void set(int i, float f) {
+        const unsigned b = (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(f));
+        unsigned& w = i < 2 ? v.x : v.y;
+        w = (i & 1) ? ((w & 0x0000ffffu) | (b << 16)) : ((w & 0xffff0000u) | b);
+    }
+};
+
+__device__ __forceinline__ double block_sum_double(double v, double* red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int i = 0; i < BN_THREADS / 32; ++i) t += red[i];
+    return t;
+}
+
+// one CTA per channel
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const T* __restrict__ x, int B, int C, int hw, float eps,
+                                                              float* __restrict__ mean, float* __restrict__ invstd,
+                                                              float* __restrict__ running_mean,
+                                                              float* __restrict__ running_var, float momentum) {
+    __shared__ double red[BN_THREADS / 32];
+    const int c = blockIdx.x;
+    float s = 0.f, q = 0.f;
+    if (VEC) {
+        const int nv = hw / 4, total = B * nv;
+#pragma unroll 4
+        for (int i = threadIdx.x; i < total; i += BN_THREADS) {
+            const int b = i / nv, j = i - b * nv;
+            Vec4<T> v;
+            v.load(x + ((size_t)b * C + c) * hw + 4 * j);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float f = v.get(e);
+                s += f;
+                q = fmaf(f, f, q);
+            }
+        }
+    } else {
+        const int total = B * hw;
+        for (int i = threadIdx.x; i < total; i += BN_THREADS) {
+            const int b = i / hw, j = i - b * hw;
+            const float f = ldf(x + ((size_t)b * C + c) * hw + j);
+            s += f;
+            q = fmaf(f, f, q);
+        }
+    }
+    const double S = block_sum_double((double)s, red);
+    const double Q = block_sum_double((double)q, red);
+    if (threadIdx.x == 0) {
+        const double n = (double)B * (double)hw;
+        const double m = S / n;
+        double var = Q / n - m * m;
+        if (var < 0.0) var = 0.0;
+        mean[c] = (float)m;
+        invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+        if (running_mean != nullptr) {  // PyTorch: running_var takes the unbiased estimate
+            const double unb = n > 1.0 ? var * n / (n - 1.0) : var;
+            running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * m);
+            running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unb);
+        }
+    }
+}
+
+// one CTA per (b, c) row
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ mean,
+                                                       const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, const T* __restrict__ residual,
+                                                       T* __restrict__ y, int relu, int C, int hw) {
+    const int row = blockIdx.x, c = row % C;
+    const float sc = invstd[c] * gamma[c], sh = beta[c] - mean[c] * sc;
+    const size_t base = (size_t)row * hw;
+    if (VEC) {
+        for (int j = threadIdx.x; j < hw / 4; j += 256) {
+            Vec4<T> v, r, o;
+            v.load(x + base + 4 * j);
+            if (residual) r.load(residual + base + 4 * j);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float f = fmaf(v.get(e), sc, sh);
+                if (residual) f += r.get(e);
+                o.set(e, relu ? fmaxf(f, 0.f) : f);
+            }
+            o.store(y + base + 4 * j);
+        }
+    } else {
+        for (int j = threadIdx.x; j < hw; j += 256) {
+            float f = fmaf(ldf(x + base + j), sc, sh);
+            if (residual) f += ldf(residual + base + j);
+            stf(y + base + j, relu ? fmaxf(f, 0.f) : f);
+        }
+    }
+}
+
+// one CTA per channel: dbeta = sum g, dgamma = sum g * xhat, g = dy * (y > 0 if relu)
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ y,
+                                                                   const T* __restrict__ x, const float* __restrict__ mean,
+                                                                   const float* __restrict__ invstd, int relu,
+                                                                   float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                   int B, int C, int hw) {
+    __shared__ double red[BN_THREADS / 32];
+    const int c = blockIdx.x;
+    const float m = mean[c], is = invstd[c];
+    float sg = 0.f, sgx = 0.f;
+    if (VEC) {
+        const int nv = hw / 4, total = B * nv;
+#pragma unroll 4
+        for (int i = threadIdx.x; i < total; i += BN_THREADS) {
+            const int b = i / nv, j = i - b * nv;
+            const size_t off = ((size_t)b * C + c) * hw + 4 * j;
+            Vec4<T> g, yy, xx;
+            g.load(dy + off);
+            xx.load(x + off);
+            if (relu) yy.load(y + off);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float gv = (!relu || yy.get(e) > 0.f) ? g.get(e) : 0.f;
+                sg += gv;
+                sgx = fmaf(gv, (xx.get(e) - m) * is, sgx);
+            }
+        }
+    } else {
+        const int total = B * hw;
+        for (int i = threadIdx.x; i < total; i += BN_THREADS) {
+            const int b = i / hw, j = i - b * hw;
+            const size_t off = ((size_t)b * C + c) * hw + j;
+            const float gv = (!relu || ldf(y + off) > 0.f) ? ldf(dy + off) : 0.f;
+            sg += gv;
+            sgx = fmaf(gv, (ldf(x + off) - m) * is, sgx);
+        }
+    }
+    const double SG = block_sum_double((double)sg, red);
+    const double SGX = block_sum_double((double)sgx, red);
+    if (threadIdx.x == 0) {
+        dbeta[c] = (float)SG;
+        dgamma[c] = (float)SGX;
+    }
+}
+
+// one CTA per (b, c) row: dx = gamma*invstd*(g - [training] (dbeta + xhat*dgamma)/n); dres = g
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ y,
+                                                           const T* __restrict__ x, const float* __restrict__ mean,
+                                                           const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                           const float* __restrict__ dgamma, const float* __restrict__ dbeta,
+                                                           int relu, int training, float inv_n, T* __restrict__ dx,
+                                                           T* __restrict__ dres, int C, int hw) {
+    const int row = blockIdx.x, c = row % C;
+    const float m = mean[c], is = invstd[c], gi = gamma[c] * is;
+    const float k1 = training ? dbeta[c] * inv_n : 0.f, k2 = training ? dgamma[c] * inv_n : 0.f;
+    const size_t base = (size_t)row * hw;
+    if (VEC) {
+        for (int j = threadIdx.x; j < hw / 4; j += 256) {
+            Vec4<T> g, yy, xx, o, r;
+            g.load(dy + base + 4 * j);
+            xx.load(x + base + 4 * j);
+            if (relu) yy.load(y + base + 4 * j);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float gv = (!relu || yy.get(e) > 0.f) ? g.get(e) : 0.f;
+                const float xh = (xx.get(e) - m) * is;
+                o.set(e, gi * (gv - k1 - xh * k2));
+                r.set(e, gv);
+            }
+            o.store(dx + base + 4 * j);
+            if (dres) r.store(dres + base + 4 * j);
+        }
+    } else {
+        for (int j = threadIdx.x; j < hw; j += 256) {
+            const float gv = (!relu || ldf(y + base + j) > 0.f) ? ldf(dy + base + j) : 0.f;
+            const float xh = (ldf(x + base + j) - m) * is;
+            stf(dx + base + j, gi * (gv - k1 - xh * k2));
+            if (dres) stf(dres + base + j, gv);
+        }
+    }
+}
+
+static bool vec_ok(int hw, const void* a, const void* b, const void* c, const void* d, const void* e, int dtype) {
+    const uintptr_t m = dtype == PM_F32 ? 15 : 7;
+    return hw % 4 == 0 && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d | (uintptr_t)e) & m) == 0;
+}
+
+}  // namespace pm
+
+static int bn_check(int B, int C, int hw, int dtype) {
+    if (dtype != PM_F32 && dtype != PM_BF16) return PM_ERR_DTYPE;
+    if (B <= 0 || C <= 0 || hw <= 0 || (long long)B * C > 0x7fffffffLL || (long long)B * hw > 0x7fffffffLL)
+        return PM_ERR_SHAPE;
+    return 0;
+}
+
+extern "C" int pm_bn_stats(const void* x, int B, int C, int hw, int dtype, float eps, float* mean, float* invstd,
+                           float* running_mean, float* running_var, float momentum, void* stream) {
+    if (!x || !mean || !invstd || ((running_mean == nullptr) != (running_var == nullptr))) return PM_ERR_NULL;
+    if (int e = bn_check(B, C, hw, dtype)) return e;
+    const bool vec = pm::vec_ok(hw, x, nullptr, nullptr, nullptr, nullptr, dtype);
+#define X_(T) (const T*)x
+    if (dtype == PM_F32) {
+        if (vec) pm::bn_stats_kernel<float, true><<<C, pm::BN_THREADS, 0, (cudaStream_t)stream>>>(X_(float), B, C, hw, eps, mean, invstd, running_mean, running_var, momentum);
+        else pm::bn_stats_kernel<float, false><<<C, pm::BN_THREADS, 0, (cudaStream_t)stream>>>(X_(float), B, C, hw, eps, mean, invstd, running_mean, running_var, momentum);
+    } else {
+        if (vec) pm::bn_stats_kernel<__nv_bfloat16, true><<<C, pm::BN_THREADS, 0, (cudaStream_t)stream>>>(X_(__nv_bfloat16), B, C, hw, eps, mean, invstd, running_mean, running_var, momentum);
+        else pm::bn_stats_kernel<__nv_bfloat16, false><<<C, pm::BN_THREADS, 0, (cudaStream_t)stream>>>(X_(__nv_bfloat16), B, C, hw, eps, mean, invstd, running_mean, running_var, momentum);
+    }
+#undef X_
+    PM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int pm_bn_apply(const void* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                           const void* residual, void* y, int relu, int B, int C, int hw, int dtype, void* stream) {
+    if (!x || !mean || !invstd || !gamma || !beta || !y) return PM_ERR_NULL;
+    if (int e = bn_check(B, C, hw, dtype)) return e;
+    const bool vec = pm::vec_ok(hw, x, residual, y, nullptr, nullptr, dtype);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == PM_F32) {
+        if (vec) pm::bn_apply_kernel<float, true><<<B * C, 256, 0, st>>>((const float*)x, mean, invstd, gamma, beta, (const float*)residual, (float*)y, relu, C, hw);
+        else pm::bn_apply_kernel<float, false><<<B * C, 256, 0, st>>>((const float*)x, mean, invstd, gamma, beta, (const float*)residual, (float*)y, relu, C, hw);
+    } else {
+        typedef __nv_bfloat16 bf;
+        if (vec) pm::bn_apply_kernel<bf, true><<<B * C, 256, 0, st>>>((const bf*)x, mean, invstd, gamma, beta, (const bf*)residual, (bf*)y, relu, C, hw);
+        else pm::bn_apply_kernel<bf, false><<<B * C, 256, 0, st>>>((const bf*)x, mean, invstd, gamma, beta, (const bf*)residual, (bf*)y, relu, C, hw);
+    }
+    PM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int pm_bn_bwd_reduce(const void* dy, const void* y, const void* x, const float* mean, const float* invstd,
+                                int relu, float* dgamma, float* dbeta, int B, int C, int hw, int dtype, void* stream) {
+    if (!dy || !x || !mean || !invstd || !dgamma || !dbeta || (relu && !y)) return PM_ERR_NULL;
+    if (int e = bn_check(B, C, hw, dtype)) return e;
+    const bool vec = pm::vec_ok(hw, dy, y, x, nullptr, nullptr, dtype);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == PM_F32) {
+        if (vec) pm::bn_bwd_reduce_kernel<float, true><<<C, pm::BN_THREADS, 0, st>>>((const float*)dy, (const float*)y, (const float*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw);
+        else pm::bn_bwd_reduce_kernel<float, false><<<C, pm::BN_THREADS, 0, st>>>((const float*)dy, (const float*)y, (const float*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw);
+    } else {
+        typedef __nv_bfloat16 bf;
+        if (vec) pm::bn_bwd_reduce_kernel<bf, true><<<C, pm::BN_THREADS, 0, st>>>((const bf*)dy, (const bf*)y, (const bf*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw);
+        else pm::bn_bwd_reduce_kernel<bf, false><<<C, pm::BN_THREADS, 0, st>>>((const bf*)dy, (const bf*)y, (const bf*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw);
+    }
+    PM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int pm_bn_bwd_apply(const void* dy, const void* y, const void* x, const float* mean, const float* invstd,
+                               const float* gamma, const float* dgamma, const float* dbeta, int relu, int training,
+                               void* dx, void* dres, int B, int C, int hw, int dtype, void* stream) {
+    if (!dy || !x || !mean || !invstd || !gamma || !dgamma || !dbeta || !dx || (relu && !y)) return PM_ERR_NULL;
+    if (int e = bn_check(B, C, hw, dtype)) return e;
+    const bool vec = pm::vec_ok(hw, dy, y, x, dx, dres, dtype);
+    const float inv_n = 1.f / ((float)B * (float)hw);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == PM_F32) {
+        if (vec) pm::bn_bwd_apply_kernel<float, true><<<B * C, 256, 0, st>>>((const float*)dy, (const float*)y, (const float*)x, mean, invstd, gamma, dgamma, dbeta, relu, training, inv_n, (float*)dx, (float*)dres, C, hw);
+        else pm::bn_bwd_apply_kernel<float, false><<<B * C, 256, 0, st>>>((const float*)dy, (const float*)y, (const float*)x, mean, invstd, gamma, dgamma, dbeta, relu, training, inv_n, (float*)dx, (float*)dres, C, hw);
+    } else {
+        typedef __nv_bfloat16 bf;
+        if (vec) pm::bn_bwd_apply_kernel<bf, true><<<B * C, 256, 0, st>>>((const bf*)dy, (const bf*)y, (const bf*)x, mean, invstd, gamma, dgamma, dbeta, relu, training, inv_n, (bf*)dx, (bf*)dres, C, hw);
+        else pm::bn_bwd_apply_kernel<bf, false><<<B * C, 256, 0, st>>>((const bf*)dy, (const bf*)y, (const bf*)x, mean, invstd, gamma, dgamma, dbeta, relu, training, inv_n, (bf*)dx, (bf*)dres, C, hw);
+    }
+    PM_CHECK_LAUNCH();
+    return 0;
+}

@@ -170,6 +170,76 @@ class _WriteFn(torch.autograd.Function):
         return df, None, None, dW, db, None, None, None
 
 
+class _BnActFn(torch.autograd.Function):
+    """y = [relu](BatchNorm2d(xc) [+ residual]) with batch (training) or given (eval) statistics."""
+
+    @staticmethod
+    def forward(ctx, xc, gamma, beta, residual, running_mean, running_var, use_batch_stats, factor, eps, relu):
+        C = xc.shape[1]
+        dev = xc.device
+        g32 = gamma.detach().to(torch.float32).contiguous()
+        b32 = beta.detach().to(torch.float32).contiguous()
+        if use_batch_stats:
+            mean = torch.empty(C, dtype=torch.float32, device=dev)
+            invstd = torch.empty(C, dtype=torch.float32, device=dev)
+            capi.bn_stats(xc, eps, mean, invstd, running_mean, running_var, factor)
+        else:
+            mean = running_mean.to(torch.float32).contiguous()
+            invstd = (running_var.to(torch.float32) + eps).rsqrt_()
+        y = torch.empty_like(xc)
+        capi.bn_apply(xc, mean, invstd, g32, b32, residual, y, relu)
+        ctx.relu, ctx.training, ctx.has_res = relu, use_batch_stats, residual is not None
+        ctx.save_for_backward(xc, y, mean, invstd, g32)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, y, mean, invstd, g32 = ctx.saved_tensors
+        C = xc.shape[1]
+        dy = dy.to(xc.dtype).contiguous()
+        dgamma = torch.empty(C, dtype=torch.float32, device=xc.device)
+        dbeta = torch.empty(C, dtype=torch.float32, device=xc.device)
+        capi.bn_bwd_reduce(dy, y, xc, mean, invstd, ctx.relu, dgamma, dbeta)
+        dx = torch.empty_like(xc)
+        dres = torch.empty_like(xc) if (ctx.has_res and ctx.needs_input_grad[3]) else None
+        capi.bn_bwd_apply(dy, y, xc, mean, invstd, g32, dgamma, dbeta, ctx.relu, ctx.training, dx, dres)
+        return dx, dgamma, dbeta, dres, None, None, None, None, None, None
+
+
+def _plain(m):
+    return not (m._forward_hooks or m._forward_pre_hooks or m._backward_hooks)
+
+
+def conv_bn_act(conv, bn, x, residual, relu):
+    """conv -> BatchNorm2d (-> + residual) (-> ReLU). The convolution is the nn.Conv2d module itself; what follows
+    runs in the fused kernels of csrc/pm_bn.cu when `bn` is a plain nn.BatchNorm2d (a converted SyncBatchNorm, a
+    hooked module or an exotic configuration falls back to calling the modules, i.e. the reference's own graph)."""
+    xc = conv(x)
+    fast = (type(bn) is nn.BatchNorm2d and bn.affine and _plain(bn) and xc.is_cuda and xc.dim() == 4
+            and xc.dtype in (torch.float32, torch.bfloat16) and bn.weight.is_cuda)
+    if not fast:
+        y = bn(xc)
+        if residual is not None:
+            y = residual + y
+        return F.relu(y) if relu else y
+    use_batch = bn.training or bn.running_mean is None
+    factor = 0.0
+    rm = rv = None
+    if bn.training and bn.track_running_stats and bn.running_mean is not None:
+        rm, rv = bn.running_mean, bn.running_var
+        if bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        factor = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+        if rm.dtype != torch.float32 or rv.dtype != torch.float32:
+            rm = rv = None  # keep exotic buffer dtypes out of the kernel (statistics are still exact)
+    elif not use_batch:
+        rm, rv = bn.running_mean, bn.running_var
+    xc = xc.contiguous()
+    if residual is not None:
+        residual = residual.to(xc.dtype).contiguous()
+    return _BnActFn.apply(xc, bn.weight, bn.bias, residual, rm, rv, use_batch, float(factor), float(bn.eps), relu)
+
+
 class Writingnet(nn.Module):
     """relu(x + BN(conv1x1(x))) -- memory.py:67-87 (stays a cuDNN/cuBLAS block)."""
 
@@ -185,6 +255,8 @@ class Writingnet(nn.Module):
         initialize_weights(self)
 
     def forward(self, x):
+        if x.is_cuda and _plain(self.writefeat) and _plain(self.writefeat[0]):
+            return conv_bn_act(self.writefeat[0], self.writefeat[1], x, x, True)
         return self.relu(x + self.writefeat(x))
 
 
@@ -260,7 +332,10 @@ class Memory_sup(nn.Module):
             readloss = 0  # memory.py:178
         else:
             self.last_label_hist = hist
-        updated_query = self.output(u)
+        if _plain(self.output) and _plain(self.output[0]) and _plain(self.output[2]):
+            updated_query = conv_bn_act(self.output[0], self.output[1], u, None, True)
+        else:
+            updated_query = self.output(u)
         return updated_query, score_query, score_memory, readloss
 
     def write(self, input, mask, writing_detach=True):
