@@ -228,8 +228,8 @@ def test_full_size_cfg2_against_oracle_on_device_and_properties():
     assert_close(r["score_memory"].sum(-1), torch.ones(8, 96, 96, device="cuda"), 1e-5, "rows of score_memory")
     assert_close(r["score_query"].reshape(-1, K).sum(0), torch.ones(K, device="cuda"), 1e-4, "cols of score_query")
     # dx is orthogonal to x (gradient of a function of x/|x|)
-    dots = (r["dx"] * o["x"]).sum(1)
-    assert float(dots.detach().abs().max()) < 1e-3 * float(r["dx"].abs().max()) * float(o["x"].norm(dim=1).max())
+    dots = (r["dx"].detach() * o["x"].detach()).sum(1)
+    assert float(dots.detach().abs().max()) < 1e-3 * float(r["dx"].abs().max()) * float(o["x"].detach().norm(dim=1).max())
 
 
 def test_read_backward_is_linear_in_upstream_gradient():
@@ -271,3 +271,67 @@ def test_write_is_permutation_invariant_over_images():
     capi.write_reduce_fwd(f[:2].contiguous(), labels[:2].contiguous(), SD3, K)
     capi.write_reduce_fwd(f[2:].contiguous(), labels[2:].contiguous(), SD3, K)
     assert_close(SD1, SD3, 1e-5, "split + add")
+
+
+# ------------------------------------------------- fused BatchNorm (+residual)(+ReLU) vs the torch modules
+
+
+@pytest.mark.parametrize("shape", [(4, 64, 12, 20), (2, 256, 7, 9), (8, 256, 48, 48)], ids=str)
+@pytest.mark.parametrize("residual", [False, True], ids=["output_block", "writenet_block"])
+@pytest.mark.parametrize("training", [True, False], ids=["train", "eval"])
+def test_fused_bn_matches_torch_modules(shape, residual, training):
+    """conv_bn_act (csrc/pm_bn.cu) == Conv2d -> BatchNorm2d (-> + x) -> ReLU of memory.py:74-87,103-107,
+    including the running-statistics update."""
+    import copy
+
+    from pinthememory_b200.memory import conv_bn_act
+
+    B, C, h, w = shape
+    torch.manual_seed(3)
+    conv = torch.nn.Conv2d(C, C, 1, bias=False).cuda()
+    bn = torch.nn.BatchNorm2d(C).cuda()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.normal_(0, 0.2)
+        bn.running_mean.normal_(0, 0.1)
+        bn.running_var.uniform_(0.5, 1.5)
+    conv_r, bn_r = copy.deepcopy(conv), copy.deepcopy(bn)
+    for m in (bn, bn_r):
+        m.train(training)
+    x = torch.randn(B, C, h, w, device="cuda")
+    G = torch.randn(B, C, h, w, device="cuda")
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya = conv_bn_act(conv, bn, xa, xa if residual else None, True)
+    t = bn_r(conv_r(xb))
+    yb = torch.relu(xb + t if residual else t)
+    (ya * G).sum().backward()
+    (yb * G).sum().backward()
+    assert_close(ya.detach(), yb.detach(), 1e-5, "y")
+    assert_close(xa.grad, xb.grad, 2e-5, "dx")
+    assert_close(conv.weight.grad, conv_r.weight.grad, 2e-5, "dW")
+    assert_close(bn.weight.grad, bn_r.weight.grad, 2e-5, "dgamma")
+    assert_close(bn.bias.grad, bn_r.bias.grad, 2e-5, "dbeta")
+    assert_close(bn.running_mean, bn_r.running_mean, 1e-6, "running_mean")
+    assert_close(bn.running_var, bn_r.running_var, 1e-6, "running_var")
+    assert int(bn.num_batches_tracked) == int(bn_r.num_batches_tracked)
+
+
+def test_fused_bn_falls_back_for_other_norm_layers():
+    """A converted SyncBatchNorm (train.py:95) or a hooked module keeps the reference's own graph."""
+    from pinthememory_b200 import capi
+    from pinthememory_b200.memory import Memory_sup
+
+    mem = Memory_sup(19, 64, 64, 0.8, 1.0, False).cuda().eval()
+    x = torch.randn(1, 64, 8, 8, device="cuda")
+    capi.reset_counters()
+    with torch.no_grad():
+        mem(x, None, False)
+    fused = capi.LAUNCHES
+    seen = []
+    mem.output[1].register_forward_hook(lambda m, i, o: seen.append(1))
+    capi.reset_counters()
+    with torch.no_grad():
+        mem(x, None, False)
+    assert seen and capi.LAUNCHES < fused  # the BatchNorm module itself ran
+    sync = torch.nn.SyncBatchNorm.convert_sync_batchnorm(Memory_sup(19, 64, 64, 0.8, 1.0, False).cuda())
+    assert type(sync.output[1]) is torch.nn.SyncBatchNorm and type(sync.writenet.writefeat[1]) is torch.nn.SyncBatchNorm
