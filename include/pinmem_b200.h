@@ -149,10 +149,12 @@ int pm_write_reduce_fwd(const void* f, const int64_t* labels, float* SD, int B, 
  * no host sync per slot), :264-272 (diversityloss), :259-262 (classification_loss).
  *   SD [K+1,C+4], M_old [K,C], W_cls [K,C], b_cls [K] fp32
  *   M_new [K,C] out (unit rows), losses float[2] out = {div, cls},
- *   saved float[2K] out = {|M'_k| (pre-normalisation norms), D_k} for the backward.
+ *   saved float[2K] out = {|M'_k| (pre-normalisation norms), D_k} for the backward,
+ *   aux: pm_update_aux_floats(K) floats of scratch, ZEROED by the caller (one CTA per row; rows meet there).
  */
+int pm_update_aux_floats(int K);
 int pm_update_fwd(const float* SD, const float* M_old, float momentum, const float* W_cls, const float* b_cls,
-                  float* M_new, float* losses, float* saved, int C, int K, void* stream);
+                  float* M_new, float* losses, float* saved, float* aux, int C, int K, void* stream);
 
 /*
  * Backward of pm_update_fwd.
@@ -163,7 +165,8 @@ int pm_update_fwd(const float* SD, const float* M_old, float momentum, const flo
  */
 int pm_update_bwd(const float* dM_new, const float* g_div, const float* g_cls, const float* M_new,
                   const float* saved, const float* W_cls, const float* b_cls, float momentum, float* dS,
-                  float* dW_cls, float* db_cls, int C, int K, void* stream);
+                  float* dW_cls, float* db_cls, float* aux /* zeroed, pm_update_aux_floats(K) */, int C, int K,
+                  void* stream);
 
 /*
  * Memory write, backward to the write feature: dv[n] = sum_k omega[n,k] dS[k];

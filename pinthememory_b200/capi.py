@@ -34,8 +34,9 @@ PROTOTYPES = {
     "pm_score_nhwc": [_c_p] * 3 + [_c_i] * 3 + [_c_p],
     "pm_rowsoftmax": [_c_p] * 3 + [_c_i] * 2 + [_c_p],
     "pm_write_reduce_fwd": [_c_p] * 3 + [_c_i] * 8 + [_c_p],
-    "pm_update_fwd": [_c_p, _c_p, _c_f] + [_c_p] * 5 + [_c_i] * 2 + [_c_p],
-    "pm_update_bwd": [_c_p] * 7 + [_c_f] + [_c_p] * 3 + [_c_i] * 2 + [_c_p],
+    "pm_update_aux_floats": [_c_i],
+    "pm_update_fwd": [_c_p, _c_p, _c_f] + [_c_p] * 6 + [_c_i] * 2 + [_c_p],
+    "pm_update_bwd": [_c_p] * 7 + [_c_f] + [_c_p] * 4 + [_c_i] * 2 + [_c_p],
     "pm_write_bwd": [_c_p] * 4 + [_c_i] * 8 + [_c_p],
     "pm_bn_stats": [_c_p] + [_c_i] * 4 + [_c_f] + [_c_p] * 4 + [_c_f, _c_p],
     "pm_bn_apply": [_c_p] * 7 + [_c_i] * 5 + [_c_p],
@@ -210,14 +211,25 @@ def write_reduce_fwd(f, labels, SD, K):
                                       _stream())
 
 
-def update_fwd(SD, M_old, momentum, W, b, M_new, losses, saved, C, K):
+def update_aux_floats(K):
+    return load().pm_update_aux_floats(int(K))
+
+
+def update_aux(device, K):
+    """Zeroed scratch for one pm_update_fwd / pm_update_bwd call."""
+    return torch.zeros(update_aux_floats(K), dtype=torch.float32, device=device)
+
+
+def update_fwd(SD, M_old, momentum, W, b, M_new, losses, saved, C, K, aux=None):
+    if aux is None:
+        aux = update_aux(SD.device, K)
     _call("pm_update_fwd", _ptr(SD), _ptr(M_old), float(momentum), _ptr(W), _ptr(b), _ptr(M_new),
-                                _ptr(losses), _ptr(saved), C, K, _stream())
+          _ptr(losses), _ptr(saved), _ptr(aux), C, K, _stream())
 
 
 def update_bwd(dM_new, g_div, g_cls, M_new, saved, W, b, momentum, dS, dW, db, C, K):
     _call("pm_update_bwd", _ptr(dM_new), _ptr(g_div), _ptr(g_cls), _ptr(M_new), _ptr(saved), _ptr(W), _ptr(b),
-                                float(momentum), _ptr(dS), _ptr(dW), _ptr(db), C, K, _stream())
+          float(momentum), _ptr(dS), _ptr(dW), _ptr(db), _ptr(update_aux(M_new.device, K)), C, K, _stream())
 
 
 def write_bwd(dS, f, labels, df, K):

@@ -213,243 +213,213 @@ __global__ void __launch_bounds__(WB_THREADS) write_bwd_kernel(const float* __re
 }
 
 // --------------------------------------------------------------------------- momentum update + losses
-// One CTA of 1024 threads (K x C is 19 x 256): pure latency work, so every phase issues all of its loads
-// up front and uses as many threads as the phase has independent items. Branch-free replacement of the
-// reference's per-slot python loop with its 19 host syncs (memory.py:233-237).
-// Shared rows have stride C+1 so threads that differ in the ROW index hit different banks.
+// K x C is 19 x 256: pure latency work. One CTA per memory row (grid = K, 256 threads, thread = channel), every
+// thread keeping its channel of ALL K rows in registers, so the K x K products (classifier logits, Gram) are
+// per-thread multiplies followed by one batched block reduction, and nothing is re-read from shared memory
+// (the first version -- one CTA, operands in shared memory -- was shared-memory-bandwidth bound: 25 us).
+// Cross-row results meet in a small zero-initialised `aux` buffer; the last CTA to arrive finalises.
+// Branch-free replacement of the reference's per-slot python loop with its 19 host syncs (memory.py:233-237).
 
-constexpr int UP_THREADS = 1024, UP_WARPS = 32, UP_KMAX = 32, UP_CMAX = 256;
+constexpr int UP_THREADS = 256, UP_WARPS = 8, UP_KMAX = 32;
 
-// zs[i][j] = M_i . W_j + b_j and gs[i][j] = M_i . M_j for all K*K pairs; `parts` threads share a pair.
-__device__ __forceinline__ void pair_dots(const float* Mn, const float* Ws, const float* __restrict__ bias, float* zs,
-                                          float* gs, float* scratch, int C, int K) {
-    const int tid = threadIdx.x, CP = C + 1, KK = K * K;
-    const int parts = UP_THREADS / KK >= 4 ? 4 : (UP_THREADS / KK >= 2 ? 2 : 1);
-    const int pair = tid / parts, part = tid - pair * parts;
-    float zz = 0.f, gg = 0.f;
-    if (pair < KK) {
-        const int i = pair / K, j = pair - i * K;
-        const int clen = C / parts, c0 = part * clen;
-        const float* mi = Mn + i * CP + c0;
-        const float* mj = Mn + j * CP + c0;
-        const float* wj = Ws + j * CP + c0;
-        float z0 = 0.f, z1 = 0.f, g0 = 0.f, g1 = 0.f;
-#pragma unroll 4
-        for (int c = 0; c < clen; c += 2) {
-            const float a0 = mi[c], a1 = mi[c + 1];
-            z0 = fmaf(a0, wj[c], z0);
-            z1 = fmaf(a1, wj[c + 1], z1);
-            g0 = fmaf(a0, mj[c], g0);
-            g1 = fmaf(a1, mj[c + 1], g1);
+// Transpose-reduce 32 per-lane values across the warp in 31 shuffles (instead of 32 x 5): at every step a lane
+// keeps the half of its values whose index bit matches its lane bit and adds the partner's copy of that half.
+// On return v[0] of lane l is the warp total of value l.
+__device__ __forceinline__ void warp_reduce32(float (&v)[32]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool hi = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < off; ++j) {
+            const float mine = hi ? v[j + off] : v[j];
+            const float theirs = hi ? v[j] : v[j + off];
+            v[j] = mine + __shfl_xor_sync(0xffffffffu, theirs, off);
         }
-        zz = z0 + z1;
-        gg = g0 + g1;
-    }
-    if (parts > 1) {
-        scratch[tid] = zz;
-        scratch[UP_THREADS + tid] = gg;
-        __syncthreads();
-        if (pair < KK && part == 0) {
-            for (int q = 1; q < parts; ++q) {
-                zz += scratch[tid + q];
-                gg += scratch[UP_THREADS + tid + q];
-            }
-        }
-    }
-    if (pair < KK && part == 0) {
-        const int i = pair / K, j = pair - i * K;
-        zs[i * UP_KMAX + j] = zz + __ldg(bias + j);
-        gs[i * UP_KMAX + j] = gg;
     }
 }
 
+// CTA total of 32 per-thread values: out[l] (l < 32) valid for every thread after the call. scratch: [UP_WARPS][32]
+__device__ __forceinline__ void block_reduce32(float (&v)[32], float* scratch, float* out) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    warp_reduce32(v);
+    scratch[wid * 32 + lane] = v[0];
+    __syncthreads();
+    if (wid == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < UP_WARPS; ++w) t += scratch[w * 32 + lane];
+        out[lane] = t;
+    }
+    __syncthreads();
+}
+
+// aux layout (floats, zeroed by the caller): [0] arrival counter (as unsigned), [2 .. 2+32) per-row CE term,
+// [34 .. 34+32) per-row positive off-diagonal Gram sum
 __global__ void __launch_bounds__(UP_THREADS) update_fwd_kernel(const float* __restrict__ SD, const float* __restrict__ M_old,
                                                                 float momentum, const float* __restrict__ W,
                                                                 const float* __restrict__ bias, float* __restrict__ M_new,
                                                                 float* __restrict__ losses, float* __restrict__ saved,
-                                                                int C, int K) {
-    extern __shared__ __align__(16) float smem[];
-    const int CP = C + 1;
-    float* Mn = smem;                  // [K][C+1] new memory
-    float* Ws = Mn + K * CP;           // [K][C+1] classifier weight
-    float* zs = Ws + K * CP;           // [K][UP_KMAX] logits
-    float* gs = zs + K * UP_KMAX;      // [K][UP_KMAX] Gram
-    float* red = gs + K * UP_KMAX;     // [2][UP_KMAX]
-    float* scratch = red + 2 * UP_KMAX;  // [2][UP_THREADS]
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, CS = C + 4;
-
-    {  // classifier weight -> shared, all loads in flight first
-        constexpr int PER = (UP_KMAX * UP_CMAX) / UP_THREADS;
-        float v[PER];
+                                                                float* __restrict__ aux, int C, int K) {
+    __shared__ float scratch[UP_WARPS * 32];
+    __shared__ float red[32], red2[32], invn[32];
+    const int tid = threadIdx.x, lane = tid & 31, i = blockIdx.x, CS = C + 4;
+    const bool on = tid < C;
+    // this thread's channel of every row; all loads are issued before the first use
+    float m[UP_KMAX], wv[UP_KMAX], sd[UP_KMAX], dk[UP_KMAX];
 #pragma unroll
-        for (int r = 0; r < PER; ++r) {
-            const int i = tid + r * UP_THREADS;
-            v[r] = (i < K * C) ? __ldg(W + i) : 0.f;
-        }
-#pragma unroll
-        for (int r = 0; r < PER; ++r) {
-            const int i = tid + r * UP_THREADS;
-            if (i < K * C) Ws[(i / C) * CP + (i % C)] = v[r];
-        }
+    for (int k = 0; k < UP_KMAX; ++k) {
+        const bool ok = k < K && on;
+        dk[k] = ok ? __ldg(SD + (size_t)k * CS + C) : 0.f;
+        m[k] = ok ? __ldg(M_old + (size_t)k * C + tid) : 0.f;
+        sd[k] = ok ? __ldg(SD + (size_t)k * CS + tid) : 0.f;
+        wv[k] = ok ? __ldg(W + (size_t)k * C + tid) : 0.f;
     }
-    if (wid < K) {  // one warp per memory row
-        const int k = wid;
-        const float D = __ldg(SD + (size_t)k * CS + C);
-        float old[UP_CMAX / 32], sd[UP_CMAX / 32];
 #pragma unroll
-        for (int t = 0; t < UP_CMAX / 32; ++t) {
-            const int c = lane + 32 * t;
-            old[t] = (c < C) ? __ldg(M_old + (size_t)k * C + c) : 0.f;
-            sd[t] = (c < C) ? __ldg(SD + (size_t)k * CS + c) : 0.f;
-        }
-        const bool present = D != 0.f;
-        const float coef = present ? (1.f - momentum) / D : 0.f;
-        float n2 = 0.f;
-#pragma unroll
-        for (int t = 0; t < UP_CMAX / 32; ++t) {
-            old[t] = present ? fmaf(coef, sd[t], momentum * old[t]) : old[t];
-            n2 = fmaf(old[t], old[t], n2);
-        }
-        n2 = warp_sum(n2);
-        const float n = sqrtf(n2), inv = 1.f / fmaxf(n, PM_NORM_EPS);
-#pragma unroll
-        for (int t = 0; t < UP_CMAX / 32; ++t) {
-            const int c = lane + 32 * t;
-            if (c < C) {
-                const float v = old[t] * inv;
-                Mn[k * CP + c] = v;
-                M_new[(size_t)k * C + c] = v;
-            }
-        }
-        if (lane == 0) {
-            saved[k] = n;
-            saved[K + k] = D;
-        }
+    for (int k = 0; k < UP_KMAX; ++k) {
+        m[k] = (dk[k] != 0.f) ? fmaf((1.f - momentum) / dk[k], sd[k], momentum * m[k]) : m[k];
+        sd[k] = m[k] * m[k];
     }
+    block_reduce32(sd, scratch, red);  // red[k] = |M'_k|^2
+    if (tid < 32) invn[tid] = 1.f / fmaxf(sqrtf(red[tid]), PM_NORM_EPS);
     __syncthreads();
-    pair_dots(Mn, Ws, bias, zs, gs, scratch, C, K);
-    __syncthreads();
-    if (wid < K) {  // per row: classification CE term and the positive off-diagonal Gram sum
-        const int i = wid;
-        const float z = lane < K ? zs[i * UP_KMAX + lane] : -INFINITY;
+#pragma unroll
+    for (int k = 0; k < UP_KMAX; ++k) m[k] *= invn[k];
+    float mi = 0.f;
+#pragma unroll
+    for (int k = 0; k < UP_KMAX; ++k)
+        if (k == i) mi = m[k];
+    if (on) M_new[(size_t)i * C + tid] = mi;
+    if (tid == 0) {
+        saved[i] = sqrtf(red[i]);
+        saved[K + i] = __ldg(SD + (size_t)i * CS + C);
+    }
+    // row i of the classifier logits (red) and of the Gram matrix (red2)
+#pragma unroll
+    for (int k = 0; k < UP_KMAX; ++k) {
+        wv[k] *= mi;
+        sd[k] = mi * m[k];
+    }
+    __syncthreads();  // red / invn consumed
+    block_reduce32(wv, scratch, red);
+    block_reduce32(sd, scratch, red2);
+    if (tid < 32) {  // CE term and positive off-diagonal Gram sum of row i
+        const float z = lane < K ? red[lane] + __ldg(bias + lane) : -INFINITY;
         const float mx = warp_max(z);
         const float sum = warp_sum(lane < K ? expf(z - mx) : 0.f);
-        const float g = (lane < K && lane != i) ? fmaxf(gs[i * UP_KMAX + lane], 0.f) : 0.f;
+        const float zii = __shfl_sync(0xffffffffu, z, i);
+        const float g = (lane < K && lane != i) ? fmaxf(red2[lane], 0.f) : 0.f;
         const float gsum = warp_sum(g);
+        unsigned t = 0;
         if (lane == 0) {
-            red[i] = mx + logf(sum) - zs[i * UP_KMAX + i];
-            red[UP_KMAX + i] = gsum;
+            aux[2 + i] = mx + logf(sum) - zii;
+            aux[2 + UP_KMAX + i] = gsum;
+            __threadfence();
+            t = atomicAdd(reinterpret_cast<unsigned*>(aux), 1u);
         }
-    }
-    __syncthreads();
-    if (wid == 0) {
-        const float c = warp_sum(lane < K ? red[lane] : 0.f);
-        const float d = warp_sum(lane < K ? red[UP_KMAX + lane] : 0.f);
-        if (lane == 0) {
-            losses[0] = d / (float)(K * (K - 1));
-            losses[1] = c / (float)K;
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t == (unsigned)K - 1) {  // last row to arrive: fixed-order (shuffle tree) sums -> deterministic losses
+            __threadfence();
+            const float c = warp_sum(lane < K ? __ldcg(aux + 2 + lane) : 0.f);
+            const float d = warp_sum(lane < K ? __ldcg(aux + 2 + UP_KMAX + lane) : 0.f);
+            if (lane == 0) {
+                losses[0] = d / (float)(K * (K - 1));
+                losses[1] = c / (float)K;
+            }
         }
     }
 }
 
+// aux layout (floats, zeroed by the caller): [0] arrival counter, [32 .. 32 + K*32) dz rows
 __global__ void __launch_bounds__(UP_THREADS) update_bwd_kernel(const float* __restrict__ dM_new, const float* __restrict__ g_div,
                                                                 const float* __restrict__ g_cls, const float* __restrict__ M_new,
                                                                 const float* __restrict__ saved, const float* __restrict__ W,
                                                                 const float* __restrict__ bias, float momentum,
                                                                 float* __restrict__ dS, float* __restrict__ dW,
-                                                                float* __restrict__ db, int C, int K) {
-    extern __shared__ __align__(16) float smem[];
-    const int CP = C + 1;
-    float* Mn = smem;               // [K][C+1]
-    float* Ws = Mn + K * CP;        // [K][C+1]
-    float* zs = Ws + K * CP;        // [K][UP_KMAX] logits -> dz
-    float* gs = zs + K * UP_KMAX;   // [K][UP_KMAX] Gram -> indicator * g_div * 2/(K(K-1))
-    float* scratch = gs + K * UP_KMAX;  // [2][UP_THREADS]
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+                                                                float* __restrict__ db, float* __restrict__ aux, int C,
+                                                                int K) {
+    __shared__ float scratch[UP_WARPS * 32];
+    __shared__ float red[32], red2[32];
+    __shared__ float dzs[UP_KMAX * UP_KMAX];
+    __shared__ int is_last;
+    const int tid = threadIdx.x, lane = tid & 31, i = blockIdx.x;
+    const bool on = tid < C;
     const float gd = g_div ? __ldg(g_div) : 0.f, gc = g_cls ? __ldg(g_cls) : 0.f;
-    // upstream gradient rows are needed last: fetch them first
-    float up[UP_CMAX / 32];
+    float m[UP_KMAX], wv[UP_KMAX], pz[UP_KMAX], pg[UP_KMAX];
 #pragma unroll
-    for (int t = 0; t < UP_CMAX / 32; ++t) {
-        const int c = lane + 32 * t;
-        up[t] = (dM_new != nullptr && wid < K && c < C) ? __ldg(dM_new + (size_t)wid * C + c) : 0.f;
+    for (int k = 0; k < UP_KMAX; ++k) {
+        m[k] = (k < K && on) ? __ldg(M_new + (size_t)k * C + tid) : 0.f;
+        wv[k] = (k < K && on) ? __ldg(W + (size_t)k * C + tid) : 0.f;
     }
-    {
-        constexpr int PER = (UP_KMAX * UP_CMAX) / UP_THREADS;
-        float v[PER], u[PER];
+    const float up = (dM_new != nullptr && on) ? __ldg(dM_new + (size_t)i * C + tid) : 0.f;
+    const float nrm = saved[i], Dn = saved[K + i];
+    float mi = 0.f;
 #pragma unroll
-        for (int r = 0; r < PER; ++r) {
-            const int i = tid + r * UP_THREADS;
-            v[r] = (i < K * C) ? __ldg(M_new + i) : 0.f;
-            u[r] = (i < K * C) ? __ldg(W + i) : 0.f;
-        }
+    for (int k = 0; k < UP_KMAX; ++k)
+        if (k == i) mi = m[k];
 #pragma unroll
-        for (int r = 0; r < PER; ++r) {
-            const int i = tid + r * UP_THREADS;
-            if (i < K * C) {
-                Mn[(i / C) * CP + (i % C)] = v[r];
-                Ws[(i / C) * CP + (i % C)] = u[r];
-            }
-        }
+    for (int k = 0; k < UP_KMAX; ++k) {
+        pz[k] = mi * wv[k];
+        pg[k] = mi * m[k];
     }
-    __syncthreads();
-    pair_dots(Mn, Ws, bias, zs, gs, scratch, C, K);
-    __syncthreads();
-    if (wid < K) {  // dz_i = g_cls (softmax(z_i) - e_i) / K ; Gram indicator scaled by g_div 2/(K(K-1))
-        const int i = wid;
-        const float z = lane < K ? zs[i * UP_KMAX + lane] : -INFINITY;
+    block_reduce32(pz, scratch, red);
+    block_reduce32(pg, scratch, red2);
+    if (tid < 32) {  // dz_i = g_cls (softmax(z_i) - e_i) / K ; Gram indicator scaled by g_div 2/(K(K-1))
+        const float z = lane < K ? red[lane] + __ldg(bias + lane) : -INFINITY;
         const float mx = warp_max(z);
         const float e = lane < K ? expf(z - mx) : 0.f;
         const float sum = warp_sum(e);
-        if (lane < K) {
-            zs[i * UP_KMAX + lane] = (gc / (float)K) * (e / sum - (lane == i ? 1.f : 0.f));
-            const float g = gs[i * UP_KMAX + lane];
-            // the reference zeroes only cos < 0 (memory.py:269-271)
-            gs[i * UP_KMAX + lane] = (lane != i && g >= 0.f) ? gd * 2.f / (float)(K * (K - 1)) : 0.f;
-        }
+        const float dz = lane < K ? (gc / (float)K) * (e / sum - (lane == i ? 1.f : 0.f)) : 0.f;
+        const float g = red2[lane];
+        // the reference zeroes only cos < 0 (memory.py:269-271)
+        const float gi = (lane < K && lane != i && g >= 0.f) ? gd * 2.f / (float)(K * (K - 1)) : 0.f;
+        red[lane] = dz;
+        red2[lane] = gi;
+        aux[32 + i * UP_KMAX + lane] = dz;
     }
     __syncthreads();
-    if (wid < K) {  // row i: dM''_i, projection through the normalisation, scale into dS_i
-        const int i = wid;
-        const float n = saved[i], D = saved[K + i];
-        float dot = 0.f;
+    // dM''_i[c], projection through the normalisation, scale into dS_i
+    float a = up;
 #pragma unroll
-        for (int t = 0; t < UP_CMAX / 32; ++t) {
-            const int c = lane + 32 * t;
-            if (c < C) {
-                float a = up[t];
-                for (int j = 0; j < K; ++j) {
-                    a = fmaf(gs[i * UP_KMAX + j], Mn[j * CP + c], a);
-                    a = fmaf(zs[i * UP_KMAX + j], Ws[j * CP + c], a);
-                }
-                up[t] = a;
-                dot = fmaf(a, Mn[i * CP + c], dot);
-            }
-        }
-        dot = warp_sum(dot);
-        const bool clamped = n <= PM_NORM_EPS;
-        const float inv = 1.f / fmaxf(n, PM_NORM_EPS);
-        const float coef = (D != 0.f) ? (1.f - momentum) / D : 0.f;
+    for (int k = 0; k < UP_KMAX; ++k) {
+        a = fmaf(red2[k], m[k], a);
+        a = fmaf(red[k], wv[k], a);
+    }
+    float dot = warp_sum(a * mi);
+    if (lane == 0) scratch[tid >> 5] = dot;
+    __syncthreads();
+    dot = 0.f;
 #pragma unroll
-        for (int t = 0; t < UP_CMAX / 32; ++t) {
-            const int c = lane + 32 * t;
-            if (c < C) {
-                const float dmp = clamped ? up[t] * inv : (up[t] - Mn[i * CP + c] * dot) * inv;
-                dS[(size_t)i * C + c] = coef * dmp;
-            }
+    for (int w = 0; w < UP_WARPS; ++w) dot += scratch[w];
+    {
+        const float inv = 1.f / fmaxf(nrm, PM_NORM_EPS);
+        const float coef = (Dn != 0.f) ? (1.f - momentum) / Dn : 0.f;
+        const float dmp = (nrm <= PM_NORM_EPS) ? a * inv : (a - mi * dot) * inv;
+        if (on) dS[(size_t)i * C + tid] = coef * dmp;
+    }
+    // the last row to arrive turns the dz rows into dW = dz^T M_new and db
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned t = atomicAdd(reinterpret_cast<unsigned*>(aux), 1u);
+        is_last = (t == (unsigned)K - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        for (int q = tid; q < K * UP_KMAX; q += UP_THREADS) dzs[q] = __ldcg(aux + 32 + q);
+        __syncthreads();
+        for (int j = 0; j < K; ++j) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < UP_KMAX; ++k) acc = fmaf(k < K ? dzs[k * UP_KMAX + j] : 0.f, m[k], acc);
+            if (on) dW[(size_t)j * C + tid] = acc;
         }
-    }
-    // dW_j = sum_i dz[i][j] M_i ; db_j = sum_i dz[i][j]
-    for (int idx = tid; idx < K * C; idx += UP_THREADS) {
-        const int j = idx / C, c = idx - j * C;
-        float a = 0.f;
-        for (int i = 0; i < K; ++i) a = fmaf(zs[i * UP_KMAX + j], Mn[i * CP + c], a);
-        dW[idx] = a;
-    }
-    if (tid < K) {
-        float a = 0.f;
-        for (int i = 0; i < K; ++i) a += zs[i * UP_KMAX + tid];
-        db[tid] = a;
+        if (tid < K) {
+            float acc = 0.f;
+            for (int k = 0; k < K; ++k) acc += dzs[k * UP_KMAX + tid];
+            db[tid] = acc;
+        }
     }
 }
 
@@ -549,32 +519,28 @@ extern "C" int pm_write_bwd(const float* dS, const void* f, const int64_t* label
     PMW_DISPATCH(PMW_DISPATCH_CW, launch_write_bwd, dS, f, labels, df, B, h, w, Hm, Wm, K, (cudaStream_t)stream);
 }
 
+extern "C" int pm_update_aux_floats(int K) { return 32 + K * pm::UP_KMAX + 68; }
+
 extern "C" int pm_update_fwd(const float* SD, const float* M_old, float momentum, const float* W_cls,
-                             const float* b_cls, float* M_new, float* losses, float* saved, int C, int K,
+                             const float* b_cls, float* M_new, float* losses, float* saved, float* aux, int C, int K,
                              void* stream) {
-    if (!SD || !M_old || !W_cls || !b_cls || !M_new || !losses || !saved) return PM_ERR_NULL;
+    if (!SD || !M_old || !W_cls || !b_cls || !M_new || !losses || !saved || !aux) return PM_ERR_NULL;
     if (C != 32 && C != 64 && C != 128 && C != 256) return PM_ERR_CHANNELS;
     if (K < 1 || K > 31) return PM_ERR_SLOTS;
-    const size_t smem = sizeof(float) * ((size_t)2 * K * (C + 1) + 2 * K * pm::UP_KMAX + 2 * pm::UP_KMAX + 2 * pm::UP_THREADS);
-    cudaError_t e = cudaFuncSetAttribute(pm::update_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    pm::update_fwd_kernel<<<1, pm::UP_THREADS, smem, (cudaStream_t)stream>>>(SD, M_old, momentum, W_cls, b_cls, M_new,
-                                                                              losses, saved, C, K);
+    pm::update_fwd_kernel<<<K, pm::UP_THREADS, 0, (cudaStream_t)stream>>>(SD, M_old, momentum, W_cls, b_cls, M_new, losses,
+                                                                          saved, aux, C, K);
     PM_CHECK_LAUNCH();
     return 0;
 }
 
 extern "C" int pm_update_bwd(const float* dM_new, const float* g_div, const float* g_cls, const float* M_new,
                              const float* saved, const float* W_cls, const float* b_cls, float momentum, float* dS,
-                             float* dW_cls, float* db_cls, int C, int K, void* stream) {
-    if (!M_new || !saved || !W_cls || !b_cls || !dS || !dW_cls || !db_cls) return PM_ERR_NULL;
+                             float* dW_cls, float* db_cls, float* aux, int C, int K, void* stream) {
+    if (!M_new || !saved || !W_cls || !b_cls || !dS || !dW_cls || !db_cls || !aux) return PM_ERR_NULL;
     if (C != 32 && C != 64 && C != 128 && C != 256) return PM_ERR_CHANNELS;
     if (K < 1 || K > 31) return PM_ERR_SLOTS;
-    const size_t smem = sizeof(float) * ((size_t)2 * K * (C + 1) + 2 * K * pm::UP_KMAX + 2 * pm::UP_THREADS);
-    cudaError_t e = cudaFuncSetAttribute(pm::update_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    pm::update_bwd_kernel<<<1, pm::UP_THREADS, smem, (cudaStream_t)stream>>>(dM_new, g_div, g_cls, M_new, saved, W_cls,
-                                                                              b_cls, momentum, dS, dW_cls, db_cls, C, K);
+    pm::update_bwd_kernel<<<K, pm::UP_THREADS, 0, (cudaStream_t)stream>>>(dM_new, g_div, g_cls, M_new, saved, W_cls, b_cls,
+                                                                          momentum, dS, dW_cls, db_cls, aux, C, K);
     PM_CHECK_LAUNCH();
     return 0;
 }

@@ -135,7 +135,10 @@ class _WriteFn(torch.autograd.Function):
     def forward(ctx, f, labels, M_old, W, b, momentum, K, group):
         B, C, h, w = f.shape
         dev = f.device
-        SD = torch.zeros(K + 1, C + 4, dtype=torch.float32, device=dev)
+        # one zeroed allocation: the class sums|counts [K+1, C+4] and the update kernel's scratch
+        nsd = (K + 1) * (C + 4)
+        zbuf = torch.zeros(nsd + capi.update_aux_floats(K), dtype=torch.float32, device=dev)
+        SD, aux = zbuf[:nsd].view(K + 1, C + 4), zbuf[nsd:]
         capi.write_reduce_fwd(f, labels, SD, K)
         if group is not None:
             sharding.all_reduce_sum_(SD, group)
@@ -145,7 +148,7 @@ class _WriteFn(torch.autograd.Function):
         M_new = torch.empty(K, C, dtype=torch.float32, device=dev)
         losses = torch.empty(2, dtype=torch.float32, device=dev)
         saved = torch.empty(2 * K, dtype=torch.float32, device=dev)
-        capi.update_fwd(SD, M_old, momentum, W, b, M_new, losses, saved, C, K)
+        capi.update_fwd(SD, M_old, momentum, W, b, M_new, losses, saved, C, K, aux=aux)
         ctx.K, ctx.momentum, ctx.group = K, momentum, group
         ctx.save_for_backward(f, labels, M_new, saved, W, b)
         ctx.mark_non_differentiable(SD)
