@@ -56,6 +56,103 @@ __device__ __forceinline__ void tile_dots(const T* xt, const float* Mt, int c0, 
     }
 }
 
+// ---- tensor-core variant of the same contraction (fp32 tiles, CW % 8 == 0) -----------------------------------
+// S[32 px][KP] (+)= X[32 px][CW ch] . Mt[CW ch][KP] with mma.sync m16n8k8 TF32 and 3xTF32 error compensation
+// (a = a_hi + a_lo, b = b_hi + b_lo; a_lo.b_hi + a_hi.b_lo + a_hi.b_hi in an fp32 accumulator): fp32-level
+// accuracy at 93 TFLOP/s effective (profiles/microbench/mma_tf32.cu), operands reused inside the tensor core
+// instead of one broadcast shared-memory load per FMA pair. The k index of an MMA is a free permutation, so
+// k = t maps to channel 2t and k = t+4 to channel 2t+1 of an 8-channel step: with that choice the B fragments
+// read the existing Mt[c][KP=20] rows without bank conflicts, and the A fragments read the chunk-swizzled tile
+// (tile_load_async_mma) without bank conflicts. Writes this warp's partial sums straight into part / pn.
+__device__ __forceinline__ unsigned to_tf32(float x) {
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0,
+                                         unsigned b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int CW, int KP>
+__device__ __forceinline__ void tile_dots_mma(const float* xt, const float* Mt, int c0, int lane, float* part_w,
+                                              float* pn_w) {
+    constexpr int NT = (KP + 7) / 8;
+    const int g = lane >> 2, t = lane & 3;
+    float acc[2][NT][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int n = 0; n < NT; ++n) acc[m][n][0] = acc[m][n][1] = acc[m][n][2] = acc[m][n][3] = 0.f;
+    float n2[4] = {0.f, 0.f, 0.f, 0.f};
+    int pos[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) pos[r] = mma_tile_pos(g + 8 * r, t);  // rows c0+8ks+2t(+1): phase ((row>>1)&3) == t
+#pragma unroll
+    for (int ks = 0; ks < CW / 8; ++ks) {
+        const float* r0 = xt + (c0 + 8 * ks + 2 * t) * 32;
+        const float* mrow = Mt + (c0 + 8 * ks + 2 * t) * KP + g;
+        unsigned ahi[4][2], alo[4][2];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float v = r0[h * 32 + pos[r]];
+                n2[r] = fmaf(v, v, n2[r]);
+                ahi[r][h] = to_tf32(v);
+                alo[r][h] = to_tf32(v - __uint_as_float(ahi[r][h]));
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            const float b0 = mrow[8 * n], b1 = mrow[KP + 8 * n];
+            const unsigned b0h = to_tf32(b0), b1h = to_tf32(b1);
+            const unsigned b0l = to_tf32(b0 - __uint_as_float(b0h)), b1l = to_tf32(b1 - __uint_as_float(b1h));
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                mma_tf32(acc[m][n], alo[2 * m][0], alo[2 * m + 1][0], alo[2 * m][1], alo[2 * m + 1][1], b0h, b1h);
+                mma_tf32(acc[m][n], ahi[2 * m][0], ahi[2 * m + 1][0], ahi[2 * m][1], ahi[2 * m + 1][1], b0l, b1l);
+                mma_tf32(acc[m][n], ahi[2 * m][0], ahi[2 * m + 1][0], ahi[2 * m][1], ahi[2 * m + 1][1], b0h, b1h);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        n2[r] += __shfl_xor_sync(0xffffffffu, n2[r], 1);
+        n2[r] += __shfl_xor_sync(0xffffffffu, n2[r], 2);
+        if (t == 0 && pn_w != nullptr) pn_w[g + 8 * r] = n2[r];
+    }
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            const int slot = 8 * n + 2 * t;
+            if (slot < KP) {
+                *reinterpret_cast<float2*>(part_w + (g + 16 * m) * KP + slot) = make_float2(acc[m][n][0], acc[m][n][1]);
+                *reinterpret_cast<float2*>(part_w + (g + 8 + 16 * m) * KP + slot) = make_float2(acc[m][n][2], acc[m][n][3]);
+            }
+        }
+}
+
+template <typename T, int CW>
+struct UseMma {
+    static constexpr bool value = false;
+};
+template <int CW>
+struct UseMma<float, CW> {
+    static constexpr bool value = (CW % 8 == 0);
+};
+
+// dispatch: load one tile for the dots phase in the layout the chosen contraction wants
+template <typename T, int C, int NTHREADS, bool MMA>
+__device__ __forceinline__ void dots_tile_load(T* smem_tile, const T* __restrict__ base, int hw, int px0) {
+    if constexpr (MMA) tile_load_async_mma<C, NTHREADS>(smem_tile, base, hw, px0);
+    else tile_load_async<T, C, NTHREADS>(smem_tile, base, hw, px0);
+}
+
 template <int KP>
 __device__ __forceinline__ void store_partial(float* part, int wid, int lane, const float2 (&a2)[KP / 2]) {
     float4* d = reinterpret_cast<float4*>(part + ((size_t)wid * TP + lane) * KP);
@@ -72,6 +169,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
                           float* __restrict__ p_out, float* __restrict__ colpart, int hw, int K, int tiles_per_img,
                           int ntiles) {
     constexpr int CW = C / TL_WARPS, NI = (KP + 7) / 8;
+    constexpr bool MMA = UseMma<T, CW>::value;
     extern __shared__ __align__(16) unsigned char smraw[];
     float* Mt = reinterpret_cast<float*>(smraw);  // [C][KP]
     float* part = Mt + C * KP;                    // [8][TP][KP]
@@ -88,7 +186,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
         const int t = tile + s * gridDim.x;
         if (t < ntiles) {
             const int b = t / tiles_per_img, px0 = (t - b * tiles_per_img) * TP;
-            tile_load_async<T, C, TL_THREADS>(xs + s * C * TP, x + (size_t)b * C * hw, hw, px0);
+            dots_tile_load<T, C, TL_THREADS, MMA>(xs + s * C * TP, x + (size_t)b * C * hw, hw, px0);
         }
         cp_async_commit();
     }
@@ -105,7 +203,10 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
         const int b = tile / tiles_per_img, px0 = (tile - b * tiles_per_img) * TP;
         const int nvalid = min(TP, hw - px0);
         const size_t n0g = (size_t)b * hw + px0;
-        {
+        if constexpr (MMA) {
+            tile_dots_mma<CW, KP>(reinterpret_cast<const float*>(xt), Mt, wid * CW, lane, part + wid * TP * KP,
+                                  pn + wid * TP);
+        } else {
             float2 a2[KP / 2];
 #pragma unroll
             for (int i = 0; i < KP / 2; ++i) a2[i] = f2(0.f, 0.f);
@@ -191,6 +292,9 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
             T* uq = u + ((size_t)b * 2 * C + wid * CW) * hw + px0 + lane;
             const size_t chw = (size_t)C * hw;
             const T* xcol = xt + wid * CW * 32 + lane;
+            int posl[4];  // the lane's word inside a swizzled row, per row phase (MMA tiles only)
+#pragma unroll
+            for (int ph = 0; ph < 4; ++ph) posl[ph] = mma_tile_pos(lane, ph);
             const float4* mbase = reinterpret_cast<const float4*>(Mt + wid * CW * KP);
 #pragma unroll
             for (int j = 0; j < CW; ++j) {
@@ -202,7 +306,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
                     acc = __ffma2_rn(p2[2 * q], f2(m.x, m.y), acc);
                     acc = __ffma2_rn(p2[2 * q + 1], f2(m.z, m.w), acc);
                 }
-                const float xq = to_float(xcol[j * 32]) * ir;
+                const float xq = (MMA ? to_float(xt[(wid * CW + j) * 32 + posl[(j >> 1) & 3]]) : to_float(xcol[j * 32])) * ir;
                 if (v) {
                     stf(uq, xq);
                     stf(uq + chw, acc.x + acc.y);
@@ -214,7 +318,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
         const int next = tile + NSTAGE * gridDim.x;
         if (next < ntiles) {
             const int nb = next / tiles_per_img, npx0 = (next - nb * tiles_per_img) * TP;
-            tile_load_async<T, C, TL_THREADS>(xs + stage * C * TP, x + (size_t)nb * C * hw, hw, npx0);
+            dots_tile_load<T, C, TL_THREADS, MMA>(xs + stage * C * TP, x + (size_t)nb * C * hw, hw, npx0);
         }
         cp_async_commit();
         stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
@@ -278,6 +382,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
                              const float* __restrict__ rl_out, float* __restrict__ ds_out, int hw, int K,
                              int tiles_per_img, int ntiles) {
     constexpr int CW = C / TL_WARPS, NI = (KP + 7) / 8;
+    constexpr bool MMA = UseMma<T, CW>::value;
     extern __shared__ __align__(16) unsigned char smraw[];
     float* Mt = reinterpret_cast<float*>(smraw);  // [C][KP]
     float* part = Mt + C * KP;                    // [8][TP][KP]
@@ -291,7 +396,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
         const int t = tile + s * gridDim.x;
         if (t < ntiles) {
             const int b = t / tiles_per_img, px0 = (t - b * tiles_per_img) * TP;
-            tile_load_async<T, C, TL_THREADS>(xs + s * C * TP, du + ((size_t)b * 2 * C + C) * hw, hw, px0);
+            dots_tile_load<T, C, TL_THREADS, MMA>(xs + s * C * TP, du + ((size_t)b * 2 * C + C) * hw, hw, px0);
         }
         cp_async_commit();
     }
@@ -317,7 +422,9 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
         cp_async_wait<NSTAGE - 1>();
         __syncthreads();
         const T* xt = xs + stage * C * TP;
-        {
+        if constexpr (MMA) {
+            tile_dots_mma<CW, KP>(reinterpret_cast<const float*>(xt), Mt, wid * CW, lane, part + wid * TP * KP, nullptr);
+        } else {
             float2 a2[KP / 2];
 #pragma unroll
             for (int i = 0; i < KP / 2; ++i) a2[i] = f2(0.f, 0.f);
@@ -354,7 +461,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
         const int next = tile + NSTAGE * gridDim.x;
         if (next < ntiles) {
             const int nb = next / tiles_per_img, npx0 = (next - nb * tiles_per_img) * TP;
-            tile_load_async<T, C, TL_THREADS>(xs + stage * C * TP, du + ((size_t)nb * 2 * C + C) * hw, hw, npx0);
+            dots_tile_load<T, C, TL_THREADS, MMA>(xs + stage * C * TP, du + ((size_t)nb * 2 * C + C) * hw, hw, npx0);
         }
         cp_async_commit();
         stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
