@@ -64,10 +64,12 @@ __device__ __forceinline__ void tile_dots(const T* xt, const float* Mt, int c0, 
 // k = t maps to channel 2t and k = t+4 to channel 2t+1 of an 8-channel step: with that choice the B fragments
 // read the existing Mt[c][KP=20] rows without bank conflicts, and the A fragments read the chunk-swizzled tile
 // (tile_load_async_mma) without bank conflicts. Writes this warp's partial sums straight into part / pn.
-__device__ __forceinline__ unsigned to_tf32(float x) {
-    unsigned r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
+// hi/lo split for 3xTF32. The tensor core ignores the low 13 mantissa bits of a TF32 operand, so the raw fp32
+// bits serve as "hi" (= x truncated to 10 mantissa bits) and lo = x - trunc(x) is exact in fp32: one LOP3 and one
+// FADD per value (cvt.rna.tf32 is emulated with ~5 instructions on sm_100 and bought nothing measurable).
+__device__ __forceinline__ unsigned tf32_hi(float x) { return __float_as_uint(x); }
+__device__ __forceinline__ unsigned tf32_lo(float x) {
+    return __float_as_uint(x - __uint_as_float(__float_as_uint(x) & 0xffffe000u));
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0,
                                          unsigned b1) {
@@ -102,15 +104,15 @@ __device__ __forceinline__ void tile_dots_mma(const float* xt, const float* Mt, 
             for (int h = 0; h < 2; ++h) {
                 const float v = r0[h * 32 + pos[r]];
                 n2[r] = fmaf(v, v, n2[r]);
-                ahi[r][h] = to_tf32(v);
-                alo[r][h] = to_tf32(v - __uint_as_float(ahi[r][h]));
+                ahi[r][h] = tf32_hi(v);
+                alo[r][h] = tf32_lo(v);
             }
         }
 #pragma unroll
         for (int n = 0; n < NT; ++n) {
             const float b0 = mrow[8 * n], b1 = mrow[KP + 8 * n];
-            const unsigned b0h = to_tf32(b0), b1h = to_tf32(b1);
-            const unsigned b0l = to_tf32(b0 - __uint_as_float(b0h)), b1l = to_tf32(b1 - __uint_as_float(b1h));
+            const unsigned b0h = tf32_hi(b0), b1h = tf32_hi(b1);
+            const unsigned b0l = tf32_lo(b0), b1l = tf32_lo(b1);
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
                 mma_tf32(acc[m][n], alo[2 * m][0], alo[2 * m + 1][0], alo[2 * m][1], alo[2 * m + 1][1], b0h, b1h);
@@ -135,6 +137,60 @@ __device__ __forceinline__ void tile_dots_mma(const float* xt, const float* Mt, 
                 *reinterpret_cast<float2*>(part_w + (g + 8 + 16 * m) * KP + slot) = make_float2(acc[m][n][2], acc[m][n][3]);
             }
         }
+}
+
+// Second contraction of the read on the tensor core: cout[32 px][CW ch] = P[32 px][K] . M[K][CW ch] for this
+// warp's channels, written straight to the second half of u (NCHW). A fragments come from p_sm[px][KP] (stride 20:
+// conflict-free), B fragments from Mt[c][KP] (same pattern); slots >= KP of the last 8-slot step are zero.
+template <typename T, int CW, int KP>
+__device__ __forceinline__ void tile_weighted_sum_mma(const float* p_sm, const float* Mt, int c0, int lane, T* uc,
+                                                      int hw, int nvalid) {
+    constexpr int NKS = (KP + 7) / 8, NNT = CW / 8;
+    const int g = lane >> 2, t = lane & 3;
+    unsigned ahi[2][NKS][4], alo[2][NKS][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int ks = 0; ks < NKS; ++ks)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int px = g + 16 * m + 8 * (e & 1), slot = 8 * ks + t + 4 * (e >> 1);
+                const float v = (slot < KP) ? p_sm[px * KP + slot] : 0.f;
+                ahi[m][ks][e] = tf32_hi(v);
+                alo[m][ks][e] = tf32_lo(v);
+            }
+#pragma unroll
+    for (int n = 0; n < NNT; ++n) {
+        float acc[2][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f;
+        const float* mrow = Mt + (c0 + 8 * n + g) * KP + t;
+#pragma unroll
+        for (int ks = 0; ks < NKS; ++ks) {
+            const float b0 = mrow[8 * ks], b1 = (8 * ks + 4 < KP) ? mrow[8 * ks + 4] : 0.f;  // KP % 4 == 0
+            const unsigned b0h = tf32_hi(b0), b1h = tf32_hi(b1), b0l = tf32_lo(b0), b1l = tf32_lo(b1);
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                mma_tf32(acc[m], alo[m][ks][0], alo[m][ks][1], alo[m][ks][2], alo[m][ks][3], b0h, b1h);
+                mma_tf32(acc[m], ahi[m][ks][0], ahi[m][ks][1], ahi[m][ks][2], ahi[m][ks][3], b0l, b1l);
+                mma_tf32(acc[m], ahi[m][ks][0], ahi[m][ks][1], ahi[m][ks][2], ahi[m][ks][3], b0h, b1h);
+            }
+        }
+        // c0:(px g, ch 2t) c1:(px g, ch 2t+1) c2:(px g+8, ch 2t) c3:(px g+8, ch 2t+1)   (+16m px, +8n ch)
+        T* base = uc + (size_t)(8 * n + 2 * t) * hw;
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            const int pa = g + 16 * m, pb = pa + 8;
+            if (pa < nvalid) {
+                stf(base + pa, acc[m][0]);
+                stf(base + hw + pa, acc[m][1]);
+            }
+            if (pb < nvalid) {
+                stf(base + pb, acc[m][2]);
+                stf(base + hw + pb, acc[m][3]);
+            }
+        }
+    }
 }
 
 template <typename T, int CW>
@@ -278,7 +334,20 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
             const int px = o / K, k = o - px * K;
             p_out[n0g * K + o] = p_sm[px * KP + k];
         }
-        {  // u = [q ; p.M]
+        if constexpr (MMA) {  // u = [q ; p.M]: p.M on the tensor core, q = x/|x| element-wise
+            tile_weighted_sum_mma<T, CW, KP>(p_sm, Mt, wid * CW, lane,
+                                             u + ((size_t)b * 2 * C + C + wid * CW) * hw + px0, hw, nvalid);
+            const float ir = invr[lane];
+            const int posl[4] = {mma_tile_pos(lane, 0), mma_tile_pos(lane, 1), mma_tile_pos(lane, 2), mma_tile_pos(lane, 3)};
+            if (lane < nvalid) {
+                T* uq = u + ((size_t)b * 2 * C + wid * CW) * hw + px0 + lane;
+#pragma unroll
+                for (int j = 0; j < CW; ++j) {
+                    stf(uq, to_float(xt[(wid * CW + j) * 32 + posl[(j >> 1) & 3]]) * ir);
+                    uq += hw;
+                }
+            }
+        } else {  // u = [q ; p.M]
             float2 p2[KP / 2];
             const float4* pr = reinterpret_cast<const float4*>(p_sm + lane * KP);
 #pragma unroll
@@ -292,9 +361,6 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
             T* uq = u + ((size_t)b * 2 * C + wid * CW) * hw + px0 + lane;
             const size_t chw = (size_t)C * hw;
             const T* xcol = xt + wid * CW * 32 + lane;
-            int posl[4];  // the lane's word inside a swizzled row, per row phase (MMA tiles only)
-#pragma unroll
-            for (int ph = 0; ph < 4; ++ph) posl[ph] = mma_tile_pos(lane, ph);
             const float4* mbase = reinterpret_cast<const float4*>(Mt + wid * CW * KP);
 #pragma unroll
             for (int j = 0; j < CW; ++j) {
@@ -306,7 +372,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
                     acc = __ffma2_rn(p2[2 * q], f2(m.x, m.y), acc);
                     acc = __ffma2_rn(p2[2 * q + 1], f2(m.z, m.w), acc);
                 }
-                const float xq = (MMA ? to_float(xt[(wid * CW + j) * 32 + posl[(j >> 1) & 3]]) : to_float(xcol[j * 32])) * ir;
+                const float xq = to_float(xcol[j * 32]) * ir;
                 if (v) {
                     stf(uq, xq);
                     stf(uq + chw, acc.x + acc.y);
