@@ -182,19 +182,24 @@ int pm_write_bwd(const float* dS, const void* f, const int64_t* labels, void* df
  * the 1x1 convolution (the convolution itself stays a library GEMM).
  *   pm_bn_stats       batch mean and 1/sqrt(biased var + eps) per channel; if running_mean/var are given they
  *                     are updated in place with `momentum` (unbiased variance), like nn.BatchNorm2d in training
- *   pm_bn_apply       y = [relu]((x - mean) * invstd * gamma + beta [+ residual])
- *   pm_bn_bwd_reduce  g = dy * (y > 0 if relu);  dbeta = sum g,  dgamma = sum g * xhat
+ *   pm_bn_apply       y = [relu]((x - mean) * invstd * gamma + beta [+ residual]); optionally also a packed ReLU
+ *                     mask (1 bit per element, pm_bn_mask_words(B,C,hw) uint32 words; needs hw % 4 == 0) that the
+ *                     backward passes read instead of y
+ *   pm_bn_bwd_reduce  g = dy * (y > 0 if relu) (from relu_mask if given, else from y);  dbeta = sum g,  dgamma = sum g * xhat
  *   pm_bn_bwd_apply   dx = gamma * invstd * (g - [training](dbeta + xhat * dgamma) / (B*hw));  dres = g (or NULL)
  */
 int pm_bn_stats(const void* x, int B, int C, int hw, int dtype, float eps, float* mean, float* invstd,
                 float* running_mean, float* running_var, float momentum, void* stream);
+int pm_bn_mask_words(int B, int C, int hw);
 int pm_bn_apply(const void* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
-                const void* residual, void* y, int relu, int B, int C, int hw, int dtype, void* stream);
-int pm_bn_bwd_reduce(const void* dy, const void* y, const void* x, const float* mean, const float* invstd, int relu,
-                     float* dgamma, float* dbeta, int B, int C, int hw, int dtype, void* stream);
-int pm_bn_bwd_apply(const void* dy, const void* y, const void* x, const float* mean, const float* invstd,
-                    const float* gamma, const float* dgamma, const float* dbeta, int relu, int training, void* dx,
-                    void* dres, int B, int C, int hw, int dtype, void* stream);
+                const void* residual, void* y, uint32_t* relu_mask, int relu, int B, int C, int hw, int dtype,
+                void* stream);
+int pm_bn_bwd_reduce(const void* dy, const void* y, const uint32_t* relu_mask, const void* x, const float* mean,
+                     const float* invstd, int relu, float* dgamma, float* dbeta, int B, int C, int hw, int dtype,
+                     void* stream);
+int pm_bn_bwd_apply(const void* dy, const void* y, const uint32_t* relu_mask, const void* x, const float* mean,
+                    const float* invstd, const float* gamma, const float* dgamma, const float* dbeta, int relu,
+                    int training, void* dx, void* dres, int B, int C, int hw, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -39,9 +39,10 @@ PROTOTYPES = {
     "pm_update_bwd": [_c_p] * 7 + [_c_f] + [_c_p] * 4 + [_c_i] * 2 + [_c_p],
     "pm_write_bwd": [_c_p] * 4 + [_c_i] * 8 + [_c_p],
     "pm_bn_stats": [_c_p] + [_c_i] * 4 + [_c_f] + [_c_p] * 4 + [_c_f, _c_p],
-    "pm_bn_apply": [_c_p] * 7 + [_c_i] * 5 + [_c_p],
-    "pm_bn_bwd_reduce": [_c_p] * 5 + [_c_i] + [_c_p] * 2 + [_c_i] * 4 + [_c_p],
-    "pm_bn_bwd_apply": [_c_p] * 8 + [_c_i] * 2 + [_c_p] * 2 + [_c_i] * 4 + [_c_p],
+    "pm_bn_mask_words": [_c_i] * 3,
+    "pm_bn_apply": [_c_p] * 8 + [_c_i] * 5 + [_c_p],
+    "pm_bn_bwd_reduce": [_c_p] * 6 + [_c_i] + [_c_p] * 2 + [_c_i] * 4 + [_c_p],
+    "pm_bn_bwd_apply": [_c_p] * 9 + [_c_i] * 2 + [_c_p] * 2 + [_c_i] * 4 + [_c_p],
 }
 EXPORTED_SYMBOLS = sorted(list(PROTOTYPES) + ["pm_status_string"])
 
@@ -245,19 +246,24 @@ def bn_stats(x, eps, mean, invstd, running_mean, running_var, momentum):
           _ptr(running_var), float(momentum), _stream())
 
 
-def bn_apply(x, mean, invstd, gamma, beta, residual, y, relu):
+def bn_mask_words(B, C, hw):
+    return load().pm_bn_mask_words(int(B), int(C), int(hw))
+
+
+def bn_apply(x, mean, invstd, gamma, beta, residual, y, relu, relu_mask=None):
     B, C, h, w = x.shape
-    _call("pm_bn_apply", _ptr(x), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(beta), _ptr(residual), _ptr(y), int(relu),
-          B, C, h * w, dtype_code(x), _stream())
+    _call("pm_bn_apply", _ptr(x), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(beta), _ptr(residual), _ptr(y),
+          _ptr(relu_mask), int(relu), B, C, h * w, dtype_code(x), _stream())
 
 
-def bn_bwd_reduce(dy, y, x, mean, invstd, relu, dgamma, dbeta):
+def bn_bwd_reduce(dy, y, relu_mask, x, mean, invstd, relu, dgamma, dbeta):
     B, C, h, w = x.shape
-    _call("pm_bn_bwd_reduce", _ptr(dy), _ptr(y), _ptr(x), _ptr(mean), _ptr(invstd), int(relu), _ptr(dgamma), _ptr(dbeta),
-          B, C, h * w, dtype_code(x), _stream())
+    _call("pm_bn_bwd_reduce", _ptr(dy), _ptr(y), _ptr(relu_mask), _ptr(x), _ptr(mean), _ptr(invstd), int(relu),
+          _ptr(dgamma), _ptr(dbeta), B, C, h * w, dtype_code(x), _stream())
 
 
-def bn_bwd_apply(dy, y, x, mean, invstd, gamma, dgamma, dbeta, relu, training, dx, dres):
+def bn_bwd_apply(dy, y, relu_mask, x, mean, invstd, gamma, dgamma, dbeta, relu, training, dx, dres):
     B, C, h, w = x.shape
-    _call("pm_bn_bwd_apply", _ptr(dy), _ptr(y), _ptr(x), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(dgamma),
-          _ptr(dbeta), int(relu), int(training), _ptr(dx), _ptr(dres), B, C, h * w, dtype_code(x), _stream())
+    _call("pm_bn_bwd_apply", _ptr(dy), _ptr(y), _ptr(relu_mask), _ptr(x), _ptr(mean), _ptr(invstd), _ptr(gamma),
+          _ptr(dgamma), _ptr(dbeta), int(relu), int(training), _ptr(dx), _ptr(dres), B, C, h * w, dtype_code(x),
+          _stream())

@@ -113,22 +113,37 @@ template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ mean,
                                                        const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, const T* __restrict__ residual,
-                                                       T* __restrict__ y, int relu, int C, int hw) {
+                                                       T* __restrict__ y, unsigned* __restrict__ relu_mask, int relu,
+                                                       int C, int hw) {
     const int row = blockIdx.x, c = row % C;
     const float sc = invstd[c] * gamma[c], sh = beta[c] - mean[c] * sc;
     const size_t base = (size_t)row * hw;
     if (VEC) {
-        for (int j = threadIdx.x; j < hw / 4; j += 256) {
-            Vec4<T> v, r, o;
-            v.load(x + base + 4 * j);
-            if (residual) r.load(residual + base + 4 * j);
+        // relu_mask (optional): 1 bit per element, bit = output > 0, 32 elements per word, rows padded to whole
+        // words: the backward reads it instead of y (1/32 of the bytes). The loop is warp-uniform so that the
+        // eight lanes that share a word can OR their nibbles with one REDUX.
+        const int nv = hw / 4, wpr = (nv + 7) / 8, lane = threadIdx.x & 31;
+        const unsigned gmask = 0xffu << (lane & 24);
+        for (int j0 = 0; j0 < nv; j0 += 256) {
+            const int j = j0 + threadIdx.x;
+            unsigned nib = 0u;
+            if (j < nv) {
+                Vec4<T> v, r, o;
+                v.load(x + base + 4 * j);
+                if (residual) r.load(residual + base + 4 * j);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float f = fmaf(v.get(e), sc, sh);
-                if (residual) f += r.get(e);
-                o.set(e, relu ? fmaxf(f, 0.f) : f);
+                for (int e = 0; e < 4; ++e) {
+                    float f = fmaf(v.get(e), sc, sh);
+                    if (residual) f += r.get(e);
+                    nib |= (f > 0.f ? 1u : 0u) << e;
+                    o.set(e, relu ? fmaxf(f, 0.f) : f);
+                }
+                o.store(y + base + 4 * j);
             }
-            o.store(y + base + 4 * j);
+            if (relu_mask != nullptr) {
+                const unsigned word = __reduce_or_sync(gmask, nib << (4 * (lane & 7)));
+                if ((lane & 7) == 0 && j < nv) relu_mask[(size_t)row * wpr + (j >> 3)] = word;
+            }
         }
     } else {
         for (int j = threadIdx.x; j < hw; j += 256) {
@@ -142,6 +157,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, 
 // one CTA per channel: dbeta = sum g, dgamma = sum g * xhat, g = dy * (y > 0 if relu)
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ y,
+                                                                   const unsigned* __restrict__ relu_mask,
                                                                    const T* __restrict__ x, const float* __restrict__ mean,
                                                                    const float* __restrict__ invstd, int relu,
                                                                    float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -151,7 +167,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const T* __re
     const float m = mean[c], is = invstd[c];
     float sg = 0.f, sgx = 0.f;
     if (VEC) {
-        const int nv = hw / 4, total = B * nv;
+        const int nv = hw / 4, total = B * nv, wpr = (nv + 7) / 8;
 #pragma unroll 4
         for (int i = threadIdx.x; i < total; i += BN_THREADS) {
             const int b = i / nv, j = i - b * nv;
@@ -159,10 +175,19 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const T* __re
             Vec4<T> g, yy, xx;
             g.load(dy + off);
             xx.load(x + off);
-            if (relu) yy.load(y + off);
+            unsigned bits = 0xfu;
+            if (relu) {
+                if (relu_mask != nullptr) {
+                    bits = (__ldg(relu_mask + ((size_t)b * C + c) * wpr + (j >> 3)) >> (4 * (j & 7))) & 0xfu;
+                } else {
+                    yy.load(y + off);
+                    bits = (yy.get(0) > 0.f ? 1u : 0u) | (yy.get(1) > 0.f ? 2u : 0u) | (yy.get(2) > 0.f ? 4u : 0u) |
+                           (yy.get(3) > 0.f ? 8u : 0u);
+                }
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float gv = (!relu || yy.get(e) > 0.f) ? g.get(e) : 0.f;
+                const float gv = ((bits >> e) & 1u) ? g.get(e) : 0.f;
                 sg += gv;
                 sgx = fmaf(gv, (xx.get(e) - m) * is, sgx);
             }
@@ -188,6 +213,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const T* __re
 // one CTA per (b, c) row: dx = gamma*invstd*(g - [training] (dbeta + xhat*dgamma)/n); dres = g
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ y,
+                                                           const unsigned* __restrict__ relu_mask,
                                                            const T* __restrict__ x, const float* __restrict__ mean,
                                                            const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                            const float* __restrict__ dgamma, const float* __restrict__ dbeta,
@@ -198,14 +224,24 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
     const float k1 = training ? dbeta[c] * inv_n : 0.f, k2 = training ? dgamma[c] * inv_n : 0.f;
     const size_t base = (size_t)row * hw;
     if (VEC) {
+        const int wpr = (hw / 4 + 7) / 8;
         for (int j = threadIdx.x; j < hw / 4; j += 256) {
             Vec4<T> g, yy, xx, o, r;
             g.load(dy + base + 4 * j);
             xx.load(x + base + 4 * j);
-            if (relu) yy.load(y + base + 4 * j);
+            unsigned bits = 0xfu;
+            if (relu) {
+                if (relu_mask != nullptr) {
+                    bits = (__ldg(relu_mask + (size_t)row * wpr + (j >> 3)) >> (4 * (j & 7))) & 0xfu;
+                } else {
+                    yy.load(y + base + 4 * j);
+                    bits = (yy.get(0) > 0.f ? 1u : 0u) | (yy.get(1) > 0.f ? 2u : 0u) | (yy.get(2) > 0.f ? 4u : 0u) |
+                           (yy.get(3) > 0.f ? 8u : 0u);
+                }
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float gv = (!relu || yy.get(e) > 0.f) ? g.get(e) : 0.f;
+                const float gv = ((bits >> e) & 1u) ? g.get(e) : 0.f;
                 const float xh = (xx.get(e) - m) * is;
                 o.set(e, gi * (gv - k1 - xh * k2));
                 r.set(e, gv);
@@ -255,57 +291,65 @@ extern "C" int pm_bn_stats(const void* x, int B, int C, int hw, int dtype, float
     return 0;
 }
 
+extern "C" int pm_bn_mask_words(int B, int C, int hw) { return hw % 4 == 0 ? B * C * ((hw / 4 + 7) / 8) : 0; }
+
 extern "C" int pm_bn_apply(const void* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
-                           const void* residual, void* y, int relu, int B, int C, int hw, int dtype, void* stream) {
+                           const void* residual, void* y, uint32_t* relu_mask, int relu, int B, int C, int hw, int dtype,
+                           void* stream) {
     if (!x || !mean || !invstd || !gamma || !beta || !y) return PM_ERR_NULL;
     if (int e = bn_check(B, C, hw, dtype)) return e;
     const bool vec = pm::vec_ok(hw, x, residual, y, nullptr, nullptr, dtype);
+    if (relu_mask != nullptr && !vec) return PM_ERR_ALIGN;  // the packed mask exists only on the vector path
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == PM_F32) {
-        if (vec) pm::bn_apply_kernel<float, true><<<B * C, 256, 0, st>>>((const float*)x, mean, invstd, gamma, beta, (const float*)residual, (float*)y, relu, C, hw);
-        else pm::bn_apply_kernel<float, false><<<B * C, 256, 0, st>>>((const float*)x, mean, invstd, gamma, beta, (const float*)residual, (float*)y, relu, C, hw);
+        if (vec) pm::bn_apply_kernel<float, true><<<B * C, 256, 0, st>>>((const float*)x, mean, invstd, gamma, beta, (const float*)residual, (float*)y, relu_mask, relu, C, hw);
+        else pm::bn_apply_kernel<float, false><<<B * C, 256, 0, st>>>((const float*)x, mean, invstd, gamma, beta, (const float*)residual, (float*)y, relu_mask, relu, C, hw);
     } else {
         typedef __nv_bfloat16 bf;
-        if (vec) pm::bn_apply_kernel<bf, true><<<B * C, 256, 0, st>>>((const bf*)x, mean, invstd, gamma, beta, (const bf*)residual, (bf*)y, relu, C, hw);
-        else pm::bn_apply_kernel<bf, false><<<B * C, 256, 0, st>>>((const bf*)x, mean, invstd, gamma, beta, (const bf*)residual, (bf*)y, relu, C, hw);
+        if (vec) pm::bn_apply_kernel<bf, true><<<B * C, 256, 0, st>>>((const bf*)x, mean, invstd, gamma, beta, (const bf*)residual, (bf*)y, relu_mask, relu, C, hw);
+        else pm::bn_apply_kernel<bf, false><<<B * C, 256, 0, st>>>((const bf*)x, mean, invstd, gamma, beta, (const bf*)residual, (bf*)y, relu_mask, relu, C, hw);
     }
     PM_CHECK_LAUNCH();
     return 0;
 }
 
-extern "C" int pm_bn_bwd_reduce(const void* dy, const void* y, const void* x, const float* mean, const float* invstd,
-                                int relu, float* dgamma, float* dbeta, int B, int C, int hw, int dtype, void* stream) {
-    if (!dy || !x || !mean || !invstd || !dgamma || !dbeta || (relu && !y)) return PM_ERR_NULL;
+extern "C" int pm_bn_bwd_reduce(const void* dy, const void* y, const uint32_t* relu_mask, const void* x, const float* mean,
+                                const float* invstd, int relu, float* dgamma, float* dbeta, int B, int C, int hw, int dtype,
+                                void* stream) {
+    if (!dy || !x || !mean || !invstd || !dgamma || !dbeta || (relu && !y && !relu_mask)) return PM_ERR_NULL;
     if (int e = bn_check(B, C, hw, dtype)) return e;
     const bool vec = pm::vec_ok(hw, dy, y, x, nullptr, nullptr, dtype);
+    if (relu && !y && !vec) return PM_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == PM_F32) {
-        if (vec) pm::bn_bwd_reduce_kernel<float, true><<<C, pm::BN_THREADS, 0, st>>>((const float*)dy, (const float*)y, (const float*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw);
-        else pm::bn_bwd_reduce_kernel<float, false><<<C, pm::BN_THREADS, 0, st>>>((const float*)dy, (const float*)y, (const float*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw);
+        if (vec) pm::bn_bwd_reduce_kernel<float, true><<<C, pm::BN_THREADS, 0, st>>>((const float*)dy, (const float*)y, relu_mask, (const float*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw);
+        else pm::bn_bwd_reduce_kernel<float, false><<<C, pm::BN_THREADS, 0, st>>>((const float*)dy, (const float*)y, relu_mask, (const float*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw);
     } else {
         typedef __nv_bfloat16 bf;
-        if (vec) pm::bn_bwd_reduce_kernel<bf, true><<<C, pm::BN_THREADS, 0, st>>>((const bf*)dy, (const bf*)y, (const bf*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw);
-        else pm::bn_bwd_reduce_kernel<bf, false><<<C, pm::BN_THREADS, 0, st>>>((const bf*)dy, (const bf*)y, (const bf*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw);
+        if (vec) pm::bn_bwd_reduce_kernel<bf, true><<<C, pm::BN_THREADS, 0, st>>>((const bf*)dy, (const bf*)y, relu_mask, (const bf*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw);
+        else pm::bn_bwd_reduce_kernel<bf, false><<<C, pm::BN_THREADS, 0, st>>>((const bf*)dy, (const bf*)y, relu_mask, (const bf*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw);
     }
     PM_CHECK_LAUNCH();
     return 0;
 }
 
-extern "C" int pm_bn_bwd_apply(const void* dy, const void* y, const void* x, const float* mean, const float* invstd,
-                               const float* gamma, const float* dgamma, const float* dbeta, int relu, int training,
-                               void* dx, void* dres, int B, int C, int hw, int dtype, void* stream) {
-    if (!dy || !x || !mean || !invstd || !gamma || !dgamma || !dbeta || !dx || (relu && !y)) return PM_ERR_NULL;
+extern "C" int pm_bn_bwd_apply(const void* dy, const void* y, const uint32_t* relu_mask, const void* x, const float* mean,
+                               const float* invstd, const float* gamma, const float* dgamma, const float* dbeta, int relu,
+                               int training, void* dx, void* dres, int B, int C, int hw, int dtype, void* stream) {
+    if (!dy || !x || !mean || !invstd || !gamma || !dgamma || !dbeta || !dx || (relu && !y && !relu_mask))
+        return PM_ERR_NULL;
     if (int e = bn_check(B, C, hw, dtype)) return e;
     const bool vec = pm::vec_ok(hw, dy, y, x, dx, dres, dtype);
+    if (relu && !y && !vec) return PM_ERR_ALIGN;
     const float inv_n = 1.f / ((float)B * (float)hw);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == PM_F32) {
-        if (vec) pm::bn_bwd_apply_kernel<float, true><<<B * C, 256, 0, st>>>((const float*)dy, (const float*)y, (const float*)x, mean, invstd, gamma, dgamma, dbeta, relu, training, inv_n, (float*)dx, (float*)dres, C, hw);
-        else pm::bn_bwd_apply_kernel<float, false><<<B * C, 256, 0, st>>>((const float*)dy, (const float*)y, (const float*)x, mean, invstd, gamma, dgamma, dbeta, relu, training, inv_n, (float*)dx, (float*)dres, C, hw);
+        if (vec) pm::bn_bwd_apply_kernel<float, true><<<B * C, 256, 0, st>>>((const float*)dy, (const float*)y, relu_mask, (const float*)x, mean, invstd, gamma, dgamma, dbeta, relu, training, inv_n, (float*)dx, (float*)dres, C, hw);
+        else pm::bn_bwd_apply_kernel<float, false><<<B * C, 256, 0, st>>>((const float*)dy, (const float*)y, relu_mask, (const float*)x, mean, invstd, gamma, dgamma, dbeta, relu, training, inv_n, (float*)dx, (float*)dres, C, hw);
     } else {
         typedef __nv_bfloat16 bf;
-        if (vec) pm::bn_bwd_apply_kernel<bf, true><<<B * C, 256, 0, st>>>((const bf*)dy, (const bf*)y, (const bf*)x, mean, invstd, gamma, dgamma, dbeta, relu, training, inv_n, (bf*)dx, (bf*)dres, C, hw);
-        else pm::bn_bwd_apply_kernel<bf, false><<<B * C, 256, 0, st>>>((const bf*)dy, (const bf*)y, (const bf*)x, mean, invstd, gamma, dgamma, dbeta, relu, training, inv_n, (bf*)dx, (bf*)dres, C, hw);
+        if (vec) pm::bn_bwd_apply_kernel<bf, true><<<B * C, 256, 0, st>>>((const bf*)dy, (const bf*)y, relu_mask, (const bf*)x, mean, invstd, gamma, dgamma, dbeta, relu, training, inv_n, (bf*)dx, (bf*)dres, C, hw);
+        else pm::bn_bwd_apply_kernel<bf, false><<<B * C, 256, 0, st>>>((const bf*)dy, (const bf*)y, relu_mask, (const bf*)x, mean, invstd, gamma, dgamma, dbeta, relu, training, inv_n, (bf*)dx, (bf*)dres, C, hw);
     }
     PM_CHECK_LAUNCH();
     return 0;

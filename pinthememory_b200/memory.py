@@ -190,22 +190,30 @@ class _BnActFn(torch.autograd.Function):
             mean = running_mean.to(torch.float32).contiguous()
             invstd = (running_var.to(torch.float32) + eps).rsqrt_()
         y = torch.empty_like(xc)
-        capi.bn_apply(xc, mean, invstd, g32, b32, residual, y, relu)
+        # packed ReLU mask (1 bit per element) for the backward, so that it does not have to re-read y
+        nwords = capi.bn_mask_words(xc.shape[0], C, xc.shape[2] * xc.shape[3]) if relu else 0
+        vec_ok = nwords > 0 and all(t is None or t.data_ptr() % 16 == 0 for t in (xc, y, residual))
+        mask = torch.empty(nwords, dtype=torch.int32, device=dev) if vec_ok else None
+        capi.bn_apply(xc, mean, invstd, g32, b32, residual, y, relu, relu_mask=mask)
         ctx.relu, ctx.training, ctx.has_res = relu, use_batch_stats, residual is not None
-        ctx.save_for_backward(xc, y, mean, invstd, g32)
+        ctx.use_mask = mask is not None
+        ctx.save_for_backward(xc, mask if mask is not None else y, mean, invstd, g32)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        xc, y, mean, invstd, g32 = ctx.saved_tensors
+        xc, y_or_mask, mean, invstd, g32 = ctx.saved_tensors
+        y, mask = (None, y_or_mask) if ctx.use_mask else (y_or_mask, None)
         C = xc.shape[1]
         dy = dy.to(xc.dtype).contiguous()
         dgamma = torch.empty(C, dtype=torch.float32, device=xc.device)
         dbeta = torch.empty(C, dtype=torch.float32, device=xc.device)
-        capi.bn_bwd_reduce(dy, y, xc, mean, invstd, ctx.relu, dgamma, dbeta)
         dx = torch.empty_like(xc)
         dres = torch.empty_like(xc) if (ctx.has_res and ctx.needs_input_grad[3]) else None
-        capi.bn_bwd_apply(dy, y, xc, mean, invstd, g32, dgamma, dbeta, ctx.relu, ctx.training, dx, dres)
+        if mask is not None and any(t is not None and t.data_ptr() % 16 for t in (dy, dx, dres)):
+            raise RuntimeError("pinmem_b200: misaligned gradient buffer on the packed-mask BatchNorm path")
+        capi.bn_bwd_reduce(dy, y, mask, xc, mean, invstd, ctx.relu, dgamma, dbeta)
+        capi.bn_bwd_apply(dy, y, mask, xc, mean, invstd, g32, dgamma, dbeta, ctx.relu, ctx.training, dx, dres)
         return dx, dgamma, dbeta, dres, None, None, None, None, None, None
 
 
