@@ -125,6 +125,21 @@ __device__ __forceinline__ void tile_load_async_mma(float* smem_tile, const floa
     }
 }
 
+// hi/lo split for 3xTF32. The tensor core ignores the low 13 mantissa bits of a TF32 operand, so the raw fp32
+// bits serve as "hi" (= x truncated to 10 mantissa bits) and lo = x - trunc(x) is exact in fp32: one LOP3 and one
+// FADD per value (cvt.rna.tf32 is emulated with ~5 instructions on sm_100 and bought nothing measurable).
+__device__ __forceinline__ unsigned tf32_hi(float x) { return __float_as_uint(x); }
+__device__ __forceinline__ unsigned tf32_lo(float x) {
+    return __float_as_uint(x - __uint_as_float(__float_as_uint(x) & 0xffffe000u));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0,
+                                         unsigned b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
 __device__ __forceinline__ float to_float(float v) { return v; }
 __device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
 __device__ __forceinline__ float tile_get(const float* t, int row, int px) { return t[row * 32 + px]; }

@@ -64,21 +64,6 @@ __device__ __forceinline__ void tile_dots(const T* xt, const float* Mt, int c0, 
 // k = t maps to channel 2t and k = t+4 to channel 2t+1 of an 8-channel step: with that choice the B fragments
 // read the existing Mt[c][KP=20] rows without bank conflicts, and the A fragments read the chunk-swizzled tile
 // (tile_load_async_mma) without bank conflicts. Writes this warp's partial sums straight into part / pn.
-// hi/lo split for 3xTF32. The tensor core ignores the low 13 mantissa bits of a TF32 operand, so the raw fp32
-// bits serve as "hi" (= x truncated to 10 mantissa bits) and lo = x - trunc(x) is exact in fp32: one LOP3 and one
-// FADD per value (cvt.rna.tf32 is emulated with ~5 instructions on sm_100 and bought nothing measurable).
-__device__ __forceinline__ unsigned tf32_hi(float x) { return __float_as_uint(x); }
-__device__ __forceinline__ unsigned tf32_lo(float x) {
-    return __float_as_uint(x - __uint_as_float(__float_as_uint(x) & 0xffffe000u));
-}
-__device__ __forceinline__ void mma_tf32(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0,
-                                         unsigned b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-
 template <int CW, int KP>
 __device__ __forceinline__ void tile_dots_mma(const float* xt, const float* Mt, int c0, int lane, float* part_w,
                                               float* pn_w) {

@@ -195,6 +195,215 @@ __global__ void __launch_bounds__(C) write_reduce_tiled_kernel(const T* __restri
     }
 }
 
+// ---- tensor-core variant (fp32): S[class][channel] += Omega^T[class][px] . V[px][channel] -----------------------
+// The class sums ARE a skinny GEMM (the reference computes them with torch.matmul, memory.py:227): per tile of
+// 32 pixels, M = classes (one or two 16-row tiles), N = channels (each warp 32 = four 8-column tiles), K = pixels.
+// mma.sync m16n8k8 TF32 with 3xTF32 compensation (see pm_read_tiled.cu); accumulators stay in registers across
+// all tiles of the persistent CTA. The soft label weights of a tile are expanded to a dense [32 px][40] table
+// in shared memory (row stride 40: conflict-free A fragments), B fragments come straight from the
+// chunk-swizzled f tile (conflict-free) and are scaled by 1/|f| on the fly. Cost no longer depends on how
+// fragmented the label map is (the run-length kernel above degenerates on noisy labels).
+
+template <int C, int KP>
+__global__ void __launch_bounds__(C) write_reduce_mma_kernel(const float* __restrict__ f, const long long* __restrict__ labels,
+                                                              float* __restrict__ SD, int h, int w, int Hm, int Wm,
+                                                              int K, float sy, float sx, int tiles_per_img,
+                                                              int ntiles) {
+    constexpr int NSTAGE = 2, NW = C / 32, CS = C + 4, OMLD = 40;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    float* om = reinterpret_cast<float*>(smraw);      // [32 px][OMLD] dense label weights of the current tile
+    float* pn = om + 32 * OMLD;                        // [NW][32]
+    float* invr = pn + NW * 32;                        // [32]
+    unsigned* cmask = reinterpret_cast<unsigned*>(invr + 32);  // [4]
+    float* ft = reinterpret_cast<float*>(cmask + 4);   // [NSTAGE][C][32] swizzled; reused as S_tile [32][CS] at the end
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, hw = h * w;
+    const int g = lane >> 2, t = lane & 3;
+    float acc[2][4][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) acc[m][n][0] = acc[m][n][1] = acc[m][n][2] = acc[m][n][3] = 0.f;
+    float Dacc = 0.f;  // lane = class, partial over this warp's pixels
+    unsigned seen = 0u;
+
+    auto tile_coords = [&](int tl, int& b, int& px0) {
+        b = tl / tiles_per_img;
+        px0 = (tl - b * tiles_per_img) * 32;
+    };
+    auto taps_for = [&](int tl) {
+        LabelTaps r;
+        int b, px0;
+        tile_coords(tl, b, px0);
+        const int px = px0 + lane;
+        if (tl < ntiles && px < hw) {
+            const int fy = px / w, fx = px - fy * w;
+            r = label_taps(labels + (size_t)b * Hm * Wm, Hm, Wm, fy, fx, sy, sx, K);
+        } else {
+            r.cls[0] = r.cls[1] = r.cls[2] = r.cls[3] = K;
+            r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0.f;
+        }
+        return r;
+    };
+
+    int tile = blockIdx.x;
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) {
+        const int tl = tile + s * gridDim.x;
+        if (tl < ntiles) {
+            int b, px0;
+            tile_coords(tl, b, px0);
+            tile_load_async_swz<float, C, C>(ft + s * C * 32, f + (size_t)b * C * hw, hw, px0);
+        }
+        cp_async_commit();
+    }
+    LabelTaps tcur;
+    if (wid == 0) tcur = taps_for(tile);
+
+    int stage = 0;
+    for (; tile < ntiles; tile += gridDim.x) {
+        LabelTaps tnext;
+        if (wid == 0) tnext = taps_for(tile + gridDim.x);  // loads in flight across this tile
+        cp_async_wait<NSTAGE - 1>();
+        __syncthreads();
+        const float* xt = ft + stage * C * 32;
+        for (int i = tid; i < 32 * OMLD / 4; i += C) reinterpret_cast<float4*>(om)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        {  // |f|^2 per pixel: lanes = pixels, each warp sums 32 of the C rows (rows wid, wid+NW, .. share a swizzle
+           // phase when NW % 8 == 0)
+            float n2 = 0.f;
+            if (NW % 8 == 0) {
+                const float* col = xt + wid * 32 + (((lane >> 2) ^ (wid & 7)) << 2) + (lane & 3);
+#pragma unroll 8
+                for (int i = 0; i < C / NW; ++i) {
+                    const float v = col[i * NW * 32];
+                    n2 = fmaf(v, v, n2);
+                }
+            } else {
+                for (int c = wid; c < C; c += NW) {
+                    const float v = xt[c * 32 + (((lane >> 2) ^ (c & 7)) << 2) + (lane & 3)];
+                    n2 = fmaf(v, v, n2);
+                }
+            }
+            pn[wid * 32 + lane] = n2;
+        }
+        __syncthreads();
+        if (wid == 0) {
+            float sacc = 0.f;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) sacc += pn[i * 32 + lane];
+            invr[lane] = 1.f / fmaxf(sqrtf(sacc), PM_NORM_EPS);
+            unsigned m = 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (tcur.w[j] != 0.f) {  // merged taps: distinct classes per pixel
+                    om[lane * OMLD + tcur.cls[j]] = tcur.w[j];
+                    m |= 1u << tcur.cls[j];
+                }
+            m = __reduce_or_sync(0xffffffffu, m);
+            if (lane == 0) cmask[0] = m;
+        }
+        __syncthreads();
+        const unsigned cm = cmask[0];
+        seen |= cm;
+        const bool hi_tile = (cm >> 16) != 0u;  // classes 16.. present in this tile (warp-uniform)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const float ir0 = invr[8 * ks + t], ir1 = invr[8 * ks + t + 4];
+            unsigned ah[2][4], al[2][4];
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                if (m == 0 || hi_tile) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float v = om[(8 * ks + t + 4 * (e >> 1)) * OMLD + 16 * m + g + 8 * (e & 1)];
+                        ah[m][e] = tf32_hi(v);
+                        al[m][e] = tf32_lo(v);
+                    }
+                }
+            }
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                const float* row = xt + (wid * 32 + 8 * n + g) * 32 + t;
+                const float b0 = row[((2 * ks) ^ g) << 2] * ir0, b1 = row[((2 * ks + 1) ^ g) << 2] * ir1;
+                const unsigned b0h = tf32_hi(b0), b1h = tf32_hi(b1), b0l = tf32_lo(b0), b1l = tf32_lo(b1);
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    if (m == 0 || hi_tile) {
+                        mma_tf32(acc[m][n], al[m][0], al[m][1], al[m][2], al[m][3], b0h, b1h);
+                        mma_tf32(acc[m][n], ah[m][0], ah[m][1], ah[m][2], ah[m][3], b0l, b1l);
+                        mma_tf32(acc[m][n], ah[m][0], ah[m][1], ah[m][2], ah[m][3], b0h, b1h);
+                    }
+                }
+            }
+        }
+        {  // soft counts: lane = class, every warp sums its own 32/NW pixels (combined at the end)
+#pragma unroll
+            for (int px = wid; px < 32; px += NW) Dacc += om[px * OMLD + lane];
+        }
+        __syncthreads();  // stage and label table consumed
+        const int next = tile + NSTAGE * gridDim.x;
+        if (next < ntiles) {
+            int nb, npx0;
+            tile_coords(next, nb, npx0);
+            tile_load_async_swz<float, C, C>(ft + stage * C * 32, f + (size_t)nb * C * hw, hw, npx0);
+        }
+        cp_async_commit();
+        if (wid == 0) tcur = tnext;
+        stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    // accumulators -> shared [32][CS] (over the tile ring), then one vector RED per touched class row
+    float* S_tile = ft;
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            const int ch = wid * 32 + 8 * n + 2 * t;
+            *reinterpret_cast<float2*>(S_tile + (16 * m + g) * CS + ch) = make_float2(acc[m][n][0], acc[m][n][1]);
+            *reinterpret_cast<float2*>(S_tile + (16 * m + g + 8) * CS + ch) = make_float2(acc[m][n][2], acc[m][n][3]);
+        }
+    pn[wid * 32 + lane] = Dacc;  // pn is free now
+    __syncthreads();
+    if (wid == 0) {
+        float d = 0.f;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) d += pn[i * 32 + lane];
+        S_tile[lane * CS + C] = d;
+        S_tile[lane * CS + C + 1] = S_tile[lane * CS + C + 2] = S_tile[lane * CS + C + 3] = 0.f;
+    }
+    __syncthreads();
+    for (int k = 0; k <= K; ++k) {
+        if (!((seen >> k) & 1u)) continue;
+        for (int i = tid; i < CS / 4; i += C)
+            atomicAdd(reinterpret_cast<float4*>(SD + (size_t)k * CS) + i,
+                      reinterpret_cast<const float4*>(S_tile + k * CS)[i]);
+    }
+}
+
+template <int C, int KP>
+int launch_write_reduce_mma(const void* f, const int64_t* labels, float* SD, int B, int h, int w, int Hm, int Wm, int K,
+                            cudaStream_t st) {
+    const size_t ring = sizeof(float) * (size_t)2 * C * 32, stile = sizeof(float) * (size_t)32 * (C + 4);
+    const size_t smem = sizeof(float) * (32 * 40 + (C / 32) * 32 + 32 + 4) + (ring > stile ? ring : stile);
+    auto kern = write_reduce_mma_kernel<C, KP>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int hw = h * w, tiles = (hw + 31) / 32, ntiles = B * tiles;
+    int per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C, smem);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    int grid = 148 * per_sm;
+    if (grid > ntiles) grid = ntiles;
+    const float sy = h > 1 ? (float)(Hm - 1) / (float)(h - 1) : 0.f;
+    const float sx = w > 1 ? (float)(Wm - 1) / (float)(w - 1) : 0.f;
+    kern<<<grid, C, smem, st>>>((const float*)f, (const long long*)labels, SD, h, w, Hm, Wm, K, sy, sx, tiles, ntiles);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
 template <typename T, int C, int KP>
 int launch_write_reduce_tiled(const void* f, const int64_t* labels, float* SD, int B, int h, int w, int Hm, int Wm,
                               int K, cudaStream_t st) {
@@ -391,8 +600,13 @@ int launch_write_bwd_tiled(const float* dS, const void* f, const int64_t* labels
 int write_reduce_tiled(const void* f, const int64_t* labels, float* SD, int B, int C, int h, int w, int Hm, int Wm,
                        int K, int dtype, cudaStream_t st) {
     if (dtype == PM_F32) {
-        if (K <= 19) { PM_WT_SWITCH_C(float, 20, launch_write_reduce_tiled, f, labels, SD, B, h, w, Hm, Wm, K, st) }
-        else { PM_WT_SWITCH_C(float, 32, launch_write_reduce_tiled, f, labels, SD, B, h, w, Hm, Wm, K, st) }
+        switch (C) {  // tensor-core variant for every fp32 case (K + 1 <= 32 classes fit two 16-row MMA tiles)
+            case 32: return launch_write_reduce_mma<32, 32>(f, labels, SD, B, h, w, Hm, Wm, K, st);
+            case 64: return launch_write_reduce_mma<64, 32>(f, labels, SD, B, h, w, Hm, Wm, K, st);
+            case 128: return launch_write_reduce_mma<128, 32>(f, labels, SD, B, h, w, Hm, Wm, K, st);
+            case 256: return launch_write_reduce_mma<256, 32>(f, labels, SD, B, h, w, Hm, Wm, K, st);
+            default: return PM_ERR_CHANNELS;
+        }
     } else {
         if (K <= 19) { PM_WT_SWITCH_C(__nv_bfloat16, 20, launch_write_reduce_tiled, f, labels, SD, B, h, w, Hm, Wm, K, st) }
         else { PM_WT_SWITCH_C(__nv_bfloat16, 32, launch_write_reduce_tiled, f, labels, SD, B, h, w, Hm, Wm, K, st) }
