@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--workload", default="cfg2_module_os8_b8", choices=sorted(synth.WORKLOADS))
     ap.add_argument("--labels", default="blocky", choices=["blocky", "iid"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="headline = kernel-by-kernel launches instead of the CUDA graph")
     return ap.parse_args()
 
 
@@ -313,10 +314,33 @@ def main():
             ms = float(t.item())
         return ms, launches, ktimes, (sampler.summary() if sampler else None)
 
-    # headline: whole module, device-resident inputs
+    # whole module, device-resident inputs, one Python-side launch per kernel
     ms, launches, _, clocks = timed(lambda: module_step(x, labels), args.steps, args.warmup, sample_clocks=True)
     ms_per_step = ms / args.steps
     value = world * N / (ms_per_step * 1e-3) / 1e6
+    eager_launch = {"value": value, "unit": UNIT, "ms_per_step": ms_per_step, "gpu_launches": launches,
+                    "what": "the same step launched kernel by kernel from Python (no CUDA graph)"}
+
+    # headline: the same step captured once into a CUDA graph (pinthememory_b200.graphed.GraphedStep: forward,
+    # the weighted losses, backward, memory carried from step to step) and replayed -- identical kernels and
+    # work, without the host launch gaps
+    graph_info = None
+    if not args.no_graph:
+        try:
+            from pinthememory_b200.graphed import GraphedStep
+
+            mem.m_items = M0.clone()
+            gstep = GraphedStep(mem, x, labels, G, loss_weights=(LOSS_W["read"], LOSS_W["div"], LOSS_W["cls"]),
+                                memory_writing=True, writing_detach=False, carry_memory=True,
+                                autocast_dtype=torch.bfloat16 if dt == torch.bfloat16 else None)
+            ms_g, _, _, clocks_g = timed(gstep.replay, args.steps, args.warmup, sample_clocks=True)
+            graph_info = {"kernels_per_replay": gstep.kernels_per_replay}
+            ms_per_step = ms_g / args.steps
+            value = world * N / (ms_per_step * 1e-3) / 1e6
+            launches = gstep.kernels_per_replay * args.steps
+            clocks = clocks_g
+        except Exception as e:  # report the eagerly launched number rather than nothing
+            graph_info = {"error": str(e)[:300]}
 
     # per-kernel durations measured live (events around every C-ABI launch) in a second timed region
     ms_k, _, ktimes, _ = timed(lambda: module_step(x, labels), args.steps, 2, kernel_timing=True)
@@ -395,7 +419,10 @@ def main():
 
     line = dict(base)
     line.update({"value": value, "ms_per_step": ms_per_step, "gpu_launches": launches, "clocks": clocks,
-                 "e2e": e2e, "roofline": roofline, "core": core, "kernels": kernels})
+                 "e2e": e2e, "roofline": roofline, "core": core, "kernels": kernels, "eager_launch": eager_launch,
+                 "cuda_graph": graph_info})
+    line["config"]["launch"] = ("CUDA graph replay of the whole step (GraphedStep)" if graph_info and "error" not in graph_info
+                                else "one Python-side launch per kernel")
 
     if rank == 0 and world == 1:
         # like-for-like GPU comparison: the oracle restatement (eager torch ops) on the same B200

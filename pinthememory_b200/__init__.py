@@ -1,7 +1,7 @@
 """pinthememory_b200 -- B200-native categorical class memory (drop-in for the reference's network/memory.py)."""
 import sys
 
-__all__ = ["Memory_sup", "Writingnet", "initialize_weights", "install", "enable_sharded_update"]
+__all__ = ["Memory_sup", "Writingnet", "initialize_weights", "install", "enable_sharded_update", "GraphedStep"]
 
 
 def __getattr__(name):
@@ -14,6 +14,10 @@ def __getattr__(name):
         from .sharding import enable_sharded_update
 
         return enable_sharded_update
+    if name == "GraphedStep":
+        from .graphed import GraphedStep
+
+        return GraphedStep
     raise AttributeError(name)
 
 
