@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--workload", default="cfg2_module_os8_b8", choices=sorted(synth.WORKLOADS))
     ap.add_argument("--labels", default="blocky", choices=["blocky", "iid"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-callers", action="store_true", help="skip the timings of the callers (main loss, prototype pooling)")
     ap.add_argument("--no-graph", action="store_true", help="headline = kernel-by-kernel launches instead of the CUDA graph")
     return ap.parse_args()
 
@@ -423,6 +424,38 @@ def main():
                  "cuda_graph": graph_info})
     line["config"]["launch"] = ("CUDA graph replay of the whole step (GraphedStep)" if graph_info and "error" not in graph_info
                                 else "one Python-side launch per kernel")
+
+    if rank == 0 and world == 1 and not args.no_callers:
+        # the callers either side of the path that run on the same kernels
+        try:
+            import torch.nn.functional as F
+
+            from pinthememory_b200.callers import PrototypePool, upsampled_cross_entropy
+
+            lg = (torch.randn(B, K, Hm // 4, Wm // 4, device=dev) * 3).requires_grad_(True)
+
+            def fused_loss():
+                lg.grad = None
+                upsampled_cross_entropy(lg, labels).backward()
+
+            def eager_loss():
+                lg.grad = None
+                up = F.interpolate(lg, size=(Hm, Wm), mode="bilinear", align_corners=True)
+                F.cross_entropy(up, labels, ignore_index=255).backward()
+
+            ms_f, _, _, _ = timed(fused_loss, 10, 3)
+            ms_t, _, _, _ = timed(eager_loss, 10, 3)
+            pool = PrototypePool(K, C, dev)
+            ms_p, _, _, _ = timed(lambda: pool.add(x, labels), 10, 3)
+            line["callers"] = {
+                "main_loss_fwd_bwd": {"fused_ms": ms_f / 10, "torch_eager_ms": ms_t / 10,
+                                      "what": "CE(bilinear_up(logits [%d,%d,%d,%d] -> %dx%d), labels) forward+backward; "
+                                              "pm_readloss_fwd vs F.interpolate+F.cross_entropy on this GPU"
+                                              % (B, K, Hm // 4, Wm // 4, Hm, Wm)},
+                "prototype_pool_add": {"ms": ms_p / 10, "Mpixels_per_s": N / (ms_p / 10 * 1e-3) / 1e6,
+                                       "what": "memory_initalize pooling of one batch (pm_write_reduce_fwd accumulating)"}}
+        except Exception as e:
+            line["callers"] = {"error": str(e)[:300]}
 
     if rank == 0 and world == 1:
         # like-for-like GPU comparison: the oracle restatement (eager torch ops) on the same B200

@@ -1,7 +1,8 @@
 """pinthememory_b200 -- B200-native categorical class memory (drop-in for the reference's network/memory.py)."""
 import sys
 
-__all__ = ["Memory_sup", "Writingnet", "initialize_weights", "install", "enable_sharded_update", "GraphedStep"]
+__all__ = ["Memory_sup", "Writingnet", "initialize_weights", "install", "enable_sharded_update", "GraphedStep", "PrototypePool", "initialize_memory",
+           "upsampled_cross_entropy"]
 
 
 def __getattr__(name):
@@ -14,6 +15,10 @@ def __getattr__(name):
         from .sharding import enable_sharded_update
 
         return enable_sharded_update
+    if name in ("PrototypePool", "initialize_memory", "upsampled_cross_entropy"):
+        from . import callers
+
+        return getattr(callers, name)
     if name == "GraphedStep":
         from .graphed import GraphedStep
 
