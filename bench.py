@@ -325,7 +325,7 @@ def main():
     # headline: the same step captured once into a CUDA graph (pinthememory_b200.graphed.GraphedStep: forward,
     # the weighted losses, backward, memory carried from step to step) and replayed -- identical kernels and
     # work, without the host launch gaps
-    graph_info = None
+    graph_info = gstep = None
     if not args.no_graph:
         try:
             from pinthememory_b200.graphed import GraphedStep
@@ -485,9 +485,19 @@ def main():
             line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "port",
                                     "sample": cb["sample"], "ms_per_step": cb["ms_per_step"]}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        # a live graph that captured the all-reduce keeps the NCCL communicator busy: release it first, and
+        # never let a stuck teardown hold the job (the result line is already out)
+        import threading
+
+        threading.Timer(30.0, lambda: os._exit(0)).start()
+        if gstep is not None:
+            gstep.release()
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 if __name__ == "__main__":

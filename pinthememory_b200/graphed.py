@@ -117,6 +117,8 @@ class GraphedStep:
 
     def replay(self):
         """Run the captured step on whatever the static input buffers hold; returns the static outputs."""
+        if self.graph is None:
+            raise RuntimeError("pinmem_b200: this GraphedStep was released")
         self.graph.replay()
         self.module.m_items = self.memory
         if self.backward:
@@ -124,6 +126,15 @@ class GraphedStep:
             for p, g in zip(self._params, self.param_grads):
                 p.grad = g
         return self.outputs
+
+    def release(self):
+        """Free the captured graph. Required before ``destroy_process_group()`` when the step contains the
+        sharded update: NCCL will not tear down a communicator that a live graph still references (it hangs)."""
+        if self.graph is not None:
+            torch.cuda.synchronize()
+            self.graph.reset()
+            self.graph = None
+        self.outputs = None
 
     def __call__(self, query=None, mask=None, grad_updated_query=None):
         if query is not None:
