@@ -358,8 +358,8 @@ def main():
         # the fused BatchNorm passes run once per conv block (2 per step); bytes are the mean of the two calls
         "pm_bn_stats": N * C * esz,
         "pm_bn_apply": N * C * esz * 2.5,        # x (+ residual in one of the two blocks) -> y
-        "pm_bn_bwd_reduce": N * C * esz * 3,     # dy, y, x
-        "pm_bn_bwd_apply": N * C * esz * 4.5,    # dy, y, x -> dx (+ dres in one of the two blocks)
+        "pm_bn_bwd_reduce": N * C * esz * 2,     # dy, x (+ the packed ReLU mask, 1/32)
+        "pm_bn_bwd_apply": N * C * esz * 3.5,    # dy, x -> dx (+ dres in one of the two blocks)
     }
     bound_note = {
         "pm_readloss_fwd": "not HBM-bound by nature: ~19 ex2 + ~60 FMA per LABEL pixel (64 label pixels per feature "

@@ -2,6 +2,7 @@
 
     python profiles/summarize.py launches gpurun_out/launches_X.csv  > profiles/rN_launches.txt
     python profiles/summarize.py raw      gpurun_out/raw_X.csv       > profiles/rN_kernels.txt
+    python profiles/summarize.py traffic  gpurun_out/launches_X.csv  > profiles/ncu_traffic.json
 (raw csv = `ncu -i prof.ncu-rep --page raw --csv`)
 """
 import collections
@@ -23,12 +24,55 @@ def launches(path):
     lines = [l for l in open(path) if not l.startswith("==")]
     d = collections.defaultdict(list)
     for row in csv.DictReader(lines):
+        if row.get("Metric Name", "gpu__time_duration.sum") != "gpu__time_duration.sum":
+            continue
         d[row["Kernel Name"][:90]].append(float(row["Metric Value"].replace(",", "")))
     tot = sum(sum(v) for v in d.values())
     print("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES)")
     print("%-92s %5s %10s %10s %6s" % ("kernel", "n", "avg_us", "total_us", "share"))
     for k, v in sorted(d.items(), key=lambda kv: -sum(kv[1])):
         print("%-92s %5d %10.1f %10.1f %5.1f%%" % (k, len(v), sum(v) / len(v) / 1e3, sum(v) / 1e3, 100 * sum(v) / tot))
+
+
+ENTRY_OF = [("read_fwd_tiled_kernel", "pm_read_fwd"), ("read_fwd_kernel", "pm_read_fwd"),
+            ("colsoftmax_apply_kernel", "pm_colsoftmax_apply"), ("readloss_kernel", "pm_readloss_fwd"),
+            ("bn_stats_kernel", "pm_bn_stats"), ("bn_apply_kernel", "pm_bn_apply"),
+            ("write_reduce_mma_kernel", "pm_write_reduce_fwd"), ("write_reduce_tiled_kernel", "pm_write_reduce_fwd"),
+            ("update_fwd_kernel", "pm_update_fwd"), ("update_bwd_kernel", "pm_update_bwd"),
+            ("write_bwd_tiled_kernel", "pm_write_bwd"), ("bn_bwd_reduce_kernel", "pm_bn_bwd_reduce"),
+            ("bn_bwd_apply_kernel", "pm_bn_bwd_apply"), ("read_bwd_ds_tiled_kernel", "pm_read_bwd.ds"),
+            ("read_bwd_dx_tiled_kernel", "pm_read_bwd.dx")]
+
+
+def traffic(path, dtype="f32"):
+    """{dtype: {C-ABI entry: dram bytes (read+write) per launch}} from a launch csv that carries
+    dram__bytes_read.sum / dram__bytes_write.sum / gpu__time_duration.sum per launch (bench.py reads it)."""
+    import json
+
+    lines = [l for l in open(path) if not l.startswith("==")]
+    per = collections.defaultdict(lambda: collections.defaultdict(float))  # launch id -> metric -> value
+    name = {}
+    for row in csv.DictReader(lines):
+        v = float(row["Metric Value"].replace(",", ""))
+        unit = row.get("Metric Unit", "")
+        v *= {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "us": 1e3, "ms": 1e6, "ns": 1.0, "usecond": 1e3,
+              "nsecond": 1.0, "msecond": 1e6}.get(unit, 1.0)
+        per[row["ID"]][row["Metric Name"]] = v
+        name[row["ID"]] = row["Kernel Name"]
+    agg = collections.defaultdict(list)
+    for i, m in per.items():
+        for pat, ent in ENTRY_OF:
+            if pat in name[i]:
+                agg[ent].append((m.get("dram__bytes_read.sum", 0.0) + m.get("dram__bytes_write.sum", 0.0),
+                                 m.get("gpu__time_duration.sum", 0.0) / 1e3))
+                break
+    out, detail = {}, {}
+    for ent, v in agg.items():
+        out[ent] = sum(a for a, _ in v) / len(v)
+        detail[ent] = {"traffic": out[ent], "ncu_us": sum(b for _, b in v) / len(v), "launches_averaged": len(v)}
+    if "pm_read_bwd.ds" in out and "pm_read_bwd.dx" in out:
+        out["pm_read_bwd"] = out["pm_read_bwd.ds"] + out["pm_read_bwd.dx"]
+    print(json.dumps({dtype: out, "_detail_" + dtype: detail}, indent=1))
 
 
 def raw(path):
@@ -44,4 +88,4 @@ def raw(path):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "raw": raw, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
