@@ -152,6 +152,164 @@ def cpu_reference_run(wl, kind, steps, warmup, sample_B):
                        (B, wl["B"], wl["h"], wl["w"], wl["Hm"], wl["Wm"], len(times)))
 
 
+# ------------------------------------------------------------------------- eval read (BASELINE cfg 5)
+
+
+def eval_read_main(args, wl):
+    """`--workload cfg5_dr101v2_eval_b1`: the eval-mode memory read (no labels, no write, Gumbel read on as in
+    the reference's default) on one full-resolution Cityscapes feature map per GPU. No collective: replicas."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    B, h, w = wl["B"], wl["h"], wl["w"]
+    N = B * h * w
+    line = {"metric": "memory read fwd (eval, no labels) Mpixels/s", "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "data": "synthetic", "dtype": args.dtype,
+            "config": {"workload": "%s: per-GPU batch %d, %dx%d feature map (OS8 of 1024x2048), C=%d, K=%d, no labels, "
+                                   "gumbel read on, eval-mode BatchNorm; replicas only (no collective)" %
+                                   (args.workload, B, h, w, C, K),
+                       "l2": "L2 flushed between timed steps by writing a 256 MB buffer (the 100 MB working set fits L2)"}}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import memory_oracle as mo
+
+        torch.manual_seed(synth.SEED)
+        ora = mo.OracleMemorySup(K, C, C, 0.8, 1.0, True).eval()
+        x = synth.make_features(B, C, h, w)
+        times = []
+        with torch.no_grad():
+            for i in range(2 + args.steps):
+                t0 = time.perf_counter()
+                ora(x, None, False)
+                if i >= 2:
+                    times.append(time.perf_counter() - t0)
+        v = N * len(times) / sum(times) / 1e6
+        line.update({"impl": "reference", "value": v, "ms_per_step": 1e3 * sum(times) / len(times), "dtype": "f32",
+                     "gpu_launches": 0,
+                     "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                      "sample": "the full per-GPU step (B=%d), %d timed steps" % (B, len(times))},
+                     "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        print(json.dumps(line))
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    import torch.distributed as dist
+
+    from pinthememory_b200 import capi
+    from pinthememory_b200.graphed import GraphedStep
+    from pinthememory_b200.memory import Memory_sup
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dt = torch.float32 if args.dtype == "f32" else torch.bfloat16
+    esz = 4 if dt == torch.float32 else 2
+    torch.manual_seed(synth.SEED)
+    mem = Memory_sup(K, C, C, 0.8, 1.0, True).to(dev).eval()
+    x_host = synth.make_features(B, C, h, w, seed=synth.SEED + 100 * rank, dtype=dt).pin_memory()
+    x = x_host.to(dev)
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+    autocast = torch.autocast("cuda", dtype=torch.bfloat16, enabled=(dt == torch.bfloat16))
+
+    def eager_step(xin=x):
+        with torch.no_grad(), autocast:
+            return mem(xin, None, False)
+
+    def run(fn, steps, warmup, clocks=False):
+        """Each timed step is bracketed by its own events; the L2 flush between steps is not counted."""
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        sampler = ClockSampler(local_rank) if clocks else None
+        if sampler:
+            sampler.__enter__()
+        evs = []
+        for _ in range(steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.__exit__()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, (sampler.summary() if sampler else None)
+
+    ms_eager, _ = run(eager_step, args.steps, args.warmup)
+    capi.enable_kernel_timing(True)
+    capi.reset_counters()
+    run(eager_step, 20, 2)
+    ktimes = capi.kernel_timings_ms()
+    launches_per_step = capi.LAUNCHES / 22.0
+    capi.enable_kernel_timing(False)
+    gstep = GraphedStep(mem, x, None, memory_writing=False, autocast_dtype=torch.bfloat16 if dt == torch.bfloat16 else None)
+    ms_graph, clocks = run(gstep.replay, args.steps, args.warmup, clocks=True)
+
+    res_host = torch.empty(N, dtype=torch.uint8).pin_memory()
+
+    def e2e_step():
+        xin = x_host.to(dev, non_blocking=True)
+        out = eager_step(xin)
+        res_host.copy_(out[2].view(N, K).argmax(1).to(torch.uint8), non_blocking=True)
+
+    ms_e2e, _ = run(e2e_step, max(args.steps // 2, 5), 3)
+    peak, peak_src = measured_peaks()
+    kavg = {k: sum(v) / len(v) for k, v in ktimes.items()}
+    alg = {"pm_read_fwd": N * (3 * C * esz + 4 * 20 + 4 * K + 4 * K),      # x -> u, s, score_memory; Gumbel noise in
+           "pm_colsoftmax_apply": N * (4 * 20 + 4 * K + 4 * K),
+           "pm_bn_apply": N * C * esz * 2}
+    kernels = {k: {"ms": round(t, 5), **({"alg_MB": round(alg[k] / 1e6, 2), "GBps": round(alg[k] / t / 1e6, 1),
+                                          "frac": round(alg[k] / t / 1e6 / peak, 4)} if k in alg else {})}
+               for k, t in kavg.items()}
+    dom = max((k for k in kavg if k in alg), key=lambda k: kavg[k])
+    a_eval = 3 * C * esz + 8 * K
+    line.update({"value": world * N / (ms_graph * 1e-3) / 1e6, "ms_per_step": ms_graph,
+                 "gpu_launches": int(gstep.kernels_per_replay * args.steps), "clocks": clocks,
+                 "eager_launch": {"value": world * N / (ms_eager * 1e-3) / 1e6, "ms_per_step": ms_eager,
+                                  "gpu_launches_per_step": launches_per_step},
+                 "cuda_graph": {"kernels_per_replay": gstep.kernels_per_replay},
+                 "e2e": {"value": world * N / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_e2e,
+                         "h2d_bytes_per_step": x_host.numel() * x_host.element_size(), "d2h_bytes_per_step": N,
+                         "what": "pinned-host features in, per-pixel memory-slot argmax (uint8) out, every step"},
+                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
+                              "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                              "alg_bytes_per_launch": alg[dom], "launch_ms": kernels[dom]["ms"]},
+                 "module_frac_of_peak": {"a_eval_bytes_per_pixel": a_eval,
+                                         "frac": N * a_eval / (ms_graph * 1e-3) / 1e9 / peak},
+                 "kernels": kernels})
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import memory_oracle as mo
+
+        ora = mo.OracleMemorySup(K, C, C, 0.8, 1.0, True).eval()
+        xc = x_host.float()
+        times = []
+        with torch.no_grad():
+            for i in range(5):
+                t0 = time.perf_counter()
+                ora(xc, None, False)
+                if i >= 2:
+                    times.append(time.perf_counter() - t0)
+        line["cpu_baseline"] = {"value": N * len(times) / sum(times) / 1e6, "unit": UNIT, "cores": torch.get_num_threads(),
+                                "kind": "port", "sample": "the full per-GPU step (B=%d), 3 timed steps" % B}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    gstep.release()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 # -------------------------------------------------------------------------------------------- main
 
 
@@ -159,7 +317,7 @@ def main():
     args = parse()
     wl = synth.WORKLOADS[args.workload]
     if wl["Hm"] == 0:
-        raise SystemExit("bench.py measures the training path; pick a workload with labels")
+        return eval_read_main(args, wl)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

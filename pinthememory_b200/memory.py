@@ -95,6 +95,7 @@ class _ReadFn(torch.autograd.Function):
             hist = torch.zeros(K + 1, dtype=torch.int64, device=dev)
         ctx.K = K
         ctx.has_loss = labels is not None
+        ctx.set_materialize_grads(False)  # unused outputs (scores, histogram) arrive as None, not as zero fills
         ctx.save_for_backward(x, M, score_m, ds_rl, rl_out)
         ctx.mark_non_differentiable(score_q, score_m, hist)
         return u, score_q.view(B, h, w, K), score_m.view(B, h, w, K), readloss, hist
@@ -150,6 +151,7 @@ class _WriteFn(torch.autograd.Function):
         saved = torch.empty(2 * K, dtype=torch.float32, device=dev)
         capi.update_fwd(SD, M_old, momentum, W, b, M_new, losses, saved, C, K, aux=aux)
         ctx.K, ctx.momentum, ctx.group = K, momentum, group
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(f, labels, M_new, saved, W, b)
         ctx.mark_non_differentiable(SD)
         return M_new, losses[0], losses[1], SD
