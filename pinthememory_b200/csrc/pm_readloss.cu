@@ -24,8 +24,9 @@
 
 namespace pm {
 
-constexpr int RL_TX = 32;          // cells per CTA along x
-constexpr int RL_LDX = RL_TX + 1;  // taps per tile row
+// cells per CTA along x: template parameter TX = 32, or 16 when a 32-wide tiling would leave >= 16 columns of the
+// last tile empty (w = 48, the OS16 shape: 64 thread columns for 48 cells); a warp is 16 lane pairs = 16 cells of one
+// cell row in both cases, so all its lanes share the cell row and the row split.
 constexpr int RL_THREADS = 256;    // 128 cells x 2 slot halves
 constexpr int RL_CHUNK = 3;        // label pixels fetched ahead (cells are 8-9 / 16-17 pixels wide: 3 divides 9 and 18)
 
@@ -60,12 +61,12 @@ __device__ __forceinline__ int first_ge(int c, float scale, int n_out, int n_in)
     return y;
 }
 
-template <int KP>
+template <int KP, int RL_TX>
 __global__ void __launch_bounds__(RL_THREADS, 2)
     readloss_kernel(const float* __restrict__ s, const long long* __restrict__ labels, float inv_T, float temperature,
                     int h, int w, int Hm, int Wm, int K, float sy, float sx, int RS, int TYC, int tiles_x, int tiles_y,
                     float* __restrict__ ds_rl, unsigned long long* __restrict__ ws, float* __restrict__ out) {
-    constexpr int KH = KP / 2, NH2 = KH / 2, NT = RL_THREADS;
+    constexpr int KH = KP / 2, NH2 = KH / 2, NT = RL_THREADS, RL_LDX = RL_TX + 1;
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int tile_elems = (TYC + 1) * RL_LDX * KP;
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(RL_THREADS, 2)
     __syncthreads();
 
     const int half = tid & 1, pair = tid >> 1;
-    const int cxl = pair & 31, rest = pair >> 5;  // rest in [0, TYC*RS)
+    const int cxl = pair % RL_TX, rest = pair / RL_TX;  // rest in [0, TYC*RS)
     const int cyl = rest / RS, split = rest - cyl * RS;
     const int cy = fy0 + cyl, cx = fx0 + cxl;
     const bool active = (cy < h) && (cx < w);
@@ -364,8 +365,8 @@ __global__ void __launch_bounds__(RL_THREADS, 2)
     }
 }
 
-template <int KP>
-static int launch_readloss(const float* s, const long long* labels, float temperature, int B, int h, int w, int Hm,
+template <int KP, int RL_TX>
+static int launch_readloss_tx(const float* s, const long long* labels, float temperature, int B, int h, int w, int Hm,
                            int Wm, int K, float* ds_rl, unsigned long long* ws, float* out, cudaStream_t st) {
     // PyTorch's align_corners scale: (in-1)/(out-1) in fp32, 0 when out == 1
     const float sy = Hm > 1 ? (float)(h - 1) / (float)(Hm - 1) : 0.f;
@@ -375,19 +376,27 @@ static int launch_readloss(const float* s, const long long* labels, float temper
     const int rows_per_cell = h > 1 ? (Hm + h - 2) / (h - 1) : Hm;
     int RS = 1;
     while (RS < 4 && cells * RS * 2 < 148LL * 512 && RS * 2 <= rows_per_cell) RS *= 2;
-    const int TYC = 4 / RS;
+    const int TYC = (RL_THREADS / 2 / RL_TX) / RS;
     const int tiles_x = (w + RL_TX - 1) / RL_TX, tiles_y = (h + TYC - 1) / TYC;
-    const size_t smem = sizeof(float) * ((size_t)2 * (TYC + 1) * RL_LDX * KP + (size_t)4 * (KP / 2) * RL_THREADS +
+    const size_t smem = sizeof(float) * ((size_t)2 * (TYC + 1) * (RL_TX + 1) * KP + (size_t)4 * (KP / 2) * RL_THREADS +
                                          (size_t)KP * (RL_THREADS / 2) + KP + 8);
     const long long grid = (long long)B * tiles_x * tiles_y;
     if (grid > 0x7fffffffLL) return PM_ERR_SHAPE;
-    auto kern = readloss_kernel<KP>;
+    auto kern = readloss_kernel<KP, RL_TX>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<(int)grid, RL_THREADS, smem, st>>>(s, labels, 1.f / temperature, temperature, h, w, Hm, Wm, K, sy, sx, RS,
                                               TYC, tiles_x, tiles_y, ds_rl, ws, out);
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
+}
+
+template <int KP>
+static int launch_readloss(const float* s, const long long* labels, float temperature, int B, int h, int w, int Hm,
+                           int Wm, int K, float* ds_rl, unsigned long long* ws, float* out, cudaStream_t st) {
+    const int pad32 = (w + 31) / 32 * 32 - w;
+    if (pad32 >= 16) return launch_readloss_tx<KP, 16>(s, labels, temperature, B, h, w, Hm, Wm, K, ds_rl, ws, out, st);
+    return launch_readloss_tx<KP, 32>(s, labels, temperature, B, h, w, Hm, Wm, K, ds_rl, ws, out, st);
 }
 
 }  // namespace pm
