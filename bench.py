@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--labels", default="blocky", choices=["blocky", "iid"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-callers", action="store_true", help="skip the timings of the callers (main loss, prototype pooling)")
+    ap.add_argument("--overlap-write", action="store_true", help="write branch on a side stream (parallel graph branch)")
     ap.add_argument("--no-graph", action="store_true", help="headline = kernel-by-kernel launches instead of the CUDA graph")
     return ap.parse_args()
 
@@ -367,6 +368,7 @@ def main():
     torch.manual_seed(synth.SEED)
     mem = Memory_sup(K, C, C, 0.8, 1.0, False).to(dev)
     mem.train()
+    mem.overlap_write = bool(args.overlap_write)
     if world > 1:
         for p in mem.parameters():
             dist.broadcast(p.data, 0)

@@ -63,6 +63,9 @@ def draw_gumbel_pair(N, K, device):
     return g_query, g_memory
 
 
+_SIDE_STREAMS = {}  # device -> stream of the write branch (module-level: modules stay deep-copyable)
+
+
 class _ReadFn(torch.autograd.Function):
     """x, M (, labels, noise) -> u = [q ; p.M], score_query, score_memory, readloss, label histogram."""
 
@@ -302,6 +305,7 @@ class Memory_sup(nn.Module):
         self.m_items = F.normalize(torch.rand((memory_size, feature_dim), dtype=torch.float), dim=1).to(dev)
         initialize_weights(self)
         # extras (not in the reference)
+        self.overlap_write = False     # run the write branch on a side stream next to the read (see forward)
         self.shard_group = None        # set by sharding.enable_sharded_update()
         self.last_label_hist = None    # int64 [K+1] label histogram of the last read with labels
         self.last_class_sums = None    # fp32 [K+1, C+4] sums|counts of the last write (after all-reduce)
@@ -309,11 +313,38 @@ class Memory_sup(nn.Module):
     # ------------------------------------------------------------------------------------- forward
 
     def forward(self, query, mask=None, memory_writing=True, writing_detach=True):
+        if memory_writing and self.overlap_write and query.is_cuda:
+            return self._forward_two_streams(query, mask, writing_detach)
         updated_query, score_query, score_memory, readloss = self.read(query, mask, memory_writing)
         if memory_writing:
             writeloss = self.write(query, mask, writing_detach)
         else:
             writeloss = [0, 0]
+        return updated_query, score_query, score_memory, readloss, writeloss
+
+    def _forward_two_streams(self, query, mask, writing_detach):
+        """Read and write only share their inputs (the query, the labels, the OLD memory), so the write runs on a
+        side stream next to the read; autograd replays each branch's backward on the stream of its forward. Under
+        CUDA-graph capture the two become parallel branches of the graph -- small-grid kernels of one branch
+        (update, BatchNorm statistics, the 1x1-conv GEMMs) fill the SMs the other leaves idle."""
+        cur = torch.cuda.current_stream(query.device)
+        side = _SIDE_STREAMS.get(query.device)
+        if side is None:
+            side = _SIDE_STREAMS[query.device] = torch.cuda.Stream(device=query.device)
+        side.wait_stream(cur)                     # fork: the write depends only on what precedes this call
+        memory_in = self.m_items
+        updated_query, score_query, score_memory, readloss = self.read(query, mask, True)   # main stream
+        memory_after_read = self.m_items          # the detached view read() installed (memory.py:323-324)
+        with torch.cuda.stream(side):
+            self.m_items = memory_after_read
+            writeloss = self.write(query, mask, writing_detach)
+            for t in (query, mask, memory_in, memory_after_read):
+                if torch.is_tensor(t):
+                    t.record_stream(side)
+        cur.wait_stream(side)
+        for t in (self.m_items, self.last_class_sums, writeloss[0], writeloss[1]):
+            if torch.is_tensor(t):
+                t.record_stream(cur)
         return updated_query, score_query, score_memory, readloss, writeloss
 
     def _memory_for_kernels(self, device):

@@ -108,3 +108,33 @@ def test_graphed_gumbel_read_draws_fresh_noise_each_replay():
     b = step(x)["score_memory"].clone()
     assert not torch.equal(a, b)
     assert_close(a.sum(-1), torch.ones_like(a.sum(-1)), 1e-5, "rows sum to one")
+
+
+@pytest.mark.parametrize("graphed", [False, True])
+def test_two_stream_forward_matches_single_stream(graphed):
+    """overlap_write: the write branch on a side stream (a parallel branch when captured) changes nothing."""
+    from pinthememory_b200.graphed import GraphedStep
+
+    B, C, h, w, Hm, Wm, K = 2, 64, 12, 16, 48, 64, 19
+    plain, forked = _pair(K, C)
+    forked.overlap_write = True
+    batches = [(synth.make_features(B, C, h, w, seed=s, device="cuda"),
+                synth.make_labels(B, Hm, Wm, K, "blocky", seed=s + 1).cuda(),
+                synth.make_upstream_grad((B, C, h, w), seed=s + 2, device="cuda")) for s in (3, 40, 77)]
+    step = GraphedStep(forked, *batches[0], loss_weights=W, memory_writing=True, writing_detach=False) if graphed else None
+    for x, lab, G in batches:
+        uq, sq, sm, rl, wl, dx = _eager_step(plain, x, lab, G)
+        if graphed:
+            out = step(x, lab, G)
+            uq2, rl2, wl2, dx2 = out["updated_query"], out["readloss"], out["writeloss"], step.query_grad
+        else:
+            uq2, _, _, rl2, wl2, dx2 = _eager_step(forked, x, lab, G)
+        torch.cuda.synchronize()
+        assert_close(uq2, uq, 1e-5, "updated_query")
+        assert_close(rl2, rl, 1e-5, "readloss")
+        assert_close(wl2[0], wl[0], 1e-5, "div")
+        assert_close(wl2[1], wl[1], 1e-5, "cls")
+        assert_close(dx2, dx, 1e-5, "dx")
+        assert_close(forked.m_items, plain.m_items, 1e-5, "memory")
+        for (n, pa), pb in zip(plain.named_parameters(), forked.parameters()):
+            assert_close(pb.grad, pa.grad, 1e-4, "grad " + n)
