@@ -511,6 +511,9 @@ def main():
     alg_bytes = {  # ALGORITHMIC bytes per launch
         "pm_read_fwd": N * (3 * C * esz + 4 * KP + 4 * K),
         "pm_read_bwd": N * (4 * C * esz + 4 * KP + 4 * K),
+        # score-plane read (the module's default: the memory folded into the output convolution)
+        "pm_read_fwd_planes": N * ((2 * C + 32) * esz + 4 * KP + 4 * K),
+        "pm_read_bwd_planes": N * ((3 * C + K) * esz + 2 * 4 * KP + 4 * K),
         "pm_readloss_fwd": N * (8 * r + 2 * 4 * KP),
         "pm_write_reduce_fwd": N * (C * esz),
         "pm_write_bwd": N * (2 * C * esz),
@@ -526,6 +529,7 @@ def main():
                            "pixel) make it FP32/MUFU-issue bound; the HBM fraction is reported because the contract asks "
                            "for it, see DESIGN.md 4/6",
         "pm_read_bwd": "one C-ABI call = two kernels (score gradients, then dx); bytes and time are their sums",
+        "pm_read_bwd_planes": "one C-ABI call = two kernels (score gradients, then dx); bytes and time are their sums",
     }
     peak, peak_src = measured_peaks()
     kernels = {}
@@ -540,7 +544,7 @@ def main():
     ncu_traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
-            ncu_traffic = json.load(fh).get(args.dtype, {}).get(dom)
+            ncu_traffic = json.load(fh).get(args.dtype, {}).get(dom.replace("_planes", ""))
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",

@@ -116,8 +116,38 @@ int pm_read_bwd(const void* du, const void* x, const float* M, const float* scor
                 int K, int dtype, void* stream);
 
 /*
+ * "Score-plane" variants of the read for the case where u feeds a bias-free 1x1 convolution, i.e. the
+ * reference's self.output[0] (memory.py:103-104, 330-334). There conv(W, [q ; p.M]) = W1.q + (W2.M^T).p with
+ * W = [W1 | W2], so instead of materialising c = p.M (C channels) the read hands the convolution
+ *   u' [B, C + PM_PLANES, h, w] = [ q ; score_memory as PM_PLANES channel planes (planes >= K are zero) ]
+ * and the caller convolves with W' = [W1 | W2.M^T | 0]: a (C+32)-wide GEMM instead of a 2C-wide one, 85 MB of u
+ * instead of 151 MB at cfg 2, and the convolution's input gradient du' = [dq0 ; dp planes] already contains
+ * dp = M.dc, so the backward skips that contraction. Same arguments as pm_read_fwd / pm_read_bwd otherwise.
+ * Only on the pipelined path: returns PM_ERR_ALIGN unless h*w is a multiple of 4 (fp32) / 8 (bf16) and the
+ * feature pointers are 16-byte aligned (callers fall back to pm_read_fwd then). ds must not be NULL.
+ */
+#define PM_PLANES 32
+int pm_read_planes(void); /* = PM_PLANES */
+int pm_read_fwd_planes(const void* x, const float* M, const float* gumbel_m, const float* gumbel_q, void* u,
+                       float* s, float* score_m, float* col_partials, int B, int C, int h, int w, int K, int dtype,
+                       void* stream);
+int pm_read_bwd_planes(const void* du, const void* x, const float* M, const float* score_m, const float* ds_rl,
+                       const float* g_loss, const float* rl_out, void* dx, float* ds, int B, int C, int h, int w,
+                       int K, int dtype, void* stream);
+
+/*
+ * The folded weight of the score-plane read and its gradient w.r.t. W (both fp32, row-major):
+ *   Wp [Co, C + PM_PLANES] = [ W[:, :C] | W[:, C:] . M^T | 0 ]        W [Co, 2C], M [K, C]
+ *   dW [Co, 2C]            = [ dWp[:, :C] | dWp[:, C:C+K] . M ]
+ * (the gradient w.r.t. M, needed only when m_items carries graph, is one small matmul left to the caller).
+ */
+int pm_fold_weight_fwd(const float* W, const float* M, float* Wp, int Co, int C, int K, void* stream);
+int pm_fold_weight_bwd(const float* dWp, const float* M, float* dW, int Co, int C, int K, void* stream);
+
+/*
  * Gradient w.r.t. the memory when m_items carries graph (meta-test read, train.py:558,570):
  * dM = sum_n score_m[n]^T dc[n] + ds[n]^T q[n].  dM [K,C] fp32 must be ZEROED by the caller.
+ * du NULL: only the second term (score-plane mode, where the first term reaches M through W2.M^T in autograd).
  */
 int pm_read_bwd_dM(const void* du, const void* x, const float* score_m, const float* ds, float* dM, int B,
                    int C, int h, int w, int K, int dtype, void* stream);

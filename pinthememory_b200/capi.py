@@ -31,6 +31,11 @@ PROTOTYPES = {
     "pm_readloss_fwd": [_c_p, _c_p, _c_f] + [_c_i] * 6 + [_c_p] * 4,
     "pm_read_bwd": [_c_p] * 9 + [_c_i] * 6 + [_c_p],
     "pm_read_bwd_dM": [_c_p] * 5 + [_c_i] * 6 + [_c_p],
+    "pm_read_planes": [],
+    "pm_read_fwd_planes": [_c_p] * 8 + [_c_i] * 6 + [_c_p],
+    "pm_read_bwd_planes": [_c_p] * 9 + [_c_i] * 6 + [_c_p],
+    "pm_fold_weight_fwd": [_c_p] * 3 + [_c_i] * 3 + [_c_p],
+    "pm_fold_weight_bwd": [_c_p] * 3 + [_c_i] * 3 + [_c_p],
     "pm_score_nhwc": [_c_p] * 3 + [_c_i] * 3 + [_c_p],
     "pm_rowsoftmax": [_c_p] * 3 + [_c_i] * 2 + [_c_p],
     "pm_write_reduce_fwd": [_c_p] * 3 + [_c_i] * 8 + [_c_p],
@@ -119,7 +124,8 @@ def score_stride(K):
 # with CUDA events on the launching stream to get per-kernel durations live.
 
 LAUNCHES = 0
-_KERNELS_PER_CALL = {"pm_colsoftmax": 2, "pm_read_bwd": 2}
+_KERNELS_PER_CALL = {"pm_colsoftmax": 2, "pm_read_bwd": 2, "pm_read_bwd_planes": 2}
+PLANES = 32  # PM_PLANES: score planes appended to q in the score-plane read
 _timing = None  # name -> list of (start_event, end_event) when enabled
 
 
@@ -161,9 +167,15 @@ def _call(name, *args):
 # --------------------------------------------------------------------------------------------- calls
 
 
-def read_fwd(x, M, gumbel_m, u, s, score_m, K, gumbel_q=None, col_partials=None):
+def planes_ok(x):
+    """The score-plane read runs only on the pipelined kernels: 16-byte rows and pointers."""
+    hw = x.shape[2] * x.shape[3]
+    return x.is_cuda and hw % (4 if x.dtype == torch.float32 else 8) == 0 and x.data_ptr() % 16 == 0
+
+
+def read_fwd(x, M, gumbel_m, u, s, score_m, K, gumbel_q=None, col_partials=None, planes=False):
     B, C, h, w = x.shape
-    _call("pm_read_fwd", _ptr(x), _ptr(M), _ptr(gumbel_m), _ptr(gumbel_q), _ptr(u), _ptr(s), _ptr(score_m),
+    _call("pm_read_fwd_planes" if planes else "pm_read_fwd", _ptr(x), _ptr(M), _ptr(gumbel_m), _ptr(gumbel_q), _ptr(u), _ptr(s), _ptr(score_m),
           _ptr(col_partials), B, C, h, w, K, dtype_code(x), _stream())
 
 
@@ -185,9 +197,9 @@ def readloss_fwd(s, labels, temperature, B, h, w, K, ds_rl, ws, out):
                                   _ptr(ws), _ptr(out), _stream())
 
 
-def read_bwd(du, x, M, score_m, ds_rl, g_loss, rl_out, dx, ds, K):
+def read_bwd(du, x, M, score_m, ds_rl, g_loss, rl_out, dx, ds, K, planes=False):
     B, C, h, w = x.shape
-    _call("pm_read_bwd", _ptr(du), _ptr(x), _ptr(M), _ptr(score_m), _ptr(ds_rl), _ptr(g_loss), _ptr(rl_out),
+    _call("pm_read_bwd_planes" if planes else "pm_read_bwd", _ptr(du), _ptr(x), _ptr(M), _ptr(score_m), _ptr(ds_rl), _ptr(g_loss), _ptr(rl_out),
                               _ptr(dx), _ptr(ds), B, C, h, w, K, dtype_code(x), _stream())
 
 
@@ -195,6 +207,14 @@ def read_bwd_dM(du, x, score_m, ds, dM, K):
     B, C, h, w = x.shape
     _call("pm_read_bwd_dM", _ptr(du), _ptr(x), _ptr(score_m), _ptr(ds), _ptr(dM), B, C, h, w, K,
                                  dtype_code(x), _stream())
+
+
+def fold_weight_fwd(W, M, Wp, Co, C, K):
+    _call("pm_fold_weight_fwd", _ptr(W), _ptr(M), _ptr(Wp), Co, C, K, _stream())
+
+
+def fold_weight_bwd(dWp, M, dW, Co, C, K):
+    _call("pm_fold_weight_bwd", _ptr(dWp), _ptr(M), _ptr(dW), Co, C, K, _stream())
 
 
 def score_nhwc(q, M, s, N, C, K):

@@ -9,12 +9,12 @@ namespace pm {
 bool tiled_ok(const void* p0, const void* p1, const void* p2, int hw, int dtype);
 
 int read_fwd_tiled(const void* x, const float* M, const float* gum_m, const float* gum_q, void* u, float* s, float* p,
-                   float* colpart, int B, int C, int hw, int K, int dtype, cudaStream_t st);
+                   float* colpart, int B, int C, int hw, int K, int dtype, int planes, cudaStream_t st);
 
 // needs a [N][stride] ds buffer (never NULL)
 int read_bwd_tiled(const void* du, const void* x, const float* M, const float* p, const float* ds_rl,
                    const float* g_loss, const float* rl_out, void* dx, float* ds, int B, int C, int hw, int K, int dtype,
-                   cudaStream_t st);
+                   int planes, cudaStream_t st);
 
 int write_reduce_tiled(const void* f, const int64_t* labels, float* SD, int B, int C, int h, int w, int Hm, int Wm,
                        int K, int dtype, cudaStream_t st);

@@ -376,11 +376,11 @@ __global__ void __launch_bounds__(C) read_bwd_dM_kernel(const T* __restrict__ du
         const int nvalid = min(P, hw - px0);
         const bool v = lane < nvalid;
         const T* xb = x + (size_t)b * C * hw + px0 + lane;
-        const T* dcb = du + ((size_t)b * 2 * C + C) * hw + px0 + lane;
+        const T* dcb = du ? du + ((size_t)b * 2 * C + C) * hw + px0 + lane : nullptr;
         float n2 = 0.f;
         for (int c = wid; c < C; c += NW) {
             float xv = v ? ldf(xb + (size_t)c * hw) : 0.f;
-            float dv = v ? ldf(dcb + (size_t)c * hw) : 0.f;
+            float dv = (v && dcb) ? ldf(dcb + (size_t)c * hw) : 0.f;
             n2 = fmaf(xv, xv, n2);
             xt[c * LD + lane] = xv;
             dct[c * LD + lane] = dv;
@@ -550,7 +550,7 @@ extern "C" int pm_read_fwd(const void* x, const float* M, const float* gumbel_m,
     if (int e = check_common(B, C, h, w, K, dtype)) return e;
     if (((uintptr_t)s & 15) != 0) return PM_ERR_ALIGN;
     if (pm::tiled_ok(x, u, s, h * w, dtype))
-        return pm::read_fwd_tiled(x, M, gumbel_m, gumbel_q, u, s, score_m, col_partials, B, C, h * w, K, dtype,
+        return pm::read_fwd_tiled(x, M, gumbel_m, gumbel_q, u, s, score_m, col_partials, B, C, h * w, K, dtype, 0,
                                   (cudaStream_t)stream);
     // generic path (any hw / alignment): un-pipelined kernel, column statistics in a separate launch
     if (int e = read_fwd_generic(x, M, gumbel_m, u, s, score_m, B, C, h, w, K, dtype, stream)) return e;
@@ -565,15 +565,38 @@ extern "C" int pm_read_bwd(const void* du, const void* x, const float* M, const 
     if (int e = check_common(B, C, h, w, K, dtype)) return e;
     if (((uintptr_t)ds & 15) != 0 || ((uintptr_t)ds_rl & 15) != 0) return PM_ERR_ALIGN;
     if (ds != nullptr && pm::tiled_ok(du, x, dx, h * w, dtype))
-        return pm::read_bwd_tiled(du, x, M, score_m, ds_rl, g_loss, rl_out, dx, ds, B, C, h * w, K, dtype,
+        return pm::read_bwd_tiled(du, x, M, score_m, ds_rl, g_loss, rl_out, dx, ds, B, C, h * w, K, dtype, 0,
                                   (cudaStream_t)stream);
     PM_DISPATCH(PM_DISPATCH_CW, launch_read_bwd, du, x, M, score_m, ds_rl, g_loss, rl_out, dx, ds, B, h * w, K,
                 (cudaStream_t)stream);
 }
 
+extern "C" int pm_read_planes(void) { return PM_PLANES; }
+
+extern "C" int pm_read_fwd_planes(const void* x, const float* M, const float* gumbel_m, const float* gumbel_q, void* u,
+                                  float* s, float* score_m, float* col_partials, int B, int C, int h, int w, int K,
+                                  int dtype, void* stream) {
+    if (!x || !M || !u || !s || !score_m) return PM_ERR_NULL;
+    if (int e = check_common(B, C, h, w, K, dtype)) return e;
+    if (((uintptr_t)s & 15) != 0 || !pm::tiled_ok(x, u, s, h * w, dtype)) return PM_ERR_ALIGN;
+    return pm::read_fwd_tiled(x, M, gumbel_m, gumbel_q, u, s, score_m, col_partials, B, C, h * w, K, dtype, 1,
+                              (cudaStream_t)stream);
+}
+
+extern "C" int pm_read_bwd_planes(const void* du, const void* x, const float* M, const float* score_m,
+                                  const float* ds_rl, const float* g_loss, const float* rl_out, void* dx, float* ds,
+                                  int B, int C, int h, int w, int K, int dtype, void* stream) {
+    if (!du || !x || !M || !score_m || !dx || !ds) return PM_ERR_NULL;
+    if (int e = check_common(B, C, h, w, K, dtype)) return e;
+    if (((uintptr_t)ds & 15) != 0 || ((uintptr_t)ds_rl & 15) != 0 || !pm::tiled_ok(du, x, dx, h * w, dtype))
+        return PM_ERR_ALIGN;
+    return pm::read_bwd_tiled(du, x, M, score_m, ds_rl, g_loss, rl_out, dx, ds, B, C, h * w, K, dtype, 1,
+                              (cudaStream_t)stream);
+}
+
 extern "C" int pm_read_bwd_dM(const void* du, const void* x, const float* score_m, const float* ds, float* dM, int B,
                               int C, int h, int w, int K, int dtype, void* stream) {
-    if (!du || !x || !score_m || !ds || !dM) return PM_ERR_NULL;
+    if (!x || !score_m || !ds || !dM) return PM_ERR_NULL;  // du NULL: only the ds (x) q term (planes mode)
     if (int e = check_common(B, C, h, w, K, dtype)) return e;
     PM_DISPATCH(PM_DISPATCH_C, launch_read_bwd_dM, du, x, score_m, ds, dM, B, h * w, K, (cudaStream_t)stream);
 }

@@ -208,8 +208,12 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
     read_fwd_tiled_kernel(const T* __restrict__ x, const float* __restrict__ M, const float* __restrict__ gum_m,
                           const float* __restrict__ gum_q, T* __restrict__ u, float* __restrict__ s_out,
                           float* __restrict__ p_out, float* __restrict__ colpart, int hw, int K, int tiles_per_img,
-                          int ntiles) {
+                          int ntiles, int planes) {
+    // planes == 0: u = [q ; p.M], 2C channels. planes == 1: u = [q ; p as PM_PLANES score planes], C + PM_PLANES
+    // channels (planes >= K are zero): the 1x1 convolution that follows is then W1.q + (W2.M^T).p, a (C+32)-wide
+    // GEMM instead of a 2C-wide one, and its input gradient hands dp back directly.
     constexpr int CW = C / TL_WARPS, NI = (KP + 7) / 8;
+    const int UC = planes ? C + PM_PLANES : 2 * C;
     constexpr bool MMA = UseMma<T, CW>::value;
     extern __shared__ __align__(16) unsigned char smraw[];
     float* Mt = reinterpret_cast<float*>(smraw);  // [C][KP]
@@ -319,13 +323,20 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
             const int px = o / K, k = o - px * K;
             p_out[n0g * K + o] = p_sm[px * KP + k];
         }
+        if (planes) {
+            for (int r = wid; r < PM_PLANES; r += TL_WARPS) {
+                const float v = (r < K) ? p_sm[lane * KP + r] : 0.f;
+                if (lane < nvalid) stf(u + ((size_t)b * UC + C + r) * hw + px0 + lane, v);
+            }
+        }
         if constexpr (MMA) {  // u = [q ; p.M]: p.M on the tensor core, q = x/|x| element-wise
-            tile_weighted_sum_mma<T, CW, KP>(p_sm, Mt, wid * CW, lane,
-                                             u + ((size_t)b * 2 * C + C + wid * CW) * hw + px0, hw, nvalid);
+            if (!planes)
+                tile_weighted_sum_mma<T, CW, KP>(p_sm, Mt, wid * CW, lane,
+                                                 u + ((size_t)b * UC + C + wid * CW) * hw + px0, hw, nvalid);
             const float ir = invr[lane];
             const int posl[4] = {mma_tile_pos(lane, 0), mma_tile_pos(lane, 1), mma_tile_pos(lane, 2), mma_tile_pos(lane, 3)};
             if (lane < nvalid) {
-                T* uq = u + ((size_t)b * 2 * C + wid * CW) * hw + px0 + lane;
+                T* uq = u + ((size_t)b * UC + wid * CW) * hw + px0 + lane;
 #pragma unroll
                 for (int j = 0; j < CW; ++j) {
                     stf(uq, to_float(xt[(wid * CW + j) * 32 + posl[(j >> 1) & 3]]) * ir);
@@ -343,26 +354,34 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
             }
             const float ir = invr[lane];
             const bool v = lane < nvalid;
-            T* uq = u + ((size_t)b * 2 * C + wid * CW) * hw + px0 + lane;
+            T* uq = u + ((size_t)b * UC + wid * CW) * hw + px0 + lane;
             const size_t chw = (size_t)C * hw;
             const T* xcol = xt + wid * CW * 32 + lane;
             const float4* mbase = reinterpret_cast<const float4*>(Mt + wid * CW * KP);
+            if (planes) {
 #pragma unroll
-            for (int j = 0; j < CW; ++j) {
-                const float4* mrow = mbase + j * (KP / 4);
-                float2 acc = f2(0.f, 0.f);
+                for (int j = 0; j < CW; ++j) {
+                    if (v) stf(uq, to_float(xcol[j * 32]) * ir);
+                    uq += hw;
+                }
+            } else {
 #pragma unroll
-                for (int q = 0; q < KP / 4; ++q) {
-                    const float4 m = mrow[q];
-                    acc = __ffma2_rn(p2[2 * q], f2(m.x, m.y), acc);
-                    acc = __ffma2_rn(p2[2 * q + 1], f2(m.z, m.w), acc);
+                for (int j = 0; j < CW; ++j) {
+                    const float4* mrow = mbase + j * (KP / 4);
+                    float2 acc = f2(0.f, 0.f);
+#pragma unroll
+                    for (int q = 0; q < KP / 4; ++q) {
+                        const float4 m = mrow[q];
+                        acc = __ffma2_rn(p2[2 * q], f2(m.x, m.y), acc);
+                        acc = __ffma2_rn(p2[2 * q + 1], f2(m.z, m.w), acc);
+                    }
+                    const float xq = to_float(xcol[j * 32]) * ir;
+                    if (v) {
+                        stf(uq, xq);
+                        stf(uq + chw, acc.x + acc.y);
+                    }
+                    uq += hw;
                 }
-                const float xq = to_float(xcol[j * 32]) * ir;
-                if (v) {
-                    stf(uq, xq);
-                    stf(uq + chw, acc.x + acc.y);
-                }
-                uq += hw;
             }
         }
         __syncthreads();  // every read of this stage is done: refill it
@@ -406,7 +425,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
 
 template <typename T, int C, int KP>
 int launch_read_fwd_tiled(const void* x, const float* M, const float* gum_m, const float* gum_q, void* u, float* s,
-                          float* p, float* colpart, int B, int hw, int K, cudaStream_t st) {
+                          float* p, float* colpart, int B, int hw, int K, int planes, cudaStream_t st) {
     constexpr int NSTAGE = 2;
     const size_t smem = sizeof(float) * ((size_t)C * KP + TL_WARPS * TP * KP + TL_WARPS * TP + 2 * TP * KP + TP) +
                         sizeof(T) * (size_t)NSTAGE * C * TP;
@@ -416,7 +435,8 @@ int launch_read_fwd_tiled(const void* x, const float* M, const float* gum_m, con
     const int tiles = (hw + TP - 1) / TP, ntiles = B * tiles;
     int grid = 2 * 148;
     if (grid > ntiles) grid = ntiles;
-    kern<<<grid, TL_THREADS, smem, st>>>((const T*)x, M, gum_m, gum_q, (T*)u, s, p, colpart, hw, K, tiles, ntiles);
+    kern<<<grid, TL_THREADS, smem, st>>>((const T*)x, M, gum_m, gum_q, (T*)u, s, p, colpart, hw, K, tiles, ntiles,
+                                         planes);
     cudaError_t le = cudaGetLastError();
     return le == cudaSuccess ? 0 : (int)le;
 }
@@ -521,6 +541,40 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
     cp_async_wait<0>();
 }
 
+// planes mode of part A: dp[n][k] = du[b][C + k][px]; ds = p * (dp - p.dp) + g_loss/(V*T) * ds_rl, one thread per pixel
+template <typename T, int KP>
+__global__ void __launch_bounds__(256)
+    read_bwd_ds_planes_kernel(const T* __restrict__ du, const float* __restrict__ p_in, const float* __restrict__ ds_rl,
+                              const float* __restrict__ g_loss, const float* __restrict__ rl_out,
+                              float* __restrict__ ds_out, int hw, int C, int K, int UC, long long N) {
+    const long long n = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (n >= N) return;
+    const int b = (int)(n / hw), px = (int)(n - (long long)b * hw);
+    const T* dp = du + ((size_t)b * UC + C) * hw + px;
+    float scale = 0.f;
+    if (ds_rl != nullptr && g_loss != nullptr && rl_out != nullptr) scale = __ldg(g_loss) * __ldg(rl_out + 1);
+    float pk[KP], d[KP], dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        pk[k] = (k < K) ? __ldg(p_in + (size_t)n * K + k) : 0.f;
+        d[k] = (k < K) ? ldf(dp + (size_t)k * hw) : 0.f;
+        dot = fmaf(pk[k], d[k], dot);
+    }
+    float4* out = reinterpret_cast<float4*>(ds_out + (size_t)n * KP);
+    const float4* rl = reinterpret_cast<const float4*>(ds_rl + (size_t)n * KP);
+#pragma unroll
+    for (int q = 0; q < KP / 4; ++q) {
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (scale != 0.f) r = __ldg(rl + q);
+        float4 o;
+        o.x = (4 * q + 0 < K) ? fmaf(scale, r.x, pk[4 * q + 0] * (d[4 * q + 0] - dot)) : 0.f;
+        o.y = (4 * q + 1 < K) ? fmaf(scale, r.y, pk[4 * q + 1] * (d[4 * q + 1] - dot)) : 0.f;
+        o.z = (4 * q + 2 < K) ? fmaf(scale, r.z, pk[4 * q + 2] * (d[4 * q + 2] - dot)) : 0.f;
+        o.w = (4 * q + 3 < K) ? fmaf(scale, r.w, pk[4 * q + 3] * (d[4 * q + 3] - dot)) : 0.f;
+        out[q] = o;
+    }
+}
+
 // -------------------------------------------------------------------------------- backward, part B: dx
 // dq = dq0 + ds.M ; q = x/|x| ; dx = (dq - q (q.dq)) / |x|. One CTA per SM, 16 warps x (C/16) channels,
 // lanes = pixels; x, dq0 and the ds rows of a tile arrive through a 2-stage async-copy ring.
@@ -531,7 +585,7 @@ template <typename T, int C, int KP, int NSTAGE>
 __global__ void __launch_bounds__(DX_THREADS, 1)
     read_bwd_dx_tiled_kernel(const T* __restrict__ du, const T* __restrict__ x, const float* __restrict__ M,
                              const float* __restrict__ ds, T* __restrict__ dx, int hw, int K, int tiles_per_img,
-                             int ntiles) {
+                             int ntiles, int UC) {  // UC: channels per image of du (2C, or C + PM_PLANES)
     constexpr int CW = C / DX_WARPS;
     extern __shared__ __align__(16) unsigned char smraw[];
     float* Mt = reinterpret_cast<float*>(smraw);        // [C][KP]
@@ -545,7 +599,7 @@ __global__ void __launch_bounds__(DX_THREADS, 1)
         const int b = t / tiles_per_img, px0 = (t - b * tiles_per_img) * TP;
         T* base = xs + (size_t)s * 2 * C * TP;
         tile_load_async<T, C, DX_THREADS>(base, x + (size_t)b * C * hw, hw, px0);
-        tile_load_async<T, C, DX_THREADS>(base + C * TP, du + (size_t)b * 2 * C * hw, hw, px0);
+        tile_load_async<T, C, DX_THREADS>(base + C * TP, du + (size_t)b * UC * hw, hw, px0);
         const size_t n0g = (size_t)b * hw + px0;
         const int nvalid = min(TP, hw - px0);
         for (int i = tid; i < TP * KP / 4; i += DX_THREADS)
@@ -641,10 +695,17 @@ __global__ void __launch_bounds__(DX_THREADS, 1)
 template <typename T, int C, int KP>
 int launch_read_bwd_tiled(const void* du, const void* x, const float* M, const float* p, const float* ds_rl,
                           const float* g_loss, const float* rl_out, void* dx, float* ds, int B, int hw, int K,
-                          cudaStream_t st) {
+                          int planes, cudaStream_t st) {
     constexpr int NSTAGE = 2;
     const int tiles = (hw + TP - 1) / TP, ntiles = B * tiles;
-    {
+    const int UC = planes ? C + PM_PLANES : 2 * C;
+    if (planes) {  // dp comes back from the convolution as planes [C, C+K) of du: per-pixel softmax backward only
+        const long long N = (long long)B * hw;
+        read_bwd_ds_planes_kernel<T, KP><<<(unsigned)((N + 255) / 256), 256, 0, st>>>((const T*)du, p, ds_rl, g_loss, rl_out,
+                                                                                    ds, hw, C, K, UC, N);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+    } else {
         const size_t smem = sizeof(float) * ((size_t)C * KP + TL_WARPS * TP * KP + TP * KP) +
                             sizeof(T) * (size_t)NSTAGE * C * TP;
         auto kern = read_bwd_ds_tiled_kernel<T, C, KP, NSTAGE>;
@@ -664,7 +725,7 @@ int launch_read_bwd_tiled(const void* du, const void* x, const float* M, const f
         if (e != cudaSuccess) return (int)e;
         int grid = 148;
         if (grid > ntiles) grid = ntiles;
-        kern<<<grid, DX_THREADS, smem, st>>>((const T*)du, (const T*)x, M, ds, (T*)dx, hw, K, tiles, ntiles);
+        kern<<<grid, DX_THREADS, smem, st>>>((const T*)du, (const T*)x, M, ds, (T*)dx, hw, K, tiles, ntiles, UC);
         e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
     }
@@ -686,25 +747,25 @@ bool tiled_ok(const void* p0, const void* p1, const void* p2, int hw, int dtype)
 }
 
 int read_fwd_tiled(const void* x, const float* M, const float* gum_m, const float* gum_q, void* u, float* s, float* p,
-                   float* colpart, int B, int C, int hw, int K, int dtype, cudaStream_t st) {
+                   float* colpart, int B, int C, int hw, int K, int dtype, int planes, cudaStream_t st) {
     if (dtype == PM_F32) {
-        if (K <= 19) { PM_TILED_SWITCH_C(float, 20, launch_read_fwd_tiled, x, M, gum_m, gum_q, u, s, p, colpart, B, hw, K, st) }
-        else { PM_TILED_SWITCH_C(float, 32, launch_read_fwd_tiled, x, M, gum_m, gum_q, u, s, p, colpart, B, hw, K, st) }
+        if (K <= 19) { PM_TILED_SWITCH_C(float, 20, launch_read_fwd_tiled, x, M, gum_m, gum_q, u, s, p, colpart, B, hw, K, planes, st) }
+        else { PM_TILED_SWITCH_C(float, 32, launch_read_fwd_tiled, x, M, gum_m, gum_q, u, s, p, colpart, B, hw, K, planes, st) }
     } else {
-        if (K <= 19) { PM_TILED_SWITCH_C(__nv_bfloat16, 20, launch_read_fwd_tiled, x, M, gum_m, gum_q, u, s, p, colpart, B, hw, K, st) }
-        else { PM_TILED_SWITCH_C(__nv_bfloat16, 32, launch_read_fwd_tiled, x, M, gum_m, gum_q, u, s, p, colpart, B, hw, K, st) }
+        if (K <= 19) { PM_TILED_SWITCH_C(__nv_bfloat16, 20, launch_read_fwd_tiled, x, M, gum_m, gum_q, u, s, p, colpart, B, hw, K, planes, st) }
+        else { PM_TILED_SWITCH_C(__nv_bfloat16, 32, launch_read_fwd_tiled, x, M, gum_m, gum_q, u, s, p, colpart, B, hw, K, planes, st) }
     }
 }
 
 int read_bwd_tiled(const void* du, const void* x, const float* M, const float* p, const float* ds_rl,
                    const float* g_loss, const float* rl_out, void* dx, float* ds, int B, int C, int hw, int K, int dtype,
-                   cudaStream_t st) {
+                   int planes, cudaStream_t st) {
     if (dtype == PM_F32) {
-        if (K <= 19) { PM_TILED_SWITCH_C(float, 20, launch_read_bwd_tiled, du, x, M, p, ds_rl, g_loss, rl_out, dx, ds, B, hw, K, st) }
-        else { PM_TILED_SWITCH_C(float, 32, launch_read_bwd_tiled, du, x, M, p, ds_rl, g_loss, rl_out, dx, ds, B, hw, K, st) }
+        if (K <= 19) { PM_TILED_SWITCH_C(float, 20, launch_read_bwd_tiled, du, x, M, p, ds_rl, g_loss, rl_out, dx, ds, B, hw, K, planes, st) }
+        else { PM_TILED_SWITCH_C(float, 32, launch_read_bwd_tiled, du, x, M, p, ds_rl, g_loss, rl_out, dx, ds, B, hw, K, planes, st) }
     } else {
-        if (K <= 19) { PM_TILED_SWITCH_C(__nv_bfloat16, 20, launch_read_bwd_tiled, du, x, M, p, ds_rl, g_loss, rl_out, dx, ds, B, hw, K, st) }
-        else { PM_TILED_SWITCH_C(__nv_bfloat16, 32, launch_read_bwd_tiled, du, x, M, p, ds_rl, g_loss, rl_out, dx, ds, B, hw, K, st) }
+        if (K <= 19) { PM_TILED_SWITCH_C(__nv_bfloat16, 20, launch_read_bwd_tiled, du, x, M, p, ds_rl, g_loss, rl_out, dx, ds, B, hw, K, planes, st) }
+        else { PM_TILED_SWITCH_C(__nv_bfloat16, 32, launch_read_bwd_tiled, du, x, M, p, ds_rl, g_loss, rl_out, dx, ds, B, hw, K, planes, st) }
     }
 }
 

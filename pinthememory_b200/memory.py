@@ -67,21 +67,27 @@ _SIDE_STREAMS = {}  # device -> stream of the write branch (module-level: module
 
 
 class _ReadFn(torch.autograd.Function):
-    """x, M (, labels, noise) -> u = [q ; p.M], score_query, score_memory, readloss, label histogram."""
+    """x, M (, labels, noise) -> u = [q ; p.M], score_query, score_memory, readloss, label histogram.
+
+    ``planes=True``: u = [q ; score_memory as 32 channel planes] for a caller that folds the memory into the
+    1x1 convolution that follows (include/pinmem_b200.h, pm_read_fwd_planes); the returned dM then only holds
+    the similarity term, the other one reaches M through the folded weight in autograd.
+    """
 
     @staticmethod
-    def forward(ctx, x, M, labels, g_query, g_memory, temperature, K):
+    def forward(ctx, x, M, labels, g_query, g_memory, temperature, K, planes=False):
         B, C, h, w = x.shape
         N = B * h * w
         dev = x.device
         KP = capi.score_stride(K)
-        u = torch.empty(B, 2 * C, h, w, dtype=x.dtype, device=dev)
+        UC = C + capi.PLANES if planes else 2 * C
+        u = torch.empty(B, UC, h, w, dtype=x.dtype, device=dev)
         s = torch.empty(N, KP, dtype=torch.float32, device=dev)
         score_m = torch.empty(N, K, dtype=torch.float32, device=dev)
         score_q = torch.empty(N, K, dtype=torch.float32, device=dev)
         M = M.contiguous()
         col_partials = torch.empty(capi.colsoftmax_workspace_floats(K), dtype=torch.float32, device=dev)
-        capi.read_fwd(x, M, g_memory, u, s, score_m, K, gumbel_q=g_query, col_partials=col_partials)
+        capi.read_fwd(x, M, g_memory, u, s, score_m, K, gumbel_q=g_query, col_partials=col_partials, planes=planes)
         capi.colsoftmax_apply(s, g_query, col_partials, score_q, N, K)
         if labels is not None:
             # one zeroed allocation: [ds_rl (N*KP floats) | workspace (40 x 8 bytes) | out (2 floats)]
@@ -96,7 +102,7 @@ class _ReadFn(torch.autograd.Function):
             ds_rl = rl_out = None
             readloss = torch.zeros((), dtype=torch.float32, device=dev)
             hist = torch.zeros(K + 1, dtype=torch.int64, device=dev)
-        ctx.K = K
+        ctx.K, ctx.planes, ctx.UC = K, planes, UC
         ctx.has_loss = labels is not None
         ctx.set_materialize_grads(False)  # unused outputs (scores, histogram) arrive as None, not as zero fills
         ctx.save_for_backward(x, M, score_m, ds_rl, rl_out)
@@ -110,7 +116,7 @@ class _ReadFn(torch.autograd.Function):
         K = ctx.K
         need_dM = ctx.needs_input_grad[1]
         if du is None:
-            du = torch.zeros(B, 2 * C, h, w, dtype=x.dtype, device=x.device)
+            du = torch.zeros(B, ctx.UC, h, w, dtype=x.dtype, device=x.device)
         du = du.to(x.dtype).contiguous()
         if ctx.has_loss and g_loss is not None:
             g_loss = g_loss.to(torch.float32).contiguous()
@@ -119,12 +125,42 @@ class _ReadFn(torch.autograd.Function):
         dx = torch.empty_like(x)
         ds = torch.empty(B * h * w, capi.score_stride(K), dtype=torch.float32, device=x.device)
         capi.read_bwd(du, x, M, score_m, ds_rl if g_loss is not None else None, g_loss,
-                      rl_out if g_loss is not None else None, dx, ds, K)
+                      rl_out if g_loss is not None else None, dx, ds, K, planes=ctx.planes)
         dM = None
         if need_dM:
             dM = torch.zeros_like(M)
-            capi.read_bwd_dM(du, x, score_m, ds, dM, K)
-        return dx, dM, None, None, None, None, None
+            capi.read_bwd_dM(None if ctx.planes else du, x, score_m, ds, dM, K)
+        return dx, dM, None, None, None, None, None, None
+
+
+class _FoldWeightFn(torch.autograd.Function):
+    """W [Co,2C,1,1], M [K,C] -> W' = [W1 | W2.M^T | 0] [Co, C+32, 1, 1] (pm_fold_weight_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, W, M):
+        Co, C2 = W.shape[0], W.shape[1]
+        C, K = C2 // 2, M.shape[0]
+        W32 = W.detach().to(torch.float32).contiguous()
+        M32 = M.detach().to(torch.float32).contiguous()
+        Wp = torch.empty(Co, C + capi.PLANES, 1, 1, dtype=torch.float32, device=W.device)
+        capi.fold_weight_fwd(W32, M32, Wp, Co, C, K)
+        ctx.save_for_backward(W32, M32)
+        ctx.wdtype = W.dtype
+        return Wp.to(W.dtype)
+
+    @staticmethod
+    def backward(ctx, dWp):
+        W32, M32 = ctx.saved_tensors
+        Co, C, K = W32.shape[0], M32.shape[1], M32.shape[0]
+        dWp = dWp.to(torch.float32).contiguous()
+        dW = dM = None
+        if ctx.needs_input_grad[0]:
+            dW = torch.empty_like(W32)
+            capi.fold_weight_bwd(dWp, M32, dW, Co, C, K)
+            dW = dW.to(ctx.wdtype)
+        if ctx.needs_input_grad[1]:  # meta-test read: the p (x) dc term of dM
+            dM = dWp[:, C:C + K, 0, 0].t() @ W32[:, C:, 0, 0]
+        return dW, dM
 
 
 class _WriteFn(torch.autograd.Function):
@@ -226,11 +262,22 @@ def _plain(m):
     return not (m._forward_hooks or m._forward_pre_hooks or m._backward_hooks)
 
 
+def _foldable(conv, C):
+    """The 1x1, bias-free, ungrouped 2C -> * convolution of the reference (memory.py:104)."""
+    return (type(conv) is nn.Conv2d and conv.kernel_size == (1, 1) and conv.stride == (1, 1) and conv.padding == (0, 0)
+            and conv.dilation == (1, 1) and conv.groups == 1 and conv.bias is None and conv.in_channels == 2 * C
+            and conv.padding_mode == "zeros")
+
+
 def conv_bn_act(conv, bn, x, residual, relu):
     """conv -> BatchNorm2d (-> + residual) (-> ReLU). The convolution is the nn.Conv2d module itself; what follows
     runs in the fused kernels of csrc/pm_bn.cu when `bn` is a plain nn.BatchNorm2d (a converted SyncBatchNorm, a
     hooked module or an exotic configuration falls back to calling the modules, i.e. the reference's own graph)."""
-    xc = conv(x)
+    return bn_act(conv(x), bn, residual, relu)
+
+
+def bn_act(xc, bn, residual, relu):
+    """BatchNorm2d (-> + residual) (-> ReLU) of an already convolved tensor (see conv_bn_act)."""
     fast = (type(bn) is nn.BatchNorm2d and bn.affine and _plain(bn) and xc.is_cuda and xc.dim() == 4
             and xc.dtype in (torch.float32, torch.bfloat16) and bn.weight.is_cuda)
     if not fast:
@@ -306,6 +353,8 @@ class Memory_sup(nn.Module):
         initialize_weights(self)
         # extras (not in the reference)
         self.overlap_write = False     # run the write branch on a side stream next to the read (see forward)
+        self.fold_memory_into_conv = True  # read hands [q ; score planes] to a convolution with the memory folded in
+        self.fold_min_pixels = 32768       # ... for feature maps of at least this many pixels per call
         self.shard_group = None        # set by sharding.enable_sharded_update()
         self.last_label_hist = None    # int64 [K+1] label histogram of the last read with labels
         self.last_class_sums = None    # fp32 [K+1, C+4] sums|counts of the last write (after all-reduce)
@@ -370,13 +419,22 @@ class Memory_sup(nn.Module):
         g_query = g_memory = None
         if self.gumbel_read:
             g_query, g_memory = draw_gumbel_pair(B * h * w, self.memory_size, query.device)
+        plain = _plain(self.output) and _plain(self.output[0]) and _plain(self.output[2])
+        # pays once the GEMMs are big enough to be compute- rather than launch-bound (break-even ~ 3e4 pixels)
+        planes = (plain and self.fold_memory_into_conv and B * h * w >= self.fold_min_pixels
+                  and _foldable(self.output[0], C) and capi.planes_ok(query))
         u, score_query, score_memory, readloss, hist = _ReadFn.apply(
-            query, M, labels, g_query, g_memory, float(self.temperature), self.memory_size)
+            query, M, labels, g_query, g_memory, float(self.temperature), self.memory_size, planes)
         if labels is None:
             readloss = 0  # memory.py:178
         else:
             self.last_label_hist = hist
-        if _plain(self.output) and _plain(self.output[0]) and _plain(self.output[2]):
+        if planes:
+            # conv(W, [q ; p.M]) = W1.q + (W2.M^T).p : the memory is folded into the weight (a [C_out, 32] block) and
+            # the convolution runs on [q ; score planes] -- C+32 input channels instead of 2C
+            Wp = _FoldWeightFn.apply(self.output[0].weight, M)                                   # [C_out, C+32, 1, 1]
+            updated_query = bn_act(F.conv2d(u, Wp), self.output[1], None, True)
+        elif plain:
             updated_query = conv_bn_act(self.output[0], self.output[1], u, None, True)
         else:
             updated_query = self.output(u)

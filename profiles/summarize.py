@@ -40,7 +40,7 @@ ENTRY_OF = [("read_fwd_tiled_kernel", "pm_read_fwd"), ("read_fwd_kernel", "pm_re
             ("write_reduce_mma_kernel", "pm_write_reduce_fwd"), ("write_reduce_tiled_kernel", "pm_write_reduce_fwd"),
             ("update_fwd_kernel", "pm_update_fwd"), ("update_bwd_kernel", "pm_update_bwd"),
             ("write_bwd_tiled_kernel", "pm_write_bwd"), ("bn_bwd_reduce_kernel", "pm_bn_bwd_reduce"),
-            ("bn_bwd_apply_kernel", "pm_bn_bwd_apply"), ("read_bwd_ds_tiled_kernel", "pm_read_bwd.ds"),
+            ("bn_bwd_apply_kernel", "pm_bn_bwd_apply"), ("read_bwd_ds_tiled_kernel", "pm_read_bwd.ds"), ("read_bwd_ds_planes_kernel", "pm_read_bwd.ds"),
             ("read_bwd_dx_tiled_kernel", "pm_read_bwd.dx")]
 
 

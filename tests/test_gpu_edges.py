@@ -335,3 +335,55 @@ def test_fused_bn_falls_back_for_other_norm_layers():
     assert seen and capi.LAUNCHES < fused  # the BatchNorm module itself ran
     sync = torch.nn.SyncBatchNorm.convert_sync_batchnorm(Memory_sup(19, 64, 64, 0.8, 1.0, False).cuda())
     assert type(sync.output[1]) is torch.nn.SyncBatchNorm and type(sync.writenet.writefeat[1]) is torch.nn.SyncBatchNorm
+
+
+@pytest.mark.parametrize("writing", [True, False])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_memory_folded_into_the_output_convolution_is_the_same_function(writing, dtype):
+    """Score-plane read (u = [q ; p planes], W' = [W1 | W2.M^T]) against the plain [q ; p.M] path: outputs, the
+    gradients of every parameter, of the query and -- in the meta-test read, where m_items carries graph -- of the
+    memory (one term from the kernel, the other through the folded weight in autograd)."""
+    from pinthememory_b200 import synth
+
+    B, C, h, w, Hm, Wm, K = 2, 64, 12, 16, 48, 64, 19
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    x0 = synth.make_features(B, C, h, w, seed=21, device="cuda")
+    lab = synth.make_labels(B, Hm, Wm, K, "blocky", seed=22).cuda()
+    G = synth.make_upstream_grad((B, C, h, w), seed=23, device="cuda")
+    res = []
+    for fold in (False, True):
+        mem = _module(K, C)
+        mem.fold_memory_into_conv = fold
+        mem.fold_min_pixels = 0
+        M = mem.m_items.clone().requires_grad_(not writing)
+        mem.m_items = M
+        x = x0.clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+            uq, sq, sm, rl, wl = mem(x.to(dtype) if dtype != torch.float32 else x, lab, writing, False)
+        outs, grads = [uq, rl], [G.to(uq.dtype), torch.tensor(0.02, device="cuda")]
+        if writing:
+            outs += [wl[0], wl[1]]
+            grads += [torch.tensor(0.4, device="cuda"), torch.tensor(0.2, device="cuda")]
+        torch.autograd.backward(outs, grads)
+        res.append(dict(uq=uq.detach().float(), sm=sm, rl=rl.detach(), dx=x.grad, dM=None if writing else M.grad,
+                        gp=[p.grad for p in mem.parameters()], names=[n for n, _ in mem.named_parameters()]))
+    a, b = res
+    assert_close(b["uq"], a["uq"], tol, "updated_query")
+    assert_close(b["sm"], a["sm"], tol, "score_memory")
+    assert_close(b["rl"], a["rl"], tol, "readloss")
+    if dtype == torch.float32:
+        close = lambda x, y, what: assert_close(x, y, 1e-4 if what.startswith(("grad", "dM")) else tol, what)
+    else:
+        # two bf16 autocast runs: each is ~4e-2 away from the fp32 gradients (BatchNorm backward in bf16), so they
+        # are compared in rel-L2 only (profiles/fold_bf16_probe.py prints both against fp32)
+        def close(x, y, what):
+            from golden_util import rel_l2
+            assert rel_l2(x, y) <= 8e-2, "%s: rel_l2=%.3e" % (what, rel_l2(x, y))
+    close(b["dx"], a["dx"], "dx")
+    if not writing:
+        close(b["dM"], a["dM"], "dM")
+    for n, ga, gb in zip(a["names"], a["gp"], b["gp"]):
+        if ga is None:
+            assert gb is None, n
+        else:
+            close(gb, ga, "grad " + n)

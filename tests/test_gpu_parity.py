@@ -39,13 +39,18 @@ def _total(uq, rl, wl, G, has_labels, writing):
     return total
 
 
+@pytest.mark.parametrize("fold", [False, True], ids=["concat", "folded"])
 @pytest.mark.parametrize("name", golden_names())
-def test_module_reproduces_reference_fixture(name, monkeypatch):
-    """Whole module (our kernels + the two torch conv blocks) vs. outputs of the unmodified reference."""
+def test_module_reproduces_reference_fixture(name, fold, monkeypatch):
+    """Whole module (our kernels + the two torch conv blocks) vs. outputs of the unmodified reference, with the
+    read handing the output convolution [q ; p.M] ("concat", the reference's graph) or [q ; score planes] with the
+    memory folded into the weight ("folded", what large feature maps use)."""
     from pinthememory_b200 import memory as pm_memory
 
     meta, fx = load_golden(name, "cuda")
     mem = _new_module(meta["K"], meta["C"], meta["momentum"], meta["temperature"], bool(meta.get("gumbel")))
+    mem.fold_memory_into_conv = fold
+    mem.fold_min_pixels = 0
     load_state(mem, fx)
     mem.train(meta["train"])
     if meta.get("gumbel"):  # replay the noise the reference drew on its CPU generator
