@@ -7,6 +7,10 @@
 // K x C memory sits transposed in shared memory (Mt[c][KP]: a channel's K values are five broadcast
 // 128-bit loads) and all multiply-adds are packed FFMA2 (fp32x2), which is what reaches the fp32 peak
 // on sm_100 (profiles/microbench/ffma2.cu: 65.9 vs 46.8 TFLOP/s for scalar FFMA).
+#include <cuda.h>
+
+#include <cstdlib>
+
 #include "pm_common.cuh"
 #include "pm_internal.h"
 
@@ -692,6 +696,207 @@ __global__ void __launch_bounds__(DX_THREADS, 1)
     cp_async_wait<0>();
 }
 
+// ---------------------------------------------------------------- backward, part B with a TMA tile ring
+// Same arithmetic as read_bwd_dx_tiled_kernel; the x and dq0 tiles arrive as two 2-D tensor-map boxes
+// ([C rows][32 pixels] of the [B*C, hw] / [B*UC, hw] matrices) and the ds rows as one 1-D bulk copy, all completing
+// on an mbarrier per stage. One thread issues a stage (3 instructions) instead of 512 threads issuing ~17 LDGSTS
+// each: the kernel is LSU / shared-memory-pipe bound, and the async proxy takes the tile fill off
+// that pipe. Columns past the end of an image row are zero-filled by the TMA unit.
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (unsigned spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (spin > (1u << 26)) __trap();  // a tile that never lands is a bug: fail loudly instead of hanging the GPU
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <typename T, int C, int KP, int NSTAGE>
+__global__ void __launch_bounds__(DX_THREADS, 1)
+    read_bwd_dx_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_du,
+                           const float* __restrict__ M, const float* __restrict__ ds, T* __restrict__ dx, int hw, int K,
+                           int tiles_per_img, int ntiles, int UC) {
+    constexpr int CW = C / DX_WARPS;
+    extern __shared__ __align__(1024) unsigned char smraw_[];
+    __shared__ __align__(8) uint64_t full[NSTAGE];
+    // TMA destinations want 128-byte alignment: round the dynamic window up ourselves (1 KB of slack is allocated)
+    unsigned char* smraw = smraw_ + ((1024u - (smem_u32(smraw_) & 1023u)) & 1023u);
+    T* xs = reinterpret_cast<T*>(smraw);                                   // [NSTAGE][2][C][TP]: x tile, dq0 tile
+    float* dss = reinterpret_cast<float*>(xs + (size_t)NSTAGE * 2 * C * TP);  // [NSTAGE][TP][KP]
+    float* Mt = dss + NSTAGE * TP * KP;                                    // [C][KP]
+    float* pn = Mt + C * KP;                                               // [16][TP]
+    float* pd = pn + DX_WARPS * TP;                                        // [16][TP]
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int t, int s) {  // one thread
+        const int b = t / tiles_per_img, px0 = (t - b * tiles_per_img) * TP;
+        const int nvalid = min(TP, hw - px0);
+        const uint32_t ds_bytes = (uint32_t)(nvalid * KP * sizeof(float));
+        T* base = xs + (size_t)s * 2 * C * TP;
+        mbar_expect_tx(&full[s], (uint32_t)(2 * C * TP * sizeof(T)) + ds_bytes);
+        tma_load_2d(base, &tm_x, px0, b * C, &full[s]);
+        tma_load_2d(base + C * TP, &tm_du, px0, b * UC, &full[s]);
+        bulk_load_1d(dss + s * TP * KP, ds + ((size_t)b * hw + px0) * KP, ds_bytes, &full[s]);
+    };
+    int tile = blockIdx.x;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) {
+            const int t = tile + s * gridDim.x;
+            if (t < ntiles) issue(t, s);
+        }
+    }
+    for (int i = tid; i < C * KP; i += DX_THREADS) {
+        const int c = i / KP, k = i - c * KP;
+        Mt[i] = (k < K) ? __ldg(M + (size_t)k * C + c) : 0.f;
+    }
+    __syncthreads();
+
+    int stage = 0;
+    unsigned phase = 0;
+    for (; tile < ntiles; tile += gridDim.x) {
+        mbar_wait(&full[stage], phase);
+        const T* xt = xs + (size_t)stage * 2 * C * TP;
+        const T* qt = xt + C * TP;
+        const int b = tile / tiles_per_img, px0 = (tile - b * tiles_per_img) * TP;
+        const int nvalid = min(TP, hw - px0);
+        const T* xcol = xt + wid * CW * 32 + lane;
+        const T* qcol = qt + wid * CW * 32 + lane;
+        float xv[CW], n2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+            xv[j] = to_float(xcol[j * 32]);
+            n2 = fmaf(xv[j], xv[j], n2);
+        }
+        pn[wid * TP + lane] = n2;
+        float2 s2[KP / 2];
+        {
+            const float4* sr = reinterpret_cast<const float4*>(dss + stage * TP * KP + lane * KP);
+#pragma unroll
+            for (int q = 0; q < KP / 4; ++q) {
+                float4 v = sr[q];
+                if (lane >= nvalid) v = make_float4(0.f, 0.f, 0.f, 0.f);  // rows past the image end are not copied
+                s2[2 * q] = f2(v.x, v.y);
+                s2[2 * q + 1] = f2(v.z, v.w);
+            }
+        }
+        float dq[CW];
+        const float4* mbase = reinterpret_cast<const float4*>(Mt + wid * CW * KP);
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+            const float4* mrow = mbase + j * (KP / 4);
+            float2 acc = f2(to_float(qcol[j * 32]), 0.f);
+#pragma unroll
+            for (int q = 0; q < KP / 4; ++q) {
+                const float4 m = mrow[q];
+                acc = __ffma2_rn(s2[2 * q], f2(m.x, m.y), acc);
+                acc = __ffma2_rn(s2[2 * q + 1], f2(m.z, m.w), acc);
+            }
+            dq[j] = acc.x + acc.y;
+        }
+        __syncthreads();
+        float nn = 0.f;
+#pragma unroll
+        for (int w = 0; w < DX_WARPS; ++w) nn += pn[w * TP + lane];
+        const float nrm = sqrtf(nn), ir = 1.f / fmaxf(nrm, PM_NORM_EPS);
+        float dot = 0.f;
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+            xv[j] *= ir;  // q
+            dot = fmaf(xv[j], dq[j], dot);
+        }
+        pd[wid * TP + lane] = dot;
+        __syncthreads();  // also: every read of this stage's tiles is done
+        const int next = tile + NSTAGE * gridDim.x;
+        if (tid == 0 && next < ntiles) issue(next, stage);
+        dot = 0.f;
+#pragma unroll
+        for (int w = 0; w < DX_WARPS; ++w) dot += pd[w * TP + lane];
+        if (nrm <= PM_NORM_EPS) dot = 0.f;
+        if (lane < nvalid) {
+            T* dxp = dx + ((size_t)b * C + wid * CW) * hw + px0 + lane;
+#pragma unroll
+            for (int j = 0; j < CW; ++j) {
+                stf(dxp, (dq[j] - xv[j] * dot) * ir);
+                dxp += hw;
+            }
+        }
+        if (++stage == NSTAGE) stage = 0, phase ^= 1u;
+    }
+}
+
+typedef CUresult (*pm_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static pm_encode_tiled_fn encode_tiled() {
+    static pm_encode_tiled_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (pm_encode_tiled_fn)p;
+        tried = true;
+    }
+    return fn;
+}
+
+// 2-D map of a row-major [rows][cols] matrix with [box_rows][box_cols] boxes, dense (unswizzled) in shared memory
+template <typename T>
+static bool make_map_2d(CUtensorMap* map, const void* base, size_t rows, size_t cols, unsigned box_rows, unsigned box_cols) {
+    pm_encode_tiled_fn enc = encode_tiled();
+    if (enc == nullptr) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)cols * sizeof(T)};
+    const cuuint32_t box[2] = {box_cols, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapDataType dt = sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    return enc(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int dx_tma_enabled() {  // PM_DX_TMA=0 keeps the cp.async ring (A/B switch)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PM_DX_TMA");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v;
+}
+
 template <typename T, int C, int KP>
 int launch_read_bwd_tiled(const void* du, const void* x, const float* M, const float* p, const float* ds_rl,
                           const float* g_loss, const float* rl_out, void* dx, float* ds, int B, int hw, int K,
@@ -720,12 +925,22 @@ int launch_read_bwd_tiled(const void* du, const void* x, const float* M, const f
     {
         const size_t smem = sizeof(float) * ((size_t)C * KP + 2 * DX_WARPS * TP + (size_t)NSTAGE * TP * KP) +
                             sizeof(T) * (size_t)NSTAGE * 2 * C * TP;
-        auto kern = read_bwd_dx_tiled_kernel<T, C, KP, NSTAGE>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
         int grid = 148;
         if (grid > ntiles) grid = ntiles;
-        kern<<<grid, DX_THREADS, smem, st>>>((const T*)du, (const T*)x, M, ds, (T*)dx, hw, K, tiles, ntiles, UC);
+        CUtensorMap tm_x, tm_du;
+        cudaError_t e;
+        if (dx_tma_enabled() && C <= 256 && make_map_2d<T>(&tm_x, x, (size_t)B * C, hw, C, TP) &&
+            make_map_2d<T>(&tm_du, du, (size_t)B * UC, hw, C, TP)) {
+            auto kern = read_bwd_dx_tma_kernel<T, C, KP, NSTAGE>;
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024);
+            if (e != cudaSuccess) return (int)e;
+            kern<<<grid, DX_THREADS, smem + 1024, st>>>(tm_x, tm_du, M, ds, (T*)dx, hw, K, tiles, ntiles, UC);
+        } else {
+            auto kern = read_bwd_dx_tiled_kernel<T, C, KP, NSTAGE>;
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            kern<<<grid, DX_THREADS, smem, st>>>((const T*)du, (const T*)x, M, ds, (T*)dx, hw, K, tiles, ntiles, UC);
+        }
         e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
     }
