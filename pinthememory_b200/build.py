@@ -28,7 +28,7 @@ def _nvcc():
 
 
 def _deps():
-    files = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "pm_common.cuh"), os.path.join(CSRC, "pm_internal.h"),
+    files = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "pm_common.cuh"), os.path.join(CSRC, "pm_internal.h"), os.path.join(CSRC, "pm_tma.cuh"),
                                                          os.path.join(PKG_DIR, "..", "include", "pinmem_b200.h")]
     return files
 

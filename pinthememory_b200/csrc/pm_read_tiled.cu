@@ -7,11 +7,10 @@
 // K x C memory sits transposed in shared memory (Mt[c][KP]: a channel's K values are five broadcast
 // 128-bit loads) and all multiply-adds are packed FFMA2 (fp32x2), which is what reaches the fp32 peak
 // on sm_100 (profiles/microbench/ffma2.cu: 65.9 vs 46.8 TFLOP/s for scalar FFMA).
-#include <cuda.h>
-
 #include <cstdlib>
 
 #include "pm_common.cuh"
+#include "pm_tma.cuh"
 #include "pm_internal.h"
 
 namespace pm {
@@ -703,39 +702,6 @@ __global__ void __launch_bounds__(DX_THREADS, 1)
 // each: the kernel is LSU / shared-memory-pipe bound, and the async proxy takes the tile fill off
 // that pipe. Columns past the end of an image row are zero-filled by the TMA unit.
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done = 0;
-    for (unsigned spin = 0; !done; ++spin) {
-        asm volatile(
-            "{\n.reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-        if (spin > (1u << 26)) __trap();  // a tile that never lands is a bug: fail loudly instead of hanging the GPU
-    }
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-            smem_u32(dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
 template <typename T, int C, int KP, int NSTAGE>
 __global__ void __launch_bounds__(DX_THREADS, 1)
     read_bwd_dx_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_du,
@@ -856,46 +822,6 @@ __global__ void __launch_bounds__(DX_THREADS, 1)
     }
 }
 
-typedef CUresult (*pm_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static pm_encode_tiled_fn encode_tiled() {
-    static pm_encode_tiled_fn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (pm_encode_tiled_fn)p;
-        tried = true;
-    }
-    return fn;
-}
-
-// 2-D map of a row-major [rows][cols] matrix with [box_rows][box_cols] boxes, dense (unswizzled) in shared memory
-template <typename T>
-static bool make_map_2d(CUtensorMap* map, const void* base, size_t rows, size_t cols, unsigned box_rows, unsigned box_cols) {
-    pm_encode_tiled_fn enc = encode_tiled();
-    if (enc == nullptr) return false;
-    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    const cuuint64_t gstride[1] = {(cuuint64_t)cols * sizeof(T)};
-    const cuuint32_t box[2] = {box_cols, box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUtensorMapDataType dt = sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-    return enc(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-static int dx_tma_enabled() {  // PM_DX_TMA=0 keeps the cp.async ring (A/B switch)
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("PM_DX_TMA");
-        v = (e && e[0] == '0') ? 0 : 1;
-    }
-    return v;
-}
 
 template <typename T, int C, int KP>
 int launch_read_bwd_tiled(const void* du, const void* x, const float* M, const float* p, const float* ds_rl,
@@ -929,8 +855,8 @@ int launch_read_bwd_tiled(const void* du, const void* x, const float* M, const f
         if (grid > ntiles) grid = ntiles;
         CUtensorMap tm_x, tm_du;
         cudaError_t e;
-        if (dx_tma_enabled() && C <= 256 && make_map_2d<T>(&tm_x, x, (size_t)B * C, hw, C, TP) &&
-            make_map_2d<T>(&tm_du, du, (size_t)B * UC, hw, C, TP)) {
+        if (tma_enabled() && C <= 256 && make_map_2d<T>(&tm_x, x, (size_t)B * C, hw, C, TP, false) &&
+            make_map_2d<T>(&tm_du, du, (size_t)B * UC, hw, C, TP, false)) {
             auto kern = read_bwd_dx_tma_kernel<T, C, KP, NSTAGE>;
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024);
             if (e != cudaSuccess) return (int)e;

@@ -1,5 +1,6 @@
 // Memory write, pipelined variants (fast path when hw is a multiple of the 16-byte chunk).
 #include "pm_common.cuh"
+#include "pm_tma.cuh"
 #include "pm_internal.h"
 
 namespace pm {
@@ -204,18 +205,23 @@ __global__ void __launch_bounds__(C) write_reduce_tiled_kernel(const T* __restri
 // chunk-swizzled f tile (conflict-free) and are scaled by 1/|f| on the fly. Cost no longer depends on how
 // fragmented the label map is (the run-length kernel above degenerates on noisy labels).
 
-template <int C, int KP>
-__global__ void __launch_bounds__(C) write_reduce_mma_kernel(const float* __restrict__ f, const long long* __restrict__ labels,
+// TMA = true: the tiles arrive as SWIZZLE_128B tensor-map boxes (the same chunk ^ (row & 7) layout) on an mbarrier ring
+template <int C, int KP, bool TMA>
+__global__ void __launch_bounds__(C) write_reduce_mma_kernel(const __grid_constant__ CUtensorMap tm_f,
+                                                              const float* __restrict__ f, const long long* __restrict__ labels,
                                                               float* __restrict__ SD, int h, int w, int Hm, int Wm,
                                                               int K, float sy, float sx, int tiles_per_img,
                                                               int ntiles) {
     constexpr int NSTAGE = 2, NW = C / 32, CS = C + 4, OMLD = 40;
-    extern __shared__ __align__(16) unsigned char smraw[];
-    float* om = reinterpret_cast<float*>(smraw);      // [32 px][OMLD] dense label weights of the current tile
+    extern __shared__ __align__(16) unsigned char smraw_[];
+    __shared__ __align__(8) uint64_t full[NSTAGE];
+    unsigned char* smraw = smem_align(smraw_, 1024);  // the swizzled TMA boxes need 1 KB alignment
+    float* ft = reinterpret_cast<float*>(smraw);       // [NSTAGE][C][32] swizzled; reused as S_tile [32][CS] at the end
+    constexpr size_t RING = (size_t)NSTAGE * C * 32 > (size_t)32 * CS ? (size_t)NSTAGE * C * 32 : (size_t)32 * CS;
+    float* om = ft + RING;                             // [32 px][OMLD] dense label weights of the current tile
     float* pn = om + 32 * OMLD;                        // [NW][32]
     float* invr = pn + NW * 32;                        // [32]
     unsigned* cmask = reinterpret_cast<unsigned*>(invr + 32);  // [4]
-    float* ft = reinterpret_cast<float*>(cmask + 4);   // [NSTAGE][C][32] swizzled; reused as S_tile [32][CS] at the end
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, hw = h * w;
     const int g = lane >> 2, t = lane & 3;
@@ -247,25 +253,44 @@ __global__ void __launch_bounds__(C) write_reduce_mma_kernel(const float* __rest
     };
 
     int tile = blockIdx.x;
+    auto issue = [&](int tl, int s) {  // TMA: one thread
+        int b, px0;
+        tile_coords(tl, b, px0);
+        mbar_expect_tx(&full[s], (uint32_t)(C * 32 * sizeof(float)));
+        tma_load_2d(ft + s * C * 32, &tm_f, px0, b * C, &full[s]);
+    };
+    if constexpr (TMA) {
+        if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < NSTAGE; ++s) {
-        const int tl = tile + s * gridDim.x;
-        if (tl < ntiles) {
-            int b, px0;
-            tile_coords(tl, b, px0);
-            tile_load_async_swz<float, C, C>(ft + s * C * 32, f + (size_t)b * C * hw, hw, px0);
+            for (int s = 0; s < NSTAGE; ++s) mbar_init(&full[s], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+            for (int s = 0; s < NSTAGE; ++s)
+                if (tile + s * (int)gridDim.x < ntiles) issue(tile + s * gridDim.x, s);
         }
-        cp_async_commit();
+    } else {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) {
+            const int tl = tile + s * gridDim.x;
+            if (tl < ntiles) {
+                int b, px0;
+                tile_coords(tl, b, px0);
+                tile_load_async_swz<float, C, C>(ft + s * C * 32, f + (size_t)b * C * hw, hw, px0);
+            }
+            cp_async_commit();
+        }
     }
     LabelTaps tcur;
     if (wid == 0) tcur = taps_for(tile);
 
     int stage = 0;
+    unsigned phase = 0;
     for (; tile < ntiles; tile += gridDim.x) {
         LabelTaps tnext;
         if (wid == 0) tnext = taps_for(tile + gridDim.x);  // loads in flight across this tile
-        cp_async_wait<NSTAGE - 1>();
+        if constexpr (!TMA) cp_async_wait<NSTAGE - 1>();
         __syncthreads();
+        if constexpr (TMA) mbar_wait(&full[stage], phase);
         const float* xt = ft + stage * C * 32;
         for (int i = tid; i < 32 * OMLD / 4; i += C) reinterpret_cast<float4*>(om)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         {  // |f|^2 per pixel: lanes = pixels, each warp sums 32 of the C rows (rows wid, wid+NW, .. share a swizzle
@@ -342,16 +367,20 @@ __global__ void __launch_bounds__(C) write_reduce_mma_kernel(const float* __rest
         }
         __syncthreads();  // stage and label table consumed
         const int next = tile + NSTAGE * gridDim.x;
-        if (next < ntiles) {
-            int nb, npx0;
-            tile_coords(next, nb, npx0);
-            tile_load_async_swz<float, C, C>(ft + stage * C * 32, f + (size_t)nb * C * hw, hw, npx0);
+        if constexpr (TMA) {
+            if (tid == 0 && next < ntiles) issue(next, stage);
+        } else {
+            if (next < ntiles) {
+                int nb, npx0;
+                tile_coords(next, nb, npx0);
+                tile_load_async_swz<float, C, C>(ft + stage * C * 32, f + (size_t)nb * C * hw, hw, npx0);
+            }
+            cp_async_commit();
         }
-        cp_async_commit();
         if (wid == 0) tcur = tnext;
-        stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
+        if (++stage == NSTAGE) stage = 0, phase ^= 1u;
     }
-    cp_async_wait<0>();
+    if constexpr (!TMA) cp_async_wait<0>();
     __syncthreads();
     // accumulators -> shared [32][CS] (over the tile ring), then one vector RED per touched class row
     float* S_tile = ft;
@@ -385,11 +414,15 @@ template <int C, int KP>
 int launch_write_reduce_mma(const void* f, const int64_t* labels, float* SD, int B, int h, int w, int Hm, int Wm, int K,
                             cudaStream_t st) {
     const size_t ring = sizeof(float) * (size_t)2 * C * 32, stile = sizeof(float) * (size_t)32 * (C + 4);
-    const size_t smem = sizeof(float) * (32 * 40 + (C / 32) * 32 + 32 + 4) + (ring > stile ? ring : stile);
-    auto kern = write_reduce_mma_kernel<C, KP>;
+    const size_t smem = sizeof(float) * (32 * 40 + (C / 32) * 32 + 32 + 4) + (ring > stile ? ring : stile) + 1024;
+    const int hw = h * w, tiles = (hw + 31) / 32, ntiles = B * tiles;
+    const float sy = h > 1 ? (float)(Hm - 1) / (float)(h - 1) : 0.f;
+    const float sx = w > 1 ? (float)(Wm - 1) / (float)(w - 1) : 0.f;
+    CUtensorMap tm_f;
+    const bool tma = tma_enabled() && make_map_2d<float>(&tm_f, f, (size_t)B * C, hw, C, 32, true);
+    auto kern = tma ? write_reduce_mma_kernel<C, KP, true> : write_reduce_mma_kernel<C, KP, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    const int hw = h * w, tiles = (hw + 31) / 32, ntiles = B * tiles;
     int per_sm = 1;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C, smem);
     if (e != cudaSuccess) return (int)e;
@@ -397,9 +430,7 @@ int launch_write_reduce_mma(const void* f, const int64_t* labels, float* SD, int
     if (per_sm > 4) per_sm = 4;
     int grid = 148 * per_sm;
     if (grid > ntiles) grid = ntiles;
-    const float sy = h > 1 ? (float)(Hm - 1) / (float)(h - 1) : 0.f;
-    const float sx = w > 1 ? (float)(Wm - 1) / (float)(w - 1) : 0.f;
-    kern<<<grid, C, smem, st>>>((const float*)f, (const long long*)labels, SD, h, w, Hm, Wm, K, sy, sx, tiles, ntiles);
+    kern<<<grid, C, smem, st>>>(tm_f, (const float*)f, (const long long*)labels, SD, h, w, Hm, Wm, K, sy, sx, tiles, ntiles);
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }
@@ -435,9 +466,12 @@ int launch_write_reduce_tiled(const void* f, const int64_t* labels, float* SD, i
 
 constexpr int WBT_THREADS = 256, WBT_WARPS = 8, WBT_STAGES = 2;
 
-template <typename T, int C, int KP>
+// TMA = true: the f tiles arrive as 2-D tensor-map boxes completing on one mbarrier per stage (one thread issues a
+// stage) instead of 8 LDGSTS per thread; `tm_f` is unused otherwise.
+template <typename T, int C, int KP, bool TMA>
 __global__ void __launch_bounds__(WBT_THREADS, 2)
-    write_bwd_tiled_kernel(const float* __restrict__ dS, const T* __restrict__ f, const long long* __restrict__ labels,
+    write_bwd_tiled_kernel(const __grid_constant__ CUtensorMap tm_f, const float* __restrict__ dS,
+                           const T* __restrict__ f, const long long* __restrict__ labels,
                            T* __restrict__ df, int h, int w, int Hm, int Wm, int K, float sy, float sx,
                            int tiles_per_img, int ntiles) {
     constexpr int NSTAGE = WBT_STAGES, CW = C / WBT_WARPS, LDS_ = C + 1;
@@ -446,7 +480,8 @@ __global__ void __launch_bounds__(WBT_THREADS, 2)
     float* pn = dSs + KP * LDS_;                        // [8][32]
     float* pd = pn + WBT_WARPS * 32;                    // [8][32]
     float2* ent = reinterpret_cast<float2*>(pd + WBT_WARPS * 32 + ((KP * LDS_) & 1));  // [2][32][4]
-    T* ft = reinterpret_cast<T*>(ent + 2 * 32 * 4);     // [NSTAGE][C][32]
+    T* ft = reinterpret_cast<T*>(smem_align(reinterpret_cast<unsigned char*>(ent + 2 * 32 * 4), 128));  // [NSTAGE][C][32]
+    __shared__ __align__(8) uint64_t full[NSTAGE];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, hw = h * w;
     auto tile_coords = [&](int t, int& b, int& px0) {
@@ -473,15 +508,32 @@ __global__ void __launch_bounds__(WBT_THREADS, 2)
     };
 
     int tile = blockIdx.x;
+    auto issue = [&](int t, int s) {  // TMA: one thread
+        int b, px0;
+        tile_coords(t, b, px0);
+        mbar_expect_tx(&full[s], (uint32_t)(C * 32 * sizeof(T)));
+        tma_load_2d(ft + s * C * 32, &tm_f, px0, b * C, &full[s]);
+    };
+    if constexpr (TMA) {
+        if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < NSTAGE; ++s) {
-        const int t = tile + s * gridDim.x;
-        if (t < ntiles) {
-            int b, px0;
-            tile_coords(t, b, px0);
-            tile_load_async<T, C, WBT_THREADS>(ft + s * C * 32, f + (size_t)b * C * hw, hw, px0);
+            for (int s = 0; s < NSTAGE; ++s) mbar_init(&full[s], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+            for (int s = 0; s < NSTAGE; ++s)
+                if (tile + s * (int)gridDim.x < ntiles) issue(tile + s * gridDim.x, s);
         }
-        cp_async_commit();
+    } else {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) {
+            const int t = tile + s * gridDim.x;
+            if (t < ntiles) {
+                int b, px0;
+                tile_coords(t, b, px0);
+                tile_load_async<T, C, WBT_THREADS>(ft + s * C * 32, f + (size_t)b * C * hw, hw, px0);
+            }
+            cp_async_commit();
+        }
     }
     for (int i = tid; i < KP * LDS_; i += WBT_THREADS) {
         const int k = i / LDS_, c = i - k * LDS_;
@@ -494,11 +546,13 @@ __global__ void __launch_bounds__(WBT_THREADS, 2)
     }
 
     int stage = 0, ebuf = 0;
+    unsigned phase = 0;
     for (; tile < ntiles; tile += gridDim.x) {
         LabelTaps tn;
         if (wid == 0) tn = taps_for(tile + gridDim.x);  // loads in flight across this tile
-        cp_async_wait<NSTAGE - 1>();
-        __syncthreads();
+        if constexpr (!TMA) cp_async_wait<NSTAGE - 1>();
+        __syncthreads();  // dS / tap entries of this tile visible (and, with cp.async, the tile itself)
+        if constexpr (TMA) mbar_wait(&full[stage], phase);
         const T* xt = ft + stage * C * 32;
         int b, px0;
         tile_coords(tile, b, px0);
@@ -553,37 +607,51 @@ __global__ void __launch_bounds__(WBT_THREADS, 2)
         }
         __syncthreads();  // stage, entries and pn/pd consumed
         const int next = tile + NSTAGE * gridDim.x;
-        if (next < ntiles) {
-            int nb, npx0;
-            tile_coords(next, nb, npx0);
-            tile_load_async<T, C, WBT_THREADS>(ft + stage * C * 32, f + (size_t)nb * C * hw, hw, npx0);
+        if constexpr (TMA) {
+            if (tid == 0 && next < ntiles) issue(next, stage);
+        } else {
+            if (next < ntiles) {
+                int nb, npx0;
+                tile_coords(next, nb, npx0);
+                tile_load_async<T, C, WBT_THREADS>(ft + stage * C * 32, f + (size_t)nb * C * hw, hw, npx0);
+            }
+            cp_async_commit();
         }
-        cp_async_commit();
         if (wid == 0) {
             compact_taps(tn);
             store_entries(ebuf ^ 1, tn);
         }
-        stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
+        if (++stage == NSTAGE) stage = 0, phase ^= 1u;
         ebuf ^= 1;
     }
-    cp_async_wait<0>();
+    if constexpr (!TMA) cp_async_wait<0>();
 }
 
 template <typename T, int C, int KP>
 int launch_write_bwd_tiled(const float* dS, const void* f, const int64_t* labels, void* df, int B, int h, int w, int Hm,
                            int Wm, int K, cudaStream_t st) {
     const size_t smem = sizeof(float) * ((size_t)KP * (C + 1) + 2 * WBT_WARPS * 32 + 1) + sizeof(float2) * 2 * 32 * 4 +
-                        sizeof(T) * (size_t)WBT_STAGES * C * 32;
-    auto kern = write_bwd_tiled_kernel<T, C, KP>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+                        sizeof(T) * (size_t)WBT_STAGES * C * 32 + 128;
     const int hw = h * w, tiles = (hw + 31) / 32, ntiles = B * tiles;
     int grid = 2 * 148;
     if (grid > ntiles) grid = ntiles;
     const float sy = h > 1 ? (float)(Hm - 1) / (float)(h - 1) : 0.f;
     const float sx = w > 1 ? (float)(Wm - 1) / (float)(w - 1) : 0.f;
-    kern<<<grid, WBT_THREADS, smem, st>>>(dS, (const T*)f, (const long long*)labels, (T*)df, h, w, Hm, Wm, K, sy, sx, tiles,
-                                          ntiles);
+    CUtensorMap tm_f;
+    cudaError_t e;
+    if (tma_enabled() && make_map_2d<T>(&tm_f, f, (size_t)B * C, hw, C, 32, false)) {
+        auto kern = write_bwd_tiled_kernel<T, C, KP, true>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        kern<<<grid, WBT_THREADS, smem, st>>>(tm_f, dS, (const T*)f, (const long long*)labels, (T*)df, h, w, Hm, Wm, K, sy,
+                                              sx, tiles, ntiles);
+    } else {
+        auto kern = write_bwd_tiled_kernel<T, C, KP, false>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        kern<<<grid, WBT_THREADS, smem, st>>>(tm_f, dS, (const T*)f, (const long long*)labels, (T*)df, h, w, Hm, Wm, K, sy,
+                                              sx, tiles, ntiles);
+    }
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }
