@@ -118,6 +118,18 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def _bind_to_gpu_numa_node(index):
+    """Run this rank (and first-touch its pinned staging buffers) on the CPUs next to its GPU, so that N ranks
+    uploading at once do not all cross the same socket link (e2e with host buffers is PCIe/host-memory bound)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+    except Exception:
+        pass
+
+
 # ------------------------------------------------------------------------------------ CPU reference
 
 
@@ -358,6 +370,7 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    _bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     dt = torch.float32 if args.dtype == "f32" else torch.bfloat16
