@@ -107,10 +107,11 @@ __device__ __forceinline__ void tile_load_async_swz(T* smem_tile, const T* __res
     }
 }
 
-// fp32 tile for the tensor-core (mma.sync) contraction: 16-byte chunk c of row r is stored at chunk
-// c ^ (2 * ((r >> 1) & 3)), which makes the A-fragment loads of m16n8k8 (lanes = 8 pixels x 4 channel pairs)
-// hit 32 distinct banks. A lane that wants pixel `px` of row `r` reads word mma_tile_pos(px, (r >> 1) & 3).
-__device__ __forceinline__ int mma_tile_pos(int px, int phase) { return (((px >> 2) ^ (2 * phase)) << 2) | (px & 3); }
+// fp32 tile for the tensor-core (mma.sync) contraction: 16-byte chunk c of row r is stored at chunk c ^ (r & 7)
+// -- the TMA SWIZZLE_128B pattern, so the same tile can be filled by cp.async or by a tensor-map box. The A-fragment
+// loads of m16n8k8 (lanes = 8 pixels x 4 rows 2t+h of an 8-row step) then hit 32 distinct banks. A lane that wants
+// pixel `px` of row `r` reads word mma_tile_pos(px, r & 7).
+__device__ __forceinline__ int mma_tile_pos(int px, int swz) { return (((px >> 2) ^ swz) << 2) | (px & 3); }
 template <int ROWS, int NTHREADS>
 __device__ __forceinline__ void tile_load_async_mma(float* smem_tile, const float* __restrict__ base, int hw, int px0) {
     static_assert(NTHREADS % 8 == 0, "thread count must be a multiple of the chunks per row");
@@ -120,7 +121,7 @@ __device__ __forceinline__ void tile_load_async_mma(float* smem_tile, const floa
     const float* src = base + (size_t)(threadIdx.x / 8) * hw + (valid ? px : 0);
     const size_t step = (size_t)(NTHREADS / 8) * hw;
     for (int row = threadIdx.x / 8; row < ROWS; row += NTHREADS / 8) {
-        cp_async16(smem_tile + row * 32 + ((ch ^ (2 * ((row >> 1) & 3))) << 2), src, valid);
+        cp_async16(smem_tile + row * 32 + ((ch ^ (row & 7)) << 2), src, valid);
         src += step;
     }
 }

@@ -66,7 +66,7 @@ __device__ __forceinline__ void tile_dots(const T* xt, const float* Mt, int c0, 
 // instead of one broadcast shared-memory load per FMA pair. The k index of an MMA is a free permutation, so
 // k = t maps to channel 2t and k = t+4 to channel 2t+1 of an 8-channel step: with that choice the B fragments
 // read the existing Mt[c][KP=20] rows without bank conflicts, and the A fragments read the chunk-swizzled tile
-// (tile_load_async_mma) without bank conflicts. Writes this warp's partial sums straight into part / pn.
+// (tile_load_async_mma, or a SWIZZLE_128B TMA box) without bank conflicts. Writes this warp's partial sums straight into part / pn.
 template <int CW, int KP>
 __device__ __forceinline__ void tile_dots_mma(const float* xt, const float* Mt, int c0, int lane, float* part_w,
                                               float* pn_w) {
@@ -78,9 +78,9 @@ __device__ __forceinline__ void tile_dots_mma(const float* xt, const float* Mt, 
 #pragma unroll
         for (int n = 0; n < NT; ++n) acc[m][n][0] = acc[m][n][1] = acc[m][n][2] = acc[m][n][3] = 0.f;
     float n2[4] = {0.f, 0.f, 0.f, 0.f};
-    int pos[4];
+    int pos[4];  // rows c0+8ks+2t+h (c0 % 8 == 0): swizzle (row & 7) = 2t + h; h = 1 flips bit 0 of the chunk = word ^ 4
 #pragma unroll
-    for (int r = 0; r < 4; ++r) pos[r] = mma_tile_pos(g + 8 * r, t);  // rows c0+8ks+2t(+1): phase ((row>>1)&3) == t
+    for (int r = 0; r < 4; ++r) pos[r] = mma_tile_pos(g + 8 * r, 2 * t);
 #pragma unroll
     for (int ks = 0; ks < CW / 8; ++ks) {
         const float* r0 = xt + (c0 + 8 * ks + 2 * t) * 32;
@@ -90,7 +90,7 @@ __device__ __forceinline__ void tile_dots_mma(const float* xt, const float* Mt, 
         for (int r = 0; r < 4; ++r) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const float v = r0[h * 32 + pos[r]];
+                const float v = r0[h * 32 + (pos[r] ^ (4 * h))];
                 n2[r] = fmaf(v, v, n2[r]);
                 ahi[r][h] = tf32_hi(v);
                 alo[r][h] = tf32_lo(v);
@@ -206,9 +206,12 @@ __device__ __forceinline__ void store_partial(float* part, int wid, int lane, co
 
 // --------------------------------------------------------------------------------------------- forward
 
-template <typename T, int C, int KP, int NSTAGE>
+// TMA = true: the x tiles arrive as tensor-map boxes (SWIZZLE_128B for the tensor-core layout, dense otherwise) on an
+// mbarrier ring; tm_x is unused with the cp.async ring.
+template <typename T, int C, int KP, int NSTAGE, bool TMA>
 __global__ void __launch_bounds__(TL_THREADS, 2)
-    read_fwd_tiled_kernel(const T* __restrict__ x, const float* __restrict__ M, const float* __restrict__ gum_m,
+    read_fwd_tiled_kernel(const __grid_constant__ CUtensorMap tm_x, const T* __restrict__ x,
+                          const float* __restrict__ M, const float* __restrict__ gum_m,
                           const float* __restrict__ gum_q, T* __restrict__ u, float* __restrict__ s_out,
                           float* __restrict__ p_out, float* __restrict__ colpart, int hw, int K, int tiles_per_img,
                           int ntiles, int planes) {
@@ -225,18 +228,36 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
     float* s_sm = pn + TL_WARPS * TP;             // [TP][KP]
     float* p_sm = s_sm + TP * KP;                 // [TP][KP]
     float* invr = p_sm + TP * KP;                 // [TP]
-    T* xs = reinterpret_cast<T*>(invr + TP);      // [NSTAGE][C][TP]
+    // [NSTAGE][C][TP]; 1 KB aligned for the swizzled TMA boxes (the launcher allocates the slack)
+    T* xs = reinterpret_cast<T*>(smem_align(reinterpret_cast<unsigned char*>(invr + TP), 1024));
+    __shared__ __align__(8) uint64_t full[NSTAGE];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     int tile = blockIdx.x;
+    auto issue = [&](int t, int s) {  // TMA: one thread
+        const int b = t / tiles_per_img, px0 = (t - b * tiles_per_img) * TP;
+        mbar_expect_tx(&full[s], (uint32_t)(C * TP * sizeof(T)));
+        tma_load_2d(xs + s * C * TP, &tm_x, px0, b * C, &full[s]);
+    };
+    if constexpr (TMA) {
+        if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < NSTAGE; ++s) {
-        const int t = tile + s * gridDim.x;
-        if (t < ntiles) {
-            const int b = t / tiles_per_img, px0 = (t - b * tiles_per_img) * TP;
-            dots_tile_load<T, C, TL_THREADS, MMA>(xs + s * C * TP, x + (size_t)b * C * hw, hw, px0);
+            for (int s = 0; s < NSTAGE; ++s) mbar_init(&full[s], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+            for (int s = 0; s < NSTAGE; ++s)
+                if (tile + s * (int)gridDim.x < ntiles) issue(tile + s * gridDim.x, s);
         }
-        cp_async_commit();
+    } else {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) {
+            const int t = tile + s * gridDim.x;
+            if (t < ntiles) {
+                const int b = t / tiles_per_img, px0 = (t - b * tiles_per_img) * TP;
+                dots_tile_load<T, C, TL_THREADS, MMA>(xs + s * C * TP, x + (size_t)b * C * hw, hw, px0);
+            }
+            cp_async_commit();
+        }
     }
     load_Mt<C, KP>(Mt, M, K);
     float cm[NI], cl[NI];  // running column (max, sum) of this thread's slots for score_query
@@ -244,9 +265,11 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
     for (int i = 0; i < NI; ++i) cm[i] = -INFINITY, cl[i] = 0.f;
 
     int stage = 0;
+    unsigned phase = 0;
     for (; tile < ntiles; tile += gridDim.x) {
-        cp_async_wait<NSTAGE - 1>();
-        __syncthreads();
+        if constexpr (!TMA) cp_async_wait<NSTAGE - 1>();
+        __syncthreads();  // Mt and the mbarriers are set up / the cp.async tile is visible
+        if constexpr (TMA) mbar_wait(&full[stage], phase);
         const T* xt = xs + stage * C * TP;
         const int b = tile / tiles_per_img, px0 = (tile - b * tiles_per_img) * TP;
         const int nvalid = min(TP, hw - px0);
@@ -337,12 +360,11 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
                 tile_weighted_sum_mma<T, CW, KP>(p_sm, Mt, wid * CW, lane,
                                                  u + ((size_t)b * UC + C + wid * CW) * hw + px0, hw, nvalid);
             const float ir = invr[lane];
-            const int posl[4] = {mma_tile_pos(lane, 0), mma_tile_pos(lane, 1), mma_tile_pos(lane, 2), mma_tile_pos(lane, 3)};
             if (lane < nvalid) {
                 T* uq = u + ((size_t)b * UC + wid * CW) * hw + px0 + lane;
 #pragma unroll
                 for (int j = 0; j < CW; ++j) {
-                    stf(uq, to_float(xt[(wid * CW + j) * 32 + posl[(j >> 1) & 3]]) * ir);
+                    stf(uq, to_float(xt[(wid * CW + j) * 32 + mma_tile_pos(lane, j & 7)]) * ir);  // CW % 8 == 0
                     uq += hw;
                 }
             }
@@ -389,14 +411,18 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
         }
         __syncthreads();  // every read of this stage is done: refill it
         const int next = tile + NSTAGE * gridDim.x;
-        if (next < ntiles) {
-            const int nb = next / tiles_per_img, npx0 = (next - nb * tiles_per_img) * TP;
-            dots_tile_load<T, C, TL_THREADS, MMA>(xs + stage * C * TP, x + (size_t)nb * C * hw, hw, npx0);
+        if constexpr (TMA) {
+            if (tid == 0 && next < ntiles) issue(next, stage);
+        } else {
+            if (next < ntiles) {
+                const int nb = next / tiles_per_img, npx0 = (next - nb * tiles_per_img) * TP;
+                dots_tile_load<T, C, TL_THREADS, MMA>(xs + stage * C * TP, x + (size_t)nb * C * hw, hw, npx0);
+            }
+            cp_async_commit();
         }
-        cp_async_commit();
-        stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
+        if (++stage == NSTAGE) stage = 0, phase ^= 1u;
     }
-    cp_async_wait<0>();
+    if constexpr (!TMA) cp_async_wait<0>();
 
     if (colpart != nullptr) {  // per-CTA column (max,sum) partials, same layout as colsoftmax_stats_kernel
         __syncthreads();
@@ -431,14 +457,17 @@ int launch_read_fwd_tiled(const void* x, const float* M, const float* gum_m, con
                           float* p, float* colpart, int B, int hw, int K, int planes, cudaStream_t st) {
     constexpr int NSTAGE = 2;
     const size_t smem = sizeof(float) * ((size_t)C * KP + TL_WARPS * TP * KP + TL_WARPS * TP + 2 * TP * KP + TP) +
-                        sizeof(T) * (size_t)NSTAGE * C * TP;
-    auto kern = read_fwd_tiled_kernel<T, C, KP, NSTAGE>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+                        sizeof(T) * (size_t)NSTAGE * C * TP + 1024;
     const int tiles = (hw + TP - 1) / TP, ntiles = B * tiles;
     int grid = 2 * 148;
     if (grid > ntiles) grid = ntiles;
-    kern<<<grid, TL_THREADS, smem, st>>>((const T*)x, M, gum_m, gum_q, (T*)u, s, p, colpart, hw, K, tiles, ntiles,
+    CUtensorMap tm_x;
+    constexpr bool MMA = UseMma<T, C / TL_WARPS>::value;  // the tensor-core layout is the 128-byte swizzle
+    const bool tma = tma_enabled() && make_map_2d<T>(&tm_x, x, (size_t)B * C, hw, C, TP, MMA);
+    auto kern = tma ? read_fwd_tiled_kernel<T, C, KP, NSTAGE, true> : read_fwd_tiled_kernel<T, C, KP, NSTAGE, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<grid, TL_THREADS, smem, st>>>(tm_x, (const T*)x, M, gum_m, gum_q, (T*)u, s, p, colpart, hw, K, tiles, ntiles,
                                          planes);
     cudaError_t le = cudaGetLastError();
     return le == cudaSuccess ? 0 : (int)le;
