@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <cstdlib>
+#include <mutex>
 
 namespace pm {
 
@@ -62,10 +63,36 @@ static pm_encode_tiled_fn encode_tiled() {
 
 // 2-D map of a row-major [rows][cols] matrix with [box_rows][box_cols] boxes; in shared memory the box is dense, or
 // (swizzle128: box rows of exactly 128 bytes, destination 1024-byte aligned) has its 16-byte chunks XOR-ed with
-// (row & 7) -- the bank-conflict-free layout the tensor-core tiles use
+// (row & 7) -- the bank-conflict-free layout the tensor-core tiles use.
+// cuTensorMapEncodeTiled costs tens of microseconds on the host, which a launch-bound (un-captured) step cannot
+// afford per kernel: maps are memoised on (address, shape, box, swizzle). A map holds no ownership, so an entry
+// stays valid when the caching allocator hands the same block out again.
+struct TensorMapKey {
+    const void* base;
+    size_t rows, cols;
+    unsigned box_rows, box_cols, esz, swz;
+    bool operator==(const TensorMapKey& o) const {
+        return base == o.base && rows == o.rows && cols == o.cols && box_rows == o.box_rows && box_cols == o.box_cols &&
+               esz == o.esz && swz == o.swz;
+    }
+};
+
 template <typename T>
 static bool make_map_2d(CUtensorMap* map, const void* base, size_t rows, size_t cols, unsigned box_rows, unsigned box_cols,
                         bool swizzle128) {
+    constexpr int SLOTS = 64;
+    static std::mutex mu;
+    static TensorMapKey keys[SLOTS];
+    static CUtensorMap maps[SLOTS];
+    static bool used[SLOTS];
+    static unsigned next = 0;
+    const TensorMapKey key{base, rows, cols, box_rows, box_cols, (unsigned)sizeof(T), swizzle128 ? 1u : 0u};
+    std::lock_guard<std::mutex> lock(mu);
+    for (int i = 0; i < SLOTS; ++i)
+        if (used[i] && keys[i] == key) {
+            *map = maps[i];
+            return true;
+        }
     pm_encode_tiled_fn enc = encode_tiled();
     if (enc == nullptr) return false;
     const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -73,8 +100,13 @@ static bool make_map_2d(CUtensorMap* map, const void* base, size_t rows, size_t 
     const cuuint32_t box[2] = {box_cols, box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUtensorMapDataType dt = sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-    return enc(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    if (enc(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    const unsigned slot = next++ % SLOTS;
+    keys[slot] = key, maps[slot] = *map, used[slot] = true;
+    return true;
 }
 
 static int tma_enabled() {  // PM_TMA=0 keeps the per-thread cp.async rings (A/B switch)
