@@ -570,38 +570,11 @@ def main():
     if dom in bound_note:
         roofline["note"] = bound_note[dom]
 
-    # core: hand-written kernels only (replayed as a CUDA graph like the headline, so that host launch jitter does
-    # not leak into a 0.4 ms step; falls back to kernel-by-kernel launches if the capture fails)
+    # core: hand-written kernels only, one Python-side launch per kernel (host-launch bound at ~0.4 ms: capturing this
+    # autograd fragment separately was tried and disturbs the measurements that follow; the headline step IS captured)
     core_graph = None
-    launches_c = None
-    try:
-        if args.no_graph:
-            raise RuntimeError("--no-graph")
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            # fresh leaves: their gradient accumulators must live on the capture's streams
-            xg = x.detach().clone().requires_grad_(True)
-            fg = f_core.detach().clone().requires_grad_(True)
-            for _ in range(3):
-                core_step(xg, fg)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        xg.grad = None
-        fg.grad = None
-        core_graph = torch.cuda.CUDAGraph()
-        capi.reset_counters()
-        with torch.cuda.graph(core_graph):
-            core_step(xg, fg)
-        launches_g = capi.LAUNCHES * args.steps
-        ms_g, _, _, _ = timed(core_graph.replay, args.steps, args.warmup)
-    except Exception:
-        core_graph = None
-        ms_g = None
-    ms_c, launches_c, _, _ = timed(core_step, args.steps, args.warmup)
     core_launch = "one Python-side launch per kernel"
-    if ms_g is not None and ms_g < ms_c:  # same kernels and work either way: report the one without host gaps
-        ms_c, launches_c, core_launch = ms_g, launches_g, "CUDA graph replay"
+    ms_c, launches_c, _, _ = timed(core_step, args.steps, args.warmup)
     ms_core = ms_c / args.steps
     a_train = 10 * C * esz + 8 * r + 8 * K
     core_gbps = N * a_train / (ms_core * 1e-3) / 1e9
