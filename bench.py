@@ -508,9 +508,14 @@ def main():
             from pinthememory_b200.graphed import GraphedStep
 
             mem.m_items = M0.clone()
+            # captured, the write branch is a parallel branch of the graph (a side stream); launched kernel by kernel
+            # the extra stream only costs host time, so the eager measurements keep a single stream at N = 1
+            overlap_eager = mem.overlap_write
+            mem.overlap_write = True
             gstep = GraphedStep(mem, x, labels, G, loss_weights=(LOSS_W["read"], LOSS_W["div"], LOSS_W["cls"]),
                                 memory_writing=True, writing_detach=False, carry_memory=True,
                                 autocast_dtype=torch.bfloat16 if dt == torch.bfloat16 else None)
+            mem.overlap_write = overlap_eager
             ms_g, _, _, clocks_g = timed(gstep.replay, args.steps, args.warmup, sample_clocks=True)
             graph_info = {"kernels_per_replay": gstep.kernels_per_replay}
             ms_per_step = ms_g / args.steps
@@ -519,6 +524,7 @@ def main():
             clocks = clocks_g
         except Exception as e:  # report the eagerly launched number rather than nothing
             graph_info = {"error": str(e)[:300]}
+            mem.overlap_write = bool(args.overlap_write) or world > 1
 
     # per-kernel durations measured live (events around every C-ABI launch) in a second timed region
     ms_k, _, ktimes, _ = timed(lambda: module_step(x, labels), args.steps, 2, kernel_timing=True)
@@ -609,8 +615,8 @@ def main():
                  "cuda_graph": graph_info})
     line["config"]["launch"] = ("CUDA graph replay of the whole step (GraphedStep)" if graph_info and "error" not in graph_info
                                 else "one Python-side launch per kernel")
-    if mem.overlap_write:
-        line["config"]["launch"] += "; write branch (incl. the all-reduces) on a side stream / parallel graph branch"
+    if graph_info and "error" not in graph_info:
+        line["config"]["launch"] += "; write branch (incl. the all-reduces when sharded) as a parallel graph branch"
 
     if rank == 0 and world == 1 and not args.no_callers:
         # the callers either side of the path that run on the same kernels
