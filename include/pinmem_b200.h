@@ -52,6 +52,8 @@ enum pm_readloss_ws_layout {
 /* Rows of the per-CTA column-softmax partials buffer ([PM_COLPART_ROWS][64] floats). */
 #define PM_COLPART_ROWS 296
 
+/* Bumped with every prototype change; the binding refuses a library whose pm_version() differs. */
+#define PM_ABI_VERSION 200
 int pm_version(void);
 const char* pm_status_string(int code);
 /* Row stride (floats) of the internal score buffers for K slots: 20 for K<=19, else 32. */
@@ -230,6 +232,36 @@ int pm_bn_bwd_reduce(const void* dy, const void* y, const uint32_t* relu_mask, c
 int pm_bn_bwd_apply(const void* dy, const void* y, const uint32_t* relu_mask, const void* x, const float* mean,
                     const float* invstd, const float* gamma, const float* dgamma, const float* dbeta, int relu,
                     int training, void* dx, void* dres, int B, int C, int hw, int dtype, void* stream);
+
+/*
+ * The two 1x1 convolutions themselves (memory.py:74-75 `Writingnet.writefeat[0]`, memory.py:103-104 `self.output[0]`,
+ * both bias-free, applied at memory.py:84/214 and :334) and their autograd, as tcgen05 GEMMs on NCHW activations
+ * (csrc/pm_gemm.cu). Per image b:   Y[b] (M x hw) = A (M x K) . X[b] (K x hw).
+ *   dtype PM_F32 computes in 3xTF32 (error-compensated, ~fp32 accuracy), PM_BF16 in bf16 with fp32 accumulation.
+ *
+ *   pm_conv1x1_prep   A = W (transpose = 0, W is [M,K] fp32) or W^T (transpose = 1, W is [K,M] fp32), padded with
+ *                     zero rows to Mpad = ceil(M/128)*128. PM_F32: A_hi, A_lo are fp32 [Mpad,K] (the TF32 split);
+ *                     PM_BF16: A_hi is bf16 [Mpad,K], A_lo unused. transpose = 0 prepares the forward convolution,
+ *                     transpose = 1 its input gradient (dX[b] = W^T . dY[b]).
+ *   pm_conv1x1_fwd    X [B,K,hw], Y [B,M,hw] in `dtype`; A_hi/A_lo from pm_conv1x1_prep. accumulate != 0 adds into Y
+ *                     (TMA reduce-add; gradient accumulation). stats: NULL, or double[2*M] ZEROED by the caller that
+ *                     receives per-row sum and sum of squares of Y over (b, pixel) -- the batch statistics of the
+ *                     BatchNorm2d that follows (memory.py:76,105), see pm_bn_finalize.
+ *                     K % 8 == 0 (PM_F32) / 16 (PM_BF16), M % 32 == 0, M <= 512, hw * sizeof(dtype) % 16 == 0.
+ *   pm_conv1x1_wgrad  dW [M,N] fp32 (+)= sum_b dY[b] (M x hw) . X[b]^T (hw x N); dY [B,M,hw], X [B,N,hw] in `dtype`;
+ *                     workspace: pm_conv1x1_wgrad_workspace_floats(B,M,N,hw,dtype) floats of scratch (split-K partials).
+ *                     M % 32 == 0, N % 32 == 0.
+ *   pm_bn_finalize    mean/invstd (fp32 [C]) and the running-stat update from the fp64 sums pm_conv1x1_fwd produced;
+ *                     count = B*hw. Same arithmetic as pm_bn_stats.
+ */
+int pm_conv1x1_prep(const float* W, int M, int K, int transpose, int dtype, void* A_hi, void* A_lo, void* stream);
+int pm_conv1x1_fwd(const void* X, const void* A_hi, const void* A_lo, void* Y, double* stats, int B, int K, int M,
+                   int hw, int accumulate, int dtype, void* stream);
+int pm_conv1x1_wgrad_workspace_floats(int B, int M, int N, int hw, int dtype);
+int pm_conv1x1_wgrad(const void* dY, const void* X, float* workspace, float* dW, int B, int M, int N, int hw,
+                     int accumulate, int dtype, void* stream);
+int pm_bn_finalize(const double* stats, int C, double count, float eps, float* mean, float* invstd,
+                   float* running_mean, float* running_var, float momentum, void* stream);
 
 #ifdef __cplusplus
 }

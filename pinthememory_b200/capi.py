@@ -16,9 +16,12 @@ WS_WORDS = 40  # PM_WS_WORDS
 WS_HIST = 4    # PM_WS_HIST
 WS_BAD = 2     # PM_WS_BAD
 
+ABI_VERSION = 200  # PM_ABI_VERSION of include/pinmem_b200.h the argtypes below were written against
+
 _c_p = ctypes.c_void_p
 _c_i = ctypes.c_int
 _c_f = ctypes.c_float
+_c_d = ctypes.c_double
 
 # name -> argtypes, exactly the prototypes of include/pinmem_b200.h
 PROTOTYPES = {
@@ -48,6 +51,11 @@ PROTOTYPES = {
     "pm_bn_apply": [_c_p] * 8 + [_c_i] * 5 + [_c_p],
     "pm_bn_bwd_reduce": [_c_p] * 6 + [_c_i] + [_c_p] * 2 + [_c_i] * 4 + [_c_p],
     "pm_bn_bwd_apply": [_c_p] * 9 + [_c_i] * 2 + [_c_p] * 2 + [_c_i] * 4 + [_c_p],
+    "pm_conv1x1_prep": [_c_p] + [_c_i] * 4 + [_c_p] * 3,
+    "pm_conv1x1_fwd": [_c_p] * 5 + [_c_i] * 6 + [_c_p],
+    "pm_conv1x1_wgrad_workspace_floats": [_c_i] * 5,
+    "pm_conv1x1_wgrad": [_c_p] * 4 + [_c_i] * 6 + [_c_p],
+    "pm_bn_finalize": [_c_p, _c_i, _c_d, _c_f] + [_c_p] * 4 + [_c_f, _c_p],
 }
 EXPORTED_SYMBOLS = sorted(list(PROTOTYPES) + ["pm_status_string"])
 
@@ -67,10 +75,20 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
-        path = _build.LIB_PATH
-        if not os.path.exists(path):
+        # build() is a no-op when the library is newer than every source; a stale .so would otherwise be called
+        # through argtypes written for newer prototypes (silent memory corruption, not an error)
+        try:
             path = _build.build()
+        except Exception:
+            if not os.path.exists(_build.LIB_PATH):
+                raise
+            path = _build.LIB_PATH  # no compiler here (e.g. a run-only box): the version check below still guards
         lib = ctypes.CDLL(path)
+        lib.pm_version.argtypes, lib.pm_version.restype = [], _c_i
+        have = lib.pm_version()
+        if have != ABI_VERSION:
+            raise RuntimeError(f"pinmem_b200: {path} has ABI version {have}, this binding needs {ABI_VERSION}; "
+                               "rebuild with `python -m pinthememory_b200.build --force`")
         for name, argtypes in PROTOTYPES.items():
             fn = getattr(lib, name)
             fn.argtypes = argtypes
@@ -87,12 +105,38 @@ def _check(code, what):
         raise RuntimeError(f"pinmem_b200: {what} failed with status {code}: {msg}")
 
 
+_tls = threading.local()
+
+
 def _ptr(t):
-    return None if t is None else t.data_ptr()
+    """Device address of a tensor argument; remembers its device so _call can refuse a cross-device launch."""
+    if t is None:
+        return None
+    if t.is_cuda:
+        devs = getattr(_tls, "devs", None)
+        if devs is None:
+            devs = _tls.devs = set()
+        devs.add(t.device.index)
+    return t.data_ptr()
 
 
 def _stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+def _check_devices(name):
+    """Every kernel launches on the CURRENT device and its current stream, so a tensor living on another GPU would be
+    dereferenced on the wrong one (an illegal address at best): refuse instead. Wrap the call in
+    ``torch.cuda.device(tensor.device)`` (or ``torch.cuda.set_device``) when the module is not on the current device."""
+    devs = getattr(_tls, "devs", None)
+    if not devs:
+        return
+    cur = torch.cuda.current_device()
+    bad = [d for d in devs if d != cur]
+    devs.clear()
+    if bad:
+        raise RuntimeError(f"pinmem_b200: {name} got tensors on cuda:{bad[0]} while the current device is cuda:{cur}; "
+                           "launch under torch.cuda.device(...) of the tensors' device")
 
 
 def dtype_code(t):
@@ -124,7 +168,7 @@ def score_stride(K):
 # with CUDA events on the launching stream to get per-kernel durations live.
 
 LAUNCHES = 0
-_KERNELS_PER_CALL = {"pm_colsoftmax": 2, "pm_read_bwd": 2, "pm_read_bwd_planes": 2}
+_KERNELS_PER_CALL = {"pm_colsoftmax": 2, "pm_read_bwd": 2, "pm_read_bwd_planes": 2, "pm_conv1x1_wgrad": 2}
 PLANES = 32  # PM_PLANES: score planes appended to q in the score-plane read
 _timing = None  # name -> list of (start_event, end_event) when enabled
 
@@ -152,6 +196,7 @@ def reset_counters():
 def _call(name, *args):
     global LAUNCHES
     fn = getattr(load(), name)
+    _check_devices(name)
     if _timing is None:
         code = fn(*args)
     else:
@@ -287,3 +332,56 @@ def bn_bwd_apply(dy, y, relu_mask, x, mean, invstd, gamma, dgamma, dbeta, relu, 
     _call("pm_bn_bwd_apply", _ptr(dy), _ptr(y), _ptr(relu_mask), _ptr(x), _ptr(mean), _ptr(invstd), _ptr(gamma),
           _ptr(dgamma), _ptr(dbeta), int(relu), int(training), _ptr(dx), _ptr(dres), B, C, h * w, dtype_code(x),
           _stream())
+
+
+# ------------------------------------------------------------------------ 1x1 convolutions (csrc/pm_gemm.cu)
+
+
+def conv1x1_prep(W2d, transpose, dtype):
+    """W2d fp32 [R,S] -> operand A = W2d (transpose False: M=R, K=S) or W2d^T (True: M=S, K=R), zero-padded to a multiple
+    of 128 rows; fp32 returns (A_hi, A_lo) fp32, bf16 returns (A, None)."""
+    R, S = W2d.shape
+    M, K = (S, R) if transpose else (R, S)
+    Mpad = (M + 127) // 128 * 128
+    W2d = _f32c(W2d, "weight")
+    hi = torch.empty(Mpad, K, dtype=dtype, device=W2d.device)
+    lo = torch.empty(Mpad, K, dtype=dtype, device=W2d.device) if dtype == torch.float32 else None
+    _call("pm_conv1x1_prep", _ptr(W2d), M, K, int(bool(transpose)), PM_F32 if dtype == torch.float32 else PM_BF16,
+          _ptr(hi), _ptr(lo), _stream())
+    return hi, lo
+
+
+def conv1x1_ok(x, M, K):
+    """Shapes/alignments the tcgen05 GEMMs take (everything the module produces on aligned feature maps)."""
+    hw = x.shape[2] * x.shape[3]
+    esz = 4 if x.dtype == torch.float32 else 2
+    return (x.is_cuda and x.dtype in (torch.float32, torch.bfloat16) and (hw * esz) % 16 == 0 and x.data_ptr() % 16 == 0
+            and K % (8 if esz == 4 else 16) == 0 and M % 32 == 0 and M <= 512 and K % 32 == 0 and K <= 1024)
+
+
+def conv1x1_fwd(x, A_hi, A_lo, M, y=None, stats=None, accumulate=False):
+    """y[b] (M x hw) (+)= A (M x K) . x[b] (K x hw); stats: zeroed double[2M] receiving per-row sum / sum of squares."""
+    B, K, h, w = x.shape
+    if y is None:
+        y = torch.empty(B, M, h, w, dtype=x.dtype, device=x.device)
+    _call("pm_conv1x1_fwd", _ptr(x), _ptr(A_hi), _ptr(A_lo), _ptr(y), _ptr(stats), B, K, M, h * w, int(bool(accumulate)),
+          dtype_code(x), _stream())
+    return y
+
+
+def conv1x1_wgrad(dy, x, dW=None, accumulate=False):
+    """dW [M,N] fp32 (+)= sum_b dy[b] (M x hw) . x[b]^T (hw x N)."""
+    B, M, h, w = dy.shape
+    N = x.shape[1]
+    if dW is None:
+        dW = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    nws = load().pm_conv1x1_wgrad_workspace_floats(B, M, N, h * w, dtype_code(x))
+    ws = torch.empty(nws, dtype=torch.float32, device=x.device)
+    _call("pm_conv1x1_wgrad", _ptr(dy), _ptr(x), _ptr(ws), _ptr(dW), B, M, N, h * w, int(bool(accumulate)), dtype_code(x),
+          _stream())
+    return dW
+
+
+def bn_finalize(stats, C, count, eps, mean, invstd, running_mean, running_var, momentum):
+    _call("pm_bn_finalize", _ptr(stats), C, float(count), float(eps), _ptr(mean), _ptr(invstd), _ptr(running_mean),
+          _ptr(running_var), float(momentum), _stream())

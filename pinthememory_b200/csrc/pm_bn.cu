@@ -264,12 +264,41 @@ static bool vec_ok(int hw, const void* a, const void* b, const void* c, const vo
     return hw % 4 == 0 && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d | (uintptr_t)e) & m) == 0;
 }
 
+// mean / invstd / running statistics from the fp64 (sum, sum of squares) pairs the convolution epilogue produced
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, int C, double n, float eps, float* __restrict__ mean,
+                                   float* __restrict__ invstd, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float momentum) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double m = stats[c] / n;
+    double var = stats[C + c] / n - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[c] = (float)m;
+    invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean != nullptr) {
+        const double unb = n > 1.0 ? var * n / (n - 1.0) : var;
+        running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * m);
+        running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unb);
+    }
+}
+
 }  // namespace pm
+
 
 static int bn_check(int B, int C, int hw, int dtype) {
     if (dtype != PM_F32 && dtype != PM_BF16) return PM_ERR_DTYPE;
     if (B <= 0 || C <= 0 || hw <= 0 || (long long)B * C > 0x7fffffffLL || (long long)B * hw > 0x7fffffffLL)
         return PM_ERR_SHAPE;
+    return 0;
+}
+
+extern "C" int pm_bn_finalize(const double* stats, int C, double count, float eps, float* mean, float* invstd,
+                              float* running_mean, float* running_var, float momentum, void* stream) {
+    if (!stats || !mean || !invstd || ((running_mean == nullptr) != (running_var == nullptr))) return PM_ERR_NULL;
+    if (C <= 0 || count <= 0.0) return PM_ERR_SHAPE;
+    pm::bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, C, count, eps, mean, invstd, running_mean,
+                                                                              running_var, momentum);
+    PM_CHECK_LAUNCH();
     return 0;
 }
 

@@ -1,0 +1,690 @@
+// The two 1x1 convolutions of the memory module as tcgen05 GEMMs.
+//
+// Reference: `self.output[0] = Conv2d(2C -> C, 1x1, bias=False)` (memory.py:103-104, applied at :334) and
+// `Writingnet.writefeat[0] = Conv2d(C -> C, 1x1, bias=False)` (memory.py:74-75, applied at :84 / :214), plus their
+// autograd (input gradient, weight gradient). On NCHW activations a 1x1 convolution is, per image b,
+//     Y[b] (M x hw) = A (M x K) . X[b] (K x hw)           A = weight  (forward), weight^T (input gradient)
+//     dW   (M x N)  = sum_b dY[b] (M x hw) . X[b]^T (hw x N)                         (weight gradient)
+// with the PIXEL axis contiguous. Both run on the 5th-generation tensor cores:
+//   * operands are staged by TMA (`cp.async.bulk.tensor.2d`, SWIZZLE_128B boxes with 128-byte rows) into a
+//     shared-memory ring; the activation tile of the first form is an MN-major UMMA operand (pixels contiguous),
+//     the weight tile a K-major one; in the weight-gradient form both activations are K-major (K = pixels);
+//   * one elected thread issues `tcgen05.mma` (M = 128 rows of output channels, N = the pixel tile / the input
+//     channels), accumulators live in TMEM (fp32, double-buffered where they fit), `tcgen05.commit` releases ring
+//     slots and hands finished accumulators to the epilogue warps through mbarriers;
+//   * fp32 I/O computes in 3xTF32 (hi.hi + hi.lo + lo.hi, hi = the 10 mantissa bits the tensor core reads,
+//     lo = x - hi exact in fp32): plain TF32 (2^-11 per product) cannot hold the 1e-5 parity bar. The weights are
+//     split once per call by `conv1x1_prep_kernel`; the activation tiles are split in shared memory by four
+//     transform warps (same swizzled offset in a second buffer, so no layout change). bf16 I/O is one
+//     `kind::f16` pass straight from the TMA tiles;
+//   * epilogue warps read TMEM with `tcgen05.ld` (thread = output channel, registers = 32 consecutive pixels), so
+//     the per-channel sum and sum of squares of the BatchNorm that follows are thread-local register sums
+//     (fp64 across tiles, one atomicAdd per channel per CTA); the tile goes out through a swizzled shared-memory
+//     stage and a TMA store (or TMA reduce-add when the caller accumulates into an existing gradient).
+#include "pm_common.cuh"
+#include "pm_umma.cuh"
+
+namespace pm {
+
+constexpr int GEMM_THREADS = 320;  // warp 0 TMA producer, 1 MMA issuer (+TMEM owner), 2-5 epilogue, 6-9 operand split
+constexpr int GEMM_RING_BYTES = 192 * 1024;
+constexpr int TILE_A_BYTES = 128 * 128;  // one 128-row K-major operand block: [128 rows][128 bytes]
+
+template <typename T>
+struct GemmTraits;
+template <>
+struct GemmTraits<float> {
+    static constexpr int PXC = 32;   // elements per 128-byte row
+    static constexpr int UK = 8;     // K per tcgen05.mma (32 bytes)
+    static constexpr uint32_t FMT = UMMA_FMT_TF32;
+    static constexpr bool SPLIT = true;
+};
+template <>
+struct GemmTraits<__nv_bfloat16> {
+    static constexpr int PXC = 64;
+    static constexpr int UK = 16;
+    static constexpr uint32_t FMT = UMMA_FMT_BF16;
+    static constexpr bool SPLIT = false;
+};
+
+template <typename T>
+__device__ __forceinline__ void umma_issue(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    if constexpr (sizeof(T) == 4) umma_tf32(d, a, b, idesc, acc);
+    else umma_bf16(d, a, b, idesc, acc);
+}
+
+// lo = x - trunc_tf32(x) for `n4` float4 of a staged tile, written at the same offsets of `lo` (optionally the
+// truncated value is written back so the tensor core sees an exact TF32 "hi" whatever it does with the low bits)
+template <bool MASK_HI>
+__device__ __forceinline__ void split_tile(float4* __restrict__ raw, float4* __restrict__ lo, int n4, int t, int nthreads) {
+    for (int i = t; i < n4; i += nthreads) {
+        const float4 v = raw[i];
+        float4 h, l;
+        h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+        h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+        h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+        h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+        l.x = v.x - h.x, l.y = v.y - h.y, l.z = v.z - h.z, l.w = v.w - h.w;
+        lo[i] = l;
+        if (MASK_HI) raw[i] = h;
+    }
+}
+
+// =================================================================================================================
+// Form 1: Y[b] = A . X[b]   (forward convolution and input gradient)
+//   mapX  : [B*K rows][hw] activations, box [KB rows][PXC pixels]           (MN-major B operand)
+//   mapAh : [Mpad rows][K] weights (fp32: TF32 "hi" part; bf16: the weight), box [128 rows][KB]   (K-major A operand)
+//   mapAl : fp32 only, the "lo" part
+//   mapY  : [B*M rows][hw] output, box [32 rows][PXC pixels]
+//   CTA tile: MT x 128 output rows (starting at 128*m_tile0) x NT pixels of one image; persistent over tiles.
+// =================================================================================================================
+template <typename T, int MT, int NT, bool MASK_HI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    conv1x1_nn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapAh,
+                      const __grid_constant__ CUtensorMap mapAl, const __grid_constant__ CUtensorMap mapY, int K, int M,
+                      int m_tile0, int tiles_per_img, int total_tiles, int accumulate, double* __restrict__ stats, int dbg) {
+    using TR = GemmTraits<T>;
+    constexpr int PXC = TR::PXC, UK = TR::UK, KB = PXC, KSTEPS = KB / UK;
+    constexpr int NCH = NT / PXC;                      // 128-byte pixel chunks per tile
+    constexpr int XCHUNK = KB * 128;                   // bytes of one [KB rows][128 B] chunk
+    constexpr int XBYTES = NCH * XCHUNK;               // = NT * KB * sizeof(T)
+    constexpr int NOPA = TR::SPLIT ? 2 : 1;
+    constexpr int STAGE = NOPA * (XBYTES + MT * TILE_A_BYTES);
+    constexpr int STAGES = (GEMM_RING_BYTES / STAGE) > 4 ? 4 : (GEMM_RING_BYTES / STAGE);
+    constexpr int ACC = (512 / (MT * NT)) >= 2 ? 2 : 1;  // accumulator stages in TMEM
+    constexpr uint32_t TX = XBYTES + NOPA * MT * TILE_A_BYTES;
+    static_assert(STAGES >= 2, "ring too small");
+    static_assert(MT * NT <= 512, "accumulators exceed TMEM");
+    constexpr uint32_t IDESC = umma_idesc(TR::FMT, false, true, 128, NT);
+
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_align(smem_raw, 1024);
+    unsigned char* stg = smem + STAGES * STAGE;                 // 4 warps x 2 x [32 rows][128 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stg + 4 * 2 * 4096);
+    uint64_t* full = bars;                 // [STAGES] TMA landed
+    uint64_t* empty = bars + STAGES;       // [STAGES] MMAs of the stage retired
+    uint64_t* xfull = bars + 2 * STAGES;   // [STAGES] lo parts written (fp32)
+    uint64_t* accf = bars + 3 * STAGES;    // [ACC] accumulator complete
+    uint64_t* acce = accf + ACC;           // [ACC] accumulator drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acce + ACC);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+            mbar_init(&xfull[i], 128);
+        }
+        for (int i = 0; i < ACC; ++i) {
+            mbar_init(&accf[i], 1);
+            mbar_init(&acce[i], 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        prefetch_tmap(&mapX);
+        prefetch_tmap(&mapAh);
+        prefetch_tmap(&mapY);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int nkb = (K + KB - 1) / KB;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ---------------------------------------------------------------- TMA producer
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int b = tile / tiles_per_img, px0 = (tile - b * tiles_per_img) * NT;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                    unsigned char* st = smem + s * STAGE;
+                    mbar_expect_tx(&full[s], TX);
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) tma_load_2d(st + c * XCHUNK, &mapX, px0 + c * PXC, b * K + kb * KB, &full[s]);
+                    unsigned char* sa = st + NOPA * XBYTES;
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        tma_load_2d(sa + mt * TILE_A_BYTES, &mapAh, kb * KB, (m_tile0 + mt) * 128, &full[s]);
+                        if (TR::SPLIT)
+                            tma_load_2d(sa + (MT + mt) * TILE_A_BYTES, &mapAl, kb * KB, (m_tile0 + mt) * 128, &full[s]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ---------------------------------------------------------------- MMA issuer
+            uint32_t it = 0, tc = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
+                const int a = tc % ACC;
+                mbar_wait(&acce[a], ((tc / ACC) & 1) ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&full[s], ph);
+                    if (TR::SPLIT) mbar_wait(&xfull[s], ph);
+                    tc_fence_after();
+                    const uint32_t sx = smem_u32(smem + s * STAGE);
+                    const uint32_t sa = sx + NOPA * XBYTES;
+                    int ksteps = (K - kb * KB) / UK;
+                    if (ksteps > KSTEPS) ksteps = KSTEPS;
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        // X: MN-major, 128-byte pixel chunks XCHUNK apart, 8-row K groups 1024 bytes apart
+                        // tf32 has one MN-major layout: 32-byte swizzle atoms, K groups of 4 rows (512 bytes apart)
+                        constexpr uint32_t XL = sizeof(T) == 4 ? UMMA_SW128_BASE32B : UMMA_SW128;
+                        constexpr uint32_t XSBO = sizeof(T) == 4 ? 512u : 1024u;
+                        const uint32_t lbo = (dbg & 1) ? XSBO : (uint32_t)XCHUNK, sbo = (dbg & 1) ? (uint32_t)XCHUNK : XSBO;
+                        const uint64_t bh = umma_desc(sx + ks * (UK * 128), lbo, sbo, XL);
+                        const uint64_t bl = umma_desc(sx + XBYTES + ks * (UK * 128), lbo, sbo, XL);
+                        const uint32_t first = (kb | ks) ? 1u : 0u;
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) {
+                            const uint32_t d = tmem + (uint32_t)((a * MT + mt) * NT);
+                            const uint64_t ah = umma_desc(sa + mt * TILE_A_BYTES + ks * 32, 16, 1024);
+                            if (TR::SPLIT) {
+                                const uint64_t al = umma_desc(sa + (MT + mt) * TILE_A_BYTES + ks * 32, 16, 1024);
+                                umma_issue<T>(d, al, bh, IDESC, first);
+                                umma_issue<T>(d, ah, bl, IDESC, 1u);
+                                umma_issue<T>(d, ah, bh, IDESC, 1u);
+                            } else {
+                                umma_issue<T>(d, ah, bh, IDESC, first);
+                            }
+                        }
+                    }
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&accf[a]);
+            }
+        }
+    } else if (warp < 6) {  // ------------------------------------------------------------------ epilogue
+        const int q = warp & 3;  // TMEM lane quarter this warp may read
+        unsigned char* mystg = stg + q * 2 * 4096;
+        int bi = 0;
+        double sum[MT], sq[MT];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) sum[mt] = 0.0, sq[mt] = 0.0;
+        uint32_t tc = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
+            const int b = tile / tiles_per_img, px0 = (tile - b * tiles_per_img) * NT;
+            const int a = tc % ACC;
+            mbar_wait(&accf[a], (tc / ACC) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const int row0 = (m_tile0 + mt) * 128 + q * 32;
+                if (row0 >= M) continue;  // padded rows of the last 128-row tile (warp-uniform)
+                float ts = 0.f, tq = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < NCH; ++c) {
+                    const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((a * MT + mt) * NT + c * PXC);
+                    uint4 out[8];
+                    if constexpr (sizeof(T) == 4) {
+                        uint32_t r[32];
+                        tmem_ld32(ta, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float v = __uint_as_float(r[j]);
+                            ts += v;
+                            tq = fmaf(v, v, tq);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) out[j] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                    } else {
+                        uint32_t r0[32], r1[32];
+                        tmem_ld32(ta, r0);
+                        tmem_ld32(ta + 32, r1);
+                        tmem_ld_wait();
+                        uint32_t pk[32];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const __nv_bfloat162 p0 = __floats2bfloat162_rn(__uint_as_float(r0[2 * j]), __uint_as_float(r0[2 * j + 1]));
+                            const __nv_bfloat162 p1 = __floats2bfloat162_rn(__uint_as_float(r1[2 * j]), __uint_as_float(r1[2 * j + 1]));
+                            pk[j] = *reinterpret_cast<const uint32_t*>(&p0);
+                            pk[16 + j] = *reinterpret_cast<const uint32_t*>(&p1);
+                            const float2 f0 = __bfloat1622float2(p0), f1 = __bfloat1622float2(p1);
+                            ts += (f0.x + f0.y) + (f1.x + f1.y);
+                            tq = fmaf(f0.x, f0.x, fmaf(f0.y, f0.y, fmaf(f1.x, f1.x, fmaf(f1.y, f1.y, tq))));
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) out[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                    }
+                    unsigned char* buf = mystg + bi * 4096;
+                    bi ^= 1;
+                    if (lane == 0) bulk_wait_read<1>();  // the store issued two chunks ago has left this buffer
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = out[j];
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (accumulate) tma_reduce_add_2d(&mapY, px0 + c * PXC, b * M + row0, buf);
+                        else tma_store_2d(&mapY, px0 + c * PXC, b * M + row0, buf);
+                        bulk_commit();
+                    }
+                }
+                sum[mt] += (double)ts;
+                sq[mt] += (double)tq;
+            }
+            tc_fence_before();
+            mbar_arrive(&acce[a]);
+        }
+        if (lane == 0) bulk_wait<0>();
+        if (stats != nullptr) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const int row = (m_tile0 + mt) * 128 + q * 32 + lane;
+                if (row < M && blockIdx.x < total_tiles) {
+                    atomicAdd(&stats[row], sum[mt]);
+                    atomicAdd(&stats[M + row], sq[mt]);
+                }
+            }
+        }
+    } else {  // --------------------------------------------------------------- operand split (fp32 only)
+        if constexpr (TR::SPLIT) {
+            const int t = threadIdx.x - 6 * 32;
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&full[s], (it / STAGES) & 1);
+                    unsigned char* st = smem + s * STAGE;
+                    split_tile<MASK_HI>(reinterpret_cast<float4*>(st), reinterpret_cast<float4*>(st + XBYTES), XBYTES / 16, t, 128);
+                    fence_proxy_async_smem();
+                    mbar_arrive(&xfull[s]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+template <typename T, int MT, int NT>
+constexpr size_t nn_smem_bytes() {
+    using TR = GemmTraits<T>;
+    constexpr int NOPA = TR::SPLIT ? 2 : 1;
+    constexpr int STAGE = NOPA * (NT * TR::PXC * (int)sizeof(T) + MT * TILE_A_BYTES);
+    constexpr int STAGES = (GEMM_RING_BYTES / STAGE) > 4 ? 4 : (GEMM_RING_BYTES / STAGE);
+    return (size_t)STAGES * STAGE + 4 * 2 * 4096 + 256 + 1024;
+}
+
+static int gemm_mask_hi() {  // PM_GEMM_MASK_HI=1: write the truncated TF32 value back instead of trusting the hardware
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PM_GEMM_MASK_HI");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v;
+}
+
+static int gemm_dbg() {  // PM_GEMM_DBG: bring-up switches (bit 0 swaps LBO/SBO of the MN-major operand descriptor)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PM_GEMM_DBG");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
+template <typename T, int MT, int NT>
+static int launch_nn(const void* X, const void* Ah, const void* Al, void* Y, double* stats, int B, int K, int M, int Mpad,
+                     int hw, int m_tile0, int accumulate, cudaStream_t st) {
+    using TR = GemmTraits<T>;
+    CUtensorMap mX, mAh, mAl, mY;
+    if (!make_map_2d<T>(&mX, X, (size_t)B * K, hw, TR::PXC, TR::PXC, sizeof(T) == 4 ? 2 : 1)) return PM_ERR_ALIGN;
+    if (!make_map_2d<T>(&mAh, Ah, Mpad, K, 128, TR::PXC, true)) return PM_ERR_ALIGN;
+    if (TR::SPLIT) {
+        if (!make_map_2d<T>(&mAl, Al, Mpad, K, 128, TR::PXC, true)) return PM_ERR_ALIGN;
+    } else {
+        mAl = mAh;
+    }
+    if (!make_map_2d<T>(&mY, Y, (size_t)B * M, hw, 32, TR::PXC, true)) return PM_ERR_ALIGN;
+    const int tiles_per_img = (hw + NT - 1) / NT, total = B * tiles_per_img;
+    int grid = 148;
+    if (grid > total) grid = total;
+    const size_t smem = nn_smem_bytes<T, MT, NT>();
+    cudaError_t e;
+    if (gemm_mask_hi()) {
+        auto kern = conv1x1_nn_kernel<T, MT, NT, true>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        kern<<<grid, GEMM_THREADS, smem, st>>>(mX, mAh, mAl, mY, K, M, m_tile0, tiles_per_img, total, accumulate, stats, gemm_dbg());
+    } else {
+        auto kern = conv1x1_nn_kernel<T, MT, NT, false>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        kern<<<grid, GEMM_THREADS, smem, st>>>(mX, mAh, mAl, mY, K, M, m_tile0, tiles_per_img, total, accumulate, stats, gemm_dbg());
+    }
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+// =================================================================================================================
+// Form 2: dW (M x N) = sum over (b, pixel) of dY[b] . X[b]^T   (weight gradient). Both operands K-major (K = pixels).
+//   mapG : [B*M rows][hw] output gradient, box [128 rows][PXC pixels]      (A operand)
+//   mapX : [B*Ntot rows][hw] layer input,  box [NW rows][PXC pixels], NI = N / NW boxes per stage   (B operand);
+//          this launch covers input channels n0 .. n0+N-1 (N <= 288) of the Ntot
+//   grid : (pixel chunks of every image, M / 128); each CTA writes its [128][N] partial to `part`
+//          part[(chunk * Mpad + row) * N + col]; wgrad_reduce_kernel sums the chunks.
+// =================================================================================================================
+constexpr int WG_NMAX = 288;
+
+template <typename T, bool MASK_HI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    conv1x1_wgrad_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapX, int M, int N,
+                         int Ntot, int n0, int NW, int hw, int chunks_per_img, int blocks_per_chunk, float* __restrict__ part,
+                         int Mpad) {
+    using TR = GemmTraits<T>;
+    constexpr int PXC = TR::PXC, UK = TR::UK, KSTEPS = PXC / UK;
+    constexpr int NOPA = TR::SPLIT ? 2 : 1;
+    constexpr int BBYTES = WG_NMAX * 128;
+    constexpr int STAGE = NOPA * (TILE_A_BYTES + BBYTES);
+    constexpr int STAGES = (212992 / STAGE) > 4 ? 4 : (212992 / STAGE);
+    static_assert(STAGES >= 2, "ring too small");
+
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_align(smem_raw, 1024);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* xfull = bars + 2 * STAGES;
+    uint64_t* accf = bars + 3 * STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accf + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+            mbar_init(&xfull[i], 128);
+        }
+        mbar_init(accf, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        prefetch_tmap(&mapG);
+        prefetch_tmap(&mapX);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const int chunk = blockIdx.x, mt = blockIdx.y;
+    const int b = chunk / chunks_per_img, cb0 = (chunk - b * chunks_per_img) * blocks_per_chunk;
+    const int nblk_img = (hw + PXC - 1) / PXC;
+    int nkb = nblk_img - cb0;
+    if (nkb > blocks_per_chunk) nkb = blocks_per_chunk;
+    if (nkb < 0) nkb = 0;
+    const int NI = N / NW;
+    const uint32_t TX = TILE_A_BYTES + (uint32_t)N * 128;
+    const uint32_t IDESC = umma_idesc(TR::FMT, false, false, 128, NW);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
+                unsigned char* st = smem + s * STAGE;
+                mbar_expect_tx(&full[s], TX);
+                const int px = (cb0 + kb) * PXC;
+                tma_load_2d(st, &mapG, px, b * M + mt * 128, &full[s]);
+                for (int j = 0; j < NI; ++j)
+                    tma_load_2d(st + NOPA * TILE_A_BYTES + j * NW * 128, &mapX, px, b * Ntot + n0 + j * NW, &full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                if (TR::SPLIT) mbar_wait(&xfull[s], ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + s * STAGE);
+                const uint32_t sb = sa + NOPA * TILE_A_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < KSTEPS; ++ks) {
+                    const uint64_t ah = umma_desc(sa + ks * 32, 16, 1024);
+                    const uint64_t al = umma_desc(sa + TILE_A_BYTES + ks * 32, 16, 1024);
+                    const uint32_t first = (kb | ks) ? 1u : 0u;
+                    for (int j = 0; j < NI; ++j) {
+                        const uint32_t d = tmem + (uint32_t)(j * NW);
+                        const uint64_t bh = umma_desc(sb + j * NW * 128 + ks * 32, 16, 1024);
+                        if (TR::SPLIT) {
+                            const uint64_t bl = umma_desc(sb + BBYTES + j * NW * 128 + ks * 32, 16, 1024);
+                            umma_issue<T>(d, al, bh, IDESC, first);
+                            umma_issue<T>(d, ah, bl, IDESC, 1u);
+                            umma_issue<T>(d, ah, bh, IDESC, 1u);
+                        } else {
+                            umma_issue<T>(d, ah, bh, IDESC, first);
+                        }
+                    }
+                }
+                umma_commit(&empty[s]);
+            }
+            umma_commit(accf);
+        }
+    } else if (warp < 6) {
+        const int q = warp & 3;
+        const int row = mt * 128 + q * 32 + lane;
+        float* dst = part + ((size_t)chunk * Mpad + row) * N;
+        if (nkb > 0) {
+            mbar_wait(accf, 0);
+            tc_fence_after();
+            for (int c = 0; c < N / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<uint4*>(dst + c * 32 + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+            }
+        } else {
+            for (int c = 0; c < N / 4; ++c) *reinterpret_cast<uint4*>(dst + 4 * c) = make_uint4(0u, 0u, 0u, 0u);
+        }
+    } else {
+        if constexpr (TR::SPLIT) {
+            const int t = threadIdx.x - 6 * 32;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(&full[s], (kb / STAGES) & 1);
+                unsigned char* st = smem + s * STAGE;
+                split_tile<MASK_HI>(reinterpret_cast<float4*>(st), reinterpret_cast<float4*>(st + TILE_A_BYTES), TILE_A_BYTES / 16, t, 128);
+                split_tile<MASK_HI>(reinterpret_cast<float4*>(st + 2 * TILE_A_BYTES), reinterpret_cast<float4*>(st + 2 * TILE_A_BYTES + BBYTES),
+                                    N * 8, t, 128);
+                fence_proxy_async_smem();
+                mbar_arrive(&xfull[s]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+// dW[m][n] (+)= sum over chunks of part[chunk][m][n]; float4 per thread
+__global__ void __launch_bounds__(128) wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dW, int M, int N,
+                                                           int Mpad, int ldw, int col0, int nchunks, int accumulate) {
+    const int i = blockIdx.x * 128 + threadIdx.x;  // float4 index in [M][N/4]
+    const int n4 = N / 4;
+    if (i >= M * n4) return;
+    const int m = i / n4, c = i - m * n4;
+    const float4* p = reinterpret_cast<const float4*>(part) + (size_t)m * n4 + c;
+    const size_t stride = (size_t)Mpad * n4;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+    int j = 0;
+    for (; j + 4 <= nchunks; j += 4) {
+        const float4 v0 = __ldg(p + (size_t)j * stride), v1 = __ldg(p + (size_t)(j + 1) * stride);
+        const float4 v2 = __ldg(p + (size_t)(j + 2) * stride), v3 = __ldg(p + (size_t)(j + 3) * stride);
+        a0.x += v0.x, a0.y += v0.y, a0.z += v0.z, a0.w += v0.w;
+        a1.x += v1.x, a1.y += v1.y, a1.z += v1.z, a1.w += v1.w;
+        a2.x += v2.x, a2.y += v2.y, a2.z += v2.z, a2.w += v2.w;
+        a3.x += v3.x, a3.y += v3.y, a3.z += v3.z, a3.w += v3.w;
+    }
+    for (; j < nchunks; ++j) {
+        const float4 v0 = __ldg(p + (size_t)j * stride);
+        a0.x += v0.x, a0.y += v0.y, a0.z += v0.z, a0.w += v0.w;
+    }
+    float4 r = make_float4((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y), (a0.z + a1.z) + (a2.z + a3.z),
+                           (a0.w + a1.w) + (a2.w + a3.w));
+    float* o = dW + (size_t)m * ldw + col0 + 4 * c;
+    if (accumulate) r.x += o[0], r.y += o[1], r.z += o[2], r.w += o[3];
+    o[0] = r.x, o[1] = r.y, o[2] = r.z, o[3] = r.w;
+}
+
+template <typename T>
+constexpr size_t wgrad_smem_bytes() {
+    using TR = GemmTraits<T>;
+    constexpr int NOPA = TR::SPLIT ? 2 : 1;
+    constexpr int STAGE = NOPA * (TILE_A_BYTES + WG_NMAX * 128);
+    constexpr int STAGES = (212992 / STAGE) > 4 ? 4 : (212992 / STAGE);
+    return (size_t)STAGES * STAGE + 256 + 1024;
+}
+
+static void wgrad_split(int B, int M, int hw, int pxc, int* chunks_per_img, int* blocks_per_chunk) {
+    const int mtiles = (M + 127) / 128, nblk = (hw + pxc - 1) / pxc;
+    int want = 148 / (mtiles * B);
+    if (want < 1) want = 1;
+    if (want > nblk) want = nblk;
+    const int bpc = (nblk + want - 1) / want;
+    *blocks_per_chunk = bpc;
+    *chunks_per_img = (nblk + bpc - 1) / bpc;
+}
+
+template <typename T>
+static int launch_wgrad(const void* dY, const void* X, float* part, float* dW, int B, int M, int Ntot, int n0, int N, int hw,
+                        int accumulate, cudaStream_t st) {
+    using TR = GemmTraits<T>;
+    const int NI = N > 256 ? 2 : 1, NW = N / NI;
+    const int Mpad = (M + 127) / 128 * 128;
+    int cpi, bpc;
+    wgrad_split(B, M, hw, TR::PXC, &cpi, &bpc);
+    CUtensorMap mG, mX;
+    if (!make_map_2d<T>(&mG, dY, (size_t)B * M, hw, 128, TR::PXC, true)) return PM_ERR_ALIGN;
+    if (!make_map_2d<T>(&mX, X, (size_t)B * Ntot, hw, NW, TR::PXC, true)) return PM_ERR_ALIGN;
+    const size_t smem = wgrad_smem_bytes<T>();
+    dim3 grid(B * cpi, Mpad / 128);
+    cudaError_t e;
+    if (gemm_mask_hi()) {
+        auto kern = conv1x1_wgrad_kernel<T, true>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        kern<<<grid, GEMM_THREADS, smem, st>>>(mG, mX, M, N, Ntot, n0, NW, hw, cpi, bpc, part, Mpad);
+    } else {
+        auto kern = conv1x1_wgrad_kernel<T, false>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        kern<<<grid, GEMM_THREADS, smem, st>>>(mG, mX, M, N, Ntot, n0, NW, hw, cpi, bpc, part, Mpad);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    const int n4 = M * (N / 4);
+    wgrad_reduce_kernel<<<(n4 + 127) / 128, 128, 0, st>>>(part, dW, M, N, Mpad, Ntot, n0, B * cpi, accumulate);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+// A[m][k] = W[m][k] (transpose = 0, W is [M][K]) or W[k][m] (transpose = 1, W is [K][M]); rows M..Mpad-1 are zero.
+// fp32: hi = the 10 mantissa bits the tensor core keeps, lo = W - hi (both fp32 [Mpad][K]); bf16: hi = bf16(W).
+template <typename T>
+__global__ void conv1x1_prep_kernel(const float* __restrict__ W, int M, int K, int Mpad, int transpose, T* __restrict__ hi,
+                                    T* __restrict__ lo) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Mpad * K) return;
+    const int m = i / K, k = i - m * K;
+    const float v = m < M ? (transpose ? W[(size_t)k * M + m] : W[(size_t)m * K + k]) : 0.f;
+    if constexpr (sizeof(T) == 4) {
+        const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        hi[i] = h;
+        lo[i] = v - h;
+    } else {
+        hi[i] = __float2bfloat16_rn(v);
+    }
+}
+
+}  // namespace pm
+
+using namespace pm;
+
+extern "C" {
+
+int pm_conv1x1_prep(const float* W, int M, int K, int transpose, int dtype, void* A_hi, void* A_lo, void* stream) {
+    if (!W || !A_hi || (dtype == PM_F32 && !A_lo)) return PM_ERR_NULL;
+    if (dtype != PM_F32 && dtype != PM_BF16) return PM_ERR_DTYPE;
+    if (M <= 0 || K <= 0) return PM_ERR_SHAPE;
+    const int Mpad = (M + 127) / 128 * 128, n = Mpad * K;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == PM_F32)
+        conv1x1_prep_kernel<float><<<(n + 255) / 256, 256, 0, st>>>(W, M, K, Mpad, transpose, (float*)A_hi, (float*)A_lo);
+    else
+        conv1x1_prep_kernel<__nv_bfloat16><<<(n + 255) / 256, 256, 0, st>>>(W, M, K, Mpad, transpose, (__nv_bfloat16*)A_hi, nullptr);
+    PM_CHECK_LAUNCH();
+    return 0;
+}
+
+int pm_conv1x1_fwd(const void* X, const void* A_hi, const void* A_lo, void* Y, double* stats, int B, int K, int M, int hw,
+                   int accumulate, int dtype, void* stream) {
+    if (!X || !A_hi || !Y || (dtype == PM_F32 && !A_lo)) return PM_ERR_NULL;
+    if (dtype != PM_F32 && dtype != PM_BF16) return PM_ERR_DTYPE;
+    const int esz = dtype == PM_F32 ? 4 : 2, uk = dtype == PM_F32 ? 8 : 16;
+    if (B <= 0 || hw <= 0 || K <= 0 || M <= 0 || K % uk || M % 32 || M > 512) return PM_ERR_SHAPE;
+    if ((hw * esz) % 16 || ((uintptr_t)X | (uintptr_t)Y | (uintptr_t)A_hi | (uintptr_t)A_lo) % 16) return PM_ERR_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Mpad = (M + 127) / 128 * 128, mtiles = Mpad / 128;
+    // two 128-row tiles per CTA where possible (the activation tile is read once for both), then the remainder
+    for (int t0 = 0; t0 < mtiles; t0 += 2) {
+        const int mt = mtiles - t0 >= 2 ? 2 : 1;
+        int rc;
+        if (dtype == PM_F32)
+            rc = mt == 2 ? launch_nn<float, 2, 128>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, st)
+                         : launch_nn<float, 1, 128>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, st);
+        else
+            rc = mt == 2 ? launch_nn<__nv_bfloat16, 2, 128>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, st)
+                         : launch_nn<__nv_bfloat16, 1, 128>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int pm_conv1x1_wgrad_workspace_floats(int B, int M, int N, int hw, int dtype) {
+    if (B <= 0 || M <= 0 || N <= 0 || hw <= 0) return 0;
+    int cpi, bpc;
+    wgrad_split(B, M, hw, dtype == PM_F32 ? 32 : 64, &cpi, &bpc);
+    const int Mpad = (M + 127) / 128 * 128;
+    const int nmax = N > WG_NMAX ? WG_NMAX : N;
+    return B * cpi * Mpad * nmax;
+}
+
+int pm_conv1x1_wgrad(const void* dY, const void* X, float* workspace, float* dW, int B, int M, int N, int hw, int accumulate,
+                     int dtype, void* stream) {
+    if (!dY || !X || !workspace || !dW) return PM_ERR_NULL;
+    if (dtype != PM_F32 && dtype != PM_BF16) return PM_ERR_DTYPE;
+    const int esz = dtype == PM_F32 ? 4 : 2;
+    if (B <= 0 || hw <= 0 || M <= 0 || N <= 0 || M % 32 || N % 32 || M > 512 || N > 1024) return PM_ERR_SHAPE;
+    if ((hw * esz) % 16 || ((uintptr_t)X | (uintptr_t)dY | (uintptr_t)workspace | (uintptr_t)dW) % 16) return PM_ERR_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    // column blocks of at most WG_NMAX input channels (TMEM: 128 lanes x 512 columns; ring: 2 x 104 KB); blocks wider
+    // than 256 channels take two N/2-wide instructions, so they must be multiples of 32 channels
+    for (int n0 = 0; n0 < N;) {
+        int nb = N - n0;
+        if (nb > WG_NMAX) nb = 256;
+        const int rc = dtype == PM_F32 ? launch_wgrad<float>(dY, X, workspace, dW, B, M, N, n0, nb, hw, accumulate, st)
+                                       : launch_wgrad<__nv_bfloat16>(dY, X, workspace, dW, B, M, N, n0, nb, hw, accumulate, st);
+        if (rc) return rc;
+        n0 += nb;
+    }
+    return 0;
+}
+
+}  // extern "C"

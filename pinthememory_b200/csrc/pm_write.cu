@@ -545,7 +545,7 @@ extern "C" int pm_update_bwd(const float* dM_new, const float* g_div, const floa
     return 0;
 }
 
-extern "C" int pm_version(void) { return 100; }
+extern "C" int pm_version(void) { return PM_ABI_VERSION; }
 
 extern "C" const char* pm_status_string(int code) {
     if (code > 0) return cudaGetErrorString((cudaError_t)code);

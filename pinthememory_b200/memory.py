@@ -258,33 +258,105 @@ class _BnActFn(torch.autograd.Function):
         return dx, dgamma, dbeta, dres, None, None, None, None, None, None
 
 
+class _ConvBnActFn(torch.autograd.Function):
+    """y = [relu](BatchNorm2d(conv1x1(x, W)) [+ residual]) -- memory.py:74-87 (Writingnet) and :103-107 (self.output).
+
+    The convolution, its input gradient and its weight gradient are the tcgen05 GEMMs of csrc/pm_gemm.cu (3xTF32 in
+    fp32, bf16 otherwise); the forward GEMM's epilogue produces the batch statistics, so the BatchNorm costs one
+    normalise pass instead of a statistics pass + a normalise pass; when the residual IS the convolution input
+    (Writingnet) the input-gradient GEMM accumulates into the residual gradient (TMA reduce-add) instead of leaving an
+    element-wise add to autograd."""
+
+    @staticmethod
+    def forward(ctx, x, W, gamma, beta, residual, running_mean, running_var, use_batch_stats, factor, eps, relu,
+                res_is_x):
+        B, K, h, w = x.shape
+        M = W.shape[0]
+        dev = x.device
+        W2 = W.detach().reshape(M, K).to(torch.float32).contiguous()
+        g32 = gamma.detach().to(torch.float32).contiguous()
+        b32 = beta.detach().to(torch.float32).contiguous()
+        hi, lo = capi.conv1x1_prep(W2, False, x.dtype)
+        if use_batch_stats:
+            stats = torch.zeros(2 * M, dtype=torch.float64, device=dev)
+            xc = capi.conv1x1_fwd(x, hi, lo, M, stats=stats)
+            mean = torch.empty(M, dtype=torch.float32, device=dev)
+            invstd = torch.empty(M, dtype=torch.float32, device=dev)
+            capi.bn_finalize(stats, M, B * h * w, eps, mean, invstd, running_mean, running_var, factor)
+        else:
+            xc = capi.conv1x1_fwd(x, hi, lo, M)
+            mean = running_mean.to(torch.float32).contiguous()
+            invstd = (running_var.to(torch.float32) + eps).rsqrt_()
+        res = x if res_is_x else residual
+        y = torch.empty_like(xc)
+        nwords = capi.bn_mask_words(B, M, h * w) if relu else 0
+        vec_ok = nwords > 0 and all(t is None or t.data_ptr() % 16 == 0 for t in (xc, y, res))
+        mask = torch.empty(nwords, dtype=torch.int32, device=dev) if vec_ok else None
+        capi.bn_apply(xc, mean, invstd, g32, b32, res, y, relu, relu_mask=mask)
+        ctx.relu, ctx.training, ctx.res_is_x, ctx.has_res = relu, use_batch_stats, res_is_x, res is not None
+        ctx.use_mask = mask is not None
+        ctx.wshape, ctx.wdtype = W.shape, W.dtype
+        ctx.save_for_backward(x, W2, xc, mask if mask is not None else y, mean, invstd, g32)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W2, xc, y_or_mask, mean, invstd, g32 = ctx.saved_tensors
+        y, mask = (None, y_or_mask) if ctx.use_mask else (y_or_mask, None)
+        M, K = W2.shape
+        dy = dy.to(xc.dtype).contiguous()
+        dgamma = torch.empty(M, dtype=torch.float32, device=xc.device)
+        dbeta = torch.empty(M, dtype=torch.float32, device=xc.device)
+        dxc = torch.empty_like(xc)
+        need_x = ctx.needs_input_grad[0]
+        need_res = ctx.has_res and (need_x if ctx.res_is_x else ctx.needs_input_grad[4])
+        dres = torch.empty_like(xc) if need_res else None
+        if mask is not None and any(t is not None and t.data_ptr() % 16 for t in (dy, dxc, dres)):
+            raise RuntimeError("pinmem_b200: misaligned gradient buffer on the packed-mask BatchNorm path")
+        capi.bn_bwd_reduce(dy, y, mask, xc, mean, invstd, ctx.relu, dgamma, dbeta)
+        capi.bn_bwd_apply(dy, y, mask, xc, mean, invstd, g32, dgamma, dbeta, ctx.relu, ctx.training, dxc, dres)
+        dW = None
+        if ctx.needs_input_grad[1]:
+            dW = capi.conv1x1_wgrad(dxc, x).view(ctx.wshape).to(ctx.wdtype)
+        dx = None
+        if need_x:
+            hiT, loT = capi.conv1x1_prep(W2, True, x.dtype)
+            if ctx.res_is_x:
+                dx = capi.conv1x1_fwd(dxc, hiT, loT, K, y=dres, accumulate=True)   # dres += W^T . dxc
+                dres = None
+            else:
+                dx = capi.conv1x1_fwd(dxc, hiT, loT, K)
+        return dx, dW, dgamma, dbeta, (None if ctx.res_is_x else dres), None, None, None, None, None, None, None
+
+
 def _plain(m):
     return not (m._forward_hooks or m._forward_pre_hooks or m._backward_hooks)
 
 
 def _foldable(conv, C):
     """The 1x1, bias-free, ungrouped 2C -> * convolution of the reference (memory.py:104)."""
+    return _pointwise(conv) and conv.in_channels == 2 * C
+
+
+def _pointwise(conv):
     return (type(conv) is nn.Conv2d and conv.kernel_size == (1, 1) and conv.stride == (1, 1) and conv.padding == (0, 0)
-            and conv.dilation == (1, 1) and conv.groups == 1 and conv.bias is None and conv.in_channels == 2 * C
-            and conv.padding_mode == "zeros")
+            and conv.dilation == (1, 1) and conv.groups == 1 and conv.bias is None and conv.padding_mode == "zeros")
 
 
-def conv_bn_act(conv, bn, x, residual, relu):
-    """conv -> BatchNorm2d (-> + residual) (-> ReLU). The convolution is the nn.Conv2d module itself; what follows
-    runs in the fused kernels of csrc/pm_bn.cu when `bn` is a plain nn.BatchNorm2d (a converted SyncBatchNorm, a
-    hooked module or an exotic configuration falls back to calling the modules, i.e. the reference's own graph)."""
-    return bn_act(conv(x), bn, residual, relu)
+_warned = set()
 
 
-def bn_act(xc, bn, residual, relu):
-    """BatchNorm2d (-> + residual) (-> ReLU) of an already convolved tensor (see conv_bn_act)."""
-    fast = (type(bn) is nn.BatchNorm2d and bn.affine and _plain(bn) and xc.is_cuda and xc.dim() == 4
-            and xc.dtype in (torch.float32, torch.bfloat16) and bn.weight.is_cuda)
-    if not fast:
-        y = bn(xc)
-        if residual is not None:
-            y = residual + y
-        return F.relu(y) if relu else y
+def _warn_once(key, msg):
+    if key not in _warned:
+        _warned.add(key)
+        import warnings
+
+        warnings.warn("pinmem_b200: " + msg, RuntimeWarning, stacklevel=3)
+
+
+def _bn_args(bn):
+    """(use_batch_stats, running_mean, running_var, momentum factor) of one nn.BatchNorm2d call, with the module's
+    own side effect (num_batches_tracked += 1) applied."""
     use_batch = bn.training or bn.running_mean is None
     factor = 0.0
     rm = rv = None
@@ -297,14 +369,58 @@ def bn_act(xc, bn, residual, relu):
             rm = rv = None  # keep exotic buffer dtypes out of the kernel (statistics are still exact)
     elif not use_batch:
         rm, rv = bn.running_mean, bn.running_var
+    return use_batch, rm, rv, float(factor)
+
+
+def _bn_fast(bn, xc):
+    return (type(bn) is nn.BatchNorm2d and bn.affine and _plain(bn) and xc.is_cuda and xc.dim() == 4
+            and xc.dtype in (torch.float32, torch.bfloat16) and bn.weight.is_cuda)
+
+
+def weight_bn_act(W, bn, x, residual, relu):
+    """[relu](BatchNorm2d(conv1x1(x, W)) [+ residual]) for a [M,K,1,1] weight: everything in this package's kernels
+    (tcgen05 GEMM with the statistics in its epilogue + one normalise pass) when the shapes allow, else the library
+    convolution followed by the fused BatchNorm passes."""
+    if torch.is_autocast_enabled():  # the nn.Conv2d this replaces would run in the autocast dtype
+        x = x.to(torch.get_autocast_gpu_dtype())
+    M, K = W.shape[0], W.shape[1]
+    if _bn_fast(bn, x) and capi.conv1x1_ok(x, M, K) and not os.environ.get("PINMEM_B200_LIBRARY_CONV"):
+        x = x.contiguous()
+        res_is_x = residual is x or (residual is not None and residual.data_ptr() == x.data_ptr()
+                                     and residual.shape == x.shape and residual.dtype == x.dtype)
+        if residual is not None and not res_is_x:
+            residual = residual.to(x.dtype).contiguous()
+        use_batch, rm, rv, factor = _bn_args(bn)
+        return _ConvBnActFn.apply(x, W, bn.weight, bn.bias, None if res_is_x else residual, rm, rv, use_batch, factor,
+                                  float(bn.eps), relu, res_is_x)
+    _warn_once("libconv", "a 1x1 convolution fell back to the library GEMM (feature rows not 16-byte aligned, or an "
+                          "unsupported channel count); the BatchNorm passes stay fused")
+    return bn_act(F.conv2d(x, W.to(x.dtype)), bn, residual, relu)
+
+
+def conv_bn_act(conv, bn, x, residual, relu):
+    """conv -> BatchNorm2d (-> + residual) (-> ReLU) for the module's 1x1 blocks."""
+    if _pointwise(conv) and _plain(conv):
+        return weight_bn_act(conv.weight, bn, x, residual, relu)
+    return bn_act(conv(x), bn, residual, relu)
+
+
+def bn_act(xc, bn, residual, relu):
+    """BatchNorm2d (-> + residual) (-> ReLU) of an already convolved tensor (see conv_bn_act)."""
+    if not _bn_fast(bn, xc):
+        y = bn(xc)
+        if residual is not None:
+            y = residual + y
+        return F.relu(y) if relu else y
+    use_batch, rm, rv, factor = _bn_args(bn)
     xc = xc.contiguous()
     if residual is not None:
         residual = residual.to(xc.dtype).contiguous()
-    return _BnActFn.apply(xc, bn.weight, bn.bias, residual, rm, rv, use_batch, float(factor), float(bn.eps), relu)
+    return _BnActFn.apply(xc, bn.weight, bn.bias, residual, rm, rv, use_batch, factor, float(bn.eps), relu)
 
 
 class Writingnet(nn.Module):
-    """relu(x + BN(conv1x1(x))) -- memory.py:67-87 (stays a cuDNN/cuBLAS block)."""
+    """relu(x + BN(conv1x1(x))) -- memory.py:67-87; conv, BN, residual and ReLU in this package's kernels."""
 
     def __init__(self, input_feature_dim, feature_dim):
         super().__init__()
@@ -433,7 +549,7 @@ class Memory_sup(nn.Module):
             # conv(W, [q ; p.M]) = W1.q + (W2.M^T).p : the memory is folded into the weight (a [C_out, 32] block) and
             # the convolution runs on [q ; score planes] -- C+32 input channels instead of 2C
             Wp = _FoldWeightFn.apply(self.output[0].weight, M)                                   # [C_out, C+32, 1, 1]
-            updated_query = bn_act(F.conv2d(u, Wp), self.output[1], None, True)
+            updated_query = weight_bn_act(Wp, self.output[1], u, None, True)
         elif plain:
             updated_query = conv_bn_act(self.output[0], self.output[1], u, None, True)
         else:
