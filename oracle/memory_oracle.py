@@ -189,6 +189,35 @@ def _init_like_reference(module):
             m.bias.data.zero_()
 
 
+class ReluGates:
+    """Tie-breaking for the two ReLUs of the module (memory.py:86,106) when the oracle checks ANOTHER implementation.
+
+    A ReLU is discontinuous in its derivative: where a pre-activation z is zero to within rounding, two correct fp32
+    implementations of the convolution + BatchNorm before it (cuDNN, MKL, 3xTF32 tensor cores: all ~1e-7..2e-6 apart)
+    legitimately land on different sides, and everything downstream of that element's gradient then differs at O(1).
+    On maps of 10^5..10^6 elements such ties are certain to occur. The checked implementation therefore records its
+    gates (z > 0) per ReLU call; the oracle replays them in call order and REPORTS every element where its own gate
+    differs, with |z| relative to max|z| -- a test accepts a replayed gate only if that ratio is at rounding level.
+    """
+
+    def __init__(self, gates=None):
+        self.gates = {k: list(v) for k, v in (gates or {}).items()}  # name -> FIFO of bool tensors
+        self.mismatches = []                                          # (name, count, numel, max |z| / max|z|)
+
+    def apply(self, name, z):
+        queue = self.gates.get(name)
+        if not queue:
+            return F.relu(z)
+        gate = queue.pop(0).to(z.device)
+        natural = z.detach() > 0
+        diff = natural != gate
+        n = int(diff.sum())
+        if n:
+            scale = float(z.detach().abs().max())
+            self.mismatches.append((name, n, z.numel(), float(z.detach().abs()[diff].max()) / max(scale, 1e-30)))
+        return z * gate.to(z.dtype)
+
+
 class _WriteFeature(nn.Module):
     """relu(x + BN(conv1x1(x))). memory.py:67-87."""
 
@@ -196,8 +225,9 @@ class _WriteFeature(nn.Module):
         super().__init__()
         self.writefeat = nn.Sequential(nn.Conv2d(dim, dim, kernel_size=1, bias=False), nn.BatchNorm2d(dim))
 
-    def forward(self, x):
-        return F.relu(x + self.writefeat(x))
+    def forward(self, x, relu_gates=None):
+        z = x + self.writefeat(x)
+        return F.relu(z) if relu_gates is None else relu_gates.apply("writenet", z)
 
 
 class OracleMemorySup(nn.Module):
@@ -219,6 +249,7 @@ class OracleMemorySup(nn.Module):
         self.m_items = F.normalize(torch.rand((memory_size, feature_dim), dtype=torch.float), dim=1)
         _init_like_reference(self)
         self.reduce_fn = None
+        self.relu_gates = None  # a ReluGates: replay another implementation's ReLU decisions (see its docstring)
 
     def forward(self, query, mask=None, memory_writing=True, writing_detach=True, noise=None):
         if memory_writing:  # memory.py:323-324
@@ -229,10 +260,14 @@ class OracleMemorySup(nn.Module):
                 noise = gumbel_noise_pair(torch.empty(B * h * w, self.memory_size, dtype=query.dtype,
                                                       device=query.device))
         r = read(query, self.m_items, mask, self.temperature, noise if self.gumbel_read else None)
-        updated_query = self.output(r["u"])
+        if self.relu_gates is None:
+            updated_query = self.output(r["u"])
+        else:
+            updated_query = self.relu_gates.apply("output", self.output[1](self.output[0](r["u"])))
         writeloss = [0, 0]
         if memory_writing:  # memory.py:199-200, 206-257
-            wr = write(self.writenet(query), mask, self.m_items, self.momentum, self.clsfier.weight,
+            f = self.writenet(query) if self.relu_gates is None else self.writenet(query, self.relu_gates)
+            wr = write(f, mask, self.m_items, self.momentum, self.clsfier.weight,
                        self.clsfier.bias, self.reduce_fn)
             self.m_items = wr["memory_new"].detach() if writing_detach else wr["memory_new"]
             writeloss = [wr["div_loss"], wr["cls_loss"]]

@@ -12,8 +12,8 @@
 //   * one elected thread issues `tcgen05.mma` (M = 128 rows of output channels, N = the pixel tile / the input
 //     channels), accumulators live in TMEM (fp32, double-buffered where they fit), `tcgen05.commit` releases ring
 //     slots and hands finished accumulators to the epilogue warps through mbarriers;
-//   * fp32 I/O computes in 3xTF32 (hi.hi + hi.lo + lo.hi, hi = the 10 mantissa bits the tensor core reads,
-//     lo = x - hi exact in fp32): plain TF32 (2^-11 per product) cannot hold the 1e-5 parity bar. The weights are
+//   * fp32 I/O computes in 3xTF32 (hi.hi + hi.lo + lo.hi, hi = x rounded to nearest TF32, lo = x - hi exact in
+//     fp32): plain TF32 (2^-11 per product) cannot hold the 1e-5 parity bar. The weights are
 //     split once per call by `conv1x1_prep_kernel`; the activation tiles are split in shared memory by four
 //     transform warps (same swizzled offset in a second buffer, so no layout change). bf16 I/O is one
 //     `kind::f16` pass straight from the TMA tiles;
@@ -53,20 +53,20 @@ __device__ __forceinline__ void umma_issue(uint32_t d, uint64_t a, uint64_t b, u
     else umma_bf16(d, a, b, idesc, acc);
 }
 
-// lo = x - trunc_tf32(x) for `n4` float4 of a staged tile, written at the same offsets of `lo` (optionally the
-// truncated value is written back so the tensor core sees an exact TF32 "hi" whatever it does with the low bits)
-template <bool MASK_HI>
+// hi = x rounded to nearest TF32 (10 mantissa bits), lo = x - hi (exact in fp32, either sign) for `n4` float4 of a
+// staged tile: hi is written back in place, lo at the same offsets of `lo`. The tensor core TRUNCATES an fp32
+// container to TF32, so leaving the raw value as "hi" would make every lo non-negative relative to x and the dropped
+// lo.lo products a coherent bias (~2^-22 per product, measured 2e-6 on the GEMM); with round-to-nearest the residuals
+// are symmetric and half as large.
+__device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x00001000u) & 0xffffe000u); }
 __device__ __forceinline__ void split_tile(float4* __restrict__ raw, float4* __restrict__ lo, int n4, int t, int nthreads) {
     for (int i = t; i < n4; i += nthreads) {
         const float4 v = raw[i];
         float4 h, l;
-        h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-        h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-        h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-        h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+        h.x = tf32_rn(v.x), h.y = tf32_rn(v.y), h.z = tf32_rn(v.z), h.w = tf32_rn(v.w);
         l.x = v.x - h.x, l.y = v.y - h.y, l.z = v.z - h.z, l.w = v.w - h.w;
         lo[i] = l;
-        if (MASK_HI) raw[i] = h;
+        raw[i] = h;
     }
 }
 
@@ -77,8 +77,12 @@ __device__ __forceinline__ void split_tile(float4* __restrict__ raw, float4* __r
 //   mapAl : fp32 only, the "lo" part
 //   mapY  : [B*M rows][hw] output, box [32 rows][PXC pixels]
 //   CTA tile: MT x 128 output rows (starting at 128*m_tile0) x NT pixels of one image; persistent over tiles.
+//   CL > 1: clusters of CL CTAs work on CL consecutive pixel tiles in lock step and share the weight blocks -- each
+//   CTA loads 1/CL of them and TMA-multicasts them to the whole cluster (the weights are re-read for every pixel tile,
+//   so at CL = 1 the L2 -> SM traffic is ~4x the activation bytes and bounds the kernel); ring slots are released
+//   cluster-wide (tcgen05.commit multicast onto every CTA's `empty` barrier).
 // =================================================================================================================
-template <typename T, int MT, int NT, bool MASK_HI>
+template <typename T, int MT, int NT, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     conv1x1_nn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapAh,
                       const __grid_constant__ CUtensorMap mapAl, const __grid_constant__ CUtensorMap mapY, int K, int M,
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&full[i], 1);
-            mbar_init(&empty[i], 1);
+            mbar_init(&empty[i], CL);
             mbar_init(&xfull[i], 128);
         }
         for (int i = 0; i < ACC; ++i) {
@@ -127,14 +131,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     if (warp == 1) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();  // every CTA's barriers are initialised before a peer multicasts onto them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const int nkb = (K + KB - 1) / KB;
+    // Work: tile group g = cluster index + i * clusters; this CTA takes tile CL*g + rank. A group past the end of an
+    // odd tile count repeats the last tile (same loads, same MMAs -- the ring must stay in lock step) and stores nothing.
+    const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+    const int ngroups = (total_tiles + CL - 1) / CL, gstride = gridDim.x / CL;
+    const int g0 = blockIdx.x / CL;
 
     if (warp == 0) {
         if (lane == 0) {  // ---------------------------------------------------------------- TMA producer
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int g = g0; g < ngroups; g += gstride) {
+                int tile = g * CL + crank;
+                if (tile >= total_tiles) tile = total_tiles - 1;
                 const int b = tile / tiles_per_img, px0 = (tile - b * tiles_per_img) * NT;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
@@ -145,10 +157,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                     for (int c = 0; c < NCH; ++c) tma_load_2d(st + c * XCHUNK, &mapX, px0 + c * PXC, b * K + kb * KB, &full[s]);
                     unsigned char* sa = st + NOPA * XBYTES;
 #pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) {
-                        tma_load_2d(sa + mt * TILE_A_BYTES, &mapAh, kb * KB, (m_tile0 + mt) * 128, &full[s]);
-                        if (TR::SPLIT)
-                            tma_load_2d(sa + (MT + mt) * TILE_A_BYTES, &mapAl, kb * KB, (m_tile0 + mt) * 128, &full[s]);
+                    for (int j = 0; j < NOPA * MT; ++j) {  // weight blocks: [hi of every row tile | lo of every row tile]
+                        const int mt = j % MT;
+                        const CUtensorMap* mp = j < MT ? &mapAh : &mapAl;
+                        if (CL == 1) tma_load_2d(sa + j * TILE_A_BYTES, mp, kb * KB, (m_tile0 + mt) * 128, &full[s]);
+                        else if (j % CL == crank)
+                            tma_load_2d_multicast(sa + j * TILE_A_BYTES, mp, kb * KB, (m_tile0 + mt) * 128, &full[s],
+                                                  (uint16_t)((1u << CL) - 1));
                     }
                 }
             }
@@ -156,7 +171,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     } else if (warp == 1) {
         if (lane == 0) {  // ---------------------------------------------------------------- MMA issuer
             uint32_t it = 0, tc = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
+            for (int g = g0; g < ngroups; g += gstride, ++tc) {
                 const int a = tc % ACC;
                 mbar_wait(&acce[a], ((tc / ACC) & 1) ^ 1);
                 tc_fence_after();
@@ -193,7 +208,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                             }
                         }
                     }
-                    umma_commit(&empty[s]);
+                    if (CL == 1) umma_commit(&empty[s]);
+                    else umma_commit_multicast(&empty[s], (uint16_t)((1u << CL) - 1));
                 }
                 umma_commit(&accf[a]);
             }
@@ -206,7 +222,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) sum[mt] = 0.0, sq[mt] = 0.0;
         uint32_t tc = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
+        for (int g = g0; g < ngroups; g += gstride, ++tc) {
+            const int tile = g * CL + crank;
             const int b = tile / tiles_per_img, px0 = (tile - b * tiles_per_img) * NT;
             const int a = tc % ACC;
             mbar_wait(&accf[a], (tc / ACC) & 1);
@@ -214,7 +231,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
                 const int row0 = (m_tile0 + mt) * 128 + q * 32;
-                if (row0 >= M) continue;  // padded rows of the last 128-row tile (warp-uniform)
+                if (row0 >= M || tile >= total_tiles) continue;  // padded rows / the repeated tile of a short group
                 float ts = 0.f, tq = 0.f;
 #pragma unroll 1
                 for (int c = 0; c < NCH; ++c) {
@@ -277,7 +294,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
                 const int row = (m_tile0 + mt) * 128 + q * 32 + lane;
-                if (row < M && blockIdx.x < total_tiles) {
+                if (row < M) {
                     atomicAdd(&stats[row], sum[mt]);
                     atomicAdd(&stats[M + row], sq[mt]);
                 }
@@ -287,12 +304,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         if constexpr (TR::SPLIT) {
             const int t = threadIdx.x - 6 * 32;
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int g = g0; g < ngroups; g += gstride) {
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
                     mbar_wait(&full[s], (it / STAGES) & 1);
                     unsigned char* st = smem + s * STAGE;
-                    split_tile<MASK_HI>(reinterpret_cast<float4*>(st), reinterpret_cast<float4*>(st + XBYTES), XBYTES / 16, t, 128);
+                    split_tile(reinterpret_cast<float4*>(st), reinterpret_cast<float4*>(st + XBYTES), XBYTES / 16, t, 128);
                     fence_proxy_async_smem();
                     mbar_arrive(&xfull[s]);
                 }
@@ -301,6 +318,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it or arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem, 512);
@@ -316,20 +334,21 @@ constexpr size_t nn_smem_bytes() {
     return (size_t)STAGES * STAGE + 4 * 2 * 4096 + 256 + 1024;
 }
 
-static int gemm_mask_hi() {  // PM_GEMM_MASK_HI=1: write the truncated TF32 value back instead of trusting the hardware
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("PM_GEMM_MASK_HI");
-        v = (e && e[0] == '1') ? 1 : 0;
-    }
-    return v;
-}
-
 static int gemm_dbg() {  // PM_GEMM_DBG: bring-up switches (bit 0 swaps LBO/SBO of the MN-major operand descriptor)
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("PM_GEMM_DBG");
         v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
+static int gemm_cluster() {  // PM_GEMM_CLUSTER = 1 | 2 | 4 (default 2): CTAs sharing the weight blocks by TMA multicast
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PM_GEMM_CLUSTER");
+        v = e ? atoi(e) : 2;
+        if (v != 1 && v != 2 && v != 4) v = 2;
     }
     return v;
 }
@@ -348,21 +367,42 @@ static int launch_nn(const void* X, const void* Ah, const void* Al, void* Y, dou
     }
     if (!make_map_2d<T>(&mY, Y, (size_t)B * M, hw, 32, TR::PXC, true)) return PM_ERR_ALIGN;
     const int tiles_per_img = (hw + NT - 1) / NT, total = B * tiles_per_img;
-    int grid = 148;
-    if (grid > total) grid = total;
     const size_t smem = nn_smem_bytes<T, MT, NT>();
+    // clusters of CL CTAs share the weight blocks by TMA multicast; the NOPA*MT blocks of a stage must split evenly
+    constexpr int NBLK = (TR::SPLIT ? 2 : 1) * MT;
+    constexpr int CLMAX = NBLK >= 4 ? 4 : NBLK;
+    int cl = gemm_cluster();
+    if (cl > CLMAX) cl = CLMAX;
+    if (total < 2 * cl) cl = 1;
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    int groups = (total + cl - 1) / cl, clusters = 148 / cl;
+    if (clusters > groups) clusters = groups;
+    cfg.gridDim = dim3(clusters * cl);
+    const int dbg = gemm_dbg();
     cudaError_t e;
-    if (gemm_mask_hi()) {
-        auto kern = conv1x1_nn_kernel<T, MT, NT, true>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        kern<<<grid, GEMM_THREADS, smem, st>>>(mX, mAh, mAl, mY, K, M, m_tile0, tiles_per_img, total, accumulate, stats, gemm_dbg());
-    } else {
-        auto kern = conv1x1_nn_kernel<T, MT, NT, false>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        kern<<<grid, GEMM_THREADS, smem, st>>>(mX, mAh, mAl, mY, K, M, m_tile0, tiles_per_img, total, accumulate, stats, gemm_dbg());
+#define PM_NN_LAUNCH(CL_)                                                                                             \
+    {                                                                                                                 \
+        auto kern = conv1x1_nn_kernel<T, MT, NT, CL_>;                                                                \
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                       \
+        if (e != cudaSuccess) return (int)e;                                                                          \
+        e = cudaLaunchKernelEx(&cfg, kern, mX, mAh, mAl, mY, K, M, m_tile0, tiles_per_img, total, accumulate, stats, dbg); \
     }
+    if (cl == 4) {
+        if constexpr (CLMAX >= 4) PM_NN_LAUNCH(4) else return PM_ERR_SHAPE;
+    } else if (cl == 2) {
+        if constexpr (CLMAX >= 2) PM_NN_LAUNCH(2) else return PM_ERR_SHAPE;
+    } else {
+        PM_NN_LAUNCH(1)
+    }
+#undef PM_NN_LAUNCH
+    if (e != cudaSuccess) return (int)e;
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }
@@ -377,7 +417,7 @@ static int launch_nn(const void* X, const void* Ah, const void* Al, void* Y, dou
 // =================================================================================================================
 constexpr int WG_NMAX = 288;
 
-template <typename T, bool MASK_HI>
+template <typename T>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     conv1x1_wgrad_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapX, int M, int N,
                          int Ntot, int n0, int NW, int hw, int chunks_per_img, int blocks_per_chunk, float* __restrict__ part,
@@ -497,8 +537,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 const int s = kb % STAGES;
                 mbar_wait(&full[s], (kb / STAGES) & 1);
                 unsigned char* st = smem + s * STAGE;
-                split_tile<MASK_HI>(reinterpret_cast<float4*>(st), reinterpret_cast<float4*>(st + TILE_A_BYTES), TILE_A_BYTES / 16, t, 128);
-                split_tile<MASK_HI>(reinterpret_cast<float4*>(st + 2 * TILE_A_BYTES), reinterpret_cast<float4*>(st + 2 * TILE_A_BYTES + BBYTES),
+                split_tile(reinterpret_cast<float4*>(st), reinterpret_cast<float4*>(st + TILE_A_BYTES), TILE_A_BYTES / 16, t, 128);
+                split_tile(reinterpret_cast<float4*>(st + 2 * TILE_A_BYTES), reinterpret_cast<float4*>(st + 2 * TILE_A_BYTES + BBYTES),
                                     N * 8, t, 128);
                 fence_proxy_async_smem();
                 mbar_arrive(&xfull[s]);
@@ -513,34 +553,44 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
 }
 
-// dW[m][n] (+)= sum over chunks of part[chunk][m][n]; float4 per thread
-__global__ void __launch_bounds__(128) wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dW, int M, int N,
+// dW[m][n] (+)= sum over chunks of part[chunk][m][n]. 256 threads = 32 float4 columns x 8 chunk groups: every thread
+// keeps its share of the chunk loads in flight, the groups meet in shared memory (fixed order: deterministic).
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dW, int M, int N,
                                                            int Mpad, int ldw, int col0, int nchunks, int accumulate) {
-    const int i = blockIdx.x * 128 + threadIdx.x;  // float4 index in [M][N/4]
-    const int n4 = N / 4;
-    if (i >= M * n4) return;
-    const int m = i / n4, c = i - m * n4;
+    __shared__ float4 red[8][32];
+    const int col = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + col;  // float4 index in [M][N/4]
+    const int n4 = N / 4, total = M * n4;
+    const int m = i < total ? i / n4 : 0, c = i < total ? i - m * n4 : 0;
     const float4* p = reinterpret_cast<const float4*>(part) + (size_t)m * n4 + c;
     const size_t stride = (size_t)Mpad * n4;
-    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
-    int j = 0;
-    for (; j + 4 <= nchunks; j += 4) {
-        const float4 v0 = __ldg(p + (size_t)j * stride), v1 = __ldg(p + (size_t)(j + 1) * stride);
-        const float4 v2 = __ldg(p + (size_t)(j + 2) * stride), v3 = __ldg(p + (size_t)(j + 3) * stride);
-        a0.x += v0.x, a0.y += v0.y, a0.z += v0.z, a0.w += v0.w;
-        a1.x += v1.x, a1.y += v1.y, a1.z += v1.z, a1.w += v1.w;
-        a2.x += v2.x, a2.y += v2.y, a2.z += v2.z, a2.w += v2.w;
-        a3.x += v3.x, a3.y += v3.y, a3.z += v3.z, a3.w += v3.w;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    if (i < total) {
+        int j = grp;
+#pragma unroll 4
+        for (; j + 8 < nchunks; j += 16) {
+            const float4 v0 = __ldg(p + (size_t)j * stride), v1 = __ldg(p + (size_t)(j + 8) * stride);
+            a0.x += v0.x, a0.y += v0.y, a0.z += v0.z, a0.w += v0.w;
+            a1.x += v1.x, a1.y += v1.y, a1.z += v1.z, a1.w += v1.w;
+        }
+        if (j < nchunks) {
+            const float4 v0 = __ldg(p + (size_t)j * stride);
+            a0.x += v0.x, a0.y += v0.y, a0.z += v0.z, a0.w += v0.w;
+        }
     }
-    for (; j < nchunks; ++j) {
-        const float4 v0 = __ldg(p + (size_t)j * stride);
-        a0.x += v0.x, a0.y += v0.y, a0.z += v0.z, a0.w += v0.w;
+    red[grp][col] = make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
+    __syncthreads();
+    if (grp == 0 && i < total) {
+        float4 r = red[0][col];
+#pragma unroll
+        for (int g = 1; g < 8; ++g) {
+            const float4 v = red[g][col];
+            r.x += v.x, r.y += v.y, r.z += v.z, r.w += v.w;
+        }
+        float* o = dW + (size_t)m * ldw + col0 + 4 * c;
+        if (accumulate) r.x += o[0], r.y += o[1], r.z += o[2], r.w += o[3];
+        *reinterpret_cast<float4*>(o) = r;
     }
-    float4 r = make_float4((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y), (a0.z + a1.z) + (a2.z + a3.z),
-                           (a0.w + a1.w) + (a2.w + a3.w));
-    float* o = dW + (size_t)m * ldw + col0 + 4 * c;
-    if (accumulate) r.x += o[0], r.y += o[1], r.z += o[2], r.w += o[3];
-    o[0] = r.x, o[1] = r.y, o[2] = r.z, o[3] = r.w;
 }
 
 template <typename T>
@@ -575,28 +625,20 @@ static int launch_wgrad(const void* dY, const void* X, float* part, float* dW, i
     if (!make_map_2d<T>(&mX, X, (size_t)B * Ntot, hw, NW, TR::PXC, true)) return PM_ERR_ALIGN;
     const size_t smem = wgrad_smem_bytes<T>();
     dim3 grid(B * cpi, Mpad / 128);
-    cudaError_t e;
-    if (gemm_mask_hi()) {
-        auto kern = conv1x1_wgrad_kernel<T, true>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        kern<<<grid, GEMM_THREADS, smem, st>>>(mG, mX, M, N, Ntot, n0, NW, hw, cpi, bpc, part, Mpad);
-    } else {
-        auto kern = conv1x1_wgrad_kernel<T, false>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        kern<<<grid, GEMM_THREADS, smem, st>>>(mG, mX, M, N, Ntot, n0, NW, hw, cpi, bpc, part, Mpad);
-    }
+    auto kern = conv1x1_wgrad_kernel<T>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<grid, GEMM_THREADS, smem, st>>>(mG, mX, M, N, Ntot, n0, NW, hw, cpi, bpc, part, Mpad);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     const int n4 = M * (N / 4);
-    wgrad_reduce_kernel<<<(n4 + 127) / 128, 128, 0, st>>>(part, dW, M, N, Mpad, Ntot, n0, B * cpi, accumulate);
+    wgrad_reduce_kernel<<<(n4 + 31) / 32, 256, 0, st>>>(part, dW, M, N, Mpad, Ntot, n0, B * cpi, accumulate);
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }
 
 // A[m][k] = W[m][k] (transpose = 0, W is [M][K]) or W[k][m] (transpose = 1, W is [K][M]); rows M..Mpad-1 are zero.
-// fp32: hi = the 10 mantissa bits the tensor core keeps, lo = W - hi (both fp32 [Mpad][K]); bf16: hi = bf16(W).
+// fp32: hi = W rounded to nearest TF32, lo = W - hi (both fp32 [Mpad][K]); bf16: hi = bf16(W).
 template <typename T>
 __global__ void conv1x1_prep_kernel(const float* __restrict__ W, int M, int K, int Mpad, int transpose, T* __restrict__ hi,
                                     T* __restrict__ lo) {
@@ -605,7 +647,7 @@ __global__ void conv1x1_prep_kernel(const float* __restrict__ W, int M, int K, i
     const int m = i / K, k = i - m * K;
     const float v = m < M ? (transpose ? W[(size_t)k * M + m] : W[(size_t)m * K + k]) : 0.f;
     if constexpr (sizeof(T) == 4) {
-        const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        const float h = tf32_rn(v);
         hi[i] = h;
         lo[i] = v - h;
     } else {

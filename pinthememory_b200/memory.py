@@ -343,6 +343,11 @@ def _pointwise(conv):
             and conv.dilation == (1, 1) and conv.groups == 1 and conv.bias is None and conv.padding_mode == "zeros")
 
 
+# Debug hook for parity tests: a dict name -> list; when set, every ReLU of the two conv blocks appends its gate
+# (output > 0) under "output" / "writenet" in call order, so a checker can replay the decisions at rounding-level ties
+# (oracle/memory_oracle.py::ReluGates). None (the default) costs nothing.
+GATE_LOG = None
+
 _warned = set()
 
 
@@ -377,10 +382,17 @@ def _bn_fast(bn, xc):
             and xc.dtype in (torch.float32, torch.bfloat16) and bn.weight.is_cuda)
 
 
-def weight_bn_act(W, bn, x, residual, relu):
+def weight_bn_act(W, bn, x, residual, relu, name=None):
     """[relu](BatchNorm2d(conv1x1(x, W)) [+ residual]) for a [M,K,1,1] weight: everything in this package's kernels
     (tcgen05 GEMM with the statistics in its epilogue + one normalise pass) when the shapes allow, else the library
     convolution followed by the fused BatchNorm passes."""
+    y = _weight_bn_act(W, bn, x, residual, relu)
+    if GATE_LOG is not None and relu and name is not None:
+        GATE_LOG.setdefault(name, []).append(y.detach() > 0)
+    return y
+
+
+def _weight_bn_act(W, bn, x, residual, relu):
     if torch.is_autocast_enabled():  # the nn.Conv2d this replaces would run in the autocast dtype
         x = x.to(torch.get_autocast_gpu_dtype())
     M, K = W.shape[0], W.shape[1]
@@ -398,11 +410,14 @@ def weight_bn_act(W, bn, x, residual, relu):
     return bn_act(F.conv2d(x, W.to(x.dtype)), bn, residual, relu)
 
 
-def conv_bn_act(conv, bn, x, residual, relu):
+def conv_bn_act(conv, bn, x, residual, relu, name=None):
     """conv -> BatchNorm2d (-> + residual) (-> ReLU) for the module's 1x1 blocks."""
     if _pointwise(conv) and _plain(conv):
-        return weight_bn_act(conv.weight, bn, x, residual, relu)
-    return bn_act(conv(x), bn, residual, relu)
+        return weight_bn_act(conv.weight, bn, x, residual, relu, name)
+    y = bn_act(conv(x), bn, residual, relu)
+    if GATE_LOG is not None and relu and name is not None:
+        GATE_LOG.setdefault(name, []).append(y.detach() > 0)
+    return y
 
 
 def bn_act(xc, bn, residual, relu):
@@ -435,7 +450,7 @@ class Writingnet(nn.Module):
 
     def forward(self, x):
         if x.is_cuda and _plain(self.writefeat) and _plain(self.writefeat[0]):
-            return conv_bn_act(self.writefeat[0], self.writefeat[1], x, x, True)
+            return conv_bn_act(self.writefeat[0], self.writefeat[1], x, x, True, "writenet")
         return self.relu(x + self.writefeat(x))
 
 
@@ -549,9 +564,9 @@ class Memory_sup(nn.Module):
             # conv(W, [q ; p.M]) = W1.q + (W2.M^T).p : the memory is folded into the weight (a [C_out, 32] block) and
             # the convolution runs on [q ; score planes] -- C+32 input channels instead of 2C
             Wp = _FoldWeightFn.apply(self.output[0].weight, M)                                   # [C_out, C+32, 1, 1]
-            updated_query = weight_bn_act(Wp, self.output[1], u, None, True)
+            updated_query = weight_bn_act(Wp, self.output[1], u, None, True, "output")
         elif plain:
-            updated_query = conv_bn_act(self.output[0], self.output[1], u, None, True)
+            updated_query = conv_bn_act(self.output[0], self.output[1], u, None, True, "output")
         else:
             updated_query = self.output(u)
         return updated_query, score_query, score_memory, readloss

@@ -4,6 +4,7 @@ import math
 import pytest
 import torch
 
+from gate_util import check_ties, record_gates
 from golden_util import assert_close
 
 pytestmark = pytest.mark.gpu
@@ -143,25 +144,34 @@ def test_m_items_aliasing_rules():
 
 
 def test_metatest_gradient_reaches_writenet_through_memory():
-    """train.py:555-575: write with graph (B), read the new memory on other data (C), backprop into writenet."""
+    """train.py:555-575: write with graph (B), read the new memory on other data (C), backprop into writenet.
+
+    These gradients pass through BatchNorm's batch statistics twice (sums with cancellation over all pixels), which
+    amplifies the fp32 rounding of ANY implementation to ~1e-4 (the fp32 oracle itself sits there), so the judge here is
+    the oracle evaluated in fp64: the CUDA path must be as close to it as fp32 arithmetic allows."""
     mem = _module()
-    ora = _oracle_like(mem)
+    ora = _oracle_like(mem).double()
+    ora.m_items = mem.m_items.double()
     xa = torch.randn(2, 64, 8, 8, device="cuda")
     xb = torch.randn(2, 64, 8, 8, device="cuda")
     la = torch.randint(0, 19, (2, 32, 32), device="cuda")
     lb = torch.randint(0, 19, (2, 32, 32), device="cuda")
     G = torch.randn(2, 64, 8, 8, device="cuda")
+    from oracle import memory_oracle as mo
+
     grads = []
-    for m in (mem, ora):
-        m.zero_grad()
-        m(xa, la, True, False)
-        uq, _, _, rl, _ = m(xb, lb, False)
-        ((uq * G).sum() + 0.02 * rl).backward()
-        grads.append({n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None})
+    with record_gates() as gates:
+        for m, dt in ((mem, torch.float32), (ora, torch.float64)):
+            if m is ora:  # rounding-level ReLU ties are broken the module's way (ReluGates); checked below
+                ora.relu_gates = mo.ReluGates(gates)
+            m.zero_grad()
+            m(xa.to(dt), la, True, False)
+            uq, _, _, rl, _ = m(xb.to(dt), lb, False)
+            ((uq * G.to(dt)).sum() + 0.02 * rl).backward()
+            grads.append({n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None})
+    check_ties(ora.relu_gates)
     assert "writenet.writefeat.0.weight" in grads[0]
     for n in grads[1]:
-        # these gradients pass through BatchNorm's batch statistics twice (sums with cancellation over
-        # all pixels), which amplifies fp32 rounding of either implementation to a few 1e-5
         assert_close(grads[0][n], grads[1][n], 1e-4, n)
 
 
@@ -303,7 +313,16 @@ def test_fused_bn_matches_torch_modules(shape, residual, training):
     xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
     ya = conv_bn_act(conv, bn, xa, xa if residual else None, True)
     t = bn_r(conv_r(xb))
-    yb = torch.relu(xb + t if residual else t)
+    z = xb + t if residual else t
+    # the tcgen05 convolution is ~2e-6 from cuDNN's fp32 one, so on a map of this size a pre-activation that is zero
+    # at rounding level can land on the other side of the ReLU: the torch side takes OUR gate (and every gate that
+    # differs from its own must be such a tie)
+    gate = ya.detach() > 0
+    flipped = gate != (z.detach() > 0)
+    if bool(flipped.any()):
+        assert float(z.detach().abs()[flipped].max()) <= 2e-5 * float(z.detach().abs().max()), "not a rounding tie"
+        assert int(flipped.sum()) <= max(3, 1e-4 * z.numel())
+    yb = z * gate.to(z.dtype)
     (ya * G).sum().backward()
     (yb * G).sum().backward()
     assert_close(ya.detach(), yb.detach(), 1e-5, "y")
