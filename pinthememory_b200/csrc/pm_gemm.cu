@@ -58,6 +58,22 @@ __device__ __forceinline__ void umma_issue(uint32_t d, uint64_t a, uint64_t b, u
 // container to TF32, so leaving the raw value as "hi" would make every lo non-negative relative to x and the dropped
 // lo.lo products a coherent bias (~2^-22 per product, measured 2e-6 on the GEMM); with round-to-nearest the residuals
 // are symmetric and half as large.
+// lo = x - trunc_tf32(x) only (the tensor core truncates the untouched fp32 container itself): one shared-memory write
+// per element instead of two. Measured on the GEMMs: the same error as the round-to-nearest split (the 2e-6 that
+// remains grows linearly with K -- it is the tensor core's truncating fp32 accumulation, not the split), so the
+// activation tiles, which are split in the inner loop, take this one; the weights (split once per call) are rounded.
+__device__ __forceinline__ void split_tile_trunc(const float4* __restrict__ raw, float4* __restrict__ lo, int n4, int t,
+                                                 int nthreads) {
+    for (int i = t; i < n4; i += nthreads) {
+        const float4 v = raw[i];
+        float4 l;
+        l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+        l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+        l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+        l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+        lo[i] = l;
+    }
+}
 __device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x00001000u) & 0xffffe000u); }
 __device__ __forceinline__ void split_tile(float4* __restrict__ raw, float4* __restrict__ lo, int n4, int t, int nthreads) {
     for (int i = t; i < n4; i += nthreads) {
@@ -82,21 +98,26 @@ __device__ __forceinline__ void split_tile(float4* __restrict__ raw, float4* __r
 //   so at CL = 1 the L2 -> SM traffic is ~4x the activation bytes and bounds the kernel); ring slots are released
 //   cluster-wide (tcgen05.commit multicast onto every CTA's `empty` barrier).
 // =================================================================================================================
-template <typename T, int MT, int NT, int CL>
+template <typename T, int MT, int NT, int KB, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     conv1x1_nn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapAh,
                       const __grid_constant__ CUtensorMap mapAl, const __grid_constant__ CUtensorMap mapY, int K, int M,
                       int m_tile0, int tiles_per_img, int total_tiles, int accumulate, double* __restrict__ stats, int dbg) {
     using TR = GemmTraits<T>;
-    constexpr int PXC = TR::PXC, UK = TR::UK, KB = PXC, KSTEPS = KB / UK;
+    constexpr int PXC = TR::PXC, UK = TR::UK, KSTEPS = KB / UK;
     constexpr int NCH = NT / PXC;                      // 128-byte pixel chunks per tile
     constexpr int XCHUNK = KB * 128;                   // bytes of one [KB rows][128 B] chunk
     constexpr int XBYTES = NCH * XCHUNK;               // = NT * KB * sizeof(T)
     constexpr int NOPA = TR::SPLIT ? 2 : 1;
-    constexpr int STAGE = NOPA * (XBYTES + MT * TILE_A_BYTES);
+    // weight block: [128 rows][KB channels] K-major; 128-byte rows use SWIZZLE_128B, 64-byte rows SWIZZLE_64B
+    constexpr int AROW = KB * (int)sizeof(T);
+    static_assert(AROW == 128 || AROW == 64, "weight rows must be 64 or 128 bytes");
+    constexpr int TILE_A = 128 * AROW;
+    constexpr uint32_t ASWZ = AROW == 128 ? UMMA_SW128 : UMMA_SW64, ASBO = 8 * AROW;
+    constexpr int STAGE = NOPA * (XBYTES + MT * TILE_A);
     constexpr int STAGES = (GEMM_RING_BYTES / STAGE) > 4 ? 4 : (GEMM_RING_BYTES / STAGE);
     constexpr int ACC = (512 / (MT * NT)) >= 2 ? 2 : 1;  // accumulator stages in TMEM
-    constexpr uint32_t TX = XBYTES + NOPA * MT * TILE_A_BYTES;
+    constexpr uint32_t TX = XBYTES + NOPA * MT * TILE_A;
     static_assert(STAGES >= 2, "ring too small");
     static_assert(MT * NT <= 512, "accumulators exceed TMEM");
     constexpr uint32_t IDESC = umma_idesc(TR::FMT, false, true, 128, NT);
@@ -160,9 +181,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                     for (int j = 0; j < NOPA * MT; ++j) {  // weight blocks: [hi of every row tile | lo of every row tile]
                         const int mt = j % MT;
                         const CUtensorMap* mp = j < MT ? &mapAh : &mapAl;
-                        if (CL == 1) tma_load_2d(sa + j * TILE_A_BYTES, mp, kb * KB, (m_tile0 + mt) * 128, &full[s]);
+                        if (CL == 1) tma_load_2d(sa + j * TILE_A, mp, kb * KB, (m_tile0 + mt) * 128, &full[s]);
                         else if (j % CL == crank)
-                            tma_load_2d_multicast(sa + j * TILE_A_BYTES, mp, kb * KB, (m_tile0 + mt) * 128, &full[s],
+                            tma_load_2d_multicast(sa + j * TILE_A, mp, kb * KB, (m_tile0 + mt) * 128, &full[s],
                                                   (uint16_t)((1u << CL) - 1));
                     }
                 }
@@ -197,9 +218,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
                         for (int mt = 0; mt < MT; ++mt) {
                             const uint32_t d = tmem + (uint32_t)((a * MT + mt) * NT);
-                            const uint64_t ah = umma_desc(sa + mt * TILE_A_BYTES + ks * 32, 16, 1024);
+                            const uint64_t ah = umma_desc(sa + mt * TILE_A + ks * 32, 16, ASBO, ASWZ);
                             if (TR::SPLIT) {
-                                const uint64_t al = umma_desc(sa + (MT + mt) * TILE_A_BYTES + ks * 32, 16, 1024);
+                                const uint64_t al = umma_desc(sa + (MT + mt) * TILE_A + ks * 32, 16, ASBO, ASWZ);
                                 umma_issue<T>(d, al, bh, IDESC, first);
                                 umma_issue<T>(d, ah, bl, IDESC, 1u);
                                 umma_issue<T>(d, ah, bh, IDESC, 1u);
@@ -309,7 +330,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                     const int s = it % STAGES;
                     mbar_wait(&full[s], (it / STAGES) & 1);
                     unsigned char* st = smem + s * STAGE;
-                    split_tile(reinterpret_cast<float4*>(st), reinterpret_cast<float4*>(st + XBYTES), XBYTES / 16, t, 128);
+                    split_tile_trunc(reinterpret_cast<float4*>(st), reinterpret_cast<float4*>(st + XBYTES), XBYTES / 16, t, 128);
                     fence_proxy_async_smem();
                     mbar_arrive(&xfull[s]);
                 }
@@ -325,11 +346,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
 }
 
-template <typename T, int MT, int NT>
+template <typename T, int MT, int NT, int KB>
 constexpr size_t nn_smem_bytes() {
     using TR = GemmTraits<T>;
     constexpr int NOPA = TR::SPLIT ? 2 : 1;
-    constexpr int STAGE = NOPA * (NT * TR::PXC * (int)sizeof(T) + MT * TILE_A_BYTES);
+    constexpr int STAGE = NOPA * (NT * KB * (int)sizeof(T) + MT * 128 * KB * (int)sizeof(T));
     constexpr int STAGES = (GEMM_RING_BYTES / STAGE) > 4 ? 4 : (GEMM_RING_BYTES / STAGE);
     return (size_t)STAGES * STAGE + 4 * 2 * 4096 + 256 + 1024;
 }
@@ -343,31 +364,41 @@ static int gemm_dbg() {  // PM_GEMM_DBG: bring-up switches (bit 0 swaps LBO/SBO 
     return v;
 }
 
-static int gemm_cluster() {  // PM_GEMM_CLUSTER = 1 | 2 | 4 (default 2): CTAs sharing the weight blocks by TMA multicast
+static int gemm_narrow() {  // PM_GEMM_NARROW=1: keep the 128-pixel fp32 tiles (A/B switch for the profiles)
     static int v = -1;
     if (v < 0) {
-        const char* e = getenv("PM_GEMM_CLUSTER");
-        v = e ? atoi(e) : 2;
-        if (v != 1 && v != 2 && v != 4) v = 2;
+        const char* e = getenv("PM_GEMM_NARROW");
+        v = (e && e[0] == '1') ? 1 : 0;
     }
     return v;
 }
 
-template <typename T, int MT, int NT>
+static int gemm_cluster() {  // PM_GEMM_CLUSTER = 1 | 2 | 4 (default 1): CTAs sharing the weight blocks by TMA multicast
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PM_GEMM_CLUSTER");
+        v = e ? atoi(e) : 1;  // measured: multicast at cluster sizes <= 4 does not reduce the SM's ingest, and lock step costs
+        if (v != 1 && v != 2 && v != 4) v = 1;
+    }
+    return v;
+}
+
+template <typename T, int MT, int NT, int KB>
 static int launch_nn(const void* X, const void* Ah, const void* Al, void* Y, double* stats, int B, int K, int M, int Mpad,
                      int hw, int m_tile0, int accumulate, cudaStream_t st) {
     using TR = GemmTraits<T>;
     CUtensorMap mX, mAh, mAl, mY;
-    if (!make_map_2d<T>(&mX, X, (size_t)B * K, hw, TR::PXC, TR::PXC, sizeof(T) == 4 ? 2 : 1)) return PM_ERR_ALIGN;
-    if (!make_map_2d<T>(&mAh, Ah, Mpad, K, 128, TR::PXC, true)) return PM_ERR_ALIGN;
+    constexpr int ASW = KB * (int)sizeof(T) == 128 ? 1 : 3;  // TMA swizzle of the weight boxes: 128-byte or 64-byte rows
+    if (!make_map_2d<T>(&mX, X, (size_t)B * K, hw, KB, TR::PXC, sizeof(T) == 4 ? 2 : 1)) return PM_ERR_ALIGN;
+    if (!make_map_2d<T>(&mAh, Ah, Mpad, K, 128, KB, ASW)) return PM_ERR_ALIGN;
     if (TR::SPLIT) {
-        if (!make_map_2d<T>(&mAl, Al, Mpad, K, 128, TR::PXC, true)) return PM_ERR_ALIGN;
+        if (!make_map_2d<T>(&mAl, Al, Mpad, K, 128, KB, ASW)) return PM_ERR_ALIGN;
     } else {
         mAl = mAh;
     }
     if (!make_map_2d<T>(&mY, Y, (size_t)B * M, hw, 32, TR::PXC, true)) return PM_ERR_ALIGN;
     const int tiles_per_img = (hw + NT - 1) / NT, total = B * tiles_per_img;
-    const size_t smem = nn_smem_bytes<T, MT, NT>();
+    const size_t smem = nn_smem_bytes<T, MT, NT, KB>();
     // clusters of CL CTAs share the weight blocks by TMA multicast; the NOPA*MT blocks of a stage must split evenly
     constexpr int NBLK = (TR::SPLIT ? 2 : 1) * MT;
     constexpr int CLMAX = NBLK >= 4 ? 4 : NBLK;
@@ -389,7 +420,7 @@ static int launch_nn(const void* X, const void* Ah, const void* Al, void* Y, dou
     cudaError_t e;
 #define PM_NN_LAUNCH(CL_)                                                                                             \
     {                                                                                                                 \
-        auto kern = conv1x1_nn_kernel<T, MT, NT, CL_>;                                                                \
+        auto kern = conv1x1_nn_kernel<T, MT, NT, KB, CL_>;                                                                \
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                       \
         if (e != cudaSuccess) return (int)e;                                                                          \
         e = cudaLaunchKernelEx(&cfg, kern, mX, mAh, mAl, mY, K, M, m_tile0, tiles_per_img, total, accumulate, stats, dbg); \
@@ -537,8 +568,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 const int s = kb % STAGES;
                 mbar_wait(&full[s], (kb / STAGES) & 1);
                 unsigned char* st = smem + s * STAGE;
-                split_tile(reinterpret_cast<float4*>(st), reinterpret_cast<float4*>(st + TILE_A_BYTES), TILE_A_BYTES / 16, t, 128);
-                split_tile(reinterpret_cast<float4*>(st + 2 * TILE_A_BYTES), reinterpret_cast<float4*>(st + 2 * TILE_A_BYTES + BBYTES),
+                split_tile_trunc(reinterpret_cast<float4*>(st), reinterpret_cast<float4*>(st + TILE_A_BYTES), TILE_A_BYTES / 16, t, 128);
+                split_tile_trunc(reinterpret_cast<float4*>(st + 2 * TILE_A_BYTES), reinterpret_cast<float4*>(st + 2 * TILE_A_BYTES + BBYTES),
                                     N * 8, t, 128);
                 fence_proxy_async_smem();
                 mbar_arrive(&xfull[s]);
@@ -688,12 +719,21 @@ int pm_conv1x1_fwd(const void* X, const void* A_hi, const void* A_lo, void* Y, d
     for (int t0 = 0; t0 < mtiles; t0 += 2) {
         const int mt = mtiles - t0 >= 2 ? 2 : 1;
         int rc;
-        if (dtype == PM_F32)
-            rc = mt == 2 ? launch_nn<float, 2, 128>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, st)
-                         : launch_nn<float, 1, 128>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, st);
-        else
-            rc = mt == 2 ? launch_nn<__nv_bfloat16, 2, 128>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, st)
-                         : launch_nn<__nv_bfloat16, 1, 128>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, st);
+        // fp32: 256-pixel tiles and 16-channel blocks -- a tile pulls the (hi, lo) weights of its row tiles through the
+        // SM's L2 port once per 256 pixels instead of once per 128 (the measured bound of the 128-pixel version);
+        // small maps keep 128-pixel tiles so that more than a handful of SMs get work
+        const bool wide = (long long)B * ((hw + 255) / 256) >= 96;
+        if (dtype == PM_F32) {
+            if (wide && !gemm_narrow())
+                rc = mt == 2 ? launch_nn<float, 2, 256, 16>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, st)
+                             : launch_nn<float, 1, 256, 16>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, st);
+            else
+                rc = mt == 2 ? launch_nn<float, 2, 128, 32>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, st)
+                             : launch_nn<float, 1, 128, 32>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, st);
+        } else {
+            rc = mt == 2 ? launch_nn<__nv_bfloat16, 2, 128, 64>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, st)
+                         : launch_nn<__nv_bfloat16, 1, 128, 64>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, st);
+        }
         if (rc) return rc;
     }
     return 0;

@@ -79,7 +79,7 @@ struct TensorMapKey {
 
 template <typename T>
 static bool make_map_2d(CUtensorMap* map, const void* base, size_t rows, size_t cols, unsigned box_rows, unsigned box_cols,
-                        int swizzle128 /* 0 none, 1 SWIZZLE_128B (16-byte chunks), 2 SWIZZLE_128B_ATOM_32B (32-byte chunks) */) {
+                        int swizzle128 /* 0 none, 1 SWIZZLE_128B (16-byte chunks), 2 SWIZZLE_128B_ATOM_32B (32-byte chunks), 3 SWIZZLE_64B */) {
     constexpr int SLOTS = 128;
     static std::mutex mu;
     static TensorMapKey keys[SLOTS];
@@ -101,7 +101,10 @@ static bool make_map_2d(CUtensorMap* map, const void* base, size_t rows, size_t 
     const cuuint32_t estr[2] = {1, 1};
     const CUtensorMapDataType dt = sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     if (enc(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            swizzle128 == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+            swizzle128 == 3   ? CU_TENSOR_MAP_SWIZZLE_64B
+            : swizzle128 == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+            : swizzle128      ? CU_TENSOR_MAP_SWIZZLE_128B
+                              : CU_TENSOR_MAP_SWIZZLE_NONE,
             CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return false;

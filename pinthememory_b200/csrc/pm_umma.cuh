@@ -34,7 +34,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  
 //   32-bit elements (TF32) MUST use type 1: 4-row K groups `sbo` apart (the only MN-major layout tf32 has).
 // These are what a TMA box with 128-byte rows writes with CU_TENSOR_MAP_SWIZZLE_128B / _128B_ATOM_32B
 // (tile base 1024-byte aligned).
-constexpr uint32_t UMMA_SW128 = 2, UMMA_SW128_BASE32B = 1;
+constexpr uint32_t UMMA_SW128 = 2, UMMA_SW128_BASE32B = 1, UMMA_SW64 = 4;  // SW64: [rows][64 bytes], 8-row groups 512 B
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
                                               uint32_t layout = UMMA_SW128) {
     uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);

@@ -58,6 +58,12 @@ def test_meta_train_step_matches_fp64_oracle(shape):
         o.relu_gates = shared
     ref = meta_step(o_net, o_upd, o_upd2, x_tr.double(), lab_tr, x_te.double(), lab_te, G_tr.double(), G_te.double(),
                     inner_lr=0.01)
+    # yardstick for the ill-conditioned gradients: the same oracle in fp32 (eager torch / cuDNN fp32) against its fp64 self
+    f_net, f_upd, f_upd2 = _trio(mo.OracleMemorySup, K, C, state, mem0)
+    shared32 = mo.ReluGates(gates)
+    for o in (f_net, f_upd, f_upd2):
+        o.relu_gates = shared32
+    ref32 = meta_step(f_net, f_upd, f_upd2, x_tr, lab_tr, x_te, lab_te, G_tr, G_te, inner_lr=0.01)
 
     check_ties(shared)
     for k in ("inner_loss", "outer_loss", "readloss_a", "div_a", "cls_a", "readloss_c"):
@@ -67,10 +73,14 @@ def test_meta_train_step_matches_fp64_oracle(shape):
     assert_close(got["memory_final"], ref["memory_final"], 1e-5, "final memory (D)")
     assert set(got["grads"]) == set(ref["grads"])
     assert "writenet.writefeat.0.weight" in got["grads"]
-    for k in ref["inner_grads"]:
-        assert_close(got["inner_grads"][k], ref["inner_grads"][k], 5e-5, "inner grad " + k)
-    for k in ref["grads"]:
-        assert_close(got["grads"][k], ref["grads"][k], 5e-5, "accumulated grad " + k)
+    # gradients that crossed the BatchNorm statistics of up to three passes: as close to fp64 as fp32 arithmetic gets,
+    # i.e. within 5e-5 or 3x the deviation of eager fp32 torch from its own fp64 evaluation, whichever is larger
+    from golden_util import max_abs_over_scale, rel_l2
+
+    for name in ("inner_grads", "grads"):
+        for k in ref[name]:
+            yard = max(rel_l2(ref32[name][k], ref[name][k]), max_abs_over_scale(ref32[name][k], ref[name][k]))
+            assert_close(got[name][k], ref[name][k], max(5e-5, 3.0 * yard), name + " " + k)
     # aliasing rules of the step: D rebinds m_items to a fresh detached tensor; the functional copies hold non-leaf
     # parameters that point back at net's
     assert not net.m_items.requires_grad
