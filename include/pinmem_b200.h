@@ -263,6 +263,20 @@ int pm_conv1x1_wgrad(const void* dY, const void* X, float* workspace, float* dW,
 int pm_bn_finalize(const double* stats, int C, double count, float eps, float* mean, float* invstd,
                    float* running_mean, float* running_var, float momentum, void* stream);
 
+/*
+ * The two write losses on an ARBITRARY memory, for the reference's public methods `diversityloss(mem)`
+ * (memory.py:264-272) and `classification_loss(mem)` (memory.py:259-262); inside write() they are fused into
+ * pm_update_fwd / pm_update_bwd. mem [K,C] fp32 (rows need not be unit length), W_cls [K,C] / b_cls [K] or both NULL
+ * (divergence loss only).
+ *   fwd: out float[2] = {div, cls}; gram [K*K] and prob [K*K] (softmax rows of the classifier) are kept for the backward
+ *        (either may be NULL when no backward follows).
+ *   bwd: g_div / g_cls device scalars (NULL = 0); dmem [K,C] out; dW_cls [K,C], db_cls [K] out or NULL.
+ */
+int pm_memory_losses_fwd(const float* mem, const float* W_cls, const float* b_cls, int K, int C, float* out, float* gram,
+                         float* prob, void* stream);
+int pm_memory_losses_bwd(const float* mem, const float* W_cls, const float* gram, const float* prob, const float* g_div,
+                         const float* g_cls, int K, int C, float* dmem, float* dW_cls, float* db_cls, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

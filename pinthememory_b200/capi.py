@@ -56,6 +56,8 @@ PROTOTYPES = {
     "pm_conv1x1_wgrad_workspace_floats": [_c_i] * 5,
     "pm_conv1x1_wgrad": [_c_p] * 4 + [_c_i] * 6 + [_c_p],
     "pm_bn_finalize": [_c_p, _c_i, _c_d, _c_f] + [_c_p] * 4 + [_c_f, _c_p],
+    "pm_memory_losses_fwd": [_c_p] * 3 + [_c_i] * 2 + [_c_p] * 4,
+    "pm_memory_losses_bwd": [_c_p] * 6 + [_c_i] * 2 + [_c_p] * 4,
 }
 EXPORTED_SYMBOLS = sorted(list(PROTOTYPES) + ["pm_status_string"])
 
@@ -385,3 +387,17 @@ def conv1x1_wgrad(dy, x, dW=None, accumulate=False):
 def bn_finalize(stats, C, count, eps, mean, invstd, running_mean, running_var, momentum):
     _call("pm_bn_finalize", _ptr(stats), C, float(count), float(eps), _ptr(mean), _ptr(invstd), _ptr(running_mean),
           _ptr(running_var), float(momentum), _stream())
+
+
+# ------------------------------------------------------------ stand-alone write losses (csrc/pm_losses.cu)
+
+
+def memory_losses_fwd(mem, W, b, out, gram, prob):
+    K, C = mem.shape
+    _call("pm_memory_losses_fwd", _ptr(mem), _ptr(W), _ptr(b), K, C, _ptr(out), _ptr(gram), _ptr(prob), _stream())
+
+
+def memory_losses_bwd(mem, W, gram, prob, g_div, g_cls, dmem, dW, db):
+    K, C = mem.shape
+    _call("pm_memory_losses_bwd", _ptr(mem), _ptr(W), _ptr(gram), _ptr(prob), _ptr(g_div), _ptr(g_cls), K, C, _ptr(dmem),
+          _ptr(dW), _ptr(db), _stream())

@@ -214,6 +214,36 @@ class _WriteFn(torch.autograd.Function):
         return df, None, None, dW, db, None, None, None
 
 
+class _MemoryLossFn(torch.autograd.Function):
+    """(div, cls) of an arbitrary memory: memory.py:264-272 and :259-262 (pm_memory_losses_fwd / _bwd).
+    W/b None -> divergence loss only (cls is returned as 0)."""
+
+    @staticmethod
+    def forward(ctx, mem, W, b):
+        K, C = mem.shape
+        dev = mem.device
+        m32 = mem.detach().to(torch.float32).contiguous()
+        W32 = None if W is None else W.detach().to(torch.float32).contiguous()
+        b32 = None if b is None else b.detach().to(torch.float32).contiguous()
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        gram = torch.empty(K * K, dtype=torch.float32, device=dev)
+        prob = torch.empty(K * K, dtype=torch.float32, device=dev) if W is not None else None
+        capi.memory_losses_fwd(m32, W32, b32, out, gram, prob)
+        ctx.has_cls = W is not None
+        ctx.save_for_backward(m32, W32, gram, prob)
+        return out[0], out[1]
+
+    @staticmethod
+    def backward(ctx, g_div, g_cls):
+        m32, W32, gram, prob = ctx.saved_tensors
+        as32 = lambda t: None if t is None else t.to(torch.float32).contiguous()
+        dmem = torch.empty_like(m32)
+        dW = torch.empty_like(W32) if ctx.has_cls else None
+        db = torch.empty(m32.shape[0], dtype=torch.float32, device=m32.device) if ctx.has_cls else None
+        capi.memory_losses_bwd(m32, W32, gram, prob, as32(g_div), as32(g_cls), dmem, dW, db)
+        return dmem, dW, db
+
+
 class _BnActFn(torch.autograd.Function):
     """y = [relu](BatchNorm2d(xc) [+ residual]) with batch (training) or given (eval) statistics."""
 
@@ -588,6 +618,17 @@ class Memory_sup(nn.Module):
         return [div_loss, cls_loss]
 
     # ----------------------------------------------------------------------- external entry points
+
+    def classification_loss(self, mem):
+        """memory.py:259-262: CE of the slot classifier on ``mem`` against the slot indices (differentiable w.r.t.
+        ``mem`` and the classifier). write() computes the same loss fused into the update kernel."""
+        capi.require_cuda(mem)
+        return _MemoryLossFn.apply(mem, self.clsfier.weight, self.clsfier.bias)[1]
+
+    def diversityloss(self, mem):
+        """memory.py:264-272: mean positive off-diagonal cosine of ``mem`` (differentiable w.r.t. ``mem``)."""
+        capi.require_cuda(mem)
+        return _MemoryLossFn.apply(mem, None, None)[0]
 
     def get_score(self, query, mask, mem):
         """memory.py:167-189 on an already normalised NHWC query (validation, train.py:891-896).

@@ -406,3 +406,68 @@ def test_memory_folded_into_the_output_convolution_is_the_same_function(writing,
             assert gb is None, n
         else:
             close(gb, ga, "grad " + n)
+
+
+# --------------------------------------------------------- the reference's public loss methods, checkpoint key
+
+
+def test_diversityloss_and_classification_loss_methods():
+    """memory.py:259-272 as callable methods on an arbitrary memory (not unit rows), with gradients."""
+    from oracle import memory_oracle as mo
+
+    mem = _module()
+    torch.manual_seed(21)
+    M = (torch.randn(19, 64, device="cuda") * 0.7)
+    Ma, Mb = M.clone().requires_grad_(True), M.clone().requires_grad_(True)
+    Wb = mem.clsfier.weight.detach().clone().requires_grad_(True)
+    bb = mem.clsfier.bias.detach().clone().requires_grad_(True)
+    div, cls = mem.diversityloss(Ma), mem.classification_loss(Ma)
+    (0.4 * div + 0.2 * cls).backward()
+    div_o, cls_o = mo.divergence_loss(Mb), mo.classification_loss(Mb, Wb, bb)
+    (0.4 * div_o + 0.2 * cls_o).backward()
+    assert_close(div.detach().reshape(1), div_o.detach().reshape(1), 1e-6, "div")
+    assert_close(cls.detach().reshape(1), cls_o.detach().reshape(1), 1e-6, "cls")
+    assert_close(Ma.grad, Mb.grad, 1e-5, "d mem")
+    assert_close(mem.clsfier.weight.grad, Wb.grad, 1e-5, "d W_cls")
+    assert_close(mem.clsfier.bias.grad, bb.grad, 1e-5, "d b_cls")
+    # the fused path of write() reports the same numbers for the memory it produced
+    x = torch.randn(2, 64, 8, 8, device="cuda")
+    labels = torch.randint(0, 19, (2, 32, 32), device="cuda")
+    with torch.no_grad():
+        _, _, _, _, wl = mem(x, labels, True, True)
+        assert_close(mem.diversityloss(mem.m_items).reshape(1), wl[0].reshape(1), 1e-5, "div of the written memory")
+        assert_close(mem.classification_loss(mem.m_items).reshape(1), wl[1].reshape(1), 1e-5, "cls of the written memory")
+
+
+def test_checkpoint_round_trip_with_memory_key(tmp_path):
+    """utils/misc.py:213-214 saves ``savedict['memory'] = net.module.memory.m_items`` next to the state_dict and
+    optimizer.py:63-68 restores it with ``m_items = checkpoint['memory'].cuda()``: m_items is NOT in the state_dict, the
+    restored module must continue exactly where the saved one stood (same read, same next write)."""
+    mem = _module()
+    x = torch.randn(2, 64, 8, 8, device="cuda")
+    labels = torch.randint(0, 19, (2, 32, 32), device="cuda")
+    mem(x, labels, True, True)  # one training step: running stats, num_batches_tracked and m_items all moved
+    path = str(tmp_path / "last.pth")
+    torch.save({"state_dict": mem.state_dict(), "memory": mem.m_items, "epoch": 1, "mean_iu": 0.0}, path)
+    ckpt = torch.load(path, map_location="cpu")
+    assert "m_items" not in ckpt["state_dict"] and ckpt["memory"].shape == (19, 64)
+    fresh = _module()
+    with torch.no_grad():
+        fresh.clsfier.weight.add_(1.0)  # make sure the load below is what aligns the two
+    fresh.load_state_dict(ckpt["state_dict"])
+    fresh.m_items = ckpt["memory"].cuda()
+    for m in (mem, fresh):
+        m.eval()
+    with torch.no_grad():
+        a = mem(x, None, False)
+        b = fresh(x, None, False)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2])
+    for m in (mem, fresh):
+        m.train()
+    wa = mem(x, labels, True, True)[4]
+    wb = fresh(x, labels, True, True)[4]
+    # (the class sums are accumulated with float REDs: equal to ~1e-7, not bitwise, from run to run)
+    assert_close(mem.m_items, fresh.m_items, 1e-6, "memory after the next write")
+    assert_close(wa[0].reshape(1), wb[0].reshape(1), 1e-6, "div")
+    assert_close(wa[1].reshape(1), wb[1].reshape(1), 1e-6, "cls")
+    assert not fresh.m_items.requires_grad
