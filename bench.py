@@ -770,16 +770,20 @@ def main():
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
+                # fresh leaves: the AccumulateGrad nodes of x / f_core were created on the main stream by earlier steps and
+                # would pull that stream into the capture
+                xg = x.detach().clone().requires_grad_(True)
+                fg = f_core.detach().clone().requires_grad_(True)
                 for _ in range(3):
-                    core_step()
+                    core_step(xg, fg)
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize()
-            x.grad = None
-            f_core.grad = None
+            xg.grad = None
+            fg.grad = None
             core_graph = torch.cuda.CUDAGraph()
             n0 = capi.LAUNCHES
             with torch.cuda.graph(core_graph):
-                core_step()
+                core_step(xg, fg)
             core_launches_per_replay = capi.LAUNCHES - n0
             core_fn = core_graph.replay
             core_launch = "CUDA graph replay of the %d launches" % core_launches_per_replay

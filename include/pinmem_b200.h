@@ -277,6 +277,21 @@ int pm_memory_losses_fwd(const float* mem, const float* W_cls, const float* b_cl
 int pm_memory_losses_bwd(const float* mem, const float* W_cls, const float* gram, const float* prob, const float* g_div,
                          const float* g_cls, int K, int C, float* dmem, float* dW_cls, float* db_cls, void* stream);
 
+/*
+ * One pass over the labels for the whole step (csrc/pm_labels.cu). Replaces memory.py:220 (`tempmask[tempmask == 255]
+ * = memory_size`) and the label side of CrossEntropyLoss(ignore_index=255) (memory.py:117,176).
+ *   labels   [n] int64 (labels_are_u8 = 0) or uint8 (labels_are_u8 = 1): class ids 0..K-1, 255 = ignore
+ *   lab8     [n] uint8 out: class id, K for ignore. Values outside [0,K) u {255} -- torch's one_hot / CE would raise a
+ *            device assert on them -- also map to K and are COUNTED in ws[PM_WS_BAD].
+ *   ws       the PM_WS_WORDS 64-bit words of the read-loss workspace, ZEROED by the caller: receives the bit-exact
+ *            label histogram (ws[PM_WS_HIST + k], bin K = ignore) and the bad-label count.
+ * pm_readloss_fwd8 is pm_readloss_fwd on that packed map (K <= 19): pass the SAME ws after pm_labels_pack (it reads the
+ * histogram for the number of valid pixels and adds the loss sum and its CTA counter).
+ */
+int pm_labels_pack(const void* labels, int labels_are_u8, long long n, int K, uint8_t* lab8, void* ws, void* stream);
+int pm_readloss_fwd8(const float* s, const uint8_t* lab8, float temperature, int B, int h, int w, int Hm, int Wm, int K,
+                     float* ds_rl, void* ws, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,7 +70,7 @@ class _UpsampledCE(torch.autograd.Function):
         ds = buf[: N * KP]
         ws = buf[N * KP: N * KP + 2 * capi.WS_WORDS]
         out = buf[N * KP + 2 * capi.WS_WORDS:]
-        capi.readloss_fwd(s, labels, 1.0, B, h, w, K, ds, ws, out)
+        capi.readloss(s, labels, 1.0, B, h, w, K, ds, ws, out)
         ctx.save_for_backward(ds, out)
         ctx.shape, ctx.dtype = (B, K, h, w), logits.dtype
         return out[0].to(logits.dtype)
@@ -92,8 +92,8 @@ def upsampled_cross_entropy(logits, labels):
     capi.require_cuda(logits, labels)
     if logits.dim() != 4 or labels.dim() != 3 or labels.shape[0] != logits.shape[0]:
         raise RuntimeError("pinmem_b200: logits must be [B,K,h,w] and labels [B,Hm,Wm]")
-    if labels.dtype != torch.int64:
-        raise RuntimeError("pinmem_b200: labels must be int64")
+    if labels.dtype not in (torch.int64, torch.uint8):
+        raise RuntimeError("pinmem_b200: labels must be int64 (or uint8 class ids)")
     if not 1 <= logits.shape[1] <= 31:
         raise RuntimeError("pinmem_b200: upsampled_cross_entropy supports 1..31 classes")
     return _UpsampledCE.apply(logits, labels.contiguous())

@@ -56,6 +56,8 @@ PROTOTYPES = {
     "pm_conv1x1_wgrad_workspace_floats": [_c_i] * 5,
     "pm_conv1x1_wgrad": [_c_p] * 4 + [_c_i] * 6 + [_c_p],
     "pm_bn_finalize": [_c_p, _c_i, _c_d, _c_f] + [_c_p] * 4 + [_c_f, _c_p],
+    "pm_labels_pack": [_c_p, _c_i, ctypes.c_longlong, _c_i, _c_p, _c_p, _c_p],
+    "pm_readloss_fwd8": [_c_p, _c_p, _c_f] + [_c_i] * 6 + [_c_p] * 4,
     "pm_memory_losses_fwd": [_c_p] * 3 + [_c_i] * 2 + [_c_p] * 4,
     "pm_memory_losses_bwd": [_c_p] * 6 + [_c_i] * 2 + [_c_p] * 4,
 }
@@ -401,3 +403,31 @@ def memory_losses_bwd(mem, W, gram, prob, g_div, g_cls, dmem, dW, db):
     K, C = mem.shape
     _call("pm_memory_losses_bwd", _ptr(mem), _ptr(W), _ptr(gram), _ptr(prob), _ptr(g_div), _ptr(g_cls), K, C, _ptr(dmem),
           _ptr(dW), _ptr(db), _stream())
+
+
+# --------------------------------------------------------------------- packed labels (csrc/pm_labels.cu)
+
+
+def labels_pack(labels, K, ws):
+    """int64 | uint8 labels -> uint8 class map (K = ignore); histogram and bad-label count into the zeroed ws."""
+    lab8 = torch.empty(labels.shape, dtype=torch.uint8, device=labels.device)
+    _call("pm_labels_pack", _ptr(labels), int(labels.dtype == torch.uint8), labels.numel(), int(K), _ptr(lab8), _ptr(ws),
+          _stream())
+    return lab8
+
+
+def readloss_fwd8(s, lab8, temperature, B, h, w, K, ds_rl, ws, out):
+    Hm, Wm = lab8.shape[1], lab8.shape[2]
+    _call("pm_readloss_fwd8", _ptr(s), _ptr(lab8), float(temperature), B, h, w, Hm, Wm, K, _ptr(ds_rl), _ptr(ws), _ptr(out),
+          _stream())
+
+
+def readloss(s, labels, temperature, B, h, w, K, ds_rl, ws, out):
+    """Read loss on int64 | uint8 labels: one label pass (pack + histogram + bad-label count) and the second-generation
+    kernel for K <= 19, the first kernel (int64 labels, any K <= 31) otherwise or with PINMEM_B200_READLOSS_V1 set."""
+    if K <= 19 and not os.environ.get("PINMEM_B200_READLOSS_V1"):
+        lab8 = labels_pack(labels, K, ws)
+        readloss_fwd8(s, lab8, temperature, B, h, w, K, ds_rl, ws, out)
+        return lab8
+    readloss_fwd(s, labels if labels.dtype == torch.int64 else labels.to(torch.int64), temperature, B, h, w, K, ds_rl, ws, out)
+    return None

@@ -1,0 +1,381 @@
+// Feature-cohesion read loss on the packed uint8 class map (pm_labels_pack), second-generation kernel.
+//
+// readloss = CE(bilinear_up(s/T -> [Hm,Wm], align_corners=True), labels; ignore 255), mean over valid label pixels
+// (reference memory.py:173-176), plus d(loss_sum)/d(s/T) scattered back to the feature pixels -- computed per label
+// pixel on the fly, the [B,K,Hm,Wm] logits never exist. Same cell decomposition as pm_readloss.cu (a "cell" = the
+// label pixels whose four bilinear taps are feature pixels (cy,cx)..(cy+1,cx+1)); what changed is the work per pixel:
+//   * ONE thread owns a cell with all KP = 20 slots in registers (the first kernel paired two threads per cell and
+//     paid the label logic, the lambda arithmetic and a shuffle twice per pixel);
+//   * inside a cell row every logit is linear in lambda_x, and lambda_x advances by the constant `sx` per label pixel,
+//     so exp2(z_k) is a GEOMETRIC sequence along the row: E_k <- E_k * r_k with r_k = exp2(c * sx * B_k). Two `ex2`
+//     per slot per ROW replace one per slot per PIXEL (the MUFU pipe is 16 lanes/clk/SM: 20 per pixel was a 20 us
+//     floor on its own) and the FFMA that formed the exponent disappears;
+//   * labels are one byte per pixel from the packed map, the histogram / valid count / bad-label count come from the
+//     pack pass, so the per-pixel label work is a byte load, a compare and the run-length bookkeeping of the one-hot
+//     term.
+// Per pixel that is ~60 instructions in one thread instead of ~2 x 91 (363 thread-instructions per label pixel measured
+// on the first kernel, profiles/r1f_ncu_full.txt). The exact per-pixel path is kept for cells whose tap spread is too
+// large for the per-cell stabiliser (tiny temperatures, un-normalised logits of the head's main loss).
+//
+// Accuracy of the recurrence: ex2.approx is 2^-22 relative and every step multiplies, so after i steps the error of a
+// probability is ~ (i + 1) * 2.4e-7 (i <= 8 at output stride 8, <= 16 at stride 16); measured against the oracle the
+// loss and ds_rl stay below 3e-6 (tests/test_gpu_parity.py). The weights lambda_x / lambda_y themselves are computed
+// exactly as PyTorch does (fp32 `scale * dst`, floor, clamp).
+#include "pm_common.cuh"
+
+namespace pm {
+
+constexpr int RL8_THREADS = 256;  // one cell (or one row-split of a cell) per thread
+constexpr int RL8_TX = 32;        // cells per CTA along x (a warp = 32 cells of one cell row, same row split)
+constexpr int RL8_KP = 20;        // padded slot count of the score rows (K <= 19)
+
+__device__ __forceinline__ float ex2a(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2a(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcpa(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ int bil_index8(float scale, int dst, int n_in) {
+    int i0 = (int)(scale * (float)dst);
+    return i0 > n_in - 1 ? n_in - 1 : i0;
+}
+// smallest dst in [0, n_out] whose bilinear source index is >= c
+__device__ __forceinline__ int first_ge8(int c, float scale, int n_out, int n_in) {
+    if (c <= 0) return 0;
+    if (c > n_in - 1 || scale <= 0.f) return n_out;
+    int y = (int)ceilf((float)c / scale);
+    y = max(0, min(y, n_out));
+    while (y > 0 && bil_index8(scale, y - 1, n_in) >= c) --y;
+    while (y < n_out && bil_index8(scale, y, n_in) < c) ++y;
+    return y;
+}
+
+__global__ void __launch_bounds__(RL8_THREADS, 1)
+    readloss8_kernel(const float* __restrict__ s, const unsigned char* __restrict__ lab8, float inv_T, float temperature, int h,
+                     int w, int Hm, int Wm, int K, float sy, float sx, int RS, int TYC, int tiles_x, int tiles_y,
+                     float* __restrict__ ds_rl, unsigned long long* __restrict__ ws, float* __restrict__ out) {
+    constexpr int KP = RL8_KP, NH = KP / 2, NT = RL8_THREADS, LDX = RL8_TX + 1;
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tile_elems = (TYC + 1) * LDX * KP;
+    float* s_tile = smem;                    // [(TYC+1)][33][KP] similarities of the tile's feature pixels
+    float* ds_tile = s_tile + tile_elems;    // same shape: gradient taps
+    float* priv = ds_tile + tile_elems;      // [4][KP][NT] one-hot tap weights, thread-private columns
+    float* red = priv + 4 * KP * NT;         // [8]
+
+    int bid = blockIdx.x;
+    const int tx_i = bid % tiles_x;
+    bid /= tiles_x;
+    const int ty_i = bid % tiles_y, b = bid / tiles_y;
+    const int fy0 = ty_i * TYC, fx0 = tx_i * RL8_TX;
+
+    for (int i = tid; i < tile_elems; i += NT) {
+        const int e = i / KP, k = i - e * KP;
+        const int ty = e / LDX, tx = e - ty * LDX;
+        const int fy = min(fy0 + ty, h - 1), fx = min(fx0 + tx, w - 1);
+        s_tile[i] = __ldg(s + ((size_t)(b * h + fy) * w + fx) * KP + k);
+        ds_tile[i] = 0.f;
+    }
+    for (int i = tid; i < 4 * KP * NT; i += NT) priv[i] = 0.f;
+    __syncthreads();
+
+    const int cxl = tid % RL8_TX, rest = tid / RL8_TX;  // rest in [0, TYC*RS)
+    const int cyl = rest / RS, split = rest - cyl * RS;
+    const int cy = fy0 + cyl, cx = fx0 + cxl;
+    const bool active = (cy < h) && (cx < w);
+    const int ly0 = cyl, ly1 = min(cy + 1, h - 1) - fy0;
+    const int lx0 = cxl, lx1 = min(cx + 1, w - 1) - fx0;
+
+    float2 G00[NH], G01[NH], G10[NH], G11[NH];
+#pragma unroll
+    for (int i = 0; i < NH; ++i) G00[i] = G01[i] = G10[i] = G11[i] = make_float2(0.f, 0.f);
+    float lossacc = 0.f;  // log2 units
+    float* pv = priv + tid;  // element (tap, k) at pv[(tap*KP + k)*NT]
+
+    int Ya = 0, Yb = 0, Xa = 0, Xb = 0;
+    if (active) {
+        Ya = first_ge8(cy, sy, Hm, h), Yb = first_ge8(cy + 1, sy, Hm, h);
+        Xa = first_ge8(cx, sx, Wm, w), Xb = first_ge8(cx + 1, sx, Wm, w);
+    }
+    // warp-uniform loop bounds (out-of-range pixels predicated off)
+    const int nr_lane = (Yb - Ya - split + RS - 1) / RS;
+    const int nr_max = __reduce_max_sync(0xffffffffu, max(nr_lane, 0));
+    const int nc_max = __reduce_max_sync(0xffffffffu, Xb - Xa);
+    const float c2 = inv_T * 1.4426950408889634f;
+    const int tl0 = active ? ly0 : 0, tl1 = active ? ly1 : 0, tx0 = active ? lx0 : 0, tx1 = active ? lx1 : 0;
+    const float2* t00 = reinterpret_cast<const float2*>(s_tile + (tl0 * LDX + tx0) * KP);
+    const float2* t01 = reinterpret_cast<const float2*>(s_tile + (tl0 * LDX + tx1) * KP);
+    const float2* t10 = reinterpret_cast<const float2*>(s_tile + (tl1 * LDX + tx0) * KP);
+    const float2* t11 = reinterpret_cast<const float2*>(s_tile + (tl1 * LDX + tx1) * KP);
+    float shift;  // softmax stabiliser (log2 units): max over the cell's taps and slots
+    bool pxmax;
+    {
+        float m = -INFINITY, n = INFINITY;
+#pragma unroll
+        for (int i = 0; i < NH; ++i) {
+            const float2 a = t00[i], bq = t01[i], c = t10[i], d = t11[i];
+            if (2 * i < K) {
+                m = fmaxf(m, fmaxf(fmaxf(a.x, bq.x), fmaxf(c.x, d.x)));
+                n = fminf(n, fminf(fminf(a.x, bq.x), fminf(c.x, d.x)));
+            }
+            if (2 * i + 1 < K) {
+                m = fmaxf(m, fmaxf(fmaxf(a.y, bq.y), fmaxf(c.y, d.y)));
+                n = fminf(n, fminf(fminf(a.y, bq.y), fminf(c.y, d.y)));
+            }
+        }
+        shift = m * c2;
+        // spread too large for the per-cell stabiliser (tiny T / un-normalised logits; also NaN/inf): exact path
+        pxmax = __any_sync(0xffffffffu, !(shift - n * c2 < 60.f));
+    }
+    // run-length state of the one-hot term
+    int cur = -1;
+    float o00 = 0.f, o01 = 0.f, o10 = 0.f, o11 = 0.f;
+    const unsigned char* lab_b = lab8 + (size_t)b * Hm * Wm;
+    const float cxf = (float)cx, cyf = (float)cy;
+    const float lam_first = fminf(fmaxf(sx * (float)Xa - cxf, 0.f), 1.f);
+
+    for (int r = 0; r < nr_max; ++r) {
+        const int Y = Ya + split + r * RS;
+        const bool rowok = active && Y < Yb;
+        const float lamy = fminf(fmaxf(sy * (float)Y - cyf, 0.f), 1.f);
+        const float hy = 1.f - lamy;
+        // per-row exponent coefficients: z_k(lambda_x) = A_k + lambda_x * B_k (log2 units, stabilised)
+        float2 E[NH], Rt[NH];  // E = exp2(z) at the current pixel; Rt = per-pixel ratio (fast path) or B_k (exact path)
+#pragma unroll
+        for (int i = 0; i < NH; ++i) {
+            const float2 v00 = t00[i], v01 = t01[i], v10 = t10[i], v11 = t11[i];
+            float l0 = fmaf(lamy, v10.x - v00.x, v00.x), l1 = fmaf(lamy, v11.x - v01.x, v01.x);
+            float Ax = fmaf(l0, c2, -shift), Bx = (l1 - l0) * c2;
+            l0 = fmaf(lamy, v10.y - v00.y, v00.y), l1 = fmaf(lamy, v11.y - v01.y, v01.y);
+            float Ay = fmaf(l0, c2, -shift), By = (l1 - l0) * c2;
+            if (2 * i >= K) Ax = -INFINITY, Bx = 0.f;
+            if (2 * i + 1 >= K) Ay = -INFINITY, By = 0.f;
+            if (!pxmax) {
+                E[i] = make_float2(ex2a(fmaf(lam_first, Bx, Ax)), ex2a(fmaf(lam_first, By, Ay)));
+                Rt[i] = make_float2(ex2a(sx * Bx), ex2a(sx * By));
+            } else {
+                E[i] = make_float2(Ax, Ay);
+                Rt[i] = make_float2(Bx, By);
+            }
+        }
+        const unsigned char* lrow = lab_b + (size_t)(rowok ? Y : 0) * Wm + Xa;
+        const int ncols = rowok ? Xb - Xa : 0;
+        float2 R0[NH], R1[NH];  // row accumulators of p*(1-lambda_x) and p*lambda_x
+#pragma unroll
+        for (int q = 0; q < NH; ++q) R0[q] = R1[q] = make_float2(0.f, 0.f);
+        float ox0 = 0.f, ox1 = 0.f;  // one-hot counterparts for the current run (this row only)
+        for (int X0 = 0; X0 < nc_max; X0 += 4) {
+            int lab[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) lab[i] = (X0 + i < ncols) ? (int)__ldg(lrow + X0 + i) : 255;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (X0 + i >= nc_max) break;  // warp-uniform
+                const int cls = lab[i];       // 0..K (K = ignore) or 255 = outside this thread's row
+                const bool ok = cls != 255;
+                const bool valid = cls < K;
+                const float lamx = fminf(fmaxf(sx * (float)(Xa + X0 + i) - cxf, 0.f), 1.f);
+                const float hx = 1.f - lamx;
+                float2 e[NH];
+                float pshift = shift;
+                if (!pxmax) {
+#pragma unroll
+                    for (int q = 0; q < NH; ++q) e[q] = E[q];
+                } else {  // exact path (warp-uniform): per-pixel maximum, one ex2 per slot
+                    float m = -INFINITY;
+#pragma unroll
+                    for (int q = 0; q < NH; ++q) {
+                        e[q] = __ffma2_rn(make_float2(lamx, lamx), Rt[q], E[q]);
+                        m = fmaxf(m, fmaxf(e[q].x, e[q].y));
+                    }
+                    pshift += m;
+#pragma unroll
+                    for (int q = 0; q < NH; ++q) e[q] = make_float2(ex2a(e[q].x - m), ex2a(e[q].y - m));
+                }
+                // softmax denominator: pairwise tree over the 10 packed pairs
+                float2 s01 = __fadd2_rn(e[0], e[1]), s23 = __fadd2_rn(e[2], e[3]), s45 = __fadd2_rn(e[4], e[5]);
+                float2 s67 = __fadd2_rn(e[6], e[7]), s89 = __fadd2_rn(e[8], e[9]);
+                s01 = __fadd2_rn(s01, s23), s45 = __fadd2_rn(s45, s67);
+                s01 = __fadd2_rn(__fadd2_rn(s01, s45), s89);
+                const float sum = s01.x + s01.y;
+                if (valid) lossacc += pshift + lg2a(sum);
+                const float inv = valid ? rcpa(sum) : 0.f;
+                const float2 ihx = make_float2(inv * hx, inv * hx), ilx = make_float2(inv * lamx, inv * lamx);
+#pragma unroll
+                for (int q = 0; q < NH; ++q) {
+                    R0[q] = __ffma2_rn(e[q], ihx, R0[q]);
+                    R1[q] = __ffma2_rn(e[q], ilx, R1[q]);
+                }
+                if (!pxmax) {
+#pragma unroll
+                    for (int q = 0; q < NH; ++q) E[q] = __fmul2_rn(E[q], Rt[q]);
+                }
+                // one-hot term: run-length accumulate, flush to the private columns when the class changes
+                if (ok && cls != cur) {
+                    if (cur >= 0 && cur < K) {
+                        pv[(0 * KP + cur) * NT] += fmaf(hy, ox0, o00);
+                        pv[(1 * KP + cur) * NT] += fmaf(hy, ox1, o01);
+                        pv[(2 * KP + cur) * NT] += fmaf(lamy, ox0, o10);
+                        pv[(3 * KP + cur) * NT] += fmaf(lamy, ox1, o11);
+                    }
+                    o00 = o01 = o10 = o11 = 0.f;
+                    ox0 = ox1 = 0.f;
+                    cur = cls;
+                }
+                ox0 += ok ? hx : 0.f;
+                ox1 += ok ? lamx : 0.f;
+            }
+        }
+        // end of row: fold the row accumulators into the four taps
+        o00 = fmaf(hy, ox0, o00), o01 = fmaf(hy, ox1, o01);
+        o10 = fmaf(lamy, ox0, o10), o11 = fmaf(lamy, ox1, o11);
+        {
+            const float2 hy2 = make_float2(hy, hy), ly2 = make_float2(lamy, lamy);
+#pragma unroll
+            for (int q = 0; q < NH; ++q) {
+                G00[q] = __ffma2_rn(R0[q], hy2, G00[q]);
+                G01[q] = __ffma2_rn(R1[q], hy2, G01[q]);
+                G10[q] = __ffma2_rn(R0[q], ly2, G10[q]);
+                G11[q] = __ffma2_rn(R1[q], ly2, G11[q]);
+            }
+        }
+    }
+    if (active) {
+        if (cur >= 0 && cur < K) {
+            pv[(0 * KP + cur) * NT] += o00;
+            pv[(1 * KP + cur) * NT] += o01;
+            pv[(2 * KP + cur) * NT] += o10;
+            pv[(3 * KP + cur) * NT] += o11;
+        }
+        // minus the logit of the labelled class: sum_px z_y = c2 * sum_{tap,k} onehot_weight[tap][k] * tap[k];
+        // then subtract the one-hot part from the tap gradients
+        float zy = 0.f;
+#pragma unroll
+        for (int q = 0; q < NH; ++q) {
+            const float a0 = pv[(0 * KP + 2 * q) * NT], a1 = pv[(0 * KP + 2 * q + 1) * NT];
+            const float b0 = pv[(1 * KP + 2 * q) * NT], b1 = pv[(1 * KP + 2 * q + 1) * NT];
+            const float c0 = pv[(2 * KP + 2 * q) * NT], c1 = pv[(2 * KP + 2 * q + 1) * NT];
+            const float d0 = pv[(3 * KP + 2 * q) * NT], d1 = pv[(3 * KP + 2 * q + 1) * NT];
+            const float2 v00 = t00[q], v01 = t01[q], v10 = t10[q], v11 = t11[q];
+            zy = fmaf(a0, v00.x, fmaf(a1, v00.y, zy));
+            zy = fmaf(b0, v01.x, fmaf(b1, v01.y, zy));
+            zy = fmaf(c0, v10.x, fmaf(c1, v10.y, zy));
+            zy = fmaf(d0, v11.x, fmaf(d1, v11.y, zy));
+            G00[q].x -= a0, G00[q].y -= a1;
+            G01[q].x -= b0, G01[q].y -= b1;
+            G10[q].x -= c0, G10[q].y -= c1;
+            G11[q].x -= d0, G11[q].y -= d1;
+        }
+        lossacc = fmaf(-c2, zy, lossacc);
+        // fold degenerate taps (last row / column clamp onto themselves)
+        if (ly1 == ly0) {
+#pragma unroll
+            for (int q = 0; q < NH; ++q) {
+                G00[q] = __fadd2_rn(G00[q], G10[q]), G01[q] = __fadd2_rn(G01[q], G11[q]);
+                G10[q] = G11[q] = make_float2(0.f, 0.f);
+            }
+        }
+        if (lx1 == lx0) {
+#pragma unroll
+            for (int q = 0; q < NH; ++q) {
+                G00[q] = __fadd2_rn(G00[q], G01[q]), G10[q] = __fadd2_rn(G10[q], G11[q]);
+                G01[q] = G11[q] = make_float2(0.f, 0.f);
+            }
+        }
+    } else {
+        lossacc = 0.f;
+    }
+
+    // merge into the tap tile: within one (tap, split) phase every active thread owns distinct addresses
+    for (int sp = 0; sp < RS; ++sp) {
+#pragma unroll
+        for (int tap = 0; tap < 4; ++tap) {
+            const bool fold = (tap >= 2 && ly1 == ly0) || ((tap & 1) && lx1 == lx0);
+            if (active && split == sp && !fold) {
+                const int ly = (tap >= 2) ? ly1 : ly0, lx = (tap & 1) ? lx1 : lx0;
+                float2* dst = reinterpret_cast<float2*>(ds_tile + (ly * LDX + lx) * KP);
+#pragma unroll
+                for (int q = 0; q < NH; ++q) {
+                    const float2 g = tap == 0 ? G00[q] : tap == 1 ? G01[q] : tap == 2 ? G10[q] : G11[q];
+                    float2 v = dst[q];
+                    v.x += g.x, v.y += g.y;
+                    dst[q] = v;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // flush taps that exist (clamped duplicates were folded and stay zero)
+    for (int i = tid; i < tile_elems / 4; i += NT) {
+        const int e = i / (KP / 4), q = i - e * (KP / 4);
+        const int ty = e / LDX, tx = e - ty * LDX;
+        const int fy = fy0 + ty, fx = fx0 + tx;
+        if (fy < h && fx < w) {
+            const float4 v = reinterpret_cast<const float4*>(ds_tile)[i];
+            if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f)
+                atomicAdd(reinterpret_cast<float4*>(ds_rl + ((size_t)(b * h + fy) * w + fx) * KP) + q, v);
+        }
+    }
+    lossacc = warp_sum(lossacc);
+    if (lane == 0) red[wid] = lossacc;
+    __syncthreads();
+    if (tid == 0) {
+        float tot = 0.f;
+        for (int i = 0; i < NT / 32; ++i) tot += red[i];
+        atomicAdd(reinterpret_cast<double*>(ws + PM_WS_LOSS_SUM), (double)tot * 0.6931471805599453);
+    }
+    // last CTA: readloss = loss_sum / V ; scale = 1 / (V*T)   (V from the histogram pm_labels_pack left in ws)
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned long long ticket = atomicAdd(ws + PM_WS_COUNTER, 1ULL);
+        if (ticket == (unsigned long long)gridDim.x - 1) {
+            __threadfence();
+            unsigned long long V = 0;
+            for (int k = 0; k < K; ++k) V += atomicAdd(ws + PM_WS_HIST + k, 0ULL);
+            const double sum = __longlong_as_double((long long)atomicAdd(ws + PM_WS_LOSS_SUM, 0ULL));
+            out[0] = (float)(sum / (double)V);  // V == 0 -> 0/0 = NaN like torch
+            out[1] = (float)(1.0 / ((double)V * (double)temperature));
+        }
+    }
+}
+
+}  // namespace pm
+
+extern "C" int pm_readloss_fwd8(const float* s, const uint8_t* lab8, float temperature, int B, int h, int w, int Hm, int Wm,
+                                int K, float* ds_rl, void* ws, float* out, void* stream) {
+    if (!s || !lab8 || !ds_rl || !ws || !out) return PM_ERR_NULL;
+    if (K < 1 || K > 19) return PM_ERR_SLOTS;
+    if (B <= 0 || h <= 0 || w <= 0 || Hm <= 0 || Wm <= 0 || !(temperature > 0.f)) return PM_ERR_SHAPE;
+    if (((uintptr_t)s & 15) || ((uintptr_t)ds_rl & 15) || ((uintptr_t)ws & 7)) return PM_ERR_ALIGN;
+    using namespace pm;
+    // PyTorch's align_corners scale: (in-1)/(out-1) in fp32, 0 when out == 1
+    const float sy = Hm > 1 ? (float)(h - 1) / (float)(Hm - 1) : 0.f;
+    const float sx = Wm > 1 ? (float)(w - 1) / (float)(Wm - 1) : 0.f;
+    // row-split factor: enough CTAs to fill the chip when there are few cells (output stride 16, small batches)
+    const long long cells = (long long)B * h * w;
+    const int rows_per_cell = h > 1 ? (Hm + h - 2) / (h - 1) : Hm;
+    int RS = 1;
+    while (RS < 8 && cells * RS < 2LL * 148 * RL8_THREADS && RS * 2 <= rows_per_cell) RS *= 2;
+    const int TYC = (RL8_THREADS / RL8_TX) / RS;
+    const int tiles_x = (w + RL8_TX - 1) / RL8_TX, tiles_y = (h + TYC - 1) / TYC;
+    const size_t smem = sizeof(float) * ((size_t)2 * (TYC + 1) * (RL8_TX + 1) * RL8_KP + (size_t)4 * RL8_KP * RL8_THREADS + 8);
+    const long long grid = (long long)B * tiles_x * tiles_y;
+    if (grid > 0x7fffffffLL) return PM_ERR_SHAPE;
+    cudaError_t e = cudaFuncSetAttribute(readloss8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    readloss8_kernel<<<(int)grid, RL8_THREADS, smem, (cudaStream_t)stream>>>(s, lab8, 1.f / temperature, temperature, h, w, Hm, Wm,
+                                                                             K, sy, sx, RS, TYC, tiles_x, tiles_y, ds_rl,
+                                                                             (unsigned long long*)ws, out);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}

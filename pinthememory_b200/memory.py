@@ -36,8 +36,9 @@ def initialize_weights(*models):
 
 
 def _check_labels(mask, B):
-    if mask.dtype != torch.int64:
-        raise RuntimeError(f"pinmem_b200: labels must be int64 (got {mask.dtype}); the reference one-hots them")
+    if mask.dtype not in (torch.int64, torch.uint8):
+        raise RuntimeError(f"pinmem_b200: labels must be int64 like the reference's (or uint8 class ids with 255 = ignore), "
+                           f"got {mask.dtype}")
     if mask.dim() != 3 or mask.shape[0] != B:
         raise RuntimeError(f"pinmem_b200: labels must be [B,Hm,Wm] with B={B}, got {tuple(mask.shape)}")
     capi.require_cuda(mask)
@@ -74,6 +75,8 @@ class _ReadFn(torch.autograd.Function):
     the similarity term, the other one reaches M through the folded weight in autograd.
     """
 
+    last_bad = None  # device int64 scalar: label values outside [0,K) u {255} seen by the last read with labels
+
     @staticmethod
     def forward(ctx, x, M, labels, g_query, g_memory, temperature, K, planes=False):
         B, C, h, w = x.shape
@@ -95,9 +98,11 @@ class _ReadFn(torch.autograd.Function):
             ds_rl = buf[: N * KP]
             ws = buf[N * KP: N * KP + 2 * capi.WS_WORDS]
             rl_out = buf[N * KP + 2 * capi.WS_WORDS:]
-            capi.readloss_fwd(s, labels, temperature, B, h, w, K, ds_rl, ws, rl_out)
+            # one pass over the labels (packed uint8 classes + histogram + bad-label count), then the read loss on it
+            capi.readloss(s, labels, temperature, B, h, w, K, ds_rl, ws, rl_out)
             readloss = rl_out[0]
             hist = ws.view(torch.int64)[capi.WS_HIST: capi.WS_HIST + K + 1]
+            _ReadFn.last_bad = ws.view(torch.int64)[capi.WS_BAD]
         else:
             ds_rl = rl_out = None
             readloss = torch.zeros((), dtype=torch.float32, device=dev)
@@ -518,6 +523,8 @@ class Memory_sup(nn.Module):
         self.fold_min_pixels = 32768       # ... for feature maps of at least this many pixels per call
         self.shard_group = None        # set by sharding.enable_sharded_update()
         self.last_label_hist = None    # int64 [K+1] label histogram of the last read with labels
+        self.last_bad_labels = None    # device int64 scalar: out-of-range label values of that read (counted as ignore)
+        self.debug_labels = False      # True: raise when last_bad_labels != 0 (costs a device synchronisation per read)
         self.last_class_sums = None    # fp32 [K+1, C+4] sums|counts of the last write (after all-reduce)
 
     # ------------------------------------------------------------------------------------- forward
@@ -590,6 +597,10 @@ class Memory_sup(nn.Module):
             readloss = 0  # memory.py:178
         else:
             self.last_label_hist = hist
+            self.last_bad_labels = _ReadFn.last_bad
+            if self.debug_labels and int(self.last_bad_labels) != 0:   # synchronises: debugging aid only
+                raise RuntimeError(f"pinmem_b200: {int(self.last_bad_labels)} label values outside [0,{self.memory_size}) "
+                                   "and != 255 (torch's one_hot / CrossEntropyLoss would raise a device assert)")
         if planes:
             # conv(W, [q ; p.M]) = W1.q + (W2.M^T).p : the memory is folded into the weight (a [C_out, 32] block) and
             # the convolution runs on [q ; score planes] -- C+32 input channels instead of 2C
@@ -608,6 +619,8 @@ class Memory_sup(nn.Module):
         if mask is None:
             raise RuntimeError("pinmem_b200: memory_writing=True needs labels (the reference crashes at memory.py:208)")
         labels = _check_labels(mask, B)
+        if labels.dtype != torch.int64:   # the class-sum kernels still read the reference's int64 maps
+            labels = labels.to(torch.int64)
         f = self.writenet(query)
         f = _check_features(f, "write feature")
         M_old = self._memory_for_kernels(query.device)
@@ -652,7 +665,7 @@ class Memory_sup(nn.Module):
                 buf = torch.zeros(N * KP + 2 * capi.WS_WORDS + 4, dtype=torch.float32, device=dev)
                 ws = buf[N * KP: N * KP + 2 * capi.WS_WORDS]
                 rl_out = buf[N * KP + 2 * capi.WS_WORDS:]
-                capi.readloss_fwd(s, labels, float(self.temperature), Bq, h, w, K, buf[: N * KP], ws, rl_out)
+                capi.readloss(s, labels, float(self.temperature), Bq, h, w, K, buf[: N * KP], ws, rl_out)
                 readloss = rl_out[0]
                 self.last_label_hist = ws.view(torch.int64)[capi.WS_HIST: capi.WS_HIST + K + 1]
             else:
