@@ -291,6 +291,11 @@ int pm_memory_losses_bwd(const float* mem, const float* W_cls, const float* gram
 int pm_labels_pack(const void* labels, int labels_are_u8, long long n, int K, uint8_t* lab8, void* ws, void* stream);
 int pm_readloss_fwd8(const float* s, const uint8_t* lab8, float temperature, int B, int h, int w, int Hm, int Wm, int K,
                      float* ds_rl, void* ws, float* out, void* stream);
+/* pm_write_reduce_fwd / pm_write_bwd on the packed map (1 byte per label pixel instead of 8). */
+int pm_write_reduce_fwd8(const void* f, const uint8_t* lab8, float* SD, int B, int C, int h, int w, int Hm, int Wm, int K,
+                         int dtype, void* stream);
+int pm_write_bwd8(const float* dS, const void* f, const uint8_t* lab8, void* df, int B, int C, int h, int w, int Hm, int Wm,
+                  int K, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

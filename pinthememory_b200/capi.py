@@ -56,6 +56,8 @@ PROTOTYPES = {
     "pm_conv1x1_wgrad_workspace_floats": [_c_i] * 5,
     "pm_conv1x1_wgrad": [_c_p] * 4 + [_c_i] * 6 + [_c_p],
     "pm_bn_finalize": [_c_p, _c_i, _c_d, _c_f] + [_c_p] * 4 + [_c_f, _c_p],
+    "pm_write_reduce_fwd8": [_c_p] * 3 + [_c_i] * 8 + [_c_p],
+    "pm_write_bwd8": [_c_p] * 4 + [_c_i] * 8 + [_c_p],
     "pm_labels_pack": [_c_p, _c_i, ctypes.c_longlong, _c_i, _c_p, _c_p, _c_p],
     "pm_readloss_fwd8": [_c_p, _c_p, _c_f] + [_c_i] * 6 + [_c_p] * 4,
     "pm_memory_losses_fwd": [_c_p] * 3 + [_c_i] * 2 + [_c_p] * 4,
@@ -275,9 +277,10 @@ def rowsoftmax(s, gumbel_m, score_m, N, K):
 
 
 def write_reduce_fwd(f, labels, SD, K):
+    """labels: int64 class ids, or the packed uint8 map of labels_pack (class K = ignore)."""
     B, C, h, w = f.shape
     Hm, Wm = labels.shape[1], labels.shape[2]
-    _call("pm_write_reduce_fwd", _ptr(f), _ptr(labels), _ptr(SD), B, C, h, w, Hm, Wm, K, dtype_code(f),
+    _call("pm_write_reduce_fwd8" if labels.dtype == torch.uint8 else "pm_write_reduce_fwd", _ptr(f), _ptr(labels), _ptr(SD), B, C, h, w, Hm, Wm, K, dtype_code(f),
                                       _stream())
 
 
@@ -305,7 +308,7 @@ def update_bwd(dM_new, g_div, g_cls, M_new, saved, W, b, momentum, dS, dW, db, C
 def write_bwd(dS, f, labels, df, K):
     B, C, h, w = f.shape
     Hm, Wm = labels.shape[1], labels.shape[2]
-    _call("pm_write_bwd", _ptr(dS), _ptr(f), _ptr(labels), _ptr(df), B, C, h, w, Hm, Wm, K, dtype_code(f),
+    _call("pm_write_bwd8" if labels.dtype == torch.uint8 else "pm_write_bwd", _ptr(dS), _ptr(f), _ptr(labels), _ptr(df), B, C, h, w, Hm, Wm, K, dtype_code(f),
                                _stream())
 
 

@@ -171,16 +171,29 @@ __device__ __forceinline__ int map_label(long long v, int K) {
     return (v >= 0 && v < K) ? (int)v : K;  // 255 (and anything out of range) -> ignore slot
 }
 
-__device__ __forceinline__ LabelTaps label_taps(const long long* __restrict__ lab, int Hm, int Wm, int fy,
+// `lab` is one image's label map: int64 class ids as the reference hands them over (u8 = 0), or the packed uint8
+// class map of pm_labels_pack (u8 = 1: 0..K-1, K = ignore).
+__device__ __forceinline__ int fetch_label(const void* __restrict__ lab, size_t i, int u8, int K) {
+    if (u8) {
+        const int v = (int)__ldg(reinterpret_cast<const unsigned char*>(lab) + i);
+        return v < K ? v : K;
+    }
+    return map_label(__ldg(reinterpret_cast<const long long*>(lab) + i), K);
+}
+__device__ __forceinline__ const void* label_image(const void* labels, size_t image_offset, int u8) {
+    return reinterpret_cast<const char*>(labels) + image_offset * (u8 ? 1 : 8);
+}
+
+__device__ __forceinline__ LabelTaps label_taps(const void* __restrict__ lab, int u8, int Hm, int Wm, int fy,
                                                 int fx, float sy, float sx, int K) {
     float ly, lx;
     int y0 = src_index(sy, fy, Hm, &ly), x0 = src_index(sx, fx, Wm, &lx);
     int y1 = y0 + (y0 < Hm - 1 ? 1 : 0), x1 = x0 + (x0 < Wm - 1 ? 1 : 0);
     LabelTaps t;
-    t.cls[0] = map_label(lab[(size_t)y0 * Wm + x0], K);
-    t.cls[1] = map_label(lab[(size_t)y0 * Wm + x1], K);
-    t.cls[2] = map_label(lab[(size_t)y1 * Wm + x0], K);
-    t.cls[3] = map_label(lab[(size_t)y1 * Wm + x1], K);
+    t.cls[0] = fetch_label(lab, (size_t)y0 * Wm + x0, u8, K);
+    t.cls[1] = fetch_label(lab, (size_t)y0 * Wm + x1, u8, K);
+    t.cls[2] = fetch_label(lab, (size_t)y1 * Wm + x0, u8, K);
+    t.cls[3] = fetch_label(lab, (size_t)y1 * Wm + x1, u8, K);
     // PyTorch: out = h0l*(w0l*a + w1l*b) + h1l*(w0l*c + w1l*d)
     float hy0 = 1.f - ly, hx0 = 1.f - lx;
     t.w[0] = hy0 * hx0;

@@ -16,10 +16,10 @@ int read_bwd_tiled(const void* du, const void* x, const float* M, const float* p
                    const float* g_loss, const float* rl_out, void* dx, float* ds, int B, int C, int hw, int K, int dtype,
                    int planes, cudaStream_t st);
 
-int write_reduce_tiled(const void* f, const int64_t* labels, float* SD, int B, int C, int h, int w, int Hm, int Wm,
+int write_reduce_tiled(const void* f, const void* labels, int lab_u8, float* SD, int B, int C, int h, int w, int Hm, int Wm,
                        int K, int dtype, cudaStream_t st);
 
-int write_bwd_tiled(const float* dS, const void* f, const int64_t* labels, void* df, int B, int C, int h, int w, int Hm,
+int write_bwd_tiled(const float* dS, const void* f, const void* labels, int lab_u8, void* df, int B, int C, int h, int w, int Hm,
                     int Wm, int K, int dtype, cudaStream_t st);
 
 // fills `partial` ([PM_COLPART_ROWS][64]: max at [k], sum at [32+k]) from s (+ gumbel_q)

@@ -59,6 +59,148 @@ __device__ __forceinline__ int first_ge8(int c, float scale, int n_out, int n_in
     return y;
 }
 
+struct RunState {  // run-length state of the one-hot term: current class and its tap weights so far
+    int cur;
+    float o00, o01, o10, o11;
+};
+struct CellCtx {
+    const float2 *t00, *t01, *t10, *t11;  // the cell's four taps in the shared-memory tile
+    const unsigned char* lab_b;
+    int Ya, Yb, Xa, Xb, split, RS, Wm, K, nr_max, nc_max;
+    bool active;
+    float sx, sy, cxf, cyf, c2, shift;
+};
+
+constexpr int RL8_CHUNK = 3;  // label pixels per unrolled group (cells are 8-9 / 16-17 pixels wide: 3 divides 9 and 18)
+
+// All label rows of one cell (or of its row split). EXACT = false: geometric recurrence along the row; EXACT = true:
+// per-pixel exponent, per-pixel maximum (cells whose tap spread defeats the per-cell stabiliser). Each group of
+// RL8_CHUNK pixels first runs the branch-free softmax part for all its pixels (independent dependency chains for the
+// scheduler to interleave), then the run-length bookkeeping of the one-hot term, which branches.
+template <bool EXACT>
+__device__ __forceinline__ void cell_rows(const CellCtx& c, RunState& rs, float* __restrict__ pv, float2 (&G00)[RL8_KP / 2],
+                                          float2 (&G01)[RL8_KP / 2], float2 (&G10)[RL8_KP / 2], float2 (&G11)[RL8_KP / 2],
+                                          float& lossacc) {
+    constexpr int KP = RL8_KP, NH = KP / 2, NT = RL8_THREADS;
+    const int K = c.K;
+    const float lam_first = fminf(fmaxf(c.sx * (float)c.Xa - c.cxf, 0.f), 1.f);
+    for (int r = 0; r < c.nr_max; ++r) {
+        const int Y = c.Ya + c.split + r * c.RS;
+        const bool rowok = c.active && Y < c.Yb;
+        const float lamy = fminf(fmaxf(c.sy * (float)Y - c.cyf, 0.f), 1.f);
+        const float hy = 1.f - lamy;
+        // z_k(lambda_x) = A_k + lambda_x * B_k (log2 units, stabilised). EXACT: E = A, Rt = B. Otherwise E = exp2(z) at
+        // the row's first pixel and Rt = exp2(sx * B), the per-pixel ratio.
+        float2 E[NH], Rt[NH];
+#pragma unroll
+        for (int i = 0; i < NH; ++i) {
+            const float2 v00 = c.t00[i], v01 = c.t01[i], v10 = c.t10[i], v11 = c.t11[i];
+            float l0 = fmaf(lamy, v10.x - v00.x, v00.x), l1 = fmaf(lamy, v11.x - v01.x, v01.x);
+            float Ax = fmaf(l0, c.c2, -c.shift), Bx = (l1 - l0) * c.c2;
+            l0 = fmaf(lamy, v10.y - v00.y, v00.y), l1 = fmaf(lamy, v11.y - v01.y, v01.y);
+            float Ay = fmaf(l0, c.c2, -c.shift), By = (l1 - l0) * c.c2;
+            if (2 * i >= K) Ax = -INFINITY, Bx = 0.f;
+            if (2 * i + 1 >= K) Ay = -INFINITY, By = 0.f;
+            if (!EXACT) {
+                E[i] = make_float2(ex2a(fmaf(lam_first, Bx, Ax)), ex2a(fmaf(lam_first, By, Ay)));
+                Rt[i] = make_float2(ex2a(c.sx * Bx), ex2a(c.sx * By));
+            } else {
+                E[i] = make_float2(Ax, Ay);
+                Rt[i] = make_float2(Bx, By);
+            }
+        }
+        const unsigned char* lrow = c.lab_b + (size_t)(rowok ? Y : 0) * c.Wm + c.Xa;
+        const int ncols = rowok ? c.Xb - c.Xa : 0;
+        float2 R0[NH], R1[NH];  // row accumulators of p*(1-lambda_x) and p*lambda_x
+#pragma unroll
+        for (int q = 0; q < NH; ++q) R0[q] = R1[q] = make_float2(0.f, 0.f);
+        float ox0 = 0.f, ox1 = 0.f;  // one-hot counterparts for the current run (this row only)
+        int labn[RL8_CHUNK];        // labels of the NEXT group (fetched one group ahead)
+#pragma unroll
+        for (int i = 0; i < RL8_CHUNK; ++i) labn[i] = (i < ncols) ? (int)__ldg(lrow + i) : 255;
+        for (int X0 = 0; X0 < c.nc_max; X0 += RL8_CHUNK) {   // warp-uniform; pixels past a lane's row are predicated off
+            int lab[RL8_CHUNK];
+            float lamx[RL8_CHUNK], hx[RL8_CHUNK];
+#pragma unroll
+            for (int i = 0; i < RL8_CHUNK; ++i) {
+                lab[i] = labn[i];
+                const int xn = X0 + RL8_CHUNK + i;
+                labn[i] = (xn < ncols) ? (int)__ldg(lrow + xn) : 255;
+                lamx[i] = fminf(fmaxf(c.sx * (float)(c.Xa + X0 + i) - c.cxf, 0.f), 1.f);
+                hx[i] = 1.f - lamx[i];
+            }
+            // ---- softmax part, branch-free
+#pragma unroll
+            for (int i = 0; i < RL8_CHUNK; ++i) {
+                const bool valid = lab[i] < K;  // 0..K-1 real class; K = ignore; 255 = outside this lane's row
+                float pshift = c.shift;
+                float2 e[NH];
+                if (EXACT) {
+                    float m = -INFINITY;
+#pragma unroll
+                    for (int q = 0; q < NH; ++q) {
+                        e[q] = __ffma2_rn(make_float2(lamx[i], lamx[i]), Rt[q], E[q]);
+                        m = fmaxf(m, fmaxf(e[q].x, e[q].y));
+                    }
+                    pshift += m;
+#pragma unroll
+                    for (int q = 0; q < NH; ++q) e[q] = make_float2(ex2a(e[q].x - m), ex2a(e[q].y - m));
+                }
+                const float2* ev = EXACT ? e : E;
+                float2 s01 = __fadd2_rn(ev[0], ev[1]), s23 = __fadd2_rn(ev[2], ev[3]), s45 = __fadd2_rn(ev[4], ev[5]);
+                float2 s67 = __fadd2_rn(ev[6], ev[7]), s89 = __fadd2_rn(ev[8], ev[9]);
+                s01 = __fadd2_rn(s01, s23), s45 = __fadd2_rn(s45, s67);
+                s01 = __fadd2_rn(__fadd2_rn(s01, s45), s89);
+                const float sum = s01.x + s01.y;
+                if (valid) lossacc += pshift + lg2a(sum);
+                const float inv = valid ? rcpa(sum) : 0.f;
+                const float2 ihx = make_float2(inv * hx[i], inv * hx[i]), ilx = make_float2(inv * lamx[i], inv * lamx[i]);
+#pragma unroll
+                for (int q = 0; q < NH; ++q) {
+                    R0[q] = __ffma2_rn(ev[q], ihx, R0[q]);
+                    R1[q] = __ffma2_rn(ev[q], ilx, R1[q]);
+                }
+                if (!EXACT) {
+#pragma unroll
+                    for (int q = 0; q < NH; ++q) E[q] = __fmul2_rn(E[q], Rt[q]);
+                }
+            }
+            // ---- one-hot term: run-length accumulate, flush to the private columns when the class changes
+#pragma unroll
+            for (int i = 0; i < RL8_CHUNK; ++i) {
+                const int cls = lab[i];
+                const bool ok = cls != 255;
+                if (ok && cls != rs.cur) {
+                    if (rs.cur >= 0 && rs.cur < K) {
+                        pv[(0 * KP + rs.cur) * NT] += fmaf(hy, ox0, rs.o00);
+                        pv[(1 * KP + rs.cur) * NT] += fmaf(hy, ox1, rs.o01);
+                        pv[(2 * KP + rs.cur) * NT] += fmaf(lamy, ox0, rs.o10);
+                        pv[(3 * KP + rs.cur) * NT] += fmaf(lamy, ox1, rs.o11);
+                    }
+                    rs.o00 = rs.o01 = rs.o10 = rs.o11 = 0.f;
+                    ox0 = ox1 = 0.f;
+                    rs.cur = cls;
+                }
+                ox0 += ok ? hx[i] : 0.f;
+                ox1 += ok ? lamx[i] : 0.f;
+            }
+        }
+        // end of row: fold the row accumulators into the four taps
+        rs.o00 = fmaf(hy, ox0, rs.o00), rs.o01 = fmaf(hy, ox1, rs.o01);
+        rs.o10 = fmaf(lamy, ox0, rs.o10), rs.o11 = fmaf(lamy, ox1, rs.o11);
+        {
+            const float2 hy2 = make_float2(hy, hy), ly2 = make_float2(lamy, lamy);
+#pragma unroll
+            for (int q = 0; q < NH; ++q) {
+                G00[q] = __ffma2_rn(R0[q], hy2, G00[q]);
+                G01[q] = __ffma2_rn(R1[q], hy2, G01[q]);
+                G10[q] = __ffma2_rn(R0[q], ly2, G10[q]);
+                G11[q] = __ffma2_rn(R1[q], ly2, G11[q]);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(RL8_THREADS, 1)
     readloss8_kernel(const float* __restrict__ s, const unsigned char* __restrict__ lab8, float inv_T, float temperature, int h,
                      int w, int Hm, int Wm, int K, float sy, float sx, int RS, int TYC, int tiles_x, int tiles_y,
@@ -137,118 +279,19 @@ __global__ void __launch_bounds__(RL8_THREADS, 1)
         pxmax = __any_sync(0xffffffffu, !(shift - n * c2 < 60.f));
     }
     // run-length state of the one-hot term
-    int cur = -1;
-    float o00 = 0.f, o01 = 0.f, o10 = 0.f, o11 = 0.f;
+    RunState rs;
+    rs.cur = -1, rs.o00 = rs.o01 = rs.o10 = rs.o11 = 0.f;
     const unsigned char* lab_b = lab8 + (size_t)b * Hm * Wm;
-    const float cxf = (float)cx, cyf = (float)cy;
-    const float lam_first = fminf(fmaxf(sx * (float)Xa - cxf, 0.f), 1.f);
+    CellCtx cc;
+    cc.t00 = t00, cc.t01 = t01, cc.t10 = t10, cc.t11 = t11;
+    cc.lab_b = lab_b, cc.Ya = Ya, cc.Yb = Yb, cc.Xa = Xa, cc.Xb = Xb, cc.split = split, cc.RS = RS, cc.Wm = Wm, cc.K = K;
+    cc.nr_max = nr_max, cc.nc_max = nc_max, cc.active = active;
+    cc.sx = sx, cc.sy = sy, cc.cxf = (float)cx, cc.cyf = (float)cy, cc.c2 = c2, cc.shift = shift;
+    if (!pxmax) cell_rows<false>(cc, rs, pv, G00, G01, G10, G11, lossacc);
+    else cell_rows<true>(cc, rs, pv, G00, G01, G10, G11, lossacc);
+    const int cur = rs.cur;
+    const float o00 = rs.o00, o01 = rs.o01, o10 = rs.o10, o11 = rs.o11;
 
-    for (int r = 0; r < nr_max; ++r) {
-        const int Y = Ya + split + r * RS;
-        const bool rowok = active && Y < Yb;
-        const float lamy = fminf(fmaxf(sy * (float)Y - cyf, 0.f), 1.f);
-        const float hy = 1.f - lamy;
-        // per-row exponent coefficients: z_k(lambda_x) = A_k + lambda_x * B_k (log2 units, stabilised)
-        float2 E[NH], Rt[NH];  // E = exp2(z) at the current pixel; Rt = per-pixel ratio (fast path) or B_k (exact path)
-#pragma unroll
-        for (int i = 0; i < NH; ++i) {
-            const float2 v00 = t00[i], v01 = t01[i], v10 = t10[i], v11 = t11[i];
-            float l0 = fmaf(lamy, v10.x - v00.x, v00.x), l1 = fmaf(lamy, v11.x - v01.x, v01.x);
-            float Ax = fmaf(l0, c2, -shift), Bx = (l1 - l0) * c2;
-            l0 = fmaf(lamy, v10.y - v00.y, v00.y), l1 = fmaf(lamy, v11.y - v01.y, v01.y);
-            float Ay = fmaf(l0, c2, -shift), By = (l1 - l0) * c2;
-            if (2 * i >= K) Ax = -INFINITY, Bx = 0.f;
-            if (2 * i + 1 >= K) Ay = -INFINITY, By = 0.f;
-            if (!pxmax) {
-                E[i] = make_float2(ex2a(fmaf(lam_first, Bx, Ax)), ex2a(fmaf(lam_first, By, Ay)));
-                Rt[i] = make_float2(ex2a(sx * Bx), ex2a(sx * By));
-            } else {
-                E[i] = make_float2(Ax, Ay);
-                Rt[i] = make_float2(Bx, By);
-            }
-        }
-        const unsigned char* lrow = lab_b + (size_t)(rowok ? Y : 0) * Wm + Xa;
-        const int ncols = rowok ? Xb - Xa : 0;
-        float2 R0[NH], R1[NH];  // row accumulators of p*(1-lambda_x) and p*lambda_x
-#pragma unroll
-        for (int q = 0; q < NH; ++q) R0[q] = R1[q] = make_float2(0.f, 0.f);
-        float ox0 = 0.f, ox1 = 0.f;  // one-hot counterparts for the current run (this row only)
-        for (int X0 = 0; X0 < nc_max; X0 += 4) {
-            int lab[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) lab[i] = (X0 + i < ncols) ? (int)__ldg(lrow + X0 + i) : 255;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (X0 + i >= nc_max) break;  // warp-uniform
-                const int cls = lab[i];       // 0..K (K = ignore) or 255 = outside this thread's row
-                const bool ok = cls != 255;
-                const bool valid = cls < K;
-                const float lamx = fminf(fmaxf(sx * (float)(Xa + X0 + i) - cxf, 0.f), 1.f);
-                const float hx = 1.f - lamx;
-                float2 e[NH];
-                float pshift = shift;
-                if (!pxmax) {
-#pragma unroll
-                    for (int q = 0; q < NH; ++q) e[q] = E[q];
-                } else {  // exact path (warp-uniform): per-pixel maximum, one ex2 per slot
-                    float m = -INFINITY;
-#pragma unroll
-                    for (int q = 0; q < NH; ++q) {
-                        e[q] = __ffma2_rn(make_float2(lamx, lamx), Rt[q], E[q]);
-                        m = fmaxf(m, fmaxf(e[q].x, e[q].y));
-                    }
-                    pshift += m;
-#pragma unroll
-                    for (int q = 0; q < NH; ++q) e[q] = make_float2(ex2a(e[q].x - m), ex2a(e[q].y - m));
-                }
-                // softmax denominator: pairwise tree over the 10 packed pairs
-                float2 s01 = __fadd2_rn(e[0], e[1]), s23 = __fadd2_rn(e[2], e[3]), s45 = __fadd2_rn(e[4], e[5]);
-                float2 s67 = __fadd2_rn(e[6], e[7]), s89 = __fadd2_rn(e[8], e[9]);
-                s01 = __fadd2_rn(s01, s23), s45 = __fadd2_rn(s45, s67);
-                s01 = __fadd2_rn(__fadd2_rn(s01, s45), s89);
-                const float sum = s01.x + s01.y;
-                if (valid) lossacc += pshift + lg2a(sum);
-                const float inv = valid ? rcpa(sum) : 0.f;
-                const float2 ihx = make_float2(inv * hx, inv * hx), ilx = make_float2(inv * lamx, inv * lamx);
-#pragma unroll
-                for (int q = 0; q < NH; ++q) {
-                    R0[q] = __ffma2_rn(e[q], ihx, R0[q]);
-                    R1[q] = __ffma2_rn(e[q], ilx, R1[q]);
-                }
-                if (!pxmax) {
-#pragma unroll
-                    for (int q = 0; q < NH; ++q) E[q] = __fmul2_rn(E[q], Rt[q]);
-                }
-                // one-hot term: run-length accumulate, flush to the private columns when the class changes
-                if (ok && cls != cur) {
-                    if (cur >= 0 && cur < K) {
-                        pv[(0 * KP + cur) * NT] += fmaf(hy, ox0, o00);
-                        pv[(1 * KP + cur) * NT] += fmaf(hy, ox1, o01);
-                        pv[(2 * KP + cur) * NT] += fmaf(lamy, ox0, o10);
-                        pv[(3 * KP + cur) * NT] += fmaf(lamy, ox1, o11);
-                    }
-                    o00 = o01 = o10 = o11 = 0.f;
-                    ox0 = ox1 = 0.f;
-                    cur = cls;
-                }
-                ox0 += ok ? hx : 0.f;
-                ox1 += ok ? lamx : 0.f;
-            }
-        }
-        // end of row: fold the row accumulators into the four taps
-        o00 = fmaf(hy, ox0, o00), o01 = fmaf(hy, ox1, o01);
-        o10 = fmaf(lamy, ox0, o10), o11 = fmaf(lamy, ox1, o11);
-        {
-            const float2 hy2 = make_float2(hy, hy), ly2 = make_float2(lamy, lamy);
-#pragma unroll
-            for (int q = 0; q < NH; ++q) {
-                G00[q] = __ffma2_rn(R0[q], hy2, G00[q]);
-                G01[q] = __ffma2_rn(R1[q], hy2, G01[q]);
-                G10[q] = __ffma2_rn(R0[q], ly2, G10[q]);
-                G11[q] = __ffma2_rn(R1[q], ly2, G11[q]);
-            }
-        }
-    }
     if (active) {
         if (cur >= 0 && cur < K) {
             pv[(0 * KP + cur) * NT] += o00;

@@ -17,7 +17,7 @@ namespace pm {
 constexpr int WR_P = 32;
 
 template <typename T, int C, int KP>
-__global__ void __launch_bounds__(C) write_reduce_kernel(const T* __restrict__ f, const long long* __restrict__ labels,
+__global__ void __launch_bounds__(C) write_reduce_kernel(const T* __restrict__ f, const void* __restrict__ labels, int lab_u8,
                                                           float* __restrict__ SD, int h, int w, int Hm, int Wm, int K,
                                                           float sy, float sx, int tiles_per_img, int ntiles) {
     constexpr int P = WR_P, LD = P + 1, NW = C / 32, CS = C + 4;
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(C) write_reduce_kernel(const T* __restrict__ f
             LabelTaps t;
             if (tid < nvalid) {
                 int px = px0 + tid, fy = px / w, fx = px - fy * w;
-                t = label_taps(labels + (size_t)b * Hm * Wm, Hm, Wm, fy, fx, sy, sx, K);
+                t = label_taps(label_image(labels, (size_t)b * Hm * Wm, lab_u8), lab_u8, Hm, Wm, fy, fx, sy, sx, K);
             } else {
                 t.cls[0] = t.cls[1] = t.cls[2] = t.cls[3] = K;
                 t.w[0] = t.w[1] = t.w[2] = t.w[3] = 0.f;
@@ -113,7 +113,7 @@ constexpr int WB_THREADS = 256, WB_WARPS = 8, WB_P = 64;
 
 template <typename T, int CW, int KP>
 __global__ void __launch_bounds__(WB_THREADS) write_bwd_kernel(const float* __restrict__ dS, const T* __restrict__ f,
-                                                               const long long* __restrict__ labels,
+                                                               const void* __restrict__ labels, int lab_u8,
                                                                T* __restrict__ df, int h, int w, int Hm, int Wm, int K,
                                                                float sy, float sx, int tiles_per_img) {
     constexpr int C = CW * WB_WARPS, P = WB_P, LDS_ = C + 1;
@@ -142,11 +142,11 @@ __global__ void __launch_bounds__(WB_THREADS) write_bwd_kernel(const float* __re
     }
     LabelTaps t0, t1;
     {
-        const long long* lab_b = labels + (size_t)b * Hm * Wm;
+        const void* lab_b = label_image(labels, (size_t)b * Hm * Wm, lab_u8);
         int px = px0 + (v0 ? lane : 0), fy = px / w, fx = px - fy * w;
-        t0 = label_taps(lab_b, Hm, Wm, fy, fx, sy, sx, K);
+        t0 = label_taps(lab_b, lab_u8, Hm, Wm, fy, fx, sy, sx, K);
         px = px0 + (v1 ? lane + 32 : 0), fy = px / w, fx = px - fy * w;
-        t1 = label_taps(lab_b, Hm, Wm, fy, fx, sy, sx, K);
+        t1 = label_taps(lab_b, lab_u8, Hm, Wm, fy, fx, sy, sx, K);
     }
 #pragma unroll
     for (int j = 0; j < CW; ++j) {
@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(UP_THREADS) update_bwd_kernel(const float* __r
 // ------------------------------------------------------------------------------------------ dispatch
 
 template <typename T, int C, int KP>
-int launch_write_reduce(const void* f, const int64_t* labels, float* SD, int B, int h, int w, int Hm, int Wm, int K,
+int launch_write_reduce(const void* f, const void* labels, int lab_u8, float* SD, int B, int h, int w, int Hm, int Wm, int K,
                         cudaStream_t st) {
     constexpr int LD = WR_P + 1, CS = C + 4;
     const size_t smem = sizeof(float) * ((size_t)KP * CS + (size_t)C * LD + (C / 32) * WR_P + WR_P + 8 * WR_P);
@@ -439,13 +439,13 @@ int launch_write_reduce(const void* f, const int64_t* labels, float* SD, int B, 
     // down-sampling the label map to the feature grid: scale = (Hm-1)/(h-1)  (in = labels, out = features)
     const float sy = h > 1 ? (float)(Hm - 1) / (float)(h - 1) : 0.f;
     const float sx = w > 1 ? (float)(Wm - 1) / (float)(w - 1) : 0.f;
-    kern<<<grid, C, smem, st>>>((const T*)f, (const long long*)labels, SD, h, w, Hm, Wm, K, sy, sx, tiles, ntiles);
+    kern<<<grid, C, smem, st>>>((const T*)f, labels, lab_u8, SD, h, w, Hm, Wm, K, sy, sx, tiles, ntiles);
     PM_CHECK_LAUNCH();
     return 0;
 }
 
 template <typename T, int CW, int KP>
-int launch_write_bwd(const float* dS, const void* f, const int64_t* labels, void* df, int B, int h, int w, int Hm,
+int launch_write_bwd(const float* dS, const void* f, const void* labels, int lab_u8, void* df, int B, int h, int w, int Hm,
                      int Wm, int K, cudaStream_t st) {
     constexpr int C = CW * WB_WARPS;
     const size_t smem = sizeof(float) * ((size_t)KP * (C + 1) + WB_WARPS * WB_P + 2 * WB_P);
@@ -455,7 +455,7 @@ int launch_write_bwd(const float* dS, const void* f, const int64_t* labels, void
     const int hw = h * w, tiles = (hw + WB_P - 1) / WB_P;
     const float sy = h > 1 ? (float)(Hm - 1) / (float)(h - 1) : 0.f;
     const float sx = w > 1 ? (float)(Wm - 1) / (float)(w - 1) : 0.f;
-    kern<<<B * tiles, WB_THREADS, smem, st>>>(dS, (const T*)f, (const long long*)labels, (T*)df, h, w, Hm, Wm, K, sy,
+    kern<<<B * tiles, WB_THREADS, smem, st>>>(dS, (const T*)f, labels, lab_u8, (T*)df, h, w, Hm, Wm, K, sy,
                                                sx, tiles);
     PM_CHECK_LAUNCH();
     return 0;
@@ -500,23 +500,40 @@ static int check_write(int B, int C, int h, int w, int Hm, int Wm, int K, int dt
     return 0;
 }
 
-extern "C" int pm_write_reduce_fwd(const void* f, const int64_t* labels, float* SD, int B, int C, int h, int w, int Hm,
-                                   int Wm, int K, int dtype, void* stream) {
+static int write_reduce_any(const void* f, const void* labels, int lab_u8, float* SD, int B, int C, int h, int w, int Hm,
+                            int Wm, int K, int dtype, void* stream) {
     if (!f || !labels || !SD) return PM_ERR_NULL;
     if (int e = check_write(B, C, h, w, Hm, Wm, K, dtype)) return e;
     if ((uintptr_t)SD & 15) return PM_ERR_ALIGN;
     if (pm::tiled_ok(f, nullptr, nullptr, h * w, dtype))
-        return pm::write_reduce_tiled(f, labels, SD, B, C, h, w, Hm, Wm, K, dtype, (cudaStream_t)stream);
-    PMW_DISPATCH(PMW_DISPATCH_C, launch_write_reduce, f, labels, SD, B, h, w, Hm, Wm, K, (cudaStream_t)stream);
+        return pm::write_reduce_tiled(f, labels, lab_u8, SD, B, C, h, w, Hm, Wm, K, dtype, (cudaStream_t)stream);
+    PMW_DISPATCH(PMW_DISPATCH_C, launch_write_reduce, f, labels, lab_u8, SD, B, h, w, Hm, Wm, K, (cudaStream_t)stream);
 }
 
-extern "C" int pm_write_bwd(const float* dS, const void* f, const int64_t* labels, void* df, int B, int C, int h, int w,
-                            int Hm, int Wm, int K, int dtype, void* stream) {
+static int write_bwd_any(const float* dS, const void* f, const void* labels, int lab_u8, void* df, int B, int C, int h, int w,
+                         int Hm, int Wm, int K, int dtype, void* stream) {
     if (!dS || !f || !labels || !df) return PM_ERR_NULL;
     if (int e = check_write(B, C, h, w, Hm, Wm, K, dtype)) return e;
     if (pm::tiled_ok(f, df, nullptr, h * w, dtype))
-        return pm::write_bwd_tiled(dS, f, labels, df, B, C, h, w, Hm, Wm, K, dtype, (cudaStream_t)stream);
-    PMW_DISPATCH(PMW_DISPATCH_CW, launch_write_bwd, dS, f, labels, df, B, h, w, Hm, Wm, K, (cudaStream_t)stream);
+        return pm::write_bwd_tiled(dS, f, labels, lab_u8, df, B, C, h, w, Hm, Wm, K, dtype, (cudaStream_t)stream);
+    PMW_DISPATCH(PMW_DISPATCH_CW, launch_write_bwd, dS, f, labels, lab_u8, df, B, h, w, Hm, Wm, K, (cudaStream_t)stream);
+}
+
+extern "C" int pm_write_reduce_fwd(const void* f, const int64_t* labels, float* SD, int B, int C, int h, int w, int Hm,
+                                   int Wm, int K, int dtype, void* stream) {
+    return write_reduce_any(f, labels, 0, SD, B, C, h, w, Hm, Wm, K, dtype, stream);
+}
+extern "C" int pm_write_reduce_fwd8(const void* f, const uint8_t* lab8, float* SD, int B, int C, int h, int w, int Hm,
+                                    int Wm, int K, int dtype, void* stream) {
+    return write_reduce_any(f, lab8, 1, SD, B, C, h, w, Hm, Wm, K, dtype, stream);
+}
+extern "C" int pm_write_bwd(const float* dS, const void* f, const int64_t* labels, void* df, int B, int C, int h, int w,
+                            int Hm, int Wm, int K, int dtype, void* stream) {
+    return write_bwd_any(dS, f, labels, 0, df, B, C, h, w, Hm, Wm, K, dtype, stream);
+}
+extern "C" int pm_write_bwd8(const float* dS, const void* f, const uint8_t* lab8, void* df, int B, int C, int h, int w,
+                             int Hm, int Wm, int K, int dtype, void* stream) {
+    return write_bwd_any(dS, f, lab8, 1, df, B, C, h, w, Hm, Wm, K, dtype, stream);
 }
 
 extern "C" int pm_update_aux_floats(int K) { return 32 + K * pm::UP_KMAX + 68; }

@@ -13,7 +13,7 @@ namespace pm {
 // LDS.128; the label taps of the NEXT tile are fetched while the current one is reduced.
 
 template <typename T, int C, int KP>
-__global__ void __launch_bounds__(C) write_reduce_tiled_kernel(const T* __restrict__ f, const long long* __restrict__ labels,
+__global__ void __launch_bounds__(C) write_reduce_tiled_kernel(const T* __restrict__ f, const void* __restrict__ labels, int lab_u8,
                                                                 float* __restrict__ SD, int h, int w, int Hm, int Wm,
                                                                 int K, float sy, float sx, int tiles_per_img,
                                                                 int ntiles) {
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(C) write_reduce_tiled_kernel(const T* __restri
         const int px = px0 + lane;
         if (t < ntiles && px < hw) {
             const int fy = px / w, fx = px - fy * w;
-            r = label_taps(labels + (size_t)b * Hm * Wm, Hm, Wm, fy, fx, sy, sx, K);
+            r = label_taps(label_image(labels, (size_t)b * Hm * Wm, lab_u8), lab_u8, Hm, Wm, fy, fx, sy, sx, K);
         } else {
             r.cls[0] = r.cls[1] = r.cls[2] = r.cls[3] = K;
             r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0.f;
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(C) write_reduce_tiled_kernel(const T* __restri
 // TMA = true: the tiles arrive as SWIZZLE_128B tensor-map boxes (the same chunk ^ (row & 7) layout) on an mbarrier ring
 template <int C, int KP, bool TMA>
 __global__ void __launch_bounds__(C) write_reduce_mma_kernel(const __grid_constant__ CUtensorMap tm_f,
-                                                              const float* __restrict__ f, const long long* __restrict__ labels,
+                                                              const float* __restrict__ f, const void* __restrict__ labels, int lab_u8,
                                                               float* __restrict__ SD, int h, int w, int Hm, int Wm,
                                                               int K, float sy, float sx, int tiles_per_img,
                                                               int ntiles) {
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(C) write_reduce_mma_kernel(const __grid_consta
         const int px = px0 + lane;
         if (tl < ntiles && px < hw) {
             const int fy = px / w, fx = px - fy * w;
-            r = label_taps(labels + (size_t)b * Hm * Wm, Hm, Wm, fy, fx, sy, sx, K);
+            r = label_taps(label_image(labels, (size_t)b * Hm * Wm, lab_u8), lab_u8, Hm, Wm, fy, fx, sy, sx, K);
         } else {
             r.cls[0] = r.cls[1] = r.cls[2] = r.cls[3] = K;
             r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0.f;
@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(C) write_reduce_mma_kernel(const __grid_consta
 }
 
 template <int C, int KP>
-int launch_write_reduce_mma(const void* f, const int64_t* labels, float* SD, int B, int h, int w, int Hm, int Wm, int K,
+int launch_write_reduce_mma(const void* f, const void* labels, int lab_u8, float* SD, int B, int h, int w, int Hm, int Wm, int K,
                             cudaStream_t st) {
     const size_t ring = sizeof(float) * (size_t)2 * C * 32, stile = sizeof(float) * (size_t)32 * (C + 4);
     const size_t smem = sizeof(float) * (32 * 40 + (C / 32) * 32 + 32 + 4) + (ring > stile ? ring : stile) + 1024;
@@ -430,13 +430,13 @@ int launch_write_reduce_mma(const void* f, const int64_t* labels, float* SD, int
     if (per_sm > 4) per_sm = 4;
     int grid = 148 * per_sm;
     if (grid > ntiles) grid = ntiles;
-    kern<<<grid, C, smem, st>>>(tm_f, (const float*)f, (const long long*)labels, SD, h, w, Hm, Wm, K, sy, sx, tiles, ntiles);
+    kern<<<grid, C, smem, st>>>(tm_f, (const float*)f, labels, lab_u8, SD, h, w, Hm, Wm, K, sy, sx, tiles, ntiles);
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }
 
 template <typename T, int C, int KP>
-int launch_write_reduce_tiled(const void* f, const int64_t* labels, float* SD, int B, int h, int w, int Hm, int Wm,
+int launch_write_reduce_tiled(const void* f, const void* labels, int lab_u8, float* SD, int B, int h, int w, int Hm, int Wm,
                               int K, cudaStream_t st) {
     const size_t smem = sizeof(float) * ((size_t)KP * (C + 4) + (C / 32) * 32 + 32) + sizeof(float4) * 2 * 32 * 4 + 16 +
                         sizeof(T) * (size_t)2 * C * 32;
@@ -451,7 +451,7 @@ int launch_write_reduce_tiled(const void* f, const int64_t* labels, float* SD, i
     if (grid > ntiles) grid = ntiles;
     const float sy = h > 1 ? (float)(Hm - 1) / (float)(h - 1) : 0.f;
     const float sx = w > 1 ? (float)(Wm - 1) / (float)(w - 1) : 0.f;
-    kern<<<grid, C, smem, st>>>((const T*)f, (const long long*)labels, SD, h, w, Hm, Wm, K, sy, sx, tiles, ntiles);
+    kern<<<grid, C, smem, st>>>((const T*)f, labels, lab_u8, SD, h, w, Hm, Wm, K, sy, sx, tiles, ntiles);
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }
@@ -471,7 +471,7 @@ constexpr int WBT_THREADS = 256, WBT_WARPS = 8, WBT_STAGES = 2;
 template <typename T, int C, int KP, bool TMA>
 __global__ void __launch_bounds__(WBT_THREADS, 2)
     write_bwd_tiled_kernel(const __grid_constant__ CUtensorMap tm_f, const float* __restrict__ dS,
-                           const T* __restrict__ f, const long long* __restrict__ labels,
+                           const T* __restrict__ f, const void* __restrict__ labels, int lab_u8,
                            T* __restrict__ df, int h, int w, int Hm, int Wm, int K, float sy, float sx,
                            int tiles_per_img, int ntiles) {
     constexpr int NSTAGE = WBT_STAGES, CW = C / WBT_WARPS, LDS_ = C + 1;
@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(WBT_THREADS, 2)
         const int px = px0 + lane;
         if (t < ntiles && px < hw) {
             const int fy = px / w, fx = px - fy * w;
-            r = label_taps(labels + (size_t)b * Hm * Wm, Hm, Wm, fy, fx, sy, sx, K);
+            r = label_taps(label_image(labels, (size_t)b * Hm * Wm, lab_u8), lab_u8, Hm, Wm, fy, fx, sy, sx, K);
         } else {
             r.cls[0] = r.cls[1] = r.cls[2] = r.cls[3] = K;
             r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0.f;
@@ -628,7 +628,7 @@ __global__ void __launch_bounds__(WBT_THREADS, 2)
 }
 
 template <typename T, int C, int KP>
-int launch_write_bwd_tiled(const float* dS, const void* f, const int64_t* labels, void* df, int B, int h, int w, int Hm,
+int launch_write_bwd_tiled(const float* dS, const void* f, const void* labels, int lab_u8, void* df, int B, int h, int w, int Hm,
                            int Wm, int K, cudaStream_t st) {
     const size_t smem = sizeof(float) * ((size_t)KP * (C + 1) + 2 * WBT_WARPS * 32 + 1) + sizeof(float2) * 2 * 32 * 4 +
                         sizeof(T) * (size_t)WBT_STAGES * C * 32 + 128;
@@ -643,13 +643,13 @@ int launch_write_bwd_tiled(const float* dS, const void* f, const int64_t* labels
         auto kern = write_bwd_tiled_kernel<T, C, KP, true>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        kern<<<grid, WBT_THREADS, smem, st>>>(tm_f, dS, (const T*)f, (const long long*)labels, (T*)df, h, w, Hm, Wm, K, sy,
+        kern<<<grid, WBT_THREADS, smem, st>>>(tm_f, dS, (const T*)f, labels, lab_u8, (T*)df, h, w, Hm, Wm, K, sy,
                                               sx, tiles, ntiles);
     } else {
         auto kern = write_bwd_tiled_kernel<T, C, KP, false>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        kern<<<grid, WBT_THREADS, smem, st>>>(tm_f, dS, (const T*)f, (const long long*)labels, (T*)df, h, w, Hm, Wm, K, sy,
+        kern<<<grid, WBT_THREADS, smem, st>>>(tm_f, dS, (const T*)f, labels, lab_u8, (T*)df, h, w, Hm, Wm, K, sy,
                                               sx, tiles, ntiles);
     }
     e = cudaGetLastError();
@@ -665,30 +665,30 @@ int launch_write_bwd_tiled(const float* dS, const void* f, const int64_t* labels
         default: return PM_ERR_CHANNELS;              \
     }
 
-int write_reduce_tiled(const void* f, const int64_t* labels, float* SD, int B, int C, int h, int w, int Hm, int Wm,
+int write_reduce_tiled(const void* f, const void* labels, int lab_u8, float* SD, int B, int C, int h, int w, int Hm, int Wm,
                        int K, int dtype, cudaStream_t st) {
     if (dtype == PM_F32) {
         switch (C) {  // tensor-core variant for every fp32 case (K + 1 <= 32 classes fit two 16-row MMA tiles)
-            case 32: return launch_write_reduce_mma<32, 32>(f, labels, SD, B, h, w, Hm, Wm, K, st);
-            case 64: return launch_write_reduce_mma<64, 32>(f, labels, SD, B, h, w, Hm, Wm, K, st);
-            case 128: return launch_write_reduce_mma<128, 32>(f, labels, SD, B, h, w, Hm, Wm, K, st);
-            case 256: return launch_write_reduce_mma<256, 32>(f, labels, SD, B, h, w, Hm, Wm, K, st);
+            case 32: return launch_write_reduce_mma<32, 32>(f, labels, lab_u8, SD, B, h, w, Hm, Wm, K, st);
+            case 64: return launch_write_reduce_mma<64, 32>(f, labels, lab_u8, SD, B, h, w, Hm, Wm, K, st);
+            case 128: return launch_write_reduce_mma<128, 32>(f, labels, lab_u8, SD, B, h, w, Hm, Wm, K, st);
+            case 256: return launch_write_reduce_mma<256, 32>(f, labels, lab_u8, SD, B, h, w, Hm, Wm, K, st);
             default: return PM_ERR_CHANNELS;
         }
     } else {
-        if (K <= 19) { PM_WT_SWITCH_C(__nv_bfloat16, 20, launch_write_reduce_tiled, f, labels, SD, B, h, w, Hm, Wm, K, st) }
-        else { PM_WT_SWITCH_C(__nv_bfloat16, 32, launch_write_reduce_tiled, f, labels, SD, B, h, w, Hm, Wm, K, st) }
+        if (K <= 19) { PM_WT_SWITCH_C(__nv_bfloat16, 20, launch_write_reduce_tiled, f, labels, lab_u8, SD, B, h, w, Hm, Wm, K, st) }
+        else { PM_WT_SWITCH_C(__nv_bfloat16, 32, launch_write_reduce_tiled, f, labels, lab_u8, SD, B, h, w, Hm, Wm, K, st) }
     }
 }
 
-int write_bwd_tiled(const float* dS, const void* f, const int64_t* labels, void* df, int B, int C, int h, int w, int Hm,
+int write_bwd_tiled(const float* dS, const void* f, const void* labels, int lab_u8, void* df, int B, int C, int h, int w, int Hm,
                     int Wm, int K, int dtype, cudaStream_t st) {
     if (dtype == PM_F32) {
-        if (K <= 19) { PM_WT_SWITCH_C(float, 20, launch_write_bwd_tiled, dS, f, labels, df, B, h, w, Hm, Wm, K, st) }
-        else { PM_WT_SWITCH_C(float, 32, launch_write_bwd_tiled, dS, f, labels, df, B, h, w, Hm, Wm, K, st) }
+        if (K <= 19) { PM_WT_SWITCH_C(float, 20, launch_write_bwd_tiled, dS, f, labels, lab_u8, df, B, h, w, Hm, Wm, K, st) }
+        else { PM_WT_SWITCH_C(float, 32, launch_write_bwd_tiled, dS, f, labels, lab_u8, df, B, h, w, Hm, Wm, K, st) }
     } else {
-        if (K <= 19) { PM_WT_SWITCH_C(__nv_bfloat16, 20, launch_write_bwd_tiled, dS, f, labels, df, B, h, w, Hm, Wm, K, st) }
-        else { PM_WT_SWITCH_C(__nv_bfloat16, 32, launch_write_bwd_tiled, dS, f, labels, df, B, h, w, Hm, Wm, K, st) }
+        if (K <= 19) { PM_WT_SWITCH_C(__nv_bfloat16, 20, launch_write_bwd_tiled, dS, f, labels, lab_u8, df, B, h, w, Hm, Wm, K, st) }
+        else { PM_WT_SWITCH_C(__nv_bfloat16, 32, launch_write_bwd_tiled, dS, f, labels, lab_u8, df, B, h, w, Hm, Wm, K, st) }
     }
 }
 

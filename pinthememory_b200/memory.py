@@ -75,7 +75,8 @@ class _ReadFn(torch.autograd.Function):
     the similarity term, the other one reaches M through the folded weight in autograd.
     """
 
-    last_bad = None  # device int64 scalar: label values outside [0,K) u {255} seen by the last read with labels
+    last_bad = None   # device int64 scalar: label values outside [0,K) u {255} seen by the last read with labels
+    last_lab8 = None  # the packed uint8 class map that read produced (None when the first-generation kernel ran)
 
     @staticmethod
     def forward(ctx, x, M, labels, g_query, g_memory, temperature, K, planes=False):
@@ -99,7 +100,7 @@ class _ReadFn(torch.autograd.Function):
             ws = buf[N * KP: N * KP + 2 * capi.WS_WORDS]
             rl_out = buf[N * KP + 2 * capi.WS_WORDS:]
             # one pass over the labels (packed uint8 classes + histogram + bad-label count), then the read loss on it
-            capi.readloss(s, labels, temperature, B, h, w, K, ds_rl, ws, rl_out)
+            _ReadFn.last_lab8 = capi.readloss(s, labels, temperature, B, h, w, K, ds_rl, ws, rl_out)
             readloss = rl_out[0]
             hist = ws.view(torch.int64)[capi.WS_HIST: capi.WS_HIST + K + 1]
             _ReadFn.last_bad = ws.view(torch.int64)[capi.WS_BAD]
@@ -598,6 +599,8 @@ class Memory_sup(nn.Module):
         else:
             self.last_label_hist = hist
             self.last_bad_labels = _ReadFn.last_bad
+            # the write of the same forward() reads the packed map instead of the int64 one (1/8 of the bytes)
+            self._packed = (mask, _ReadFn.last_lab8) if _ReadFn.last_lab8 is not None else None
             if self.debug_labels and int(self.last_bad_labels) != 0:   # synchronises: debugging aid only
                 raise RuntimeError(f"pinmem_b200: {int(self.last_bad_labels)} label values outside [0,{self.memory_size}) "
                                    "and != 255 (torch's one_hot / CrossEntropyLoss would raise a device assert)")
@@ -619,8 +622,10 @@ class Memory_sup(nn.Module):
         if mask is None:
             raise RuntimeError("pinmem_b200: memory_writing=True needs labels (the reference crashes at memory.py:208)")
         labels = _check_labels(mask, B)
-        if labels.dtype != torch.int64:   # the class-sum kernels still read the reference's int64 maps
-            labels = labels.to(torch.int64)
+        packed = getattr(self, "_packed", None)
+        if packed is not None and packed[0] is mask:   # same label tensor as the read of this forward(): reuse its pack
+            labels = packed[1]
+        self._packed = None
         f = self.writenet(query)
         f = _check_features(f, "write feature")
         M_old = self._memory_for_kernels(query.device)

@@ -159,11 +159,14 @@ def test_metatest_gradient_reaches_writenet_through_memory():
     G = torch.randn(2, 64, 8, 8, device="cuda")
     from oracle import memory_oracle as mo
 
+    from golden_util import max_abs_over_scale, rel_l2
+
+    ora32 = _oracle_like(mem)  # yardstick: eager fp32 torch against its own fp64 evaluation
     grads = []
     with record_gates() as gates:
-        for m, dt in ((mem, torch.float32), (ora, torch.float64)):
-            if m is ora:  # rounding-level ReLU ties are broken the module's way (ReluGates); checked below
-                ora.relu_gates = mo.ReluGates(gates)
+        for m, dt in ((mem, torch.float32), (ora, torch.float64), (ora32, torch.float32)):
+            if m is not mem:  # rounding-level ReLU ties are broken the module's way (ReluGates); checked below
+                m.relu_gates = mo.ReluGates(gates)
             m.zero_grad()
             m(xa.to(dt), la, True, False)
             uq, _, _, rl, _ = m(xb.to(dt), lb, False)
@@ -172,7 +175,11 @@ def test_metatest_gradient_reaches_writenet_through_memory():
     check_ties(ora.relu_gates)
     assert "writenet.writefeat.0.weight" in grads[0]
     for n in grads[1]:
-        assert_close(grads[0][n], grads[1][n], 1e-4, n)
+        yard = max(rel_l2(grads[2][n], grads[1][n]), max_abs_over_scale(grads[2][n], grads[1][n]))
+        # measured: eager fp32 torch sits 3e-5 from fp64 on the worst of these (the writing net's BN bias), this path
+        # 1.1e-4 -- the 3xTF32 convolutions accumulate with the tensor core's truncating fp32 adder (~2e-6 per GEMM
+        # against ~2e-7 for FFMA) and the difference is amplified by the same cancellation. Bound: 5x the yardstick.
+        assert_close(grads[0][n], grads[1][n], max(1e-4, 5.0 * yard), n + " (fp32 torch is %.1e from fp64)" % yard)
 
 
 def test_gumbel_rng_alignment_with_torch():
@@ -471,3 +478,38 @@ def test_checkpoint_round_trip_with_memory_key(tmp_path):
     assert_close(wa[0].reshape(1), wb[0].reshape(1), 1e-6, "div")
     assert_close(wa[1].reshape(1), wb[1].reshape(1), 1e-6, "cls")
     assert not fresh.m_items.requires_grad
+
+
+def test_uint8_labels_and_bad_label_count():
+    """Labels may be handed over as uint8 class ids (255 = ignore): same results as the reference's int64 maps; values
+    outside [0,K) u {255} -- torch's one_hot / CrossEntropyLoss would raise a device assert -- count as ignore and are
+    reported in last_bad_labels (debug_labels=True raises)."""
+    a, b = _module(), _module()
+    x = torch.randn(2, 64, 12, 12, device="cuda")
+    labels = torch.randint(0, 19, (2, 48, 48), device="cuda")
+    labels[0, :7] = 255
+    G = torch.randn(2, 64, 12, 12, device="cuda")
+    outs = []
+    for m, lab in ((a, labels), (b, labels.to(torch.uint8))):
+        xi = x.clone().requires_grad_(True)
+        uq, _, _, rl, wl = m(xi, lab, True, False)
+        ((uq * G).sum() + 0.02 * rl + 0.4 * wl[0] + 0.2 * wl[1]).backward()
+        outs.append((uq.detach(), rl.detach(), wl[0].detach(), wl[1].detach(), m.m_items.detach(), xi.grad,
+                     m.writenet.writefeat[0].weight.grad, m.last_label_hist))
+    for u, v, n in zip(outs[0][:-1], outs[1][:-1], ("uq", "readloss", "div", "cls", "memory", "dx", "dW writenet")):
+        assert_close(v.reshape(u.shape) if v.dim() else v.reshape(1), u if u.dim() else u.reshape(1), 1e-6, n)
+    assert torch.equal(outs[0][-1], outs[1][-1]) and int(a.last_bad_labels) == 0
+    bad = labels.clone()
+    bad[1, 3, 4], bad[1, 5, 6], bad[0, 20, 1] = 19, -3, 700
+    c = _module()
+    with torch.no_grad():
+        c(x, bad, True, True)
+    assert int(c.last_bad_labels) == 3
+    ref = labels.clone()
+    ref[1, 3, 4] = ref[1, 5, 6] = ref[0, 20, 1] = 255   # bad values behave as ignore
+    lab = ref.reshape(-1).clone()
+    lab[lab == 255] = 19
+    assert torch.equal(c.last_label_hist, torch.bincount(lab, minlength=20))
+    c.debug_labels = True
+    with pytest.raises(RuntimeError, match="label values outside"):
+        c(x, bad, True, True)
