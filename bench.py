@@ -565,13 +565,15 @@ def main():
 
     Wc, bc = mem.clsfier.weight, mem.clsfier.bias
 
-    def core_step(xi=None, fi=None):
+    def core_step(xi=None, fi=None, Wi=None, bi=None):
         xi = x if xi is None else xi
         fi = f_core if fi is None else fi
+        Wi = Wc if Wi is None else Wi
+        bi = bc if bi is None else bi
         xi.grad = None
         fi.grad = None
         u, _, _, rl, _ = _ReadFn.apply(xi, M0, labels, None, None, 1.0, K)
-        M_new, div, cls, _ = _WriteFn.apply(fi, labels, M0, Wc, bc, 0.8, K, mem.shard_group)
+        M_new, div, cls, _ = _WriteFn.apply(fi, labels, M0, Wi, bi, 0.8, K, mem.shard_group)
         torch.autograd.backward([u, rl, div, cls], [Gu, gw[0], gw[1], gw[2]])
 
     res_host = torch.empty(3 + K * C, dtype=torch.float32).pin_memory()
@@ -775,16 +777,17 @@ def main():
                 # would pull that stream into the capture
                 xg = x.detach().clone().requires_grad_(True)
                 fg = f_core.detach().clone().requires_grad_(True)
+                Wg = Wc.detach().clone().requires_grad_(True)
+                bg = bc.detach().clone().requires_grad_(True)
                 for _ in range(3):
-                    core_step(xg, fg)
+                    core_step(xg, fg, Wg, bg)
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize()
-            xg.grad = None
-            fg.grad = None
+            xg.grad = fg.grad = Wg.grad = bg.grad = None
             core_graph = torch.cuda.CUDAGraph()
             n0 = capi.LAUNCHES
             with torch.cuda.graph(core_graph):
-                core_step(xg, fg)
+                core_step(xg, fg, Wg, bg)
             core_launches_per_replay = capi.LAUNCHES - n0
             core_fn = core_graph.replay
             core_launch = "CUDA graph replay of the %d launches" % core_launches_per_replay

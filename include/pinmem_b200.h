@@ -297,6 +297,34 @@ int pm_write_reduce_fwd8(const void* f, const uint8_t* lab8, float* SD, int B, i
 int pm_write_bwd8(const float* dS, const void* f, const uint8_t* lab8, void* df, int B, int C, int h, int w, int Hm, int Wm,
                   int K, int dtype, void* stream);
 
+/*
+ * The sharded update with its exchange FUSED into the update kernels over NVLink peer memory (the one
+ * collective of the path is the all-reduce of the [K+1,C+4] class sums|counts before the update, and -- its autograd
+ * mirror -- of the [K,C] gradient w.r.t. the sums). Instead of an NCCL launch before pm_update_fwd and another after
+ * pm_update_bwd, every rank keeps a "symmetric" buffer of PM_PEER_BYTES (host side: torch.distributed._symmetric_memory;
+ * `peer_bufs` is the DEVICE array of all ranks' buffer addresses as peer-mapped pointers):
+ *   bytes [0, PM_PEER_DS_OFF)     this rank's sums|counts  -- pm_write_reduce_fwd[8] accumulates straight into it
+ *                                 (zero it first)
+ *   bytes [PM_PEER_DS_OFF, ...)   this rank's dS share     -- written by pm_update_bwd_peer itself
+ *   bytes [PM_PEER_FLAG_OFF, ...) arrival flags, zeroed once at allocation
+ * CTA i raises a flag in every peer's buffer, waits for all ranks' flags, reads row i (forward: all rows) out of the
+ * peers' buffers and sums in rank order -- identical on every rank, so the new memory is bit-identical across ranks.
+ * `epoch`: one device uint32 per kernel kind (two in total), zeroed at allocation, owned by the kernels.
+ * SD_sum [K+1,C+4] (may be NULL) receives the all-reduced sums|counts; dS [K,C] the all-reduced gradient.
+ * Every rank of the group must launch the same sequence of these two kernels (they spin on each other, bounded: a peer
+ * that never arrives traps instead of hanging).
+ */
+#define PM_PEER_DS_OFF 36864
+#define PM_PEER_FLAG_OFF 73728
+#define PM_PEER_BYTES 131072
+int pm_peer_buffer_bytes(void);
+int pm_update_fwd_peer(const void* peer_bufs, int rank, int world, unsigned* epoch, float* SD_sum, const float* M_old,
+                       float momentum, const float* W_cls, const float* b_cls, float* M_new, float* losses, float* saved,
+                       float* aux, int C, int K, void* stream);
+int pm_update_bwd_peer(const void* peer_bufs, int rank, int world, unsigned* epoch, const float* dM_new, const float* g_div,
+                       const float* g_cls, const float* M_new, const float* saved, const float* W_cls, const float* b_cls,
+                       float momentum, float* dS, float* dW_cls, float* db_cls, float* aux, int C, int K, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

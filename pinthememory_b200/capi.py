@@ -58,6 +58,9 @@ PROTOTYPES = {
     "pm_bn_finalize": [_c_p, _c_i, _c_d, _c_f] + [_c_p] * 4 + [_c_f, _c_p],
     "pm_write_reduce_fwd8": [_c_p] * 3 + [_c_i] * 8 + [_c_p],
     "pm_write_bwd8": [_c_p] * 4 + [_c_i] * 8 + [_c_p],
+    "pm_peer_buffer_bytes": [],
+    "pm_update_fwd_peer": [_c_p, _c_i, _c_i, _c_p, _c_p, _c_p, _c_f] + [_c_p] * 6 + [_c_i] * 2 + [_c_p],
+    "pm_update_bwd_peer": [_c_p, _c_i, _c_i, _c_p] + [_c_p] * 7 + [_c_f] + [_c_p] * 4 + [_c_i] * 2 + [_c_p],
     "pm_labels_pack": [_c_p, _c_i, ctypes.c_longlong, _c_i, _c_p, _c_p, _c_p],
     "pm_readloss_fwd8": [_c_p, _c_p, _c_f] + [_c_i] * 6 + [_c_p] * 4,
     "pm_memory_losses_fwd": [_c_p] * 3 + [_c_i] * 2 + [_c_p] * 4,
@@ -434,3 +437,21 @@ def readloss(s, labels, temperature, B, h, w, K, ds_rl, ws, out):
         return lab8
     readloss_fwd(s, labels if labels.dtype == torch.int64 else labels.to(torch.int64), temperature, B, h, w, K, ds_rl, ws, out)
     return None
+
+
+# ------------------------------------- sharded update with the exchange fused over peer memory (csrc/pm_write.cu)
+
+PEER_DS_OFF, PEER_FLAG_OFF, PEER_BYTES = 36864, 73728, 131072  # PM_PEER_* of the header
+
+
+def update_fwd_peer(peer, SD_sum, M_old, momentum, W, b, M_new, losses, saved, C, K, aux=None):
+    if aux is None:
+        aux = update_aux(M_old.device, K)
+    _call("pm_update_fwd_peer", peer.bufs_dev, peer.rank, peer.world_size, _ptr(peer.epochs[0:1]), _ptr(SD_sum), _ptr(M_old),
+          float(momentum), _ptr(W), _ptr(b), _ptr(M_new), _ptr(losses), _ptr(saved), _ptr(aux), C, K, _stream())
+
+
+def update_bwd_peer(peer, dM_new, g_div, g_cls, M_new, saved, W, b, momentum, dS, dW, db, C, K):
+    _call("pm_update_bwd_peer", peer.bufs_dev, peer.rank, peer.world_size, _ptr(peer.epochs[1:2]), _ptr(dM_new), _ptr(g_div),
+          _ptr(g_cls), _ptr(M_new), _ptr(saved), _ptr(W), _ptr(b), float(momentum), _ptr(dS), _ptr(dW), _ptr(db),
+          _ptr(update_aux(M_new.device, K)), C, K, _stream())

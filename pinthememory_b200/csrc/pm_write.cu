@@ -254,9 +254,55 @@ __device__ __forceinline__ void block_reduce32(float (&v)[32], float* scratch, f
     __syncthreads();
 }
 
+// ---- the sharded update's exchange, fused into the update kernels over NVLink peer memory --------------------------
+// Every rank owns one "symmetric" buffer (allocated and exchanged by torch.distributed._symmetric_memory on the host
+// side; `bufs` is the device array of all ranks' base addresses, peer-mapped) laid out as
+//   [0, PM_PEER_DS_OFF)            SD  : this rank's class sums|counts [K+1, C+4] (pm_write_reduce_fwd adds into it)
+//   [PM_PEER_DS_OFF, FLAG_OFF)     dS  : this rank's gradient w.r.t. the class sums [K, C]
+//   [PM_PEER_FLAG_OFF, ...)        flags[kind 0..3][row 0..31][rank 0..15] (u32, monotone epochs)
+// CTA i of the update kernels is the only one that touches row-slot i: it raises flag (kind, i, my rank) = epoch in
+// EVERY peer's buffer (st.release.sys), spins on its own copies until all ranks have raised theirs (ld.acquire.sys),
+// then reads the operand straight out of the peers' buffers and sums in rank order -- the same order on every rank,
+// so the updated memory is bit-identical across ranks. A second flag round ("done") at the end of the kernel keeps a
+// rank from zeroing / overwriting its buffer for the next step while a slower peer still reads it. No NCCL launch,
+// no extra kernel: ~21 KB per rank cross NVSwitch inside the kernel that needs them.
+struct PeerCtx {
+    const unsigned long long* bufs;  // device array [world] of symmetric-buffer base addresses; nullptr = not sharded
+    int rank, world;
+    unsigned* epoch;                 // device counter of this kernel's launches (one per kernel kind)
+};
+
+__device__ __forceinline__ unsigned* peer_flag(unsigned long long base, int kind, int row, int rank) {
+    return reinterpret_cast<unsigned*>(base + PM_PEER_FLAG_OFF) + ((kind * 32 + row) * 16 + rank);
+}
+// all threads of the CTA call both; data written by this CTA before peer_signal is visible to the peers after their wait
+__device__ __forceinline__ void peer_signal(const PeerCtx& p, int kind, int row, unsigned e) {
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < p.world) {
+        unsigned* f = peer_flag(p.bufs[threadIdx.x], kind, row, p.rank);
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(e) : "memory");
+    }
+}
+__device__ __forceinline__ void peer_wait(const PeerCtx& p, int kind, int row, unsigned e) {
+    if ((int)threadIdx.x < p.world) {
+        const unsigned* f = peer_flag(p.bufs[p.rank], kind, row, threadIdx.x);
+        unsigned v = 0;
+        for (unsigned spin = 0;; ++spin) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if ((int)(v - e) >= 0) break;
+            if (spin > (1u << 27)) __trap();  // a peer that never arrives (crashed rank): fail loudly, do not hang the GPU
+            __nanosleep(32);
+        }
+    }
+    __syncthreads();
+}
+
 // aux layout (floats, zeroed by the caller): [0] arrival counter (as unsigned), [2 .. 2+32) per-row CE term,
 // [34 .. 34+32) per-row positive off-diagonal Gram sum
-__global__ void __launch_bounds__(UP_THREADS) update_fwd_kernel(const float* __restrict__ SD, const float* __restrict__ M_old,
+template <bool PEER>
+__global__ void __launch_bounds__(UP_THREADS) update_fwd_kernel(const float* __restrict__ SD, PeerCtx peer,
+                                                                float* __restrict__ SD_sum, const float* __restrict__ M_old,
                                                                 float momentum, const float* __restrict__ W,
                                                                 const float* __restrict__ bias, float* __restrict__ M_new,
                                                                 float* __restrict__ losses, float* __restrict__ saved,
@@ -267,14 +313,57 @@ __global__ void __launch_bounds__(UP_THREADS) update_fwd_kernel(const float* __r
     const bool on = tid < C;
     // this thread's channel of every row; all loads are issued before the first use
     float m[UP_KMAX], wv[UP_KMAX], sd[UP_KMAX], dk[UP_KMAX];
+    unsigned epoch = 0;
+    if (PEER) {  // every rank's class sums are complete (its write_reduce kernel precedes this one in stream order)
+        epoch = *peer.epoch + 1;
+        peer_signal(peer, 0, i, epoch);
+        peer_wait(peer, 0, i, epoch);
+    }
 #pragma unroll
     for (int k = 0; k < UP_KMAX; ++k) {
         const bool ok = k < K && on;
-        dk[k] = ok ? __ldg(SD + (size_t)k * CS + C) : 0.f;
         m[k] = ok ? __ldg(M_old + (size_t)k * C + tid) : 0.f;
-        sd[k] = ok ? __ldg(SD + (size_t)k * CS + tid) : 0.f;
         wv[k] = ok ? __ldg(W + (size_t)k * C + tid) : 0.f;
+        if (!PEER) {
+            dk[k] = ok ? __ldg(SD + (size_t)k * CS + C) : 0.f;
+            sd[k] = ok ? __ldg(SD + (size_t)k * CS + tid) : 0.f;
+        } else {
+            dk[k] = sd[k] = 0.f;
+        }
     }
+    if (PEER) {  // sum over the ranks in rank order, straight out of their buffers (plain loads: peer memory is not
+                 // cached in the local L2, and the flags above ordered these reads after the peers' writes)
+        float rowK = 0.f, rowKc = 0.f;
+        for (int r = 0; r < peer.world; ++r) {
+            const volatile float* P = reinterpret_cast<const volatile float*>(peer.bufs[r]);
+#pragma unroll
+            for (int k = 0; k < UP_KMAX; ++k) {
+                if (k < K && on) {
+                    dk[k] += P[(size_t)k * CS + C];
+                    sd[k] += P[(size_t)k * CS + tid];
+                }
+            }
+            if (i == 0) {  // the ignore row only feeds last_class_sums
+                if (on) rowK += P[(size_t)K * CS + tid];
+                if (tid == 0) rowKc += P[(size_t)K * CS + C];
+            }
+        }
+        if (SD_sum != nullptr) {  // the all-reduced sums|counts for the host side (CTA i owns row i, CTA 0 also row K)
+            float si = 0.f, di = 0.f;
+#pragma unroll
+            for (int k = 0; k < UP_KMAX; ++k)
+                if (k == i) si = sd[k], di = dk[k];
+            if (on) SD_sum[(size_t)i * CS + tid] = si;
+            if (tid == 0) SD_sum[(size_t)i * CS + C] = di;
+            if (i == 0 && on) SD_sum[(size_t)K * CS + tid] = rowK;
+            if (i == 0 && tid == 0) SD_sum[(size_t)K * CS + C] = rowKc;
+        }
+        peer_signal(peer, 1, i, epoch);  // done reading the peers' sums
+    }
+    float d_own = 0.f;
+#pragma unroll
+    for (int k = 0; k < UP_KMAX; ++k)
+        if (k == i) d_own = dk[k];
 #pragma unroll
     for (int k = 0; k < UP_KMAX; ++k) {
         m[k] = (dk[k] != 0.f) ? fmaf((1.f - momentum) / dk[k], sd[k], momentum * m[k]) : m[k];
@@ -292,7 +381,7 @@ __global__ void __launch_bounds__(UP_THREADS) update_fwd_kernel(const float* __r
     if (on) M_new[(size_t)i * C + tid] = mi;
     if (tid == 0) {
         saved[i] = sqrtf(red[i]);
-        saved[K + i] = __ldg(SD + (size_t)i * CS + C);
+        saved[K + i] = d_own;
     }
     // row i of the classifier logits (red) and of the Gram matrix (red2)
 #pragma unroll
@@ -325,17 +414,20 @@ __global__ void __launch_bounds__(UP_THREADS) update_fwd_kernel(const float* __r
             if (lane == 0) {
                 losses[0] = d / (float)(K * (K - 1));
                 losses[1] = c / (float)K;
+                if (PEER) *peer.epoch = epoch;  // every CTA has read the counter (it arrived above); next launch sees epoch
             }
         }
     }
+    if (PEER) peer_wait(peer, 1, i, epoch);  // no peer still reads this rank's sums: the buffer may be zeroed again
 }
 
 // aux layout (floats, zeroed by the caller): [0] arrival counter, [32 .. 32 + K*32) dz rows
+template <bool PEER>
 __global__ void __launch_bounds__(UP_THREADS) update_bwd_kernel(const float* __restrict__ dM_new, const float* __restrict__ g_div,
                                                                 const float* __restrict__ g_cls, const float* __restrict__ M_new,
                                                                 const float* __restrict__ saved, const float* __restrict__ W,
                                                                 const float* __restrict__ bias, float momentum,
-                                                                float* __restrict__ dS, float* __restrict__ dW,
+                                                                float* __restrict__ dS, PeerCtx peer, float* __restrict__ dW,
                                                                 float* __restrict__ db, float* __restrict__ aux, int C,
                                                                 int K) {
     __shared__ float scratch[UP_WARPS * 32];
@@ -395,7 +487,25 @@ __global__ void __launch_bounds__(UP_THREADS) update_bwd_kernel(const float* __r
         const float inv = 1.f / fmaxf(nrm, PM_NORM_EPS);
         const float coef = (Dn != 0.f) ? (1.f - momentum) / Dn : 0.f;
         const float dmp = (nrm <= PM_NORM_EPS) ? a * inv : (a - mi * dot) * inv;
-        if (on) dS[(size_t)i * C + tid] = coef * dmp;
+        if (!PEER) {
+            if (on) dS[(size_t)i * C + tid] = coef * dmp;
+        } else {
+            // this rank's share goes into its symmetric buffer; row i is then summed over the ranks (rank order) out of
+            // the peers' buffers into dS -- the gradient of the GLOBAL class sums, identical on every rank
+            const unsigned epoch = *peer.epoch + 1;
+            float* mine = reinterpret_cast<float*>(peer.bufs[peer.rank] + PM_PEER_DS_OFF);
+            if (on) mine[(size_t)i * C + tid] = coef * dmp;
+            peer_signal(peer, 2, i, epoch);
+            peer_wait(peer, 2, i, epoch);
+            float acc = 0.f;
+            for (int r = 0; r < peer.world; ++r) {
+                const volatile float* P = reinterpret_cast<const volatile float*>(peer.bufs[r] + PM_PEER_DS_OFF);
+                if (on) acc += P[(size_t)i * C + tid];
+            }
+            if (on) dS[(size_t)i * C + tid] = acc;
+            peer_signal(peer, 3, i, epoch);
+            peer_wait(peer, 3, i, epoch);   // nobody still reads this rank's row: the next launch may overwrite it
+        }
     }
     // the last row to arrive turns the dz rows into dW = dz^T M_new and db
     __threadfence();
@@ -420,6 +530,7 @@ __global__ void __launch_bounds__(UP_THREADS) update_bwd_kernel(const float* __r
             for (int k = 0; k < K; ++k) acc += dzs[k * UP_KMAX + tid];
             db[tid] = acc;
         }
+        if (PEER && tid == 0) *peer.epoch = *peer.epoch + 1;  // last CTA: every other CTA has read the counter already
     }
 }
 
@@ -544,8 +655,25 @@ extern "C" int pm_update_fwd(const float* SD, const float* M_old, float momentum
     if (!SD || !M_old || !W_cls || !b_cls || !M_new || !losses || !saved || !aux) return PM_ERR_NULL;
     if (C != 32 && C != 64 && C != 128 && C != 256) return PM_ERR_CHANNELS;
     if (K < 1 || K > 31) return PM_ERR_SLOTS;
-    pm::update_fwd_kernel<<<K, pm::UP_THREADS, 0, (cudaStream_t)stream>>>(SD, M_old, momentum, W_cls, b_cls, M_new, losses,
-                                                                          saved, aux, C, K);
+    pm::update_fwd_kernel<false><<<K, pm::UP_THREADS, 0, (cudaStream_t)stream>>>(SD, pm::PeerCtx{nullptr, 0, 1, nullptr}, nullptr,
+                                                                                 M_old, momentum, W_cls, b_cls, M_new, losses,
+                                                                                 saved, aux, C, K);
+    PM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int pm_peer_buffer_bytes(void) { return PM_PEER_BYTES; }
+
+extern "C" int pm_update_fwd_peer(const void* peer_bufs, int rank, int world, unsigned* epoch, float* SD_sum,
+                                  const float* M_old, float momentum, const float* W_cls, const float* b_cls, float* M_new,
+                                  float* losses, float* saved, float* aux, int C, int K, void* stream) {
+    if (!peer_bufs || !epoch || !M_old || !W_cls || !b_cls || !M_new || !losses || !saved || !aux) return PM_ERR_NULL;
+    if (C != 32 && C != 64 && C != 128 && C != 256) return PM_ERR_CHANNELS;
+    if (K < 1 || K > 31) return PM_ERR_SLOTS;
+    if (world < 1 || world > 16 || rank < 0 || rank >= world) return PM_ERR_SHAPE;
+    pm::PeerCtx p{(const unsigned long long*)peer_bufs, rank, world, epoch};
+    pm::update_fwd_kernel<true><<<K, pm::UP_THREADS, 0, (cudaStream_t)stream>>>(nullptr, p, SD_sum, M_old, momentum, W_cls, b_cls,
+                                                                                M_new, losses, saved, aux, C, K);
     PM_CHECK_LAUNCH();
     return 0;
 }
@@ -556,8 +684,24 @@ extern "C" int pm_update_bwd(const float* dM_new, const float* g_div, const floa
     if (!M_new || !saved || !W_cls || !b_cls || !dS || !dW_cls || !db_cls || !aux) return PM_ERR_NULL;
     if (C != 32 && C != 64 && C != 128 && C != 256) return PM_ERR_CHANNELS;
     if (K < 1 || K > 31) return PM_ERR_SLOTS;
-    pm::update_bwd_kernel<<<K, pm::UP_THREADS, 0, (cudaStream_t)stream>>>(dM_new, g_div, g_cls, M_new, saved, W_cls, b_cls,
-                                                                          momentum, dS, dW_cls, db_cls, aux, C, K);
+    pm::update_bwd_kernel<false><<<K, pm::UP_THREADS, 0, (cudaStream_t)stream>>>(dM_new, g_div, g_cls, M_new, saved, W_cls, b_cls,
+                                                                                 momentum, dS, pm::PeerCtx{nullptr, 0, 1, nullptr},
+                                                                                 dW_cls, db_cls, aux, C, K);
+    PM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int pm_update_bwd_peer(const void* peer_bufs, int rank, int world, unsigned* epoch, const float* dM_new,
+                                  const float* g_div, const float* g_cls, const float* M_new, const float* saved,
+                                  const float* W_cls, const float* b_cls, float momentum, float* dS, float* dW_cls,
+                                  float* db_cls, float* aux, int C, int K, void* stream) {
+    if (!peer_bufs || !epoch || !M_new || !saved || !W_cls || !b_cls || !dS || !dW_cls || !db_cls || !aux) return PM_ERR_NULL;
+    if (C != 32 && C != 64 && C != 128 && C != 256) return PM_ERR_CHANNELS;
+    if (K < 1 || K > 31) return PM_ERR_SLOTS;
+    if (world < 1 || world > 16 || rank < 0 || rank >= world) return PM_ERR_SHAPE;
+    pm::PeerCtx p{(const unsigned long long*)peer_bufs, rank, world, epoch};
+    pm::update_bwd_kernel<true><<<K, pm::UP_THREADS, 0, (cudaStream_t)stream>>>(dM_new, g_div, g_cls, M_new, saved, W_cls, b_cls,
+                                                                                momentum, dS, p, dW_cls, db_cls, aux, C, K);
     PM_CHECK_LAUNCH();
     return 0;
 }

@@ -181,20 +181,29 @@ class _WriteFn(torch.autograd.Function):
     def forward(ctx, f, labels, M_old, W, b, momentum, K, group):
         B, C, h, w = f.shape
         dev = f.device
+        peer = group.peer if (group is not None and group.world_size > 1) else None
         # one zeroed allocation: the class sums|counts [K+1, C+4] and the update kernel's scratch
         nsd = (K + 1) * (C + 4)
         zbuf = torch.zeros(nsd + capi.update_aux_floats(K), dtype=torch.float32, device=dev)
         SD, aux = zbuf[:nsd].view(K + 1, C + 4), zbuf[nsd:]
-        capi.write_reduce_fwd(f, labels, SD, K)
-        if group is not None:
-            sharding.all_reduce_sum_(SD, group)
         M_old = M_old.detach().contiguous()
         W = W.detach().to(torch.float32).contiguous()
         b = b.detach().to(torch.float32).contiguous()
         M_new = torch.empty(K, C, dtype=torch.float32, device=dev)
         losses = torch.empty(2, dtype=torch.float32, device=dev)
         saved = torch.empty(2 * K, dtype=torch.float32, device=dev)
-        capi.update_fwd(SD, M_old, momentum, W, b, M_new, losses, saved, C, K, aux=aux)
+        if peer is not None:
+            # the rank's sums go into its peer-mapped buffer; the update kernel itself gathers and sums all ranks' rows
+            # over NVLink (and leaves the all-reduced sums in SD for the host side)
+            mine = peer.sums_view(K, C)
+            mine.zero_()
+            capi.write_reduce_fwd(f, labels, mine, K)
+            capi.update_fwd_peer(peer, SD, M_old, momentum, W, b, M_new, losses, saved, C, K, aux=aux)
+        else:
+            capi.write_reduce_fwd(f, labels, SD, K)
+            if group is not None:
+                sharding.all_reduce_sum_(SD, group)
+            capi.update_fwd(SD, M_old, momentum, W, b, M_new, losses, saved, C, K, aux=aux)
         ctx.K, ctx.momentum, ctx.group = K, momentum, group
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(f, labels, M_new, saved, W, b)
@@ -210,9 +219,14 @@ class _WriteFn(torch.autograd.Function):
         dS = torch.empty(K, C, dtype=torch.float32, device=dev)
         dW = torch.empty(K, C, dtype=torch.float32, device=dev)
         db = torch.empty(K, dtype=torch.float32, device=dev)
-        capi.update_bwd(as32(dM_new), as32(g_div), as32(g_cls), M_new, saved, W, b, ctx.momentum, dS, dW, db, C, K)
-        if ctx.group is not None:
-            sharding.all_reduce_sum_(dS, ctx.group)
+        peer = ctx.group.peer if (ctx.group is not None and ctx.group.world_size > 1) else None
+        if peer is not None:
+            capi.update_bwd_peer(peer, as32(dM_new), as32(g_div), as32(g_cls), M_new, saved, W, b, ctx.momentum, dS, dW, db,
+                                 C, K)
+        else:
+            capi.update_bwd(as32(dM_new), as32(g_div), as32(g_cls), M_new, saved, W, b, ctx.momentum, dS, dW, db, C, K)
+            if ctx.group is not None:
+                sharding.all_reduce_sum_(dS, ctx.group)
         df = None
         if ctx.needs_input_grad[0]:
             df = torch.empty_like(f)

@@ -51,10 +51,14 @@ def _state(device):
     return ora
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, exchange):
     import torch.distributed as dist
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if exchange == "nccl":
+        os.environ["PINMEM_B200_NCCL_EXCHANGE"] = "1"
+    else:
+        os.environ.pop("PINMEM_B200_NCCL_EXCHANGE", None)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -68,7 +72,7 @@ def _worker(rank, world, port, out):
         mem = Memory_sup(K, C, C, 0.8, 1.0, False).to(dev).eval()
         mem.load_state_dict(ora.state_dict())
         mem.m_items = ora.m_items.clone()
-        sharding.enable_sharded_update(mem)
+        shard = sharding.enable_sharded_update(mem)
         x, labels, G = _inputs(dev)
         n = B // world
         sl = slice(rank * n, (rank + 1) * n)
@@ -77,13 +81,16 @@ def _worker(rank, world, port, out):
         ((uq * G[sl]).sum() + LW["read"] * rl + LW["div"] * wl[0] + LW["cls"] * wl[1]).backward()
         out[rank] = dict(m_items=mem.m_items.detach().cpu(), dx=xr.grad.cpu(), rl=rl.detach().cpu(),
                          grads={k: p.grad.cpu() for k, p in mem.named_parameters() if p.grad is not None},
-                         D=mem.last_class_sums[:, C].cpu())
+                         D=mem.last_class_sums[:, C].cpu(), peer=shard.peer is not None, peer_error=shard.peer_error)
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_rank_nccl_sharded_module_equals_global_batch():
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+def test_two_rank_nccl_sharded_module_equals_global_batch(exchange):
+    """exchange = "peer": the all-reduce of the class sums (and of their gradient) fused into the update kernels over
+    NVLink peer memory (pm_update_fwd_peer / pm_update_bwd_peer); "nccl": two NCCL all-reduces around the kernels."""
     import torch.multiprocessing as mp
 
     from golden_util import assert_close
@@ -92,7 +99,10 @@ def test_two_rank_nccl_sharded_module_equals_global_batch():
     world = 2
     mgr = mp.get_context("spawn").Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), out, exchange), nprocs=world, join=True)
+    if exchange == "peer" and not out[0]["peer"]:
+        pytest.skip("no symmetric-memory peer exchange on this box: %s" % out[0]["peer_error"])
+    assert out[0]["peer"] == (exchange == "peer")
 
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
