@@ -43,16 +43,28 @@ __global__ void __launch_bounds__(256) labels_pack_kernel(const TIN* __restrict_
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = PM_IGNORE_LABEL;
         }
+        int cls[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const bool ok = v[j] >= 0 && v[j] < K;
-            const int c = ok ? (int)v[j] : K;
+            cls[j] = ok ? (int)v[j] : K;
             bad += (!ok && v[j] != PM_IGNORE_LABEL) ? 1 : 0;
-            packed |= (unsigned long long)c << (8 * j);
-            // warp-aggregated histogram: lanes with the same class elect one adder (bin 32 swallows the idle lanes)
-            const int bin = live ? c : 32;
+            packed |= (unsigned long long)cls[j] << (8 * j);
+        }
+        // warp-aggregated histogram: lanes with the same class elect one adder (bin 32 swallows the idle lanes). Label
+        // maps are piecewise constant, so usually every lane's 8 pixels are one class: one match instead of eight.
+        const bool uniform = packed == (unsigned long long)cls[0] * 0x0101010101010101ull;
+        if (__all_sync(0xffffffffu, uniform)) {
+            const int bin = live ? cls[0] : 32;
             const unsigned peers = __match_any_sync(0xffffffffu, bin);
-            if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[bin], __popc(peers));
+            if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[bin], 8 * __popc(peers));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int bin = live ? cls[j] : 32;
+                const unsigned peers = __match_any_sync(0xffffffffu, bin);
+                if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[bin], __popc(peers));
+            }
         }
         if (live) *reinterpret_cast<unsigned long long*>(lab8 + 8 * i) = packed;
     }

@@ -331,34 +331,40 @@ __global__ void __launch_bounds__(UP_THREADS) update_fwd_kernel(const float* __r
             dk[k] = sd[k] = 0.f;
         }
     }
-    if (PEER) {  // sum over the ranks in rank order, straight out of their buffers (plain loads: peer memory is not
-                 // cached in the local L2, and the flags above ordered these reads after the peers' writes)
-        float rowK = 0.f, rowKc = 0.f;
+    if (PEER) {
+        // CTA i gathers ROW i over the ranks in rank order, straight out of their buffers (volatile loads: peer memory is
+        // not cached locally, and the flags above ordered these reads after the peers' writes), leaves the sum in
+        // SD_sum (local) and releases the peers; the K CTAs of THIS rank then meet on a local counter and every CTA reads
+        // all summed rows from SD_sum -- one row per CTA crosses NVLink instead of K.
+        float si = 0.f, di = 0.f, rowK = 0.f, rowKc = 0.f;
         for (int r = 0; r < peer.world; ++r) {
             const volatile float* P = reinterpret_cast<const volatile float*>(peer.bufs[r]);
-#pragma unroll
-            for (int k = 0; k < UP_KMAX; ++k) {
-                if (k < K && on) {
-                    dk[k] += P[(size_t)k * CS + C];
-                    sd[k] += P[(size_t)k * CS + tid];
-                }
-            }
+            if (on) si += P[(size_t)i * CS + tid];
+            if (tid == 0) di += P[(size_t)i * CS + C];
             if (i == 0) {  // the ignore row only feeds last_class_sums
                 if (on) rowK += P[(size_t)K * CS + tid];
                 if (tid == 0) rowKc += P[(size_t)K * CS + C];
             }
         }
-        if (SD_sum != nullptr) {  // the all-reduced sums|counts for the host side (CTA i owns row i, CTA 0 also row K)
-            float si = 0.f, di = 0.f;
-#pragma unroll
-            for (int k = 0; k < UP_KMAX; ++k)
-                if (k == i) si = sd[k], di = dk[k];
-            if (on) SD_sum[(size_t)i * CS + tid] = si;
-            if (tid == 0) SD_sum[(size_t)i * CS + C] = di;
-            if (i == 0 && on) SD_sum[(size_t)K * CS + tid] = rowK;
-            if (i == 0 && tid == 0) SD_sum[(size_t)K * CS + C] = rowKc;
+        if (on) SD_sum[(size_t)i * CS + tid] = si;
+        if (tid == 0) SD_sum[(size_t)i * CS + C] = di;
+        if (i == 0 && on) SD_sum[(size_t)K * CS + tid] = rowK;
+        if (i == 0 && tid == 0) SD_sum[(size_t)K * CS + C] = rowKc;
+        peer_signal(peer, 1, i, epoch);  // done reading the peers' sums (also: __threadfence_system + __syncthreads)
+        if (tid == 0) {                   // local grid barrier: all K rows of SD_sum are written
+            unsigned* cnt = reinterpret_cast<unsigned*>(aux) + 1;
+            atomicAdd(cnt, 1u);
+            for (unsigned spin = 0; atomicAdd(cnt, 0u) < (unsigned)K; ++spin)
+                if (spin > (1u << 27)) __trap();
+            __threadfence();
         }
-        peer_signal(peer, 1, i, epoch);  // done reading the peers' sums
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < UP_KMAX; ++k) {
+            const bool ok = k < K && on;
+            dk[k] = ok ? __ldcg(SD_sum + (size_t)k * CS + C) : 0.f;
+            sd[k] = ok ? __ldcg(SD_sum + (size_t)k * CS + tid) : 0.f;
+        }
     }
     float d_own = 0.f;
 #pragma unroll
