@@ -257,6 +257,13 @@ int pm_bn_bwd_apply(const void* dy, const void* y, const uint32_t* relu_mask, co
 int pm_conv1x1_prep(const float* W, int M, int K, int transpose, int dtype, void* A_hi, void* A_lo, void* stream);
 int pm_conv1x1_fwd(const void* X, const void* A_hi, const void* A_lo, void* Y, double* stats, int B, int K, int M,
                    int hw, int accumulate, int dtype, void* stream);
+/* Y[b] = [relu](scale[m] * (A . X[b]) + shift[m]): the convolution with the eval-mode BatchNorm2d (+ ReLU) that follows it
+ * (memory.py:103-107 with running statistics: scale = gamma / sqrt(var + eps), shift = beta - mean * scale) folded into
+ * the GEMM epilogue -- the inference read (BASELINE config 5) then has no separate normalise pass. scale, shift fp32 [M]. */
+int pm_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps,
+                      int C, float* scale, float* shift, void* stream);
+int pm_conv1x1_fwd_affine(const void* X, const void* A_hi, const void* A_lo, void* Y, const float* scale, const float* shift,
+                          int relu, int B, int K, int M, int hw, int dtype, void* stream);
 int pm_conv1x1_wgrad_workspace_floats(int B, int M, int N, int hw, int dtype);
 int pm_conv1x1_wgrad(const void* dY, const void* X, float* workspace, float* dW, int B, int M, int N, int hw,
                      int accumulate, int dtype, void* stream);

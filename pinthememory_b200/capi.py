@@ -53,6 +53,8 @@ PROTOTYPES = {
     "pm_bn_bwd_apply": [_c_p] * 9 + [_c_i] * 2 + [_c_p] * 2 + [_c_i] * 4 + [_c_p],
     "pm_conv1x1_prep": [_c_p] + [_c_i] * 4 + [_c_p] * 3,
     "pm_conv1x1_fwd": [_c_p] * 5 + [_c_i] * 6 + [_c_p],
+    "pm_bn_eval_affine": [_c_p] * 4 + [_c_f, _c_i] + [_c_p] * 3,
+    "pm_conv1x1_fwd_affine": [_c_p] * 6 + [_c_i] * 6 + [_c_p],
     "pm_conv1x1_wgrad_workspace_floats": [_c_i] * 5,
     "pm_conv1x1_wgrad": [_c_p] * 4 + [_c_i] * 6 + [_c_p],
     "pm_bn_finalize": [_c_p, _c_i, _c_d, _c_f] + [_c_p] * 4 + [_c_f, _c_p],
@@ -376,6 +378,25 @@ def conv1x1_fwd(x, A_hi, A_lo, M, y=None, stats=None, accumulate=False):
         y = torch.empty(B, M, h, w, dtype=x.dtype, device=x.device)
     _call("pm_conv1x1_fwd", _ptr(x), _ptr(A_hi), _ptr(A_lo), _ptr(y), _ptr(stats), B, K, M, h * w, int(bool(accumulate)),
           dtype_code(x), _stream())
+    return y
+
+
+def bn_eval_affine(gamma, beta, running_mean, running_var, eps):
+    """Eval-mode BatchNorm2d as (scale, shift) fp32 [C] for pm_conv1x1_fwd_affine."""
+    C = gamma.shape[0]
+    scale = torch.empty(C, dtype=torch.float32, device=gamma.device)
+    shift = torch.empty(C, dtype=torch.float32, device=gamma.device)
+    _call("pm_bn_eval_affine", _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), float(eps), C, _ptr(scale),
+          _ptr(shift), _stream())
+    return scale, shift
+
+
+def conv1x1_fwd_affine(x, A_hi, A_lo, M, scale, shift, relu):
+    """y[b] = [relu](scale[m] * (A . x[b]) + shift[m]) -- convolution + eval-mode BatchNorm (+ ReLU) in one kernel."""
+    B, K, h, w = x.shape
+    y = torch.empty(B, M, h, w, dtype=x.dtype, device=x.device)
+    _call("pm_conv1x1_fwd_affine", _ptr(x), _ptr(A_hi), _ptr(A_lo), _ptr(y), _ptr(scale), _ptr(shift), int(bool(relu)), B, K, M,
+          h * w, dtype_code(x), _stream())
     return y
 
 

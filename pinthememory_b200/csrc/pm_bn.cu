@@ -292,6 +292,29 @@ static int bn_check(int B, int C, int hw, int dtype) {
     return 0;
 }
 
+namespace pm {
+// eval-mode BatchNorm as a per-channel affine: scale = gamma / sqrt(var + eps), shift = beta - mean * scale
+__global__ void bn_eval_affine_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ mean, const float* __restrict__ var, float eps, int C,
+                                      float* __restrict__ scale, float* __restrict__ shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float sc = gamma[c] * rsqrtf(var[c] + eps);
+    scale[c] = sc;
+    shift[c] = fmaf(-mean[c], sc, beta[c]);
+}
+}  // namespace pm
+
+extern "C" int pm_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                                 float eps, int C, float* scale, float* shift, void* stream) {
+    if (!gamma || !beta || !running_mean || !running_var || !scale || !shift) return PM_ERR_NULL;
+    if (C <= 0) return PM_ERR_SHAPE;
+    pm::bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gamma, beta, running_mean, running_var, eps, C,
+                                                                                 scale, shift);
+    PM_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" int pm_bn_finalize(const double* stats, int C, double count, float eps, float* mean, float* invstd,
                               float* running_mean, float* running_var, float momentum, void* stream) {
     if (!stats || !mean || !invstd || ((running_mean == nullptr) != (running_var == nullptr))) return PM_ERR_NULL;

@@ -102,7 +102,8 @@ template <typename T, int MT, int NT, int KB, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     conv1x1_nn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapAh,
                       const __grid_constant__ CUtensorMap mapAl, const __grid_constant__ CUtensorMap mapY, int K, int M,
-                      int m_tile0, int tiles_per_img, int total_tiles, int accumulate, double* __restrict__ stats, int dbg) {
+                      int m_tile0, int tiles_per_img, int total_tiles, int accumulate, double* __restrict__ stats,
+                      const float* __restrict__ ep_scale, const float* __restrict__ ep_shift, int ep_relu, int dbg) {
     using TR = GemmTraits<T>;
     constexpr int PXC = TR::PXC, UK = TR::UK, KSTEPS = KB / UK;
     constexpr int NCH = NT / PXC;                      // 128-byte pixel chunks per tile
@@ -253,6 +254,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             for (int mt = 0; mt < MT; ++mt) {
                 const int row0 = (m_tile0 + mt) * 128 + q * 32;
                 if (row0 >= M || tile >= total_tiles) continue;  // padded rows / the repeated tile of a short group
+                // optional per-row affine (+ ReLU) of the output: the eval-mode BatchNorm (+ ReLU) that follows the
+                // convolution, folded into the epilogue (this thread's row = one output channel)
+                const float sc = ep_scale != nullptr ? __ldg(ep_scale + row0 + lane) : 1.f;
+                const float sh = ep_scale != nullptr ? __ldg(ep_shift + row0 + lane) : 0.f;
                 float ts = 0.f, tq = 0.f;
 #pragma unroll 1
                 for (int c = 0; c < NCH; ++c) {
@@ -262,6 +267,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                         uint32_t r[32];
                         tmem_ld32(ta, r);
                         tmem_ld_wait();
+                        if (ep_scale != nullptr) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                float v = fmaf(__uint_as_float(r[j]), sc, sh);
+                                if (ep_relu) v = fmaxf(v, 0.f);
+                                r[j] = __float_as_uint(v);
+                            }
+                        }
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const float v = __uint_as_float(r[j]);
@@ -275,6 +288,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                         tmem_ld32(ta, r0);
                         tmem_ld32(ta + 32, r1);
                         tmem_ld_wait();
+                        if (ep_scale != nullptr) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                float v0 = fmaf(__uint_as_float(r0[j]), sc, sh), v1 = fmaf(__uint_as_float(r1[j]), sc, sh);
+                                if (ep_relu) v0 = fmaxf(v0, 0.f), v1 = fmaxf(v1, 0.f);
+                                r0[j] = __float_as_uint(v0), r1[j] = __float_as_uint(v1);
+                            }
+                        }
                         uint32_t pk[32];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
@@ -385,7 +406,8 @@ static int gemm_cluster() {  // PM_GEMM_CLUSTER = 1 | 2 | 4 (default 1): CTAs sh
 
 template <typename T, int MT, int NT, int KB>
 static int launch_nn(const void* X, const void* Ah, const void* Al, void* Y, double* stats, int B, int K, int M, int Mpad,
-                     int hw, int m_tile0, int accumulate, cudaStream_t st) {
+                     int hw, int m_tile0, int accumulate, const float* ep_scale, const float* ep_shift, int ep_relu,
+                     cudaStream_t st) {
     using TR = GemmTraits<T>;
     CUtensorMap mX, mAh, mAl, mY;
     constexpr int ASW = KB * (int)sizeof(T) == 128 ? 1 : 3;  // TMA swizzle of the weight boxes: 128-byte or 64-byte rows
@@ -423,7 +445,8 @@ static int launch_nn(const void* X, const void* Ah, const void* Al, void* Y, dou
         auto kern = conv1x1_nn_kernel<T, MT, NT, KB, CL_>;                                                                \
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                       \
         if (e != cudaSuccess) return (int)e;                                                                          \
-        e = cudaLaunchKernelEx(&cfg, kern, mX, mAh, mAl, mY, K, M, m_tile0, tiles_per_img, total, accumulate, stats, dbg); \
+        e = cudaLaunchKernelEx(&cfg, kern, mX, mAh, mAl, mY, K, M, m_tile0, tiles_per_img, total, accumulate, stats,     \
+                               ep_scale, ep_shift, ep_relu, dbg);                                                \
     }
     if (cl == 4) {
         if constexpr (CLMAX >= 4) PM_NN_LAUNCH(4) else return PM_ERR_SHAPE;
@@ -706,9 +729,9 @@ int pm_conv1x1_prep(const float* W, int M, int K, int transpose, int dtype, void
     return 0;
 }
 
-int pm_conv1x1_fwd(const void* X, const void* A_hi, const void* A_lo, void* Y, double* stats, int B, int K, int M, int hw,
-                   int accumulate, int dtype, void* stream) {
-    if (!X || !A_hi || !Y || (dtype == PM_F32 && !A_lo)) return PM_ERR_NULL;
+static int conv1x1_fwd_impl(const void* X, const void* A_hi, const void* A_lo, void* Y, double* stats, int B, int K, int M, int hw,
+                            int accumulate, const float* ep_scale, const float* ep_shift, int ep_relu, int dtype, void* stream) {
+    if (!X || !A_hi || !Y || (dtype == PM_F32 && !A_lo) || ((ep_scale == nullptr) != (ep_shift == nullptr))) return PM_ERR_NULL;
     if (dtype != PM_F32 && dtype != PM_BF16) return PM_ERR_DTYPE;
     const int esz = dtype == PM_F32 ? 4 : 2, uk = dtype == PM_F32 ? 8 : 16;
     if (B <= 0 || hw <= 0 || K <= 0 || M <= 0 || K % uk || M % 32 || M > 512) return PM_ERR_SHAPE;
@@ -725,18 +748,29 @@ int pm_conv1x1_fwd(const void* X, const void* A_hi, const void* A_lo, void* Y, d
         const bool wide = (long long)B * ((hw + 255) / 256) >= 96;
         if (dtype == PM_F32) {
             if (wide && !gemm_narrow())
-                rc = mt == 2 ? launch_nn<float, 2, 256, 16>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, st)
-                             : launch_nn<float, 1, 256, 16>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, st);
+                rc = mt == 2 ? launch_nn<float, 2, 256, 16>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, ep_scale, ep_shift, ep_relu, st)
+                             : launch_nn<float, 1, 256, 16>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, ep_scale, ep_shift, ep_relu, st);
             else
-                rc = mt == 2 ? launch_nn<float, 2, 128, 32>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, st)
-                             : launch_nn<float, 1, 128, 32>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, st);
+                rc = mt == 2 ? launch_nn<float, 2, 128, 32>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, ep_scale, ep_shift, ep_relu, st)
+                             : launch_nn<float, 1, 128, 32>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, ep_scale, ep_shift, ep_relu, st);
         } else {
-            rc = mt == 2 ? launch_nn<__nv_bfloat16, 2, 128, 64>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, st)
-                         : launch_nn<__nv_bfloat16, 1, 128, 64>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, st);
+            rc = mt == 2 ? launch_nn<__nv_bfloat16, 2, 128, 64>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, ep_scale, ep_shift, ep_relu, st)
+                         : launch_nn<__nv_bfloat16, 1, 128, 64>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, ep_scale, ep_shift, ep_relu, st);
         }
         if (rc) return rc;
     }
     return 0;
+}
+
+int pm_conv1x1_fwd(const void* X, const void* A_hi, const void* A_lo, void* Y, double* stats, int B, int K, int M, int hw,
+                   int accumulate, int dtype, void* stream) {
+    return conv1x1_fwd_impl(X, A_hi, A_lo, Y, stats, B, K, M, hw, accumulate, nullptr, nullptr, 0, dtype, stream);
+}
+
+int pm_conv1x1_fwd_affine(const void* X, const void* A_hi, const void* A_lo, void* Y, const float* scale, const float* shift,
+                          int relu, int B, int K, int M, int hw, int dtype, void* stream) {
+    if (!scale || !shift) return PM_ERR_NULL;
+    return conv1x1_fwd_impl(X, A_hi, A_lo, Y, nullptr, B, K, M, hw, 0, scale, shift, relu, dtype, stream);
 }
 
 int pm_conv1x1_wgrad_workspace_floats(int B, int M, int N, int hw, int dtype) {

@@ -432,22 +432,36 @@ def _bn_fast(bn, xc):
             and xc.dtype in (torch.float32, torch.bfloat16) and bn.weight.is_cuda)
 
 
-def weight_bn_act(W, bn, x, residual, relu, name=None):
+def weight_bn_act(W, bn, x, residual, relu, name=None, prepared=None):
     """[relu](BatchNorm2d(conv1x1(x, W)) [+ residual]) for a [M,K,1,1] weight: everything in this package's kernels
     (tcgen05 GEMM with the statistics in its epilogue + one normalise pass) when the shapes allow, else the library
     convolution followed by the fused BatchNorm passes."""
-    y = _weight_bn_act(W, bn, x, residual, relu)
+    y = _weight_bn_act(W, bn, x, residual, relu, prepared)
     if GATE_LOG is not None and relu and name is not None:
         GATE_LOG.setdefault(name, []).append(y.detach() > 0)
     return y
 
 
-def _weight_bn_act(W, bn, x, residual, relu):
+def _inference_block(bn, x, residual):
+    """conv + eval-mode BN (+ ReLU) can run as ONE kernel: no batch statistics, no residual, nothing to differentiate."""
+    return (_bn_fast(bn, x) and not bn.training and bn.running_mean is not None and residual is None
+            and not torch.is_grad_enabled() and bn.running_mean.dtype == torch.float32
+            and bn.running_var.dtype == torch.float32 and not os.environ.get("PINMEM_B200_LIBRARY_CONV"))
+
+
+def _weight_bn_act(W, bn, x, residual, relu, prepared=None):
     if torch.is_autocast_enabled():  # the nn.Conv2d this replaces would run in the autocast dtype
         x = x.to(torch.get_autocast_gpu_dtype())
     M, K = W.shape[0], W.shape[1]
     if _bn_fast(bn, x) and capi.conv1x1_ok(x, M, K) and not os.environ.get("PINMEM_B200_LIBRARY_CONV"):
         x = x.contiguous()
+        if _inference_block(bn, x, residual):
+            # inference read (BASELINE config 5): the eval-mode BatchNorm and the ReLU ride in the GEMM epilogue
+            hi, lo = prepared if prepared is not None else capi.conv1x1_prep(
+                W.detach().reshape(M, K).to(torch.float32).contiguous(), False, x.dtype)
+            scale, shift = capi.bn_eval_affine(bn.weight.detach().float().contiguous(), bn.bias.detach().float().contiguous(),
+                                               bn.running_mean, bn.running_var, bn.eps)
+            return capi.conv1x1_fwd_affine(x, hi, lo, M, scale, shift, relu)
         res_is_x = residual is x or (residual is not None and residual.data_ptr() == x.data_ptr()
                                      and residual.shape == x.shape and residual.dtype == x.dtype)
         if residual is not None and not res_is_x:
@@ -579,6 +593,27 @@ class Memory_sup(nn.Module):
                 t.record_stream(cur)
         return updated_query, score_query, score_memory, readloss, writeloss
 
+    def _inference_weights(self, M, u):
+        """Folded + split weight of the output convolution for the inference read, cached while neither the weight nor
+        the memory changes (same tensor objects, same in-place version counters). Never used while a CUDA graph is being
+        captured: a replay must recompute it from whatever the memory buffer holds then."""
+        W = self.output[0].weight
+        Co, C, K = W.shape[0], self.feature_dim, self.memory_size
+        self._folded_shape = torch.empty(Co, C + capi.PLANES, 0, 0, device="meta")  # shape carrier only (M, K of the GEMM)
+        key = (W, W._version, M, M._version, u.dtype)
+        cached = getattr(self, "_infer_cache", None)
+        capturing = torch.cuda.is_current_stream_capturing()
+        if (not capturing and cached is not None and cached[0][0] is W and cached[0][2] is M and cached[0][1] == key[1]
+                and cached[0][3] == key[3] and cached[0][4] == key[4]):
+            return cached[1]
+        W32 = W.detach().to(torch.float32).contiguous()
+        Wp = torch.empty(Co, C + capi.PLANES, dtype=torch.float32, device=W.device)
+        capi.fold_weight_fwd(W32, M.detach().to(torch.float32).contiguous(), Wp, Co, C, K)
+        prepared = capi.conv1x1_prep(Wp, False, u.dtype)
+        if not capturing:
+            self._infer_cache = (key, prepared)
+        return prepared
+
     def _memory_for_kernels(self, device):
         M = self.m_items
         if not M.is_cuda:
@@ -621,8 +656,11 @@ class Memory_sup(nn.Module):
         if planes:
             # conv(W, [q ; p.M]) = W1.q + (W2.M^T).p : the memory is folded into the weight (a [C_out, 32] block) and
             # the convolution runs on [q ; score planes] -- C+32 input channels instead of 2C
-            Wp = _FoldWeightFn.apply(self.output[0].weight, M)                                   # [C_out, C+32, 1, 1]
-            updated_query = weight_bn_act(Wp, self.output[1], u, None, True, "output")
+            prepared = (self._inference_weights(M, u)
+                        if (_inference_block(self.output[1], u, None)
+                            and capi.conv1x1_ok(u, self.output[0].weight.shape[0], C + capi.PLANES)) else None)
+            Wp = self._folded_shape if prepared is not None else _FoldWeightFn.apply(self.output[0].weight, M)
+            updated_query = weight_bn_act(Wp, self.output[1], u, None, True, "output", prepared)  # Wp [C_out, C+32, 1, 1]
         elif plain:
             updated_query = conv_bn_act(self.output[0], self.output[1], u, None, True, "output")
         else:

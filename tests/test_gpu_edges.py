@@ -513,3 +513,47 @@ def test_uint8_labels_and_bad_label_count():
     c.debug_labels = True
     with pytest.raises(RuntimeError, match="label values outside"):
         c(x, bad, True, True)
+
+
+def test_inference_read_fused_bn_epilogue_and_weight_cache():
+    """eval() + no_grad (BASELINE config 5, deepv2.py:263-268): conv + eval-mode BatchNorm + ReLU run as one GEMM kernel on
+    a cached folded weight. Same numbers as the differentiable eval path and as the oracle; the cache follows in-place
+    updates of the weight and rebinding / in-place updates of m_items."""
+    from pinthememory_b200 import capi
+
+    mem = _module(C=64).eval()
+    mem.fold_min_pixels = 0
+    with torch.no_grad():
+        for bn in (mem.output[1], mem.writenet.writefeat[1]):
+            bn.running_mean.normal_(0, 0.1)
+            bn.running_var.uniform_(0.5, 1.5)
+            bn.weight.uniform_(0.5, 1.5)
+    ora = _oracle_like(mem).eval()
+    x = torch.randn(2, 64, 16, 16, device="cuda")
+
+    def check(tag):
+        capi.reset_counters()
+        with torch.no_grad():
+            a = mem(x, None, False)[0]
+        n_inf = capi.LAUNCHES
+        xg = x.clone().requires_grad_(True)
+        b = mem(xg, None, False)[0]           # grad-enabled eval path: separate BatchNorm pass
+        ora.load_state_dict(mem.state_dict())
+        ora.m_items = mem.m_items.detach().clone()
+        with torch.no_grad():
+            c = ora(x, None, False)[0]
+        assert_close(a, b.detach(), 1e-6, tag + ": fused epilogue vs separate pass")
+        assert_close(a, c, 2e-5, tag + ": vs oracle")
+        return n_inf
+
+    n1 = check("first")
+    n2 = check("cached")
+    assert n2 < n1, "the second inference call must reuse the folded weight (fewer launches)"
+    with torch.no_grad():
+        mem.output[0].weight.mul_(1.5)        # in-place: version counter moves
+    check("after weight update")
+    mem.m_items = torch.nn.functional.normalize(torch.rand(19, 64, device="cuda"), dim=1)   # rebinding
+    check("after memory rebinding")
+    with torch.no_grad():
+        mem.m_items.mul_(-1.0)                # in-place
+    check("after in-place memory update")
