@@ -229,6 +229,12 @@ int pm_bn_apply(const void* x, const float* mean, const float* invstd, const flo
 int pm_bn_bwd_reduce(const void* dy, const void* y, const uint32_t* relu_mask, const void* x, const float* mean,
                      const float* invstd, int relu, float* dgamma, float* dbeta, int B, int C, int hw, int dtype,
                      void* stream);
+/* pm_bn_bwd_reduce with every channel split over 4 CTAs (256 channels alone are 1.7 waves of long serial loops on 148
+ * SMs); scratch: pm_bn_bwd_scratch_bytes(C) bytes, ZEROED by the caller; partials are added in split order (deterministic). */
+int pm_bn_bwd_scratch_bytes(int C);
+int pm_bn_bwd_reduce_split(const void* dy, const void* y, const uint32_t* relu_mask, const void* x, const float* mean,
+                           const float* invstd, int relu, float* dgamma, float* dbeta, int B, int C, int hw, int dtype,
+                           void* scratch, void* stream);
 int pm_bn_bwd_apply(const void* dy, const void* y, const uint32_t* relu_mask, const void* x, const float* mean,
                     const float* invstd, const float* gamma, const float* dgamma, const float* dbeta, int relu,
                     int training, void* dx, void* dres, int B, int C, int hw, int dtype, void* stream);

@@ -161,15 +161,20 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const T* __re
                                                                    const T* __restrict__ x, const float* __restrict__ mean,
                                                                    const float* __restrict__ invstd, int relu,
                                                                    float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                                   int B, int C, int hw) {
+                                                                   int B, int C, int hw, double* __restrict__ scratch) {
+    // grid (C, S): a channel's B*hw elements are split over S CTAs (256 channels alone are 1.7 waves of long serial loops
+    // on 148 SMs); partial sums meet in `scratch` ([S][C][2] doubles + C arrival counters, zeroed by the caller) and the
+    // last CTA of a channel adds them in split order -- deterministic. S = 1 (scratch NULL) is the single-CTA form.
     __shared__ double red[BN_THREADS / 32];
-    const int c = blockIdx.x;
+    __shared__ int last_sm;
+    const int c = blockIdx.x, S = gridDim.y, sp = blockIdx.y;
     const float m = mean[c], is = invstd[c];
     float sg = 0.f, sgx = 0.f;
     if (VEC) {
         const int nv = hw / 4, total = B * nv, wpr = (nv + 7) / 8;
+        const int per = (total + S - 1) / S, i0 = sp * per, i1 = min(total, i0 + per);
 #pragma unroll 4
-        for (int i = threadIdx.x; i < total; i += BN_THREADS) {
+        for (int i = i0 + threadIdx.x; i < i1; i += BN_THREADS) {
             const int b = i / nv, j = i - b * nv;
             const size_t off = ((size_t)b * C + c) * hw + 4 * j;
             Vec4<T> g, yy, xx;
@@ -194,7 +199,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const T* __re
         }
     } else {
         const int total = B * hw;
-        for (int i = threadIdx.x; i < total; i += BN_THREADS) {
+        const int per = (total + S - 1) / S, i0 = sp * per, i1 = min(total, i0 + per);
+        for (int i = i0 + threadIdx.x; i < i1; i += BN_THREADS) {
             const int b = i / hw, j = i - b * hw;
             const size_t off = ((size_t)b * C + c) * hw + j;
             const float gv = (!relu || ldf(y + off) > 0.f) ? ldf(dy + off) : 0.f;
@@ -204,9 +210,29 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const T* __re
     }
     const double SG = block_sum_double((double)sg, red);
     const double SGX = block_sum_double((double)sgx, red);
+    if (S == 1) {
+        if (threadIdx.x == 0) {
+            dbeta[c] = (float)SG;
+            dgamma[c] = (float)SGX;
+        }
+        return;
+    }
     if (threadIdx.x == 0) {
-        dbeta[c] = (float)SG;
-        dgamma[c] = (float)SGX;
+        scratch[((size_t)sp * C + c) * 2] = SG;
+        scratch[((size_t)sp * C + c) * 2 + 1] = SGX;
+        __threadfence();
+        unsigned* counters = reinterpret_cast<unsigned*>(scratch + (size_t)S * C * 2);
+        last_sm = atomicAdd(counters + c, 1u) == (unsigned)S - 1;
+        if (last_sm) {
+            __threadfence();
+            double a = 0.0, b2 = 0.0;
+            for (int q = 0; q < S; ++q) {
+                a += __ldcg(scratch + ((size_t)q * C + c) * 2);
+                b2 += __ldcg(scratch + ((size_t)q * C + c) * 2 + 1);
+            }
+            dbeta[c] = (float)a;
+            dgamma[c] = (float)b2;
+        }
     }
 }
 
@@ -365,21 +391,42 @@ extern "C" int pm_bn_apply(const void* x, const float* mean, const float* invstd
     return 0;
 }
 
+#define PM_BN_SPLITS 4
+extern "C" int pm_bn_bwd_scratch_bytes(int C) { return C > 0 ? PM_BN_SPLITS * C * 2 * 8 + C * 4 : 0; }
+
+static int bn_bwd_reduce_impl(const void* dy, const void* y, const uint32_t* relu_mask, const void* x, const float* mean,
+                              const float* invstd, int relu, float* dgamma, float* dbeta, int B, int C, int hw, int dtype,
+                              double* scratch, void* stream);
+
 extern "C" int pm_bn_bwd_reduce(const void* dy, const void* y, const uint32_t* relu_mask, const void* x, const float* mean,
                                 const float* invstd, int relu, float* dgamma, float* dbeta, int B, int C, int hw, int dtype,
                                 void* stream) {
+    return bn_bwd_reduce_impl(dy, y, relu_mask, x, mean, invstd, relu, dgamma, dbeta, B, C, hw, dtype, nullptr, stream);
+}
+/* the same with each channel split over PM_BN_SPLITS CTAs; scratch: pm_bn_bwd_scratch_bytes(C) bytes, ZEROED, 8-byte aligned */
+extern "C" int pm_bn_bwd_reduce_split(const void* dy, const void* y, const uint32_t* relu_mask, const void* x,
+                                      const float* mean, const float* invstd, int relu, float* dgamma, float* dbeta, int B,
+                                      int C, int hw, int dtype, void* scratch, void* stream) {
+    if (!scratch || ((uintptr_t)scratch & 7)) return PM_ERR_NULL;
+    return bn_bwd_reduce_impl(dy, y, relu_mask, x, mean, invstd, relu, dgamma, dbeta, B, C, hw, dtype, (double*)scratch, stream);
+}
+
+static int bn_bwd_reduce_impl(const void* dy, const void* y, const uint32_t* relu_mask, const void* x, const float* mean,
+                              const float* invstd, int relu, float* dgamma, float* dbeta, int B, int C, int hw, int dtype,
+                              double* scratch, void* stream) {
     if (!dy || !x || !mean || !invstd || !dgamma || !dbeta || (relu && !y && !relu_mask)) return PM_ERR_NULL;
     if (int e = bn_check(B, C, hw, dtype)) return e;
     const bool vec = pm::vec_ok(hw, dy, y, x, nullptr, nullptr, dtype);
     if (relu && !y && !vec) return PM_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid(C, scratch != nullptr ? PM_BN_SPLITS : 1);
     if (dtype == PM_F32) {
-        if (vec) pm::bn_bwd_reduce_kernel<float, true><<<C, pm::BN_THREADS, 0, st>>>((const float*)dy, (const float*)y, relu_mask, (const float*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw);
-        else pm::bn_bwd_reduce_kernel<float, false><<<C, pm::BN_THREADS, 0, st>>>((const float*)dy, (const float*)y, relu_mask, (const float*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw);
+        if (vec) pm::bn_bwd_reduce_kernel<float, true><<<grid, pm::BN_THREADS, 0, st>>>((const float*)dy, (const float*)y, relu_mask, (const float*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw, scratch);
+        else pm::bn_bwd_reduce_kernel<float, false><<<grid, pm::BN_THREADS, 0, st>>>((const float*)dy, (const float*)y, relu_mask, (const float*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw, scratch);
     } else {
         typedef __nv_bfloat16 bf;
-        if (vec) pm::bn_bwd_reduce_kernel<bf, true><<<C, pm::BN_THREADS, 0, st>>>((const bf*)dy, (const bf*)y, relu_mask, (const bf*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw);
-        else pm::bn_bwd_reduce_kernel<bf, false><<<C, pm::BN_THREADS, 0, st>>>((const bf*)dy, (const bf*)y, relu_mask, (const bf*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw);
+        if (vec) pm::bn_bwd_reduce_kernel<bf, true><<<grid, pm::BN_THREADS, 0, st>>>((const bf*)dy, (const bf*)y, relu_mask, (const bf*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw, scratch);
+        else pm::bn_bwd_reduce_kernel<bf, false><<<grid, pm::BN_THREADS, 0, st>>>((const bf*)dy, (const bf*)y, relu_mask, (const bf*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw, scratch);
     }
     PM_CHECK_LAUNCH();
     return 0;
