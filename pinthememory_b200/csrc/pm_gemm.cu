@@ -74,6 +74,61 @@ __device__ __forceinline__ void split_tile_trunc(const float4* __restrict__ raw,
         lo[i] = l;
     }
 }
+// ---- "mixed" error compensation (fp32 I/O, default): D = tf32(A).tf32(X)  +  [bf16(A_lo) | bf16(A_hi)] . [bf16(X) ; bf16(X_lo)]
+// The two correction products are 2^-11 of the main one, so 8 mantissa bits are plenty for THEIR operands: they run as
+// one bf16 MMA pass over a K-concatenated operand pair (kind::f16 retires K = 16 per instruction, twice the TF32 rate),
+// i.e. 2 tensor passes instead of 3 for the same ~2e-6 result. x_hi is what the tensor core keeps of the raw fp32
+// container (truncation), x_lo = x - x_hi; the weights are split once per call (round-to-nearest hi).
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    const __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&p);
+}
+__device__ __forceinline__ float tf32_resid(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// MN-major activation tile (form 1). raw: fp32 [KB rows][NT pixels] as 32-pixel chunks of [KB][128 B] with 32-byte
+// atoms swizzled by (row & 3) (SWIZZLE_128B_ATOM_32B). out: bf16 [2*KB rows][NT pixels] as 64-pixel chunks of
+// [2*KB][128 B] with 16-byte chunks swizzled by (row & 7) (SWIZZLE_128B); per group of 16 channels rows
+// [32g, 32g+16) = bf16(x) and [32g+16, 32g+32) = bf16(x_lo) -- the K order of the prepared weight operand.
+template <int KB, int NT>
+__device__ __forceinline__ void mix_tile_mn(const unsigned char* __restrict__ raw, unsigned char* __restrict__ out, int t,
+                                            int nthreads) {
+    constexpr int NC32 = NT / 32, ATOMS = KB * NC32 * 4;
+    for (int i = t; i < ATOMS; i += nthreads) {
+        const int a = i & 3, k = (i >> 2) % KB, c = (i >> 2) / KB;
+        const float4* src = reinterpret_cast<const float4*>(raw + c * (KB * 128) + k * 128 + ((a ^ (k & 3)) << 5));
+        const float4 v0 = src[0], v1 = src[1];
+        uint4 hi, lo;
+        hi.x = pack_bf16(v0.x, v0.y), hi.y = pack_bf16(v0.z, v0.w), hi.z = pack_bf16(v1.x, v1.y), hi.w = pack_bf16(v1.z, v1.w);
+        lo.x = pack_bf16(tf32_resid(v0.x), tf32_resid(v0.y)), lo.y = pack_bf16(tf32_resid(v0.z), tf32_resid(v0.w));
+        lo.z = pack_bf16(tf32_resid(v1.x), tf32_resid(v1.y)), lo.w = pack_bf16(tf32_resid(v1.z), tf32_resid(v1.w));
+        const int j = ((c & 1) << 2) | a;                 // 16-byte chunk of the 64-pixel row
+        const int r0 = ((k >> 4) << 5) | (k & 15), r1 = r0 + 16;
+        unsigned char* base = out + (c >> 1) * (2 * KB * 128);
+        *reinterpret_cast<uint4*>(base + r0 * 128 + ((j ^ (r0 & 7)) << 4)) = hi;
+        *reinterpret_cast<uint4*>(base + r1 * 128 + ((j ^ (r1 & 7)) << 4)) = lo;
+    }
+}
+// K-major tile (form 2: K = pixels). raw: fp32 [rows][32 pixels] (128-byte rows, 16-byte chunks swizzled by row & 7);
+// out: bf16 [rows][64] (128-byte rows, same swizzle). hi_first = false: [bf16(x_lo) | bf16(x)] (the A operand);
+// hi_first = true: [bf16(x) | bf16(x_lo)] (the B operand) -- so that the concatenated K pairs lo.x with x.lo.
+__device__ __forceinline__ void mix_tile_k(const unsigned char* __restrict__ raw, unsigned char* __restrict__ out, int rows,
+                                           bool hi_first, int t, int nthreads) {
+    for (int i = t; i < rows * 4; i += nthreads) {
+        const int m = i & 3, r = i >> 2;  // pixels 8m .. 8m+7 of row r = fp32 chunks 2m, 2m+1
+        const unsigned char* rr = raw + r * 128;
+        const float4 v0 = *reinterpret_cast<const float4*>(rr + (((2 * m) ^ (r & 7)) << 4));
+        const float4 v1 = *reinterpret_cast<const float4*>(rr + (((2 * m + 1) ^ (r & 7)) << 4));
+        uint4 hi, lo;
+        hi.x = pack_bf16(v0.x, v0.y), hi.y = pack_bf16(v0.z, v0.w), hi.z = pack_bf16(v1.x, v1.y), hi.w = pack_bf16(v1.z, v1.w);
+        lo.x = pack_bf16(tf32_resid(v0.x), tf32_resid(v0.y)), lo.y = pack_bf16(tf32_resid(v0.z), tf32_resid(v0.w));
+        lo.z = pack_bf16(tf32_resid(v1.x), tf32_resid(v1.y)), lo.w = pack_bf16(tf32_resid(v1.z), tf32_resid(v1.w));
+        unsigned char* ro = out + r * 128;
+        const int jh = hi_first ? m : 4 + m, jl = hi_first ? 4 + m : m;
+        *reinterpret_cast<uint4*>(ro + ((jh ^ (r & 7)) << 4)) = hi;
+        *reinterpret_cast<uint4*>(ro + ((jl ^ (r & 7)) << 4)) = lo;
+    }
+}
+
 __device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x00001000u) & 0xffffe000u); }
 __device__ __forceinline__ void split_tile(float4* __restrict__ raw, float4* __restrict__ lo, int n4, int t, int nthreads) {
     for (int i = t; i < n4; i += nthreads) {
@@ -98,7 +153,7 @@ __device__ __forceinline__ void split_tile(float4* __restrict__ raw, float4* __r
 //   so at CL = 1 the L2 -> SM traffic is ~4x the activation bytes and bounds the kernel); ring slots are released
 //   cluster-wide (tcgen05.commit multicast onto every CTA's `empty` barrier).
 // =================================================================================================================
-template <typename T, int MT, int NT, int KB, int CL>
+template <typename T, int MT, int NT, int KB, int CL, bool MIX>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     conv1x1_nn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapAh,
                       const __grid_constant__ CUtensorMap mapAl, const __grid_constant__ CUtensorMap mapY, int K, int M,
@@ -122,6 +177,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     static_assert(STAGES >= 2, "ring too small");
     static_assert(MT * NT <= 512, "accumulators exceed TMEM");
     constexpr uint32_t IDESC = umma_idesc(TR::FMT, false, true, 128, NT);
+    constexpr uint32_t IDESC_B = umma_idesc(UMMA_FMT_BF16, false, true, 128, NT);  // the bf16 correction pass (MIX)
+    static_assert(!MIX || (TR::SPLIT && KB % 16 == 0 && NT % 64 == 0), "mixed compensation: fp32 I/O, 16-channel groups");
 
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_align(smem_raw, 1024);
@@ -182,9 +239,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                     for (int j = 0; j < NOPA * MT; ++j) {  // weight blocks: [hi of every row tile | lo of every row tile]
                         const int mt = j % MT;
                         const CUtensorMap* mp = j < MT ? &mapAh : &mapAl;
-                        if (CL == 1) tma_load_2d(sa + j * TILE_A, mp, kb * KB, (m_tile0 + mt) * 128, &full[s]);
+                        const int col = (MIX && j >= MT) ? 2 * kb * KB : kb * KB;  // the bf16 operand is 2K columns wide
+                        if (CL == 1) tma_load_2d(sa + j * TILE_A, mp, col, (m_tile0 + mt) * 128, &full[s]);
                         else if (j % CL == crank)
-                            tma_load_2d_multicast(sa + j * TILE_A, mp, kb * KB, (m_tile0 + mt) * 128, &full[s],
+                            tma_load_2d_multicast(sa + j * TILE_A, mp, col, (m_tile0 + mt) * 128, &full[s],
                                                   (uint16_t)((1u << CL) - 1));
                     }
                 }
@@ -220,13 +278,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                         for (int mt = 0; mt < MT; ++mt) {
                             const uint32_t d = tmem + (uint32_t)((a * MT + mt) * NT);
                             const uint64_t ah = umma_desc(sa + mt * TILE_A + ks * 32, 16, ASBO, ASWZ);
-                            if (TR::SPLIT) {
+                            if (MIX) {
+                                umma_issue<T>(d, ah, bh, IDESC, first);
+                            } else if (TR::SPLIT) {
                                 const uint64_t al = umma_desc(sa + (MT + mt) * TILE_A + ks * 32, 16, ASBO, ASWZ);
                                 umma_issue<T>(d, al, bh, IDESC, first);
                                 umma_issue<T>(d, ah, bl, IDESC, 1u);
                                 umma_issue<T>(d, ah, bh, IDESC, 1u);
                             } else {
                                 umma_issue<T>(d, ah, bh, IDESC, first);
+                            }
+                        }
+                    }
+                    if (MIX) {
+                        // correction pass: [bf16(A_lo) | bf16(A_hi)] (K-major, 2*KB wide) . [bf16(X) ; bf16(X_lo)] (MN-major,
+                        // 64-pixel chunks of [2*KB rows][128 B]), K = 16 per instruction
+                        const int ksb = 2 * ksteps * UK / 16;
+                        for (int ks = 0; ks < ksb; ++ks) {
+                            const uint64_t bb = umma_desc(sx + XBYTES + ks * (16 * 128), 2 * KB * 128, 1024, UMMA_SW128);
+#pragma unroll
+                            for (int mt = 0; mt < MT; ++mt) {
+                                const uint32_t d = tmem + (uint32_t)((a * MT + mt) * NT);
+                                const uint64_t ab = umma_desc(sa + (MT + mt) * TILE_A + ks * 32, 16, ASBO, ASWZ);
+                                umma_bf16(d, ab, bb, IDESC_B, 1u);
                             }
                         }
                     }
@@ -351,7 +425,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                     const int s = it % STAGES;
                     mbar_wait(&full[s], (it / STAGES) & 1);
                     unsigned char* st = smem + s * STAGE;
-                    split_tile_trunc(reinterpret_cast<float4*>(st), reinterpret_cast<float4*>(st + XBYTES), XBYTES / 16, t, 128);
+                    if (MIX) mix_tile_mn<KB, NT>(st, st + XBYTES, t, 128);
+                    else split_tile_trunc(reinterpret_cast<float4*>(st), reinterpret_cast<float4*>(st + XBYTES), XBYTES / 16, t, 128);
                     fence_proxy_async_smem();
                     mbar_arrive(&xfull[s]);
                 }
@@ -385,6 +460,15 @@ static int gemm_dbg() {  // PM_GEMM_DBG: bring-up switches (bit 0 swaps LBO/SBO 
     return v;
 }
 
+static int gemm_mix() {  // PM_GEMM_3XTF32=1: three TF32 passes instead of TF32 + one bf16 correction pass (A/B switch)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PM_GEMM_3XTF32");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v;
+}
+
 static int gemm_narrow() {  // PM_GEMM_NARROW=1: keep the 128-pixel fp32 tiles (A/B switch for the profiles)
     static int v = -1;
     if (v < 0) {
@@ -413,7 +497,10 @@ static int launch_nn(const void* X, const void* Ah, const void* Al, void* Y, dou
     constexpr int ASW = KB * (int)sizeof(T) == 128 ? 1 : 3;  // TMA swizzle of the weight boxes: 128-byte or 64-byte rows
     if (!make_map_2d<T>(&mX, X, (size_t)B * K, hw, KB, TR::PXC, sizeof(T) == 4 ? 2 : 1)) return PM_ERR_ALIGN;
     if (!make_map_2d<T>(&mAh, Ah, Mpad, K, 128, KB, ASW)) return PM_ERR_ALIGN;
-    if (TR::SPLIT) {
+    const bool mix = TR::SPLIT && gemm_mix() && K % 16 == 0;
+    if (mix) {
+        if (!make_map_2d<__nv_bfloat16>(&mAl, Al, Mpad, 2 * (size_t)K, 128, 2 * KB, ASW)) return PM_ERR_ALIGN;
+    } else if (TR::SPLIT) {
         if (!make_map_2d<T>(&mAl, Al, Mpad, K, 128, KB, ASW)) return PM_ERR_ALIGN;
     } else {
         mAl = mAh;
@@ -442,7 +529,7 @@ static int launch_nn(const void* X, const void* Ah, const void* Al, void* Y, dou
     cudaError_t e;
 #define PM_NN_LAUNCH(CL_)                                                                                             \
     {                                                                                                                 \
-        auto kern = conv1x1_nn_kernel<T, MT, NT, KB, CL_>;                                                                \
+        auto kern = mix ? conv1x1_nn_kernel<T, MT, NT, KB, CL_, TR::SPLIT> : conv1x1_nn_kernel<T, MT, NT, KB, CL_, false>; \
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                       \
         if (e != cudaSuccess) return (int)e;                                                                          \
         e = cudaLaunchKernelEx(&cfg, kern, mX, mAh, mAl, mY, K, M, m_tile0, tiles_per_img, total, accumulate, stats,     \
@@ -471,7 +558,7 @@ static int launch_nn(const void* X, const void* Ah, const void* Al, void* Y, dou
 // =================================================================================================================
 constexpr int WG_NMAX = 288;
 
-template <typename T>
+template <typename T, bool MIX>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     conv1x1_wgrad_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapX, int M, int N,
                          int Ntot, int n0, int NW, int hw, int chunks_per_img, int blocks_per_chunk, float* __restrict__ part,
@@ -552,7 +639,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                     for (int j = 0; j < NI; ++j) {
                         const uint32_t d = tmem + (uint32_t)(j * NW);
                         const uint64_t bh = umma_desc(sb + j * NW * 128 + ks * 32, 16, 1024);
-                        if (TR::SPLIT) {
+                        if (MIX) {
+                            // main TF32 pass + the bf16 correction over the concatenated K ([lo | x] . [x ; lo]): each
+                            // K step covers 16 bf16 = 32 bytes of the 128-byte rows, like a TF32 step
+                            const uint64_t bb = umma_desc(sb + BBYTES + j * NW * 128 + ks * 32, 16, 1024);
+                            umma_issue<T>(d, ah, bh, IDESC, first);
+                            umma_bf16(d, al, bb, umma_idesc(UMMA_FMT_BF16, false, false, 128, NW), 1u);
+                        } else if (TR::SPLIT) {
                             const uint64_t bl = umma_desc(sb + BBYTES + j * NW * 128 + ks * 32, 16, 1024);
                             umma_issue<T>(d, al, bh, IDESC, first);
                             umma_issue<T>(d, ah, bl, IDESC, 1u);
@@ -591,9 +684,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 const int s = kb % STAGES;
                 mbar_wait(&full[s], (kb / STAGES) & 1);
                 unsigned char* st = smem + s * STAGE;
-                split_tile_trunc(reinterpret_cast<float4*>(st), reinterpret_cast<float4*>(st + TILE_A_BYTES), TILE_A_BYTES / 16, t, 128);
-                split_tile_trunc(reinterpret_cast<float4*>(st + 2 * TILE_A_BYTES), reinterpret_cast<float4*>(st + 2 * TILE_A_BYTES + BBYTES),
-                                    N * 8, t, 128);
+                if (MIX) {
+                    mix_tile_k(st, st + TILE_A_BYTES, 128, false, t, 128);
+                    mix_tile_k(st + 2 * TILE_A_BYTES, st + 2 * TILE_A_BYTES + BBYTES, N, true, t, 128);
+                } else {
+                    split_tile_trunc(reinterpret_cast<float4*>(st), reinterpret_cast<float4*>(st + TILE_A_BYTES), TILE_A_BYTES / 16, t, 128);
+                    split_tile_trunc(reinterpret_cast<float4*>(st + 2 * TILE_A_BYTES), reinterpret_cast<float4*>(st + 2 * TILE_A_BYTES + BBYTES),
+                                     N * 8, t, 128);
+                }
                 fence_proxy_async_smem();
                 mbar_arrive(&xfull[s]);
             }
@@ -679,7 +777,10 @@ static int launch_wgrad(const void* dY, const void* X, float* part, float* dW, i
     if (!make_map_2d<T>(&mX, X, (size_t)B * Ntot, hw, NW, TR::PXC, true)) return PM_ERR_ALIGN;
     const size_t smem = wgrad_smem_bytes<T>();
     dim3 grid(B * cpi, Mpad / 128);
-    auto kern = conv1x1_wgrad_kernel<T>;
+    // measured at cfg 2: the mixed pass does not pay here (77 vs 74.5 us) -- this kernel is bound by shared-memory traffic
+    // and by the operand ingest of a 128 x 288 tile, and the bf16 conversion costs the split warps more than the MMAs save
+    static const bool wg_mix = getenv("PM_GEMM_WGRAD_MIX") != nullptr;
+    auto kern = (TR::SPLIT && wg_mix) ? conv1x1_wgrad_kernel<T, TR::SPLIT> : conv1x1_wgrad_kernel<T, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<grid, GEMM_THREADS, smem, st>>>(mG, mX, M, N, Ntot, n0, NW, hw, cpi, bpc, part, Mpad);
@@ -693,9 +794,11 @@ static int launch_wgrad(const void* dY, const void* X, float* part, float* dW, i
 
 // A[m][k] = W[m][k] (transpose = 0, W is [M][K]) or W[k][m] (transpose = 1, W is [K][M]); rows M..Mpad-1 are zero.
 // fp32: hi = W rounded to nearest TF32, lo = W - hi (both fp32 [Mpad][K]); bf16: hi = bf16(W).
+// fp32, mixed compensation (mix != 0): `lo` is instead the bf16 operand of the correction pass, [Mpad][2K]: per group g of 16
+// channels, columns [32g, 32g+16) = bf16(W - hi) and [32g+16, 32g+32) = bf16(hi) (same bytes as an fp32 [Mpad][K]).
 template <typename T>
 __global__ void conv1x1_prep_kernel(const float* __restrict__ W, int M, int K, int Mpad, int transpose, T* __restrict__ hi,
-                                    T* __restrict__ lo) {
+                                    T* __restrict__ lo, int mix) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Mpad * K) return;
     const int m = i / K, k = i - m * K;
@@ -703,7 +806,13 @@ __global__ void conv1x1_prep_kernel(const float* __restrict__ W, int M, int K, i
     if constexpr (sizeof(T) == 4) {
         const float h = tf32_rn(v);
         hi[i] = h;
-        lo[i] = v - h;
+        if (mix) {
+            __nv_bfloat16* lb = reinterpret_cast<__nv_bfloat16*>(lo) + (size_t)m * 2 * K + ((k >> 4) << 5) + (k & 15);
+            lb[0] = __float2bfloat16_rn(v - h);
+            lb[16] = __float2bfloat16_rn(h);
+        } else {
+            lo[i] = v - h;
+        }
     } else {
         hi[i] = __float2bfloat16_rn(v);
     }
@@ -722,9 +831,10 @@ int pm_conv1x1_prep(const float* W, int M, int K, int transpose, int dtype, void
     const int Mpad = (M + 127) / 128 * 128, n = Mpad * K;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == PM_F32)
-        conv1x1_prep_kernel<float><<<(n + 255) / 256, 256, 0, st>>>(W, M, K, Mpad, transpose, (float*)A_hi, (float*)A_lo);
+        conv1x1_prep_kernel<float><<<(n + 255) / 256, 256, 0, st>>>(W, M, K, Mpad, transpose, (float*)A_hi, (float*)A_lo,
+                                                                    (gemm_mix() && K % 16 == 0) ? 1 : 0);
     else
-        conv1x1_prep_kernel<__nv_bfloat16><<<(n + 255) / 256, 256, 0, st>>>(W, M, K, Mpad, transpose, (__nv_bfloat16*)A_hi, nullptr);
+        conv1x1_prep_kernel<__nv_bfloat16><<<(n + 255) / 256, 256, 0, st>>>(W, M, K, Mpad, transpose, (__nv_bfloat16*)A_hi, nullptr, 0);
     PM_CHECK_LAUNCH();
     return 0;
 }
