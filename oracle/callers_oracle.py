@@ -46,3 +46,19 @@ def upsampled_cross_entropy(logits, labels):
     """mynn.py:57-62 + loss.py:175-180: mean over non-ignored label pixels (NaN when there is none)."""
     up = F.interpolate(logits, size=labels.shape[-2:], mode="bilinear", align_corners=True)
     return F.nll_loss(F.log_softmax(up, dim=1), labels, reduction="mean", ignore_index=IGNORE_LABEL)
+
+
+def class_mean_vectors(features, labels, num_class):
+    """tsnelib.py:48-74 (``input2basket``): normalise, bilinear up-sample (align_corners=True) to the label size, per-class
+    sum over the hard one-hot labels (255 -> extra class), divide by the pixel count. Returns (means [K,C], counts [K]);
+    rows of empty classes are zero (the reference skips them)."""
+    b, c, h, w = features.shape
+    H, W = labels.shape[-2:]
+    f = F.interpolate(F.normalize(features, dim=1), [H, W], mode="bilinear", align_corners=True).view(b, c, -1)
+    gt = labels.clone()
+    gt[gt == IGNORE_LABEL] = num_class
+    onehot = F.one_hot(gt, num_classes=num_class + 1).view(b, -1, num_class + 1).to(features.dtype)
+    counts = onehot.sum(1).sum(0)[:num_class]
+    sums = torch.matmul(f, onehot).sum(0).t()[:num_class]
+    safe = torch.where(counts == 0, torch.ones_like(counts), counts)
+    return sums / safe.unsqueeze(1), counts

@@ -86,6 +86,25 @@ def reference_main_loss(logits, labels):
     return loss.detach(), logits.grad
 
 
+def reference_input2basket(features, labels, K):
+    """tsnelib.py:48-74 executed from the reference source on a stand-in ``self``; returns (vectors, class ids)."""
+    import textwrap
+
+    body = textwrap.dedent(_extract(os.path.join(REF, "tsnelib.py"), ["input2basket"])["input2basket"])
+    ns = {"torch": torch, "F": F}
+    exec(compile(body, "reference:tsnelib.py:input2basket", "exec"), ns)
+    fake = types.SimpleNamespace(num_class=K, selected_clsid=list(range(K)), name2domId={"d": 0},
+                                 feat_vecs=torch.tensor([]), feat_vec_labels=torch.tensor([]),
+                                 feat_vec_domlabels=torch.tensor([]))
+    t_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        ns["input2basket"](fake, features, labels, "d")
+    finally:
+        torch.Tensor.cuda = t_cuda
+    return fake.feat_vecs, fake.feat_vec_labels.reshape(-1).long()
+
+
 def main():
     if not os.path.isdir(REF):
         sys.exit("reference tree not present")
@@ -118,7 +137,16 @@ def main():
         cases[name + ".loss"], cases[name + ".grad"] = loss.numpy(), grad.numpy()
     cases["meta"] = np.array(repr({"K": K, "cases": ["os4", "ragged"], "torch": torch.__version__}))
     np.savez_compressed(os.path.join(OUT, "main_loss.npz"), **cases)
-    print("wrote init_prototypes.npz, main_loss.npz")
+    # row 3: t-SNE class-mean vectors (one class absent, an ignore band, non-integer up-sampling ratio)
+    # (the reference function only works for batch size 1: it flattens the labels of the whole batch into one image,
+    # tsnelib.py:57, and is called from the batch-1 evaluation loop)
+    feat = synth.make_features(1, C, 12, 16, seed=81)
+    lab = synth.make_labels(1, 45, 61, K, "blocky", seed=82, block=8)
+    lab[lab == 5] = 255
+    vecs, ids = reference_input2basket(feat, lab, K)
+    np.savez_compressed(os.path.join(OUT, "tsne_basket.npz"), features=feat.numpy(), labels=lab.numpy(), vectors=vecs.numpy(),
+                        class_ids=ids.numpy(), meta=np.array(repr({"K": K, "C": C, "torch": torch.__version__})))
+    print("wrote init_prototypes.npz, main_loss.npz, tsne_basket.npz")
 
 
 if __name__ == "__main__":

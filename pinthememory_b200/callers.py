@@ -1,4 +1,4 @@
-"""The two callers either side of the memory path, on the same kernels.
+"""The callers either side of the memory path, on the same kernels.
 
 * ``PrototypePool`` / ``initialize_memory`` -- the reference's ``Trainer.memory_initalize``
   (train.py:1000-1042): class prototypes pooled over the training set. One ``pm_write_reduce_fwd`` launch
@@ -8,6 +8,12 @@
   (network/deepv3plus.py:575-578, mynn.py:57-62, loss.py:167-180) through ``pm_readloss_fwd``: the
   ``[B,K,Hm,Wm]`` up-sampled logits and their log-softmax never exist in memory (for K=19 at 768x768 and
   batch 8 that is 358 MB written and re-read several times by the eager path).
+
+* ``class_mean_vectors`` -- the t-SNE tooling's per-class mean of the UP-SAMPLED normalised features
+  (tsnelib.py:48-74 ``input2basket``): sum over the label pixels of class k of bilinear_up(x/|x|), divided by the pixel
+  count. The bilinear weights are transposed onto the feature grid by ``pm_readloss_fwd`` (with all-zero logits and one
+  spare slot its gradient IS ``W/K' - onehot`` scattered back), and ``pm_read_bwd_dM`` contracts them with the
+  normalised features -- the [B,C,Hm,Wm] up-sampled map (1.2 GB at 8 x 768 x 768) never exists.
 
 CUDA only, like the rest of the package.
 """
@@ -97,3 +103,41 @@ def upsampled_cross_entropy(logits, labels):
     if not 1 <= logits.shape[1] <= 31:
         raise RuntimeError("pinmem_b200: upsampled_cross_entropy supports 1..31 classes")
     return _UpsampledCE.apply(logits, labels.contiguous())
+
+
+def class_mean_vectors(features, labels, num_class):
+    """tsnelib.py:48-74: ``(means [K,C], counts [K])`` with ``means[k] = sum_{label px of class k} up(x/|x|)[px] / counts[k]``
+    (zero rows where a class has no pixel), ``up`` = bilinear, align_corners=True, to the label size. The reference
+    appends ``means[k]`` for every selected class with ``counts[k] != 0`` to its basket.
+
+    features [B,C,h,w] fp32|bf16 CUDA (C in 32/64/128/256), labels [B,Hm,Wm] int64, num_class <= 30.
+    """
+    capi.require_cuda(features, labels)
+    if features.dim() != 4 or labels.dim() != 3 or labels.shape[0] != features.shape[0]:
+        raise RuntimeError("pinmem_b200: features must be [B,C,h,w] and labels [B,Hm,Wm]")
+    if labels.dtype != torch.int64:
+        raise RuntimeError("pinmem_b200: labels must be int64")
+    K = int(num_class)
+    if not 1 <= K <= 30:
+        raise RuntimeError("pinmem_b200: class_mean_vectors supports 1..30 classes")
+    B, C, h, w = features.shape
+    N, dev = B * h * w, features.device
+    x = features.detach().contiguous()
+    labels = labels.contiguous()
+    K1 = K + 1                      # one spare slot no pixel is labelled with: its "gradient" is the plain tap weight / K1
+    KP = capi.score_stride(K1)
+    s = torch.zeros(N, KP, dtype=torch.float32, device=dev)       # all logits equal -> softmax = 1/K1 everywhere
+    buf = torch.zeros(N * KP + 2 * capi.WS_WORDS + 4, dtype=torch.float32, device=dev)
+    ds, ws, out = buf[: N * KP], buf[N * KP: N * KP + 2 * capi.WS_WORDS], buf[N * KP + 2 * capi.WS_WORDS:]
+    # labels >= K (and 255) are "ignore" for the K1-slot loss exactly as for the reference's one_hot(K+1) trick
+    capi.readloss_fwd(s, labels, 1.0, B, h, w, K1, ds, ws, out)
+    ds = ds.view(N, KP)
+    # ds[n,k] = sum_px w(px->n) (1/K1 - [label(px) = k]); slot K is never labelled: ds[n,K] = sum_px w(px->n) / K1
+    omega = torch.zeros(N, KP, dtype=torch.float32, device=dev)
+    omega[:, :K] = ds[:, K:K1] - ds[:, :K]                          # transposed bilinear weights per class
+    sums = torch.zeros(K1, C, dtype=torch.float32, device=dev)
+    score_dummy = torch.zeros(N, K1, dtype=torch.float32, device=dev)
+    capi.read_bwd_dM(None, x, score_dummy, omega, sums, K1)          # sums[k] = sum_n omega[n,k] x[n]/|x[n]|
+    counts = ws.view(torch.int64)[capi.WS_HIST: capi.WS_HIST + K].to(torch.float32)
+    safe = torch.where(counts == 0, torch.ones_like(counts), counts)
+    return sums[:K] / safe.unsqueeze(1), counts

@@ -681,6 +681,12 @@ class Memory_sup(nn.Module):
         f = self.writenet(query)
         f = _check_features(f, "write feature")
         M_old = self._memory_for_kernels(query.device)
+        if M_old.requires_grad and torch.is_grad_enabled():
+            # memory.py:236 blends the NON-detached self.m_items[slot]; forward() never gets here with a grad-carrying
+            # memory (read() detaches it first when writing, memory.py:323-324). A direct write() on one would silently
+            # drop d loss / d m_items: refuse instead of returning a wrong gradient.
+            raise RuntimeError("pinmem_b200: write() on a grad-carrying m_items is not differentiable w.r.t. the old memory "
+                               "here; detach it first (forward(..., memory_writing=True) does)")
         M_new, div_loss, cls_loss, SD = _WriteFn.apply(f, labels, M_old, self.clsfier.weight, self.clsfier.bias,
                                                        float(self.momentum), self.memory_size, self.shard_group)
         self.last_class_sums = SD

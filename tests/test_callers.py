@@ -105,3 +105,35 @@ def test_upsampled_cross_entropy_matches_reference_fixture_and_oracle():
     # all-ignore -> NaN like torch
     nan = upsampled_cross_entropy(logits.detach(), torch.full_like(labels, 255))
     assert torch.isnan(nan)
+
+
+def test_oracle_class_means_match_reference_fixture():
+    """tsnelib.py:48-74 executed from the reference source (oracle/make_golden_callers.py) vs the oracle restatement."""
+    meta, fx = _load("tsne_basket.npz")
+    means, counts = co.class_mean_vectors(fx["features"], fx["labels"], meta["K"])
+    present = (counts != 0).nonzero().flatten()
+    assert torch.equal(present, fx["class_ids"]), "the reference appends exactly the classes that have pixels"
+    assert_close(means[present], fx["vectors"], 2e-6, "class-mean vectors")
+    assert int(counts[5]) == 0 and torch.all(means[5] == 0)
+
+
+@pytest.mark.gpu
+def test_class_mean_vectors_match_reference_fixture_and_oracle():
+    from pinthememory_b200.callers import class_mean_vectors
+    from pinthememory_b200 import synth
+
+    meta, fx = _load("tsne_basket.npz")
+    means, counts = class_mean_vectors(fx["features"].cuda(), fx["labels"].cuda(), meta["K"])
+    present = (counts != 0).nonzero().flatten().cpu()
+    assert torch.equal(present, fx["class_ids"])
+    assert_close(means.cpu()[present], fx["vectors"], 1e-5, "class-mean vectors vs the reference")
+    lab = fx["labels"].reshape(-1).clone()
+    lab[lab == 255] = meta["K"]
+    assert torch.equal(counts.cpu().long(), torch.bincount(lab, minlength=meta["K"] + 1)[: meta["K"]]), "counts are exact"
+    # a batch of full-size maps against the oracle on the same device (the reference itself only takes batch 1)
+    f = synth.make_features(2, 256, 48, 48, seed=5, device="cuda")
+    l = synth.make_labels(2, 384, 384, 19, "blocky", seed=6, device="cuda")
+    m1, c1 = class_mean_vectors(f, l, 19)
+    m2, c2 = co.class_mean_vectors(f, l, 19)
+    assert_close(m1, m2, 1e-5, "batch of maps vs oracle")
+    assert torch.equal(c1, c2)
