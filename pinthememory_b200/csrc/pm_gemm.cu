@@ -460,11 +460,14 @@ static int gemm_dbg() {  // PM_GEMM_DBG: bring-up switches (bit 0 swaps LBO/SBO 
     return v;
 }
 
-static int gemm_mix() {  // PM_GEMM_3XTF32=1: three TF32 passes instead of TF32 + one bf16 correction pass (A/B switch)
+static int gemm_mix() {
+    // PM_GEMM_MIX=1: TF32 + one bf16 correction pass instead of three TF32 passes. Measured at cfg 2: forward 51 vs 56 us,
+    // input gradient 76 vs 80 us -- but 1.1e-6 instead of 4e-7 at K = 64 (the correction operands carry 8 mantissa bits),
+    // which pushes the module's ill-conditioned gradients past the 1e-5 parity bar on two fixtures. Parity first: off.
     static int v = -1;
     if (v < 0) {
-        const char* e = getenv("PM_GEMM_3XTF32");
-        v = (e && e[0] == '1') ? 0 : 1;
+        const char* e = getenv("PM_GEMM_MIX");
+        v = (e && e[0] == '1') ? 1 : 0;
     }
     return v;
 }

@@ -450,8 +450,8 @@ def _inference_block(bn, x, residual):
 
 
 def _weight_bn_act(W, bn, x, residual, relu, prepared=None):
-    if torch.is_autocast_enabled():  # the nn.Conv2d this replaces would run in the autocast dtype
-        x = x.to(torch.get_autocast_gpu_dtype())
+    if torch.is_autocast_enabled("cuda"):  # the nn.Conv2d this replaces would run in the autocast dtype
+        x = x.to(torch.get_autocast_dtype("cuda"))
     M, K = W.shape[0], W.shape[1]
     if _bn_fast(bn, x) and capi.conv1x1_ok(x, M, K) and not os.environ.get("PINMEM_B200_LIBRARY_CONV"):
         x = x.contiguous()
