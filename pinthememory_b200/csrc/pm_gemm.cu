@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], CL);
-            mbar_init(&xfull[i], 128);
+            mbar_init(&xfull[i], 4);  // one arrival per operand-split warp
         }
         for (int i = 0; i < ACC; ++i) {
             mbar_init(&accf[i], 1);
@@ -428,7 +428,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                     if (MIX) mix_tile_mn<KB, NT>(st, st + XBYTES, t, 128);
                     else split_tile_trunc(reinterpret_cast<float4*>(st), reinterpret_cast<float4*>(st + XBYTES), XBYTES / 16, t, 128);
                     fence_proxy_async_smem();
-                    mbar_arrive(&xfull[s]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&xfull[s]);
                 }
             }
         }
@@ -588,7 +589,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
-            mbar_init(&xfull[i], 128);
+            mbar_init(&xfull[i], 4);  // one arrival per operand-split warp
         }
         mbar_init(accf, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -696,7 +697,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                                      N * 8, t, 128);
                 }
                 fence_proxy_async_smem();
-                mbar_arrive(&xfull[s]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&xfull[s]);
             }
         }
     }
