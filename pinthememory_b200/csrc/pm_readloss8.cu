@@ -25,7 +25,8 @@
 
 namespace pm {
 
-constexpr int RL8_THREADS = 256;  // one cell (or one row-split of a cell) per thread
+constexpr int RL8_THREADS = 128;  // one cell (or one row-split of a cell) per thread; 2 CTAs per SM (249 registers) so that
+                                  // one CTA's tile load / merge / flush phases overlap the other's label loop
 constexpr int RL8_TX = 32;        // cells per CTA along x (a warp = 32 cells of one cell row, same row split)
 constexpr int RL8_KP = 20;        // padded slot count of the score rows (K <= 19)
 
@@ -201,7 +202,7 @@ __device__ __forceinline__ void cell_rows(const CellCtx& c, RunState& rs, float*
     }
 }
 
-__global__ void __launch_bounds__(RL8_THREADS, 1)
+__global__ void __launch_bounds__(RL8_THREADS, 2)
     readloss8_kernel(const float* __restrict__ s, const unsigned char* __restrict__ lab8, float inv_T, float temperature, int h,
                      int w, int Hm, int Wm, int K, float sy, float sx, int RS, int TYC, int tiles_x, int tiles_y,
                      float* __restrict__ ds_rl, unsigned long long* __restrict__ ws, float* __restrict__ out) {
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(RL8_THREADS, 1)
         s_tile[i] = __ldg(s + ((size_t)(b * h + fy) * w + fx) * KP + k);
         ds_tile[i] = 0.f;
     }
-    for (int i = tid; i < 4 * KP * NT; i += NT) priv[i] = 0.f;
+    for (int i = tid; i < KP * NT; i += NT) reinterpret_cast<float4*>(priv)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
 
     const int cxl = tid % RL8_TX, rest = tid / RL8_TX;  // rest in [0, TYC*RS)
@@ -408,7 +409,7 @@ extern "C" int pm_readloss_fwd8(const float* s, const uint8_t* lab8, float tempe
     const long long cells = (long long)B * h * w;
     const int rows_per_cell = h > 1 ? (Hm + h - 2) / (h - 1) : Hm;
     int RS = 1;
-    while (RS < 8 && cells * RS < 2LL * 148 * RL8_THREADS && RS * 2 <= rows_per_cell) RS *= 2;
+    while (RS < 4 && cells * RS < 4LL * 148 * RL8_THREADS && RS * 2 <= rows_per_cell) RS *= 2;
     const int TYC = (RL8_THREADS / RL8_TX) / RS;
     const int tiles_x = (w + RL8_TX - 1) / RL8_TX, tiles_y = (h + TYC - 1) / TYC;
     const size_t smem = sizeof(float) * ((size_t)2 * (TYC + 1) * (RL8_TX + 1) * RL8_KP + (size_t)4 * RL8_KP * RL8_THREADS + 8);
