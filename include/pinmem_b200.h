@@ -49,7 +49,7 @@ enum pm_readloss_ws_layout {
     PM_WS_WORDS = 40
 };
 
-/* Rows of the per-CTA column-softmax partials buffer ([PM_COLPART_ROWS][64] floats). */
+/* Rows of the per-CTA column-softmax partials ([PM_COLPART_ROWS + 1][64] floats; row PM_COLPART_ROWS = combined). */
 #define PM_COLPART_ROWS 296
 
 /* Bumped with every prototype change; the binding refuses a library whose pm_version() differs. */
@@ -58,7 +58,8 @@ int pm_version(void);
 const char* pm_status_string(int code);
 /* Row stride (floats) of the internal score buffers for K slots: 20 for K<=19, else 32. */
 int pm_score_stride(int K);
-/* Floats of the column-softmax partials buffer (PM_COLPART_ROWS * 64). */
+/* Floats of the column-softmax partials buffer ((PM_COLPART_ROWS + 1) * 64: the last row receives the combined column
+ * maximum and 1/sum). */
 int pm_colsoftmax_workspace_floats(int K);
 
 /*
@@ -84,7 +85,8 @@ int pm_read_fwd(const void* x, const float* M, const float* gumbel_m, const floa
  */
 int pm_colsoftmax(const float* s, const float* gumbel_q, float* score_q, float* workspace, int N, int K,
                   void* stream);
-/* Second pass only: normalise with the column partials produced by pm_read_fwd. */
+/* Second pass only: combine the column partials produced by pm_read_fwd (one small CTA), then normalise. col_partials'
+ * last row is written. */
 int pm_colsoftmax_apply(const float* s, const float* gumbel_q, const float* col_partials, float* score_q, int N,
                         int K, void* stream);
 

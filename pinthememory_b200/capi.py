@@ -181,7 +181,7 @@ def score_stride(K):
 # with CUDA events on the launching stream to get per-kernel durations live.
 
 LAUNCHES = 0
-_KERNELS_PER_CALL = {"pm_colsoftmax": 2, "pm_read_bwd": 2, "pm_read_bwd_planes": 2, "pm_conv1x1_wgrad": 2}
+_KERNELS_PER_CALL = {"pm_colsoftmax": 3, "pm_colsoftmax_apply": 2, "pm_read_bwd": 2, "pm_read_bwd_planes": 2, "pm_conv1x1_wgrad": 2}
 PLANES = 32  # PM_PLANES: score planes appended to q in the score-plane read
 _timing = None  # name -> list of (start_event, end_event) when enabled
 

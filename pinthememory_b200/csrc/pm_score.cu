@@ -43,47 +43,51 @@ __global__ void __launch_bounds__(256) colsoftmax_stats_kernel(const float* __re
     }
 }
 
+// Combine the PM_COLPART_ROWS per-CTA (max, sum) partials of every column ONCE (one CTA) into the final column maximum and
+// 1/sum, stored in row PM_COLPART_ROWS of the partials buffer ([0..32) max, [32..64) 1/sum). The apply kernel that follows
+// then runs on as many small CTAs as there are rows to normalise (the round-1 version re-combined the 296 x 64 partials
+// in every one of its <= 296 CTAs: 75 KB of L2 reads and a dependent latency chain per CTA, 18 us for 11 MB of work).
+__global__ void __launch_bounds__(256) colsoftmax_combine_kernel(float* __restrict__ partial, int K) {
+    __shared__ float sm_m[256], sm_l[256];
+    const int t = threadIdx.x, k = t % K, r0 = t / K, rstep = blockDim.x / K;
+    constexpr int MAXJ = (CS_MAXG + 7) / 8;  // rstep >= 8 for K <= 31
+    float pm_[MAXJ], pl_[MAXJ];
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {  // all loads issued before the first use (independent L2 hits)
+        const int i = r0 + j * rstep;
+        const bool ok = i < CS_MAXG;
+        pm_[j] = ok ? __ldcg(partial + (size_t)i * 64 + k) : -INFINITY;
+        pl_[j] = ok ? __ldcg(partial + (size_t)i * 64 + 32 + k) : 0.f;
+    }
+    float M = -INFINITY, L = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) M = fmaxf(M, pm_[j]);
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j)
+        if (pm_[j] > -INFINITY) L += pl_[j] * expf(pm_[j] - M);
+    sm_m[t] = M;
+    sm_l[t] = L;
+    __syncthreads();
+    if (t < K) {
+        float Mx = -INFINITY;
+        for (int i = 0; i < rstep; ++i) Mx = fmaxf(Mx, sm_m[i * K + t]);
+        float Ls = 0.f;
+        for (int i = 0; i < rstep; ++i) {
+            const float mi = sm_m[i * K + t];
+            if (mi > -INFINITY) Ls += sm_l[i * K + t] * expf(mi - Mx);
+        }
+        partial[(size_t)CS_MAXG * 64 + t] = Mx;
+        partial[(size_t)CS_MAXG * 64 + 32 + t] = 1.f / Ls;
+    }
+}
+
 __global__ void __launch_bounds__(256) colsoftmax_apply_kernel(const float* __restrict__ s, const float* __restrict__ g,
                                                                const float* __restrict__ partial,
                                                                float* __restrict__ out, int N, int K, int KP,
                                                                int rows_per_cta) {
-    __shared__ float sm_m[256], sm_l[256], col_m[32], col_il[32];
     const int t = threadIdx.x, k = t % K, r0 = t / K, rstep = blockDim.x / K;
-    {  // combine the PM_COLPART_ROWS per-CTA partials of column k: rstep threads per column, then one.
-        // All loads are issued before the first use (they are independent L2 hits).
-        constexpr int MAXJ = (CS_MAXG + 7) / 8;  // rstep >= 8 for K <= 31
-        float pm_[MAXJ], pl_[MAXJ];
-#pragma unroll
-        for (int j = 0; j < MAXJ; ++j) {
-            const int i = r0 + j * rstep;
-            const bool ok = i < CS_MAXG;
-            pm_[j] = ok ? __ldg(partial + (size_t)i * 64 + k) : -INFINITY;
-            pl_[j] = ok ? __ldg(partial + (size_t)i * 64 + 32 + k) : 0.f;
-        }
-        float M = -INFINITY, L = 0.f;
-#pragma unroll
-        for (int j = 0; j < MAXJ; ++j) M = fmaxf(M, pm_[j]);
-#pragma unroll
-        for (int j = 0; j < MAXJ; ++j)
-            if (pm_[j] > -INFINITY) L += pl_[j] * expf(pm_[j] - M);
-        sm_m[t] = M;
-        sm_l[t] = L;
-    }
-    __syncthreads();
-    if (t < K) {
-        float M = -INFINITY;
-        for (int i = 0; i < rstep; ++i) M = fmaxf(M, sm_m[i * K + t]);
-        float L = 0.f;
-        for (int i = 0; i < rstep; ++i) {
-            const float mi = sm_m[i * K + t];
-            if (mi > -INFINITY) L += sm_l[i * K + t] * expf(mi - M);
-        }
-        col_m[t] = M;
-        col_il[t] = 1.f / L;
-    }
-    __syncthreads();
+    const float M = __ldg(partial + (size_t)CS_MAXG * 64 + k), il = __ldg(partial + (size_t)CS_MAXG * 64 + 32 + k);
     const int start = blockIdx.x * rows_per_cta, end = min(N, start + rows_per_cta);
-    const float M = col_m[k], il = col_il[k];
     for (int r = start + r0; r < end; r += rstep) {
         float z = __ldg(s + (size_t)r * KP + k);
         if (g != nullptr) z += __ldg(g + (size_t)r * K + k);
@@ -119,7 +123,7 @@ __global__ void __launch_bounds__(256) rowsoftmax_kernel(const float* __restrict
 }  // namespace pm
 
 extern "C" int pm_score_stride(int K) { return K <= 19 ? 20 : 32; }
-extern "C" int pm_colsoftmax_workspace_floats(int K) { return pm::CS_MAXG * 64; }
+extern "C" int pm_colsoftmax_workspace_floats(int K) { return (pm::CS_MAXG + 1) * 64; }  // + the combined row
 
 namespace pm {
 int colsoftmax_stats(const float* s, const float* gumbel_q, float* partial, int N, int K, cudaStream_t st) {
@@ -137,10 +141,10 @@ extern "C" int pm_colsoftmax_apply(const float* s, const float* gumbel_q, const 
     if (K < 1 || K > 31) return PM_ERR_SLOTS;
     if (N <= 0) return PM_ERR_SHAPE;
     const int KP = pm_score_stride(K), tpb = K * (256 / K), rstep = tpb / K;
-    int G = (N + rstep * 8 - 1) / (rstep * 8);  // >= 8 rows per thread
-    if (G > 2 * 148) G = 2 * 148;                // every CTA re-combines the partials: keep them few
-    const int rows_per_cta = (N + G - 1) / G;
-    G = (N + rows_per_cta - 1) / rows_per_cta;
+    // the partials are written by another kernel of this stream and only read here, except for the combined row
+    pm::colsoftmax_combine_kernel<<<1, tpb, 0, (cudaStream_t)stream>>>(const_cast<float*>(col_partials), K);
+    const int rows_per_cta = rstep * 5;   // 5 rows per thread: ~1100 small CTAs at cfg 2
+    const int G = (N + rows_per_cta - 1) / rows_per_cta;
     pm::colsoftmax_apply_kernel<<<G, tpb, 0, (cudaStream_t)stream>>>(s, gumbel_q, col_partials, score_q, N, K, KP,
                                                                        rows_per_cta);
     PM_CHECK_LAUNCH();
