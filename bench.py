@@ -713,8 +713,15 @@ def main():
         "pm_read_fwd_planes": N * ((2 * C + 32) * esz + 4 * KP + 4 * K),
         "pm_read_bwd_planes": N * ((3 * C + K) * esz + 2 * 4 * KP + 4 * K),
         "pm_readloss_fwd": N * (8 * r + 2 * 4 * KP),
+        # second-generation read loss: the label pass (int64 in, uint8 out, histogram) + the loss on the packed map; the
+        # pair is what SURVEY 8d budgets as ONE read of the int64 labels (8r) + the score / gradient rows
+        "pm_labels_pack": N * r * 9,
+        "pm_readloss_fwd8": N * (r + 2 * 4 * KP),
+        "pm_readloss (pm_labels_pack + pm_readloss_fwd8)": N * (8 * r + 2 * 4 * KP),
         "pm_write_reduce_fwd": N * (C * esz),
         "pm_write_bwd": N * (2 * C * esz),
+        "pm_write_reduce_fwd8": N * (C * esz),
+        "pm_write_bwd8": N * (2 * C * esz),
         "pm_colsoftmax_apply": N * (4 * KP + 4 * K),
         # the fused BatchNorm passes run once per conv block (2 per step); bytes are the mean of the two calls
         "pm_bn_stats": N * C * esz,
@@ -722,7 +729,14 @@ def main():
         "pm_bn_bwd_reduce": N * C * esz * 2,     # dy, x (+ the packed ReLU mask, 1/32)
         "pm_bn_bwd_apply": N * C * esz * 3.5,    # dy, x -> dx (+ dres in one of the two blocks)
     }
+    if "pm_labels_pack" in kavg and "pm_readloss_fwd8" in kavg:
+        kavg["pm_readloss (pm_labels_pack + pm_readloss_fwd8)"] = kavg["pm_labels_pack"] + kavg["pm_readloss_fwd8"]
     bound_note = {
+        "pm_readloss (pm_labels_pack + pm_readloss_fwd8)":
+            "two launches reported as one logical kernel (time and bytes are their sums; bytes as SURVEY 8d counts them: "
+            "int64 labels read once). Not HBM-bound by nature: ~65 instructions per LABEL pixel (64 label pixels per "
+            "feature pixel) in one thread per bilinear cell at 8 warps per SM -- latency-bound, see DESIGN.md 6; DRAM "
+            "traffic = algorithmic bytes (no re-reads)",
         "pm_readloss_fwd": "not HBM-bound by nature: ~19 ex2 + ~60 FMA per LABEL pixel (64 label pixels per feature "
                            "pixel) make it FP32/MUFU-issue bound; the HBM fraction is reported because the contract asks "
                            "for it, see DESIGN.md 4/6",
@@ -750,11 +764,15 @@ def main():
             ent["GBps"] = round(alg_bytes[k] / (t_ms * 1e-3) / 1e9, 1)
             ent["frac"] = round(ent["GBps"] / peak, 4)
         kernels[k] = ent
-    dom = max((k for k in kavg if k in alg_bytes), key=lambda k: kavg[k])
+    dom = max((k for k in kavg if k in alg_bytes and k not in ("pm_labels_pack", "pm_readloss_fwd8")), key=lambda k: kavg[k])
     ncu_traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
-            ncu_traffic = json.load(fh).get(args.dtype, {}).get(dom.replace("_planes", ""))
+            tr = json.load(fh).get(args.dtype, {})
+        if dom.startswith("pm_readloss ("):
+            ncu_traffic = tr.get("pm_labels_pack", 0.0) + tr.get("pm_readloss_fwd8", 0.0) or None
+        else:
+            ncu_traffic = tr.get(dom, tr.get(dom.replace("_planes", "")))
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",

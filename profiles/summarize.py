@@ -17,7 +17,13 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_xu.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-        "lts__t_sector_hit_rate.pct", "smsp__cycles_active.avg"]
+        "lts__t_sector_hit_rate.pct", "smsp__cycles_active.avg",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__pcsamp_warps_issue_stalled_long_scoreboard", "smsp__pcsamp_warps_issue_stalled_wait",
+        "smsp__pcsamp_warps_issue_stalled_barrier", "smsp__pcsamp_warps_issue_stalled_short_scoreboard",
+        "smsp__pcsamp_warps_issue_stalled_selected", "smsp__pcsamp_warps_issue_stalled_math_pipe_throttle"]
 
 
 def launches(path):
@@ -34,14 +40,16 @@ def launches(path):
         print("%-92s %5d %10.1f %10.1f %5.1f%%" % (k, len(v), sum(v) / len(v) / 1e3, sum(v) / 1e3, 100 * sum(v) / tot))
 
 
-ENTRY_OF = [("read_fwd_tiled_kernel", "pm_read_fwd"), ("read_fwd_kernel", "pm_read_fwd"),
+ENTRY_OF = [("readloss8_kernel", "pm_readloss_fwd8"), ("labels_pack_kernel", "pm_labels_pack"),
+            ("conv1x1_nn_kernel", "pm_conv1x1_fwd"), ("conv1x1_wgrad_kernel", "pm_conv1x1_wgrad"),
+            ("read_fwd_tiled_kernel", "pm_read_fwd"), ("read_fwd_kernel", "pm_read_fwd"),
             ("colsoftmax_apply_kernel", "pm_colsoftmax_apply"), ("readloss_kernel", "pm_readloss_fwd"),
             ("bn_stats_kernel", "pm_bn_stats"), ("bn_apply_kernel", "pm_bn_apply"),
             ("write_reduce_mma_kernel", "pm_write_reduce_fwd"), ("write_reduce_tiled_kernel", "pm_write_reduce_fwd"),
             ("update_fwd_kernel", "pm_update_fwd"), ("update_bwd_kernel", "pm_update_bwd"),
             ("write_bwd_tiled_kernel", "pm_write_bwd"), ("bn_bwd_reduce_kernel", "pm_bn_bwd_reduce"),
             ("bn_bwd_apply_kernel", "pm_bn_bwd_apply"), ("read_bwd_ds_tiled_kernel", "pm_read_bwd.ds"), ("read_bwd_ds_planes_kernel", "pm_read_bwd.ds"),
-            ("read_bwd_dx_tiled_kernel", "pm_read_bwd.dx")]
+            ("read_bwd_dx_tiled_kernel", "pm_read_bwd.dx"), ("read_bwd_dx_tma_kernel", "pm_read_bwd.dx")]
 
 
 def traffic(path, dtype="f32"):
@@ -72,6 +80,9 @@ def traffic(path, dtype="f32"):
         detail[ent] = {"traffic": out[ent], "ncu_us": sum(b for _, b in v) / len(v), "launches_averaged": len(v)}
     if "pm_read_bwd.ds" in out and "pm_read_bwd.dx" in out:
         out["pm_read_bwd"] = out["pm_read_bwd.ds"] + out["pm_read_bwd.dx"]
+    for alias, ent in (("pm_read_fwd_planes", "pm_read_fwd"), ("pm_read_bwd_planes", "pm_read_bwd")):
+        if ent in out:
+            out[alias] = out[ent]
     print(json.dumps({dtype: out, "_detail_" + dtype: detail}, indent=1))
 
 
