@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--labels", default="blocky", choices=["blocky", "iid"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-callers", action="store_true", help="skip the timings of the callers (main loss, prototype pooling)")
+    ap.add_argument("--core-serial", action="store_true", help="core graph as one linear chain (no parallel write branch)")
     ap.add_argument("--overlap-write", action="store_true", help="write branch on a side stream (parallel graph branch)")
     ap.add_argument("--no-graph", action="store_true", help="headline = kernel-by-kernel launches instead of the CUDA graph")
     ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other BASELINE configs (cfg 3/4/5)")
@@ -70,6 +71,16 @@ def tensor_peak(dt):
     if dt == torch.float32:
         return bf16 / 2.0, src + " / 2 for TF32"
     return bf16, src
+
+
+def exchange_name(module):
+    """Which exchange a sharded module uses for the class sums / their gradient."""
+    g = getattr(module, "shard_group", None)
+    if g is None or g.world_size <= 1:
+        return "none (single rank)"
+    if getattr(g, "peer", None) is not None:
+        return "fused into the update kernels over NVLink peer memory (pm_update_fwd_peer / pm_update_bwd_peer), no NCCL node"
+    return "two NCCL all-reduces (%s)" % (getattr(g, "peer_error", None) or "peer exchange disabled")
 
 
 def measured_peaks():
@@ -401,8 +412,8 @@ def extra_configs(args, dev, dt, world, rank, mem0, timed):
         out["cfg4_dp_os16_global_batch_64"] = {
             "ms_per_step": ms, "value": Bg * w4["h"] * w4["w"] / (ms * 1e-3) / 1e6, "unit": UNIT, "scaling": "strong",
             "per_gpu_batch": Bl, "what": "DR50V3P shape (48x48 features, 768x768 labels), global batch 64 split over %d "
-                                         "GPU(s), NCCL all-reduce of the class sums|counts before the update, CUDA graph "
-                                         "replay" % world}
+                                         "GPU(s), class sums|counts exchanged before the update (%s), CUDA graph "
+                                         "replay" % (world, exchange_name(m))}
         gs.release()
         del gs, m, x4, l4, G4
     except Exception as e:
@@ -565,6 +576,8 @@ def main():
 
     Wc, bc = mem.clsfier.weight, mem.clsfier.bias
 
+    core_side = [None]
+
     def core_step(xi=None, fi=None, Wi=None, bi=None):
         xi = x if xi is None else xi
         fi = f_core if fi is None else fi
@@ -573,7 +586,14 @@ def main():
         xi.grad = None
         fi.grad = None
         u, _, _, rl, _ = _ReadFn.apply(xi, M0, labels, None, None, 1.0, K)
-        M_new, div, cls, _ = _WriteFn.apply(fi, labels, M0, Wi, bi, 0.8, K, mem.shard_group)
+        if core_side[0] is not None:      # write branch as a parallel branch (its backward follows it onto that stream)
+            cur = torch.cuda.current_stream(dev)
+            core_side[0].wait_stream(cur)
+            with torch.cuda.stream(core_side[0]):
+                M_new, div, cls, _ = _WriteFn.apply(fi, labels, M0, Wi, bi, 0.8, K, mem.shard_group)
+            cur.wait_stream(core_side[0])
+        else:
+            M_new, div, cls, _ = _WriteFn.apply(fi, labels, M0, Wi, bi, 0.8, K, mem.shard_group)
         torch.autograd.backward([u, rl, div, cls], [Gu, gw[0], gw[1], gw[2]])
 
     res_host = torch.empty(3 + K * C, dtype=torch.float32).pin_memory()
@@ -744,42 +764,84 @@ def main():
         "pm_read_bwd_planes": "one C-ABI call = two kernels (score gradients, then dx); bytes and time are their sums",
     }
     peak, peak_src = measured_peaks()
-    # the two 1x1 convolutions: tensor-bound. FLOPs per call (mean over the calls of a step: forward and input-gradient
-    # GEMMs of both blocks / both weight-gradient GEMMs), x3 passes in fp32 (3xTF32)
+    # the two 1x1 convolutions: tensor-bound. ALGORITHMIC FLOPs per step (2*M*N*K of the fp32 product, one pass): forward
+    # of both blocks + input gradient of both blocks for pm_conv1x1_fwd (the same kernel; the 288-row input gradient of
+    # the folded output convolution is two launches), both weight gradients for pm_conv1x1_wgrad. fp32 I/O EXECUTES
+    # three TF32 passes per product (3xTF32 error compensation) -- reported separately as executed_*.
     passes = 3 if dt == torch.float32 else 1
-    conv_flops = {"pm_conv1x1_fwd": 2.0 * N * C * (C + (C + 32)) / 2 * passes,
-                  "pm_conv1x1_wgrad": 2.0 * N * C * (C + (C + 32)) / 2 * passes}
+    calls = {k: len(v) / float(args.steps) for k, v in ktimes.items()}          # launches per step
+    kstep = {k: sum(v) / float(args.steps) for k, v in ktimes.items()}          # ms per step
+    conv_flops_step = {"pm_conv1x1_fwd": 2.0 * N * C * (4 * C + 64), "pm_conv1x1_wgrad": 2.0 * N * C * (2 * C + 32)}
     tpeak, tpeak_src = tensor_peak(dt)
     kernels = {}
     for k, t_ms in kavg.items():
         ent = {"ms": round(t_ms, 5)}
-        if k in conv_flops:
+        if k in calls:
+            ent["launches_per_step"] = round(calls[k], 2)
+            ent["ms_per_step"] = round(kstep[k], 5)
+        if k in conv_flops_step and k in kstep:
+            alg = conv_flops_step[k] / (kstep[k] * 1e-3) / 1e12
             ent["bound"] = "tensor"
-            ent["TFLOPs"] = round(conv_flops[k] / (t_ms * 1e-3) / 1e12, 1)
+            ent["TFLOPs"] = round(alg, 1)
+            ent["executed_TFLOPs"] = round(alg * passes, 1)
             ent["tensor_peak_TFLOPs"] = tpeak
-            ent["frac"] = round(ent["TFLOPs"] / tpeak, 4)
-            ent["note"] = ("%d-pass %s tcgen05 GEMM; peak = %s" % (passes, "TF32" if passes == 3 else "bf16", tpeak_src))
+            ent["frac"] = round(alg / tpeak, 4)
+            ent["executed_frac"] = round(alg * passes / tpeak, 4)
+            ent["note"] = ("%d-pass %s tcgen05 GEMM; TFLOPs = algorithmic 2MNK per launch / launch time, executed_* = "
+                           "x%d passes; peak = %s" % (passes, "TF32" if passes == 3 else "bf16", passes, tpeak_src))
         if k in alg_bytes:
             ent["alg_MB"] = round(alg_bytes[k] / 1e6, 3)
             ent["GBps"] = round(alg_bytes[k] / (t_ms * 1e-3) / 1e9, 1)
             ent["frac"] = round(ent["GBps"] / peak, 4)
         kernels[k] = ent
-    dom = max((k for k in kavg if k in alg_bytes and k not in ("pm_labels_pack", "pm_readloss_fwd8")), key=lambda k: kavg[k])
-    ncu_traffic = None
+    comb = "pm_readloss (pm_labels_pack + pm_readloss_fwd8)"
+    if comb in kavg:
+        kstep[comb] = kstep["pm_labels_pack"] + kstep["pm_readloss_fwd8"]
+    # the DOMINANT kernel = the one with the largest share of the step (launches x duration), among those with a budget
+    cand = [k for k in kstep if (k in alg_bytes or k in conv_flops_step) and k not in ("pm_labels_pack", "pm_readloss_fwd8")]
+    dom = max(cand, key=lambda k: kstep[k])
+    dom_hbm = max((k for k in cand if k in alg_bytes), key=lambda k: kstep[k])
+    tr = {}
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
             tr = json.load(fh).get(args.dtype, {})
-        if dom.startswith("pm_readloss ("):
-            ncu_traffic = tr.get("pm_labels_pack", 0.0) + tr.get("pm_readloss_fwd8", 0.0) or None
-        else:
-            ncu_traffic = tr.get(dom, tr.get(dom.replace("_planes", "")))
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[dom]["frac"], "traffic": ncu_traffic, "peak_source": peak_src,
-                "alg_bytes_per_launch": alg_bytes[dom], "launch_ms": kernels[dom]["ms"]}
-    if dom in bound_note:
-        roofline["note"] = bound_note[dom]
+
+    def traffic_of(k):
+        if k.startswith("pm_readloss ("):
+            return (tr.get("pm_labels_pack", 0.0) + tr.get("pm_readloss_fwd8", 0.0)) or None
+        for cand_k in (k, k.replace("_planes", ""), k.rstrip("8")):
+            if cand_k in tr:
+                return tr[cand_k]
+        return None
+
+    def hbm_entry(k):
+        ent = {"bound": "hbm", "kernel": k, "achieved": kernels[k]["GBps"], "peak": peak, "unit": "GB/s",
+               "frac": kernels[k]["frac"], "traffic": traffic_of(k), "peak_source": peak_src,
+               "alg_bytes_per_launch": alg_bytes[k], "launch_ms": kernels[k]["ms"],
+               "share_of_step": round(kstep[k] / sum(v for q, v in kstep.items() if q != comb), 4)}
+        if k in bound_note:
+            ent["note"] = bound_note[k]
+        return ent
+
+    if dom in conv_flops_step:
+        e = kernels[dom]
+        roofline = {"bound": "tensor", "kernel": dom, "achieved": e["TFLOPs"], "peak": tpeak, "unit": "TFLOP/s",
+                    "frac": e["frac"], "traffic": traffic_of(dom), "peak_source": tpeak_src,
+                    "alg_flops_per_launch": conv_flops_step[dom] / calls[dom], "launch_ms": e["ms"],
+                    "launches_per_step": e["launches_per_step"],
+                    "share_of_step": round(kstep[dom] / sum(v for q, v in kstep.items() if q != comb), 4),
+                    "executed_TFLOPs": e["executed_TFLOPs"], "executed_frac": e["executed_frac"],
+                    "note": "dominant by share of the step (launches x duration). achieved = ALGORITHMIC flops (2MNK of "
+                            "the fp32 product, averaged over the step's launches of this kernel) / mean launch time. "
+                            + ("fp32 I/O computes every product as three TF32 tensor-core passes (hi*hi + hi*lo + lo*hi) "
+                               "to hold the 1e-5 parity bar, so the algorithmic fraction is bounded by 1/3 of the TF32 "
+                               "peak; executed_* counts the three passes (tensor-pipe view). " if passes == 3 else "")
+                            + "The streaming kernels' HBM rooflines are in `hbm_dominant`, `core` and `kernels`.",
+                    "hbm_dominant": hbm_entry(dom_hbm)}
+    else:
+        roofline = hbm_entry(dom)
 
     # core: hand-written kernels only, one Python-side launch per kernel (host-launch bound at ~0.4 ms: capturing this
     # autograd fragment separately was tried and disturbs the measurements that follow; the headline step IS captured)
@@ -804,11 +866,16 @@ def main():
             xg.grad = fg.grad = Wg.grad = bg.grad = None
             core_graph = torch.cuda.CUDAGraph()
             n0 = capi.LAUNCHES
+            core_side[0] = None if args.core_serial else torch.cuda.Stream(device=dev)
             with torch.cuda.graph(core_graph):
                 core_step(xg, fg, Wg, bg)
+            core_side[0] = None
             core_launches_per_replay = capi.LAUNCHES - n0
             core_fn = core_graph.replay
-            core_launch = "CUDA graph replay of the %d launches" % core_launches_per_replay
+            core_launch = "CUDA graph replay of the %d launches%s" % (
+                core_launches_per_replay, "" if args.core_serial else
+                "; the write branch (class sums, update and their backward) is a parallel branch of the graph, as in the "
+                "captured module step")
         except Exception as e:
             core_graph, core_fn = None, core_step
             core_launch = "one Python-side launch per kernel (capture failed: %s)" % str(e)[:120]
@@ -902,9 +969,11 @@ def main():
                     rel = float((Mn.double() - M_ref).norm() / M_ref.norm())
             line["sharded_parity"] = {"memory_bit_identical_across_ranks": bool(identical),
                                       "memory_vs_oracle_global_batch_rel_l2": rel, "images": world * B,
-                                      "what": "pm_write_reduce_fwd on each rank's shard + NCCL all-reduce of the [K+1,C+4] "
-                                              "sums|counts + pm_update_fwd, against the fp64 oracle update of the "
+                                      "exchange": exchange_name(mem),
+                                      "what": "pm_write_reduce_fwd on each rank's shard + exchange of the [K+1,C+4] "
+                                              "sums|counts + update, against the fp64 oracle update of the "
                                               "concatenated %d-image batch (write features given)" % (world * B)}
+            line["exchange"] = exchange_name(mem)
         except Exception as e:
             line["sharded_parity"] = {"error": str(e)[:300]}
 

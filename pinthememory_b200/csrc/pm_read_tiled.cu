@@ -181,6 +181,128 @@ __device__ __forceinline__ void tile_weighted_sum_mma(const float* p_sm, const f
     }
 }
 
+// ---- bf16 tiles on the tensor core (mma.sync m16n8k16, fp32 accumulate) ------------------------------------------
+// The tile is [C][32 px] bf16 (64-byte rows) in the TMA SWIZZLE_64B layout: 16-byte chunk c of row r sits at chunk
+// c ^ ((r >> 1) & 3), so the eight 16-byte rows of an 8-channel x 8-pixel block fall into eight distinct bank groups
+// and `ldmatrix.trans` -- which hands thread (g, t) the pair (channel 2t, 2t+1) of pixel g, exactly the A fragment of
+// a [pixels x channels] operand -- reads a block in one wavefront. The memory is the B operand, kept in shared memory
+// as bf16 pairs over channels, split hi + lo (M = hi + lo to 2^-17), so the only rounding left is the feature map's own.
+__device__ __forceinline__ int bf16_tile_off(int row, int px) {  // element offset of (row, px) in a SWIZZLE_64B tile
+    return row * 32 + ((((px >> 3) ^ ((row >> 1) & 3)) << 3) | (px & 7));
+}
+template <int ROWS, int NTHREADS>
+__device__ __forceinline__ void tile_load_async_mma16(__nv_bfloat16* smem_tile, const __nv_bfloat16* __restrict__ base, int hw,
+                                                      int px0) {
+    static_assert(NTHREADS % 4 == 0, "thread count must be a multiple of the chunks per row");
+    const int ch = threadIdx.x % 4;
+    const int px = px0 + ch * 8;
+    const bool valid = px < hw;
+    const __nv_bfloat16* src = base + (size_t)(threadIdx.x / 4) * hw + (valid ? px : 0);
+    const size_t step = (size_t)(NTHREADS / 4) * hw;
+    for (int row = threadIdx.x / 4; row < ROWS; row += NTHREADS / 4) {
+        cp_async16(smem_tile + row * 32 + ((ch ^ ((row >> 1) & 3)) << 3), src, valid);
+        src += step;
+    }
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(unsigned (&r)[4], uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(saddr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ unsigned pack_bf16(float lo, float hi) {  // lo -> bits 0..15
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<unsigned*>(&v);
+}
+__device__ __forceinline__ float bf16_lo_f(unsigned w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi_f(unsigned w) { return __uint_as_float(w & 0xffff0000u); }
+
+template <int KP>
+struct MbLayout {
+    static constexpr int NT = (KP + 7) / 8;
+    // row stride in words: rows t = 0..3 (and 4..7) of a B-fragment load must land in distinct 8-bank groups
+    static constexpr int LD = (NT == 3) ? 24 : 40;
+};
+// Mb_hi / Mb_lo [C/2][LD] words: word (cp, k) = bf16 pair (M[k][2cp], M[k][2cp+1])
+template <int C, int KP>
+__device__ __forceinline__ void load_Mb(unsigned* Mb_hi, unsigned* Mb_lo, const float* __restrict__ M, int K) {
+    constexpr int LD = MbLayout<KP>::LD;
+    for (int i = threadIdx.x; i < (C / 2) * LD; i += TL_THREADS) {
+        const int cp = i / LD, k = i - cp * LD;
+        float a = 0.f, b = 0.f;
+        if (k < K) {
+            const float2 v = __ldg(reinterpret_cast<const float2*>(M + (size_t)k * C) + cp);
+            a = v.x, b = v.y;
+        }
+        const float ah = __bfloat162float(__float2bfloat16_rn(a)), bh = __bfloat162float(__float2bfloat16_rn(b));
+        Mb_hi[i] = pack_bf16(ah, bh);
+        Mb_lo[i] = pack_bf16(a - ah, b - bh);
+    }
+}
+
+// S[32 px][KP] = X[32 px][CW ch] . M^T for this warp's CW channels (CW % 16 == 0) + the partial squared norms
+template <int CW, int KP>
+__device__ __forceinline__ void tile_dots_mma_bf16(const __nv_bfloat16* xt, const unsigned* Mb_hi, const unsigned* Mb_lo,
+                                                   int c0, int lane, float* part_w, float* pn_w) {
+    constexpr int NT = MbLayout<KP>::NT, LD = MbLayout<KP>::LD;
+    const int g = lane >> 2, t = lane & 3;
+    float acc[2][NT][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int n = 0; n < NT; ++n) acc[m][n][0] = acc[m][n][1] = acc[m][n][2] = acc[m][n][3] = 0.f;
+    float n2[4] = {0.f, 0.f, 0.f, 0.f};  // pixels g, g+8, g+16, g+24
+    const uint32_t xbase = smem_u32(xt);
+    const int mj = lane >> 3, rr = lane & 7;  // ldmatrix: this lane addresses row rr of matrix mj
+#pragma unroll
+    for (int ks = 0; ks < CW / 16; ++ks) {
+        const int cb = c0 + 16 * ks;
+        unsigned a[2][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            const int row = cb + (mj >> 1) * 8 + rr, chunk = 2 * m + (mj & 1);
+            ldmatrix_x4_trans(a[m], xbase + (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)));
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float lo = bf16_lo_f(a[m][e]), hi = bf16_hi_f(a[m][e]);
+                n2[2 * m + (e & 1)] = fmaf(lo, lo, fmaf(hi, hi, n2[2 * m + (e & 1)]));
+            }
+        }
+        const unsigned* bh = Mb_hi + ((cb >> 1) + t) * LD + g;
+        const unsigned* bl = Mb_lo + ((cb >> 1) + t) * LD + g;
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            const unsigned b0h = bh[8 * n], b1h = bh[4 * LD + 8 * n], b0l = bl[8 * n], b1l = bl[4 * LD + 8 * n];
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                mma_bf16(acc[m][n], a[m], b0l, b1l);
+                mma_bf16(acc[m][n], a[m], b0h, b1h);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        n2[r] += __shfl_xor_sync(0xffffffffu, n2[r], 1);
+        n2[r] += __shfl_xor_sync(0xffffffffu, n2[r], 2);
+        if (t == 0 && pn_w != nullptr) pn_w[g + 8 * r] = n2[r];
+    }
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            const int slot = 8 * n + 2 * t;
+            if (slot < KP) {
+                *reinterpret_cast<float2*>(part_w + (g + 16 * m) * KP + slot) = make_float2(acc[m][n][0], acc[m][n][1]);
+                *reinterpret_cast<float2*>(part_w + (g + 8 + 16 * m) * KP + slot) = make_float2(acc[m][n][2], acc[m][n][3]);
+            }
+        }
+}
+
 template <typename T, int CW>
 struct UseMma {
     static constexpr bool value = false;
@@ -189,11 +311,16 @@ template <int CW>
 struct UseMma<float, CW> {
     static constexpr bool value = (CW % 8 == 0);
 };
+template <int CW>
+struct UseMma<__nv_bfloat16, CW> {
+    static constexpr bool value = (CW % 16 == 0);
+};
 
 // dispatch: load one tile for the dots phase in the layout the chosen contraction wants
 template <typename T, int C, int NTHREADS, bool MMA>
 __device__ __forceinline__ void dots_tile_load(T* smem_tile, const T* __restrict__ base, int hw, int px0) {
-    if constexpr (MMA) tile_load_async_mma<C, NTHREADS>(smem_tile, base, hw, px0);
+    if constexpr (MMA && sizeof(T) == 4) tile_load_async_mma<C, NTHREADS>(reinterpret_cast<float*>(smem_tile), reinterpret_cast<const float*>(base), hw, px0);
+    else if constexpr (MMA) tile_load_async_mma16<C, NTHREADS>(reinterpret_cast<__nv_bfloat16*>(smem_tile), reinterpret_cast<const __nv_bfloat16*>(base), hw, px0);
     else tile_load_async<T, C, NTHREADS>(smem_tile, base, hw, px0);
 }
 
@@ -228,8 +355,12 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
     float* s_sm = pn + TL_WARPS * TP;             // [TP][KP]
     float* p_sm = s_sm + TP * KP;                 // [TP][KP]
     float* invr = p_sm + TP * KP;                 // [TP]
+    constexpr bool MMA16 = MMA && sizeof(T) == 2;
+    constexpr int MB_WORDS = MMA16 ? (C / 2) * MbLayout<KP>::LD : 0;
+    unsigned* Mb_hi = reinterpret_cast<unsigned*>(invr + TP);  // [C/2][LD] x 2: the memory as bf16 pairs (bf16 tiles only)
+    unsigned* Mb_lo = Mb_hi + MB_WORDS;
     // [NSTAGE][C][TP]; 1 KB aligned for the swizzled TMA boxes (the launcher allocates the slack)
-    T* xs = reinterpret_cast<T*>(smem_align(reinterpret_cast<unsigned char*>(invr + TP), 1024));
+    T* xs = reinterpret_cast<T*>(smem_align(reinterpret_cast<unsigned char*>(Mb_lo + MB_WORDS), 1024));
     __shared__ __align__(8) uint64_t full[NSTAGE];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -260,6 +391,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
         }
     }
     load_Mt<C, KP>(Mt, M, K);
+    if constexpr (MMA16) load_Mb<C, KP>(Mb_hi, Mb_lo, M, K);
     float cm[NI], cl[NI];  // running column (max, sum) of this thread's slots for score_query
 #pragma unroll
     for (int i = 0; i < NI; ++i) cm[i] = -INFINITY, cl[i] = 0.f;
@@ -274,7 +406,10 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
         const int b = tile / tiles_per_img, px0 = (tile - b * tiles_per_img) * TP;
         const int nvalid = min(TP, hw - px0);
         const size_t n0g = (size_t)b * hw + px0;
-        if constexpr (MMA) {
+        if constexpr (MMA16) {
+            tile_dots_mma_bf16<CW, KP>(reinterpret_cast<const __nv_bfloat16*>(xt), Mb_hi, Mb_lo, wid * CW, lane,
+                                       part + wid * TP * KP, pn + wid * TP);
+        } else if constexpr (MMA) {
             tile_dots_mma<CW, KP>(reinterpret_cast<const float*>(xt), Mt, wid * CW, lane, part + wid * TP * KP,
                                   pn + wid * TP);
         } else {
@@ -355,7 +490,24 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
                 if (lane < nvalid) stf(u + ((size_t)b * UC + C + r) * hw + px0 + lane, v);
             }
         }
-        if constexpr (MMA) {  // u = [q ; p.M]: p.M on the tensor core, q = x/|x| element-wise
+        if constexpr (MMA16) {  // bf16: two channel rows x 16 pixel pairs per store instruction (2 x 64 bytes)
+            if (!planes)
+                tile_weighted_sum_mma<T, CW, KP>(p_sm, Mt, wid * CW, lane,
+                                                 u + ((size_t)b * UC + C + wid * CW) * hw + px0, hw, nvalid);
+            const int half = lane >> 4, pp = (lane & 15) * 2;
+            const float ir0 = invr[pp], ir1 = invr[pp + 1];
+            if (pp < nvalid) {  // hw % 8 == 0: a pixel pair is valid or not as a whole
+                const unsigned* xw = reinterpret_cast<const unsigned*>(xt);
+                unsigned* uq = reinterpret_cast<unsigned*>(u + ((size_t)b * UC + wid * CW + half) * hw + px0 + pp);
+#pragma unroll
+                for (int j = 0; j < CW / 2; ++j) {
+                    const int row = wid * CW + 2 * j + half;
+                    const unsigned v = xw[bf16_tile_off(row, pp) >> 1];
+                    *uq = pack_bf16(bf16_lo_f(v) * ir0, bf16_hi_f(v) * ir1);
+                    uq += hw;  // two rows of bf16 = hw 32-bit words
+                }
+            }
+        } else if constexpr (MMA) {  // u = [q ; p.M]: p.M on the tensor core, q = x/|x| element-wise
             if (!planes)
                 tile_weighted_sum_mma<T, CW, KP>(p_sm, Mt, wid * CW, lane,
                                                  u + ((size_t)b * UC + C + wid * CW) * hw + px0, hw, nvalid);
@@ -456,14 +608,17 @@ template <typename T, int C, int KP>
 int launch_read_fwd_tiled(const void* x, const float* M, const float* gum_m, const float* gum_q, void* u, float* s,
                           float* p, float* colpart, int B, int hw, int K, int planes, cudaStream_t st) {
     constexpr int NSTAGE = 2;
+    constexpr bool MMA = UseMma<T, C / TL_WARPS>::value;  // the tensor-core layouts are swizzled
+    constexpr bool MMA16 = MMA && sizeof(T) == 2;
     const size_t smem = sizeof(float) * ((size_t)C * KP + TL_WARPS * TP * KP + TL_WARPS * TP + 2 * TP * KP + TP) +
+                        (MMA16 ? sizeof(unsigned) * 2 * (C / 2) * MbLayout<KP>::LD : 0) +
                         sizeof(T) * (size_t)NSTAGE * C * TP + 1024;
     const int tiles = (hw + TP - 1) / TP, ntiles = B * tiles;
     int grid = 2 * 148;
     if (grid > ntiles) grid = ntiles;
     CUtensorMap tm_x;
-    constexpr bool MMA = UseMma<T, C / TL_WARPS>::value;  // the tensor-core layout is the 128-byte swizzle
-    const bool tma = tma_enabled() && make_map_2d<T>(&tm_x, x, (size_t)B * C, hw, C, TP, MMA);
+    // fp32 tiles: 128-byte rows, SWIZZLE_128B; bf16 tiles: 64-byte rows, SWIZZLE_64B
+    const bool tma = tma_enabled() && make_map_2d<T>(&tm_x, x, (size_t)B * C, hw, C, TP, MMA16 ? 3 : (MMA ? 1 : 0));
     auto kern = tma ? read_fwd_tiled_kernel<T, C, KP, NSTAGE, true> : read_fwd_tiled_kernel<T, C, KP, NSTAGE, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -485,7 +640,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
                              const float* __restrict__ rl_out, float* __restrict__ ds_out, int hw, int K,
                              int tiles_per_img, int ntiles) {
     constexpr int CW = C / TL_WARPS, NI = (KP + 7) / 8;
-    constexpr bool MMA = UseMma<T, CW>::value;
+    constexpr bool MMA = UseMma<T, CW>::value && sizeof(T) == 4;  // (the bf16 tensor-core path exists in the forward only)
     extern __shared__ __align__(16) unsigned char smraw[];
     float* Mt = reinterpret_cast<float*>(smraw);  // [C][KP]
     float* part = Mt + C * KP;                    // [8][TP][KP]
@@ -852,6 +1007,192 @@ __global__ void __launch_bounds__(DX_THREADS, 1)
 }
 
 
+// ---------------------------------------------------------------- backward, part B for bf16 maps on the tensor core
+// Same arithmetic; what changes is who does it. The K-slot contraction dq = dq0 + ds . M runs on mma.sync m16n8k16
+// (ds and M split bf16 hi + lo, three products, fp32 accumulate: 2^-16 relative), the x and dq0 values arrive as
+// `ldmatrix.trans` fragments in the accumulator layout (no 2-byte shared-memory loads, no conversions per element),
+// the result is packed back in place over the dq0 tile with `stmatrix.trans` and leaves as ONE TMA store per tile.
+// 8 warps x C/8 channels, 2 CTAs per SM. One barrier pair per tile: |x|^2 and x.dq are reduced together
+// (q.dq = x.dq / |x|).
+__device__ __forceinline__ void stmatrix_x4_trans(uint32_t saddr, const unsigned (&r)[4]) {
+    asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3])
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_tile_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+constexpr int DXB_THREADS = 256, DXB_WARPS = 8;
+
+template <int C, int KP, int NSTAGE>
+__global__ void __launch_bounds__(DXB_THREADS, 2)
+    read_bwd_dx_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_du,
+                            const __grid_constant__ CUtensorMap tm_dx, const float* __restrict__ M,
+                            const float* __restrict__ ds, int hw, int K, int tiles_per_img, int ntiles, int UC) {
+    using T = __nv_bfloat16;
+    constexpr int CW = C / DXB_WARPS, NN = CW / 8, KS = 2, LDK = C + 8;  // LDK % 32 == 8
+    static_assert(CW % 8 == 0 && KP <= 32, "channel slice must be whole 8-channel blocks");
+    extern __shared__ __align__(1024) unsigned char smraw_[];
+    __shared__ __align__(8) uint64_t full[NSTAGE];
+    unsigned char* smraw = smraw_ + ((1024u - (smem_u32(smraw_) & 1023u)) & 1023u);
+    T* xs = reinterpret_cast<T*>(smraw);                                      // [NSTAGE][2][C][TP]: x tile, dq0 tile
+    float* dss = reinterpret_cast<float*>(xs + (size_t)NSTAGE * 2 * C * TP);   // [NSTAGE][TP][KP]
+    unsigned* Mk_hi = reinterpret_cast<unsigned*>(dss + NSTAGE * TP * KP);     // [16][LDK]: (M[2kp][c], M[2kp+1][c])
+    unsigned* Mk_lo = Mk_hi + 8 * KS * LDK;
+    float* pn = reinterpret_cast<float*>(Mk_lo + 8 * KS * LDK);                // [8][TP]
+    float* pd = pn + DXB_WARPS * TP;                                           // [8][TP]
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int tl, int s) {  // one thread
+        const int b = tl / tiles_per_img, px0 = (tl - b * tiles_per_img) * TP;
+        const int nvalid = min(TP, hw - px0);
+        const uint32_t ds_bytes = (uint32_t)(nvalid * KP * sizeof(float));
+        T* base = xs + (size_t)s * 2 * C * TP;
+        mbar_expect_tx(&full[s], (uint32_t)(2 * C * TP * sizeof(T)) + ds_bytes);
+        tma_load_2d(base, &tm_x, px0, b * C, &full[s]);
+        tma_load_2d(base + C * TP, &tm_du, px0, b * UC, &full[s]);
+        bulk_load_1d(dss + s * TP * KP, ds + ((size_t)b * hw + px0) * KP, ds_bytes, &full[s]);
+    };
+    int tile = blockIdx.x;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) {
+            const int tl = tile + s * gridDim.x;
+            if (tl < ntiles) issue(tl, s);
+        }
+    }
+    for (int i = tid; i < 8 * KS * C; i += DXB_THREADS) {
+        const int kp = i / C, c = i - kp * C;
+        const float a = (2 * kp < K) ? __ldg(M + (size_t)(2 * kp) * C + c) : 0.f;
+        const float b = (2 * kp + 1 < K) ? __ldg(M + (size_t)(2 * kp + 1) * C + c) : 0.f;
+        const float ah = __bfloat162float(__float2bfloat16_rn(a)), bh = __bfloat162float(__float2bfloat16_rn(b));
+        Mk_hi[kp * LDK + c] = pack_bf16(ah, bh);
+        Mk_lo[kp * LDK + c] = pack_bf16(a - ah, b - bh);
+    }
+    __syncthreads();
+
+    const int c0 = wid * CW;
+    const int mj = lane >> 3, rr = lane & 7;  // ldmatrix / stmatrix: this lane addresses row rr of matrix mj
+    int stage = 0, pending = -1;              // `pending`: stage whose tile was handed to the TMA store last iteration
+    unsigned phase = 0;
+    for (; tile < ntiles; tile += gridDim.x) {
+        if (tid == 0 && pending >= 0) {  // refill the previous stage once its store has finished reading shared memory
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            const int next = tile + (NSTAGE - 1) * (int)gridDim.x;
+            if (next < ntiles) issue(next, pending);
+        }
+        mbar_wait(&full[stage], phase);
+        T* xt = xs + (size_t)stage * 2 * C * TP;
+        T* qt = xt + C * TP;
+        const int b = tile / tiles_per_img, px0 = (tile - b * tiles_per_img) * TP;
+        const int nvalid = min(TP, hw - px0);
+        // A fragments of ds [32 px][32 slots]: a[m][ks] = rows g+16m / g+8+16m, slots 16ks+2t(+1) / +8
+        unsigned ahi[2][KS][4], alo[2][KS][4];
+        {
+            const float* dsr = dss + stage * TP * KP;
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int px = g + 16 * m + 8 * (e & 1), k = 16 * ks + 2 * t + 8 * (e >> 1);
+                        float2 v = make_float2(0.f, 0.f);
+                        if (k < KP && px < nvalid) v = *reinterpret_cast<const float2*>(dsr + px * KP + k);  // KP even
+                        const float hx = __bfloat162float(__float2bfloat16_rn(v.x)), hy = __bfloat162float(__float2bfloat16_rn(v.y));
+                        ahi[m][ks][e] = pack_bf16(hx, hy);
+                        alo[m][ks][e] = pack_bf16(v.x - hx, v.y - hy);
+                    }
+        }
+        float dq[NN][2][4];      // [n][m][c-fragment]
+        unsigned xr[NN][4];      // x fragments: block j = pixels 8j..8j+7, halves = channels 2t, 2t+1 of the n-th block
+        float n2[4] = {0.f, 0.f, 0.f, 0.f}, xd[4] = {0.f, 0.f, 0.f, 0.f};  // pixels g + 8j
+#pragma unroll
+        for (int n = 0; n < NN; ++n) {
+            const int row = c0 + 8 * n + rr;
+            const uint32_t off = (uint32_t)(row * 64 + ((mj ^ ((row >> 1) & 3)) << 4));
+            unsigned qr[4];
+            ldmatrix_x4_trans(xr[n], smem_u32(xt) + off);
+            ldmatrix_x4_trans(qr, smem_u32(qt) + off);
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                dq[n][m][0] = bf16_lo_f(qr[2 * m]), dq[n][m][1] = bf16_hi_f(qr[2 * m]);
+                dq[n][m][2] = bf16_lo_f(qr[2 * m + 1]), dq[n][m][3] = bf16_hi_f(qr[2 * m + 1]);
+            }
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const int cidx = (8 * ks + t) * LDK + c0 + 8 * n + g;
+                const unsigned b0h = Mk_hi[cidx], b1h = Mk_hi[cidx + 4 * LDK], b0l = Mk_lo[cidx], b1l = Mk_lo[cidx + 4 * LDK];
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    mma_bf16(dq[n][m], alo[m][ks], b0h, b1h);
+                    mma_bf16(dq[n][m], ahi[m][ks], b0l, b1l);
+                    mma_bf16(dq[n][m], ahi[m][ks], b0h, b1h);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float x0 = bf16_lo_f(xr[n][j]), x1 = bf16_hi_f(xr[n][j]);
+                const float d0 = dq[n][j >> 1][2 * (j & 1)], d1 = dq[n][j >> 1][2 * (j & 1) + 1];
+                n2[j] = fmaf(x0, x0, fmaf(x1, x1, n2[j]));
+                xd[j] = fmaf(x0, d0, fmaf(x1, d1, xd[j]));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            n2[j] += __shfl_xor_sync(0xffffffffu, n2[j], 1);
+            n2[j] += __shfl_xor_sync(0xffffffffu, n2[j], 2);
+            xd[j] += __shfl_xor_sync(0xffffffffu, xd[j], 1);
+            xd[j] += __shfl_xor_sync(0xffffffffu, xd[j], 2);
+            if (t == 0) pn[wid * TP + g + 8 * j] = n2[j], pd[wid * TP + g + 8 * j] = xd[j];
+        }
+        __syncthreads();
+        float ir[4], cf[4];  // 1/|x| and (x.dq)/|x|^2 of pixels g + 8j
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float nn = 0.f, dd = 0.f;
+#pragma unroll
+            for (int w = 0; w < DXB_WARPS; ++w) nn += pn[w * TP + g + 8 * j], dd += pd[w * TP + g + 8 * j];
+            const float nrm = sqrtf(nn);
+            ir[j] = 1.f / fmaxf(nrm, PM_NORM_EPS);
+            cf[j] = (nrm <= PM_NORM_EPS) ? 0.f : dd * ir[j] * ir[j];  // F.normalize clamps: no projection below eps
+        }
+#pragma unroll
+        for (int n = 0; n < NN; ++n) {
+            unsigned o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float x0 = bf16_lo_f(xr[n][j]), x1 = bf16_hi_f(xr[n][j]);
+                const float d0 = dq[n][j >> 1][2 * (j & 1)], d1 = dq[n][j >> 1][2 * (j & 1) + 1];
+                o[j] = pack_bf16((d0 - x0 * cf[j]) * ir[j], (d1 - x1 * cf[j]) * ir[j]);
+            }
+            const int row = c0 + 8 * n + rr;
+            stmatrix_x4_trans(smem_u32(qt) + (uint32_t)(row * 64 + ((mj ^ ((row >> 1) & 3)) << 4)), o);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();  // the dx tile is complete in shared memory; every read of this stage is done
+        if (tid == 0) {
+            tma_store_tile_2d(&tm_dx, qt, px0, b * C);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        (void)nvalid;
+        pending = stage;
+        if (++stage == NSTAGE) stage = 0, phase ^= 1u;
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 template <typename T, int C, int KP>
 int launch_read_bwd_tiled(const void* du, const void* x, const float* M, const float* p, const float* ds_rl,
                           const float* g_loss, const float* rl_out, void* dx, float* ds, int B, int hw, int K,
@@ -884,6 +1225,24 @@ int launch_read_bwd_tiled(const void* du, const void* x, const float* M, const f
         if (grid > ntiles) grid = ntiles;
         CUtensorMap tm_x, tm_du;
         cudaError_t e;
+        if constexpr (sizeof(T) == 2 && (C == 128 || C == 256)) {
+            static const bool off = getenv("PM_BF16_MMA_OFF") != nullptr;  // A/B switch
+            CUtensorMap tm_dx;
+            if (!off && tma_enabled() && make_map_2d<T>(&tm_x, x, (size_t)B * C, hw, C, TP, 3) &&
+                make_map_2d<T>(&tm_du, du, (size_t)B * UC, hw, C, TP, 3) && make_map_2d<T>(&tm_dx, dx, (size_t)B * C, hw, C, TP, 3)) {
+                constexpr int NS = 2;
+                const size_t sm = sizeof(T) * (size_t)NS * 2 * C * TP + sizeof(float) * ((size_t)NS * TP * KP + 2 * DXB_WARPS * TP) +
+                                  sizeof(unsigned) * 2 * 16 * (C + 8) + 1024;
+                auto kern = read_bwd_dx_bf16_kernel<C, KP, NS>;
+                e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                if (e != cudaSuccess) return (int)e;
+                int g2 = 2 * 148;
+                if (g2 > ntiles) g2 = ntiles;
+                kern<<<g2, DXB_THREADS, sm, st>>>(tm_x, tm_du, tm_dx, M, ds, hw, K, tiles, ntiles, UC);
+                e = cudaGetLastError();
+                return e == cudaSuccess ? 0 : (int)e;
+            }
+        }
         if (tma_enabled() && C <= 256 && make_map_2d<T>(&tm_x, x, (size_t)B * C, hw, C, TP, false) &&
             make_map_2d<T>(&tm_du, du, (size_t)B * UC, hw, C, TP, false)) {
             auto kern = read_bwd_dx_tma_kernel<T, C, KP, NSTAGE>;

@@ -1,4 +1,6 @@
 // Memory write, pipelined variants (fast path when hw is a multiple of the 16-byte chunk).
+#include <cstdlib>
+
 #include "pm_common.cuh"
 #include "pm_tma.cuh"
 #include "pm_internal.h"
@@ -410,6 +412,244 @@ __global__ void __launch_bounds__(C) write_reduce_mma_kernel(const __grid_consta
     }
 }
 
+// ---- tensor-core variant for bf16 maps: mma.sync m16n8k16, fp32 accumulate ---------------------------------------
+// Same GEMM. The f tile ([C][32 px] bf16, TMA SWIZZLE_64B) IS the B operand: a 32-bit word of a channel row holds the
+// pixel pair (2t, 2t+1) an m16n8k16 B fragment wants, and with the 64-byte swizzle the eight rows of a fragment load
+// fall into distinct bank groups. 1/|f| scales the A operand (the label weights of the pixel) instead of the features,
+// so the bf16 feature values enter the product unrounded; A is split hi + lo (two MMAs).
+template <int C, int KP, bool TMA>
+__global__ void __launch_bounds__(C) write_reduce_mma16_kernel(const __grid_constant__ CUtensorMap tm_f,
+                                                                const __nv_bfloat16* __restrict__ f,
+                                                                const void* __restrict__ labels, int lab_u8,
+                                                                float* __restrict__ SD, int h, int w, int Hm, int Wm, int K,
+                                                                float sy, float sx, int tiles_per_img, int ntiles) {
+    using T = __nv_bfloat16;
+    constexpr int NSTAGE = 2, NW = C / 32, CS = C + 4, OMLD = 40;
+    extern __shared__ __align__(16) unsigned char smraw_[];
+    __shared__ __align__(8) uint64_t full[NSTAGE];
+    unsigned char* smraw = smem_align(smraw_, 1024);
+    T* ft = reinterpret_cast<T*>(smraw);  // [NSTAGE][C][32] swizzled; the region is reused as S_tile [32][CS] fp32 at the end
+    constexpr size_t RING_B = sizeof(T) * NSTAGE * C * 32 > sizeof(float) * 32 * CS ? sizeof(T) * NSTAGE * C * 32 : sizeof(float) * 32 * CS;
+    float* om = reinterpret_cast<float*>(smraw + RING_B);  // [32 px][OMLD] dense label weights of the current tile
+    float* pn = om + 32 * OMLD;                            // [NW][32]
+    float* invr = pn + NW * 32;                            // [32]
+    unsigned* cmask = reinterpret_cast<unsigned*>(invr + 32);
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, hw = h * w;
+    const int g = lane >> 2, t = lane & 3;
+    float acc[2][4][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) acc[m][n][0] = acc[m][n][1] = acc[m][n][2] = acc[m][n][3] = 0.f;
+    float Dacc = 0.f;
+    unsigned seen = 0u;
+
+    auto tile_coords = [&](int tl, int& b, int& px0) {
+        b = tl / tiles_per_img;
+        px0 = (tl - b * tiles_per_img) * 32;
+    };
+    auto taps_for = [&](int tl) {
+        LabelTaps r;
+        int b, px0;
+        tile_coords(tl, b, px0);
+        const int px = px0 + lane;
+        if (tl < ntiles && px < hw) {
+            const int fy = px / w, fx = px - fy * w;
+            r = label_taps(label_image(labels, (size_t)b * Hm * Wm, lab_u8), lab_u8, Hm, Wm, fy, fx, sy, sx, K);
+        } else {
+            r.cls[0] = r.cls[1] = r.cls[2] = r.cls[3] = K;
+            r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0.f;
+        }
+        return r;
+    };
+    auto load_tile = [&](int tl, int s) {  // cp.async ring: all threads, the SWIZZLE_64B pattern by hand
+        int b, px0;
+        tile_coords(tl, b, px0);
+        const T* base = f + (size_t)b * C * hw;
+        const int ch = tid % 4, px = px0 + ch * 8;
+        const bool valid = px < hw;
+        for (int row = tid / 4; row < C; row += C / 4)
+            cp_async16(ft + (size_t)s * C * 32 + row * 32 + ((ch ^ ((row >> 1) & 3)) << 3), base + (size_t)row * hw + (valid ? px : 0),
+                       valid);
+    };
+    int tile = blockIdx.x;
+    auto issue = [&](int tl, int s) {  // TMA: one thread
+        int b, px0;
+        tile_coords(tl, b, px0);
+        mbar_expect_tx(&full[s], (uint32_t)(C * 32 * sizeof(T)));
+        tma_load_2d(ft + (size_t)s * C * 32, &tm_f, px0, b * C, &full[s]);
+    };
+    if constexpr (TMA) {
+        if (tid == 0) {
+#pragma unroll
+            for (int s = 0; s < NSTAGE; ++s) mbar_init(&full[s], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+            for (int s = 0; s < NSTAGE; ++s)
+                if (tile + s * (int)gridDim.x < ntiles) issue(tile + s * gridDim.x, s);
+        }
+    } else {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) {
+            if (tile + s * (int)gridDim.x < ntiles) load_tile(tile + s * gridDim.x, s);
+            cp_async_commit();
+        }
+    }
+    LabelTaps tcur;
+    if (wid == 0) tcur = taps_for(tile);
+
+    int stage = 0;
+    unsigned phase = 0;
+    for (; tile < ntiles; tile += gridDim.x) {
+        LabelTaps tnext;
+        if (wid == 0) tnext = taps_for(tile + gridDim.x);
+        if constexpr (!TMA) cp_async_wait<NSTAGE - 1>();
+        __syncthreads();
+        if constexpr (TMA) mbar_wait(&full[stage], phase);
+        const T* xt = ft + (size_t)stage * C * 32;
+        const unsigned* xw = reinterpret_cast<const unsigned*>(xt);
+        for (int i = tid; i < 32 * OMLD / 4; i += C) reinterpret_cast<float4*>(om)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        {  // |f|^2 per pixel: lane l sums pixel pair (2(l&15), +1) over the rows wid*32 + 2i + (l>>4); halves combined below
+            const int half = lane >> 4, pp = (lane & 15) * 2;
+            float na = 0.f, nb = 0.f;
+#pragma unroll 8
+            for (int i = 0; i < 16; ++i) {
+                const int row = wid * 32 + 2 * i + half;
+                const unsigned v = xw[(row * 32 + ((((pp >> 3) ^ ((row >> 1) & 3)) << 3) | (pp & 7))) >> 1];
+                const float lo = __uint_as_float(v << 16), hi = __uint_as_float(v & 0xffff0000u);
+                na = fmaf(lo, lo, na), nb = fmaf(hi, hi, nb);
+            }
+            na += __shfl_xor_sync(0xffffffffu, na, 16);
+            nb += __shfl_xor_sync(0xffffffffu, nb, 16);
+            if (half == 0) pn[wid * 32 + pp] = na, pn[wid * 32 + pp + 1] = nb;
+        }
+        __syncthreads();
+        if (wid == 0) {
+            float sacc = 0.f;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) sacc += pn[i * 32 + lane];
+            invr[lane] = 1.f / fmaxf(sqrtf(sacc), PM_NORM_EPS);
+            unsigned m = 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (tcur.w[j] != 0.f) {
+                    om[lane * OMLD + tcur.cls[j]] = tcur.w[j];
+                    m |= 1u << tcur.cls[j];
+                }
+            m = __reduce_or_sync(0xffffffffu, m);
+            if (lane == 0) cmask[0] = m;
+        }
+        __syncthreads();
+        const unsigned cm = cmask[0];
+        seen |= cm;
+        const bool hi_tile = (cm >> 16) != 0u;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {  // 16 pixels per step
+            // A[class][px]: a0 = (class g, px 2t,2t+1), a1 = (class g+8, ..), a2 = (class g, px 2t+8,..), a3 = (class g+8, ..)
+            unsigned ah[2][4], al[2][4];
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                if (m == 0 || hi_tile) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int px = 16 * ks + 2 * t + 8 * (e >> 1), cls = 16 * m + g + 8 * (e & 1);
+                        const float v0 = om[px * OMLD + cls] * invr[px], v1 = om[(px + 1) * OMLD + cls] * invr[px + 1];
+                        const float h0 = __bfloat162float(__float2bfloat16_rn(v0)), h1 = __bfloat162float(__float2bfloat16_rn(v1));
+                        __nv_bfloat162 hh = __floats2bfloat162_rn(h0, h1), ll = __floats2bfloat162_rn(v0 - h0, v1 - h1);
+                        ah[m][e] = *reinterpret_cast<unsigned*>(&hh);
+                        al[m][e] = *reinterpret_cast<unsigned*>(&ll);
+                    }
+                }
+            }
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                const int row = wid * 32 + 8 * n + g, sw = (row >> 1) & 3;
+                const unsigned b0 = xw[row * 16 + (((2 * ks) ^ sw) << 2) + t], b1 = xw[row * 16 + (((2 * ks + 1) ^ sw) << 2) + t];
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    if (m == 0 || hi_tile) {
+                        asm volatile(
+                            "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                            : "+f"(acc[m][n][0]), "+f"(acc[m][n][1]), "+f"(acc[m][n][2]), "+f"(acc[m][n][3])
+                            : "r"(al[m][0]), "r"(al[m][1]), "r"(al[m][2]), "r"(al[m][3]), "r"(b0), "r"(b1));
+                        asm volatile(
+                            "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                            : "+f"(acc[m][n][0]), "+f"(acc[m][n][1]), "+f"(acc[m][n][2]), "+f"(acc[m][n][3])
+                            : "r"(ah[m][0]), "r"(ah[m][1]), "r"(ah[m][2]), "r"(ah[m][3]), "r"(b0), "r"(b1));
+                    }
+                }
+            }
+        }
+        {
+#pragma unroll
+            for (int px = wid; px < 32; px += NW) Dacc += om[px * OMLD + lane];
+        }
+        __syncthreads();
+        const int next = tile + NSTAGE * gridDim.x;
+        if constexpr (TMA) {
+            if (tid == 0 && next < ntiles) issue(next, stage);
+        } else {
+            if (next < ntiles) load_tile(next, stage);
+            cp_async_commit();
+        }
+        if (wid == 0) tcur = tnext;
+        if (++stage == NSTAGE) stage = 0, phase ^= 1u;
+    }
+    if constexpr (!TMA) cp_async_wait<0>();
+    __syncthreads();
+    float* S_tile = reinterpret_cast<float*>(smraw);
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            const int ch = wid * 32 + 8 * n + 2 * t;
+            *reinterpret_cast<float2*>(S_tile + (16 * m + g) * CS + ch) = make_float2(acc[m][n][0], acc[m][n][1]);
+            *reinterpret_cast<float2*>(S_tile + (16 * m + g + 8) * CS + ch) = make_float2(acc[m][n][2], acc[m][n][3]);
+        }
+    pn[wid * 32 + lane] = Dacc;
+    __syncthreads();
+    if (wid == 0) {
+        float d = 0.f;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) d += pn[i * 32 + lane];
+        S_tile[lane * CS + C] = d;
+        S_tile[lane * CS + C + 1] = S_tile[lane * CS + C + 2] = S_tile[lane * CS + C + 3] = 0.f;
+    }
+    __syncthreads();
+    for (int k = 0; k <= K; ++k) {
+        if (!((seen >> k) & 1u)) continue;
+        for (int i = tid; i < CS / 4; i += C)
+            atomicAdd(reinterpret_cast<float4*>(SD + (size_t)k * CS) + i, reinterpret_cast<const float4*>(S_tile + k * CS)[i]);
+    }
+}
+
+template <int C, int KP>
+int launch_write_reduce_mma16(const void* f, const void* labels, int lab_u8, float* SD, int B, int h, int w, int Hm, int Wm,
+                              int K, cudaStream_t st) {
+    using T = __nv_bfloat16;
+    const size_t ring = sizeof(T) * (size_t)2 * C * 32, stile = sizeof(float) * (size_t)32 * (C + 4);
+    const size_t smem = sizeof(float) * (32 * 40 + (C / 32) * 32 + 32 + 4) + (ring > stile ? ring : stile) + 1024;
+    const int hw = h * w, tiles = (hw + 31) / 32, ntiles = B * tiles;
+    const float sy = h > 1 ? (float)(Hm - 1) / (float)(h - 1) : 0.f;
+    const float sx = w > 1 ? (float)(Wm - 1) / (float)(w - 1) : 0.f;
+    CUtensorMap tm_f;
+    const bool tma = tma_enabled() && make_map_2d<T>(&tm_f, f, (size_t)B * C, hw, C, 32, 3);
+    auto kern = tma ? write_reduce_mma16_kernel<C, KP, true> : write_reduce_mma16_kernel<C, KP, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C, smem);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    int grid = 148 * per_sm;
+    if (grid > ntiles) grid = ntiles;
+    kern<<<grid, C, smem, st>>>(tm_f, (const T*)f, labels, lab_u8, SD, h, w, Hm, Wm, K, sy, sx, tiles, ntiles);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
 template <int C, int KP>
 int launch_write_reduce_mma(const void* f, const void* labels, int lab_u8, float* SD, int B, int h, int w, int Hm, int Wm, int K,
                             cudaStream_t st) {
@@ -676,6 +916,15 @@ int write_reduce_tiled(const void* f, const void* labels, int lab_u8, float* SD,
             default: return PM_ERR_CHANNELS;
         }
     } else {
+        static const bool mma_off = getenv("PM_BF16_MMA_OFF") != nullptr;  // A/B switch: the run-length FFMA2 kernel
+        if (!mma_off) {
+            switch (C) {  // tensor-core variant (whole 32-channel warps, >= 64 threads for the tile loads)
+                case 64: return launch_write_reduce_mma16<64, 32>(f, labels, lab_u8, SD, B, h, w, Hm, Wm, K, st);
+                case 128: return launch_write_reduce_mma16<128, 32>(f, labels, lab_u8, SD, B, h, w, Hm, Wm, K, st);
+                case 256: return launch_write_reduce_mma16<256, 32>(f, labels, lab_u8, SD, B, h, w, Hm, Wm, K, st);
+                default: break;
+            }
+        }
         if (K <= 19) { PM_WT_SWITCH_C(__nv_bfloat16, 20, launch_write_reduce_tiled, f, labels, lab_u8, SD, B, h, w, Hm, Wm, K, st) }
         else { PM_WT_SWITCH_C(__nv_bfloat16, 32, launch_write_reduce_tiled, f, labels, lab_u8, SD, B, h, w, Hm, Wm, K, st) }
     }
