@@ -472,8 +472,28 @@ def extra_configs(args, dev, dt, world, rank, mem0, timed):
             ms, _, _, _ = timed(step3, 5, 2, min_total_ms=100.0)
             ms /= 5
             n3 = 2 * w3["B"] * w3["h"] * w3["w"]
+            graphed = None
+            if not args.no_graph:   # the same seven passes captured once and replayed (no host work between kernels)
+                try:
+                    side = torch.cuda.Stream(device=dev)
+                    side.wait_stream(torch.cuda.current_stream(dev))
+                    with torch.cuda.stream(side):
+                        for _ in range(2):
+                            step3()
+                    torch.cuda.current_stream(dev).wait_stream(side)
+                    torch.cuda.synchronize()
+                    g3 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g3):
+                        step3()
+                    msg, _, _, _ = timed(g3.replay, 10, 3, min_total_ms=100.0)
+                    graphed = {"ms_per_step": msg / 10, "value": n3 / (msg / 10 * 1e-3) / 1e6,
+                               "what": "the same step captured as one CUDA graph and replayed"}
+                    g3.reset()
+                    del g3
+                except Exception as e:
+                    graphed = {"error": str(e)[:200]}
             out["cfg3_meta_train_step"] = {
-                "ms_per_step": ms, "value": n3 / (ms * 1e-3) / 1e6, "unit": UNIT,
+                "ms_per_step": ms, "value": n3 / (ms * 1e-3) / 1e6, "unit": UNIT, "cuda_graph": graphed,
                 "what": "4 forwards + 3 backwards of the module per step as in train.py:530-583 (write with graph + "
                         "backward(retain_graph), functional theta' through _parameters, write on the saved memory, read of "
                         "the graph-carrying memory + backward, no-grad eval write), OS16 batch 4 meta-train + 4 meta-test "

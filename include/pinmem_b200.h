@@ -49,17 +49,17 @@ enum pm_readloss_ws_layout {
     PM_WS_WORDS = 40
 };
 
-/* Rows of the per-CTA column-softmax partials ([PM_COLPART_ROWS + 1][64] floats; row PM_COLPART_ROWS = combined). */
+/* Rows of the per-CTA column-softmax partials ([PM_COLPART_ROWS + 2][64] floats; row PM_COLPART_ROWS = combined column
+ * maximum | 1/sum, row PM_COLPART_ROWS + 1 = arrival ticket of the fused combine: ZERO on entry, left zero). */
 #define PM_COLPART_ROWS 296
 
 /* Bumped with every prototype change; the binding refuses a library whose pm_version() differs. */
-#define PM_ABI_VERSION 200
+#define PM_ABI_VERSION 201
 int pm_version(void);
 const char* pm_status_string(int code);
 /* Row stride (floats) of the internal score buffers for K slots: 20 for K<=19, else 32. */
 int pm_score_stride(int K);
-/* Floats of the column-softmax partials buffer ((PM_COLPART_ROWS + 1) * 64: the last row receives the combined column
- * maximum and 1/sum). */
+/* Floats of the column-softmax partials buffer ((PM_COLPART_ROWS + 2) * 64, layout above). */
 int pm_colsoftmax_workspace_floats(int K);
 
 /*
@@ -71,9 +71,10 @@ int pm_colsoftmax_workspace_floats(int K);
  *   u        [B,2C,h,w] dtype out     = [x/|x| ; softmax_k(s+g).M]
  *   s        [N,stride] fp32 out      raw similarities (internal score buffer)
  *   score_m  [N,K] fp32 out           softmax over slots (score_memory)
- *   col_partials  NULL, or pm_colsoftmax_workspace_floats(K) floats out: per-CTA (max,sum) of every column of
- *                 s + gumbel_q, the first pass of the dim-0 softmax fused into this kernel; feed it to
- *                 pm_colsoftmax_apply.
+ *   col_partials  NULL, or pm_colsoftmax_workspace_floats(K) floats whose LAST 64 (the ticket row) the caller has
+ *                 ZEROED: per-CTA (max,sum) of every column of s + gumbel_q -- the first pass of the dim-0 softmax
+ *                 fused into this kernel -- and, from the last CTA to finish, their combination (column maximum and
+ *                 1/sum); feed it to pm_colsoftmax_apply.
  */
 int pm_read_fwd(const void* x, const float* M, const float* gumbel_m, const float* gumbel_q, void* u, float* s,
                 float* score_m, float* col_partials, int B, int C, int h, int w, int K, int dtype, void* stream);
@@ -85,8 +86,8 @@ int pm_read_fwd(const void* x, const float* M, const float* gumbel_m, const floa
  */
 int pm_colsoftmax(const float* s, const float* gumbel_q, float* score_q, float* workspace, int N, int K,
                   void* stream);
-/* Second pass only: combine the column partials produced by pm_read_fwd (one small CTA), then normalise. col_partials'
- * last row is written. */
+/* Second pass only: normalise with the combined column statistics pm_read_fwd[_planes] left in col_partials (one
+ * launch; the round-1 library combined the partials in a launch of its own here). */
 int pm_colsoftmax_apply(const float* s, const float* gumbel_q, const float* col_partials, float* score_q, int N,
                         int K, void* stream);
 
@@ -136,8 +137,11 @@ int pm_read_fwd_planes(const void* x, const float* M, const float* gumbel_m, con
                        float* s, float* score_m, float* col_partials, int B, int C, int h, int w, int K, int dtype,
                        void* stream);
 int pm_read_bwd_planes(const void* du, const void* x, const float* M, const float* score_m, const float* ds_rl,
-                       const float* g_loss, const float* rl_out, void* dx, float* ds, int B, int C, int h, int w,
-                       int K, int dtype, void* stream);
+                       const float* g_loss, const float* rl_out, void* dx, const void* dx_add, float* ds, int B, int C,
+                       int h, int w, int K, int dtype, void* stream);
+/*   dx_add   NULL, or [B,C,h,w] dtype: a second gradient of x (the write branch's, when query feeds both the read and
+ *            the writing net) that the kernel sums into dx -- the accumulation autograd would otherwise do with an
+ *            element-wise add of three feature-sized tensors. */
 
 /*
  * The folded weight of the score-plane read and its gradient w.r.t. W (both fp32, row-major):

@@ -16,7 +16,7 @@ WS_WORDS = 40  # PM_WS_WORDS
 WS_HIST = 4    # PM_WS_HIST
 WS_BAD = 2     # PM_WS_BAD
 
-ABI_VERSION = 200  # PM_ABI_VERSION of include/pinmem_b200.h the argtypes below were written against
+ABI_VERSION = 201  # PM_ABI_VERSION of include/pinmem_b200.h the argtypes below were written against
 
 _c_p = ctypes.c_void_p
 _c_i = ctypes.c_int
@@ -36,7 +36,7 @@ PROTOTYPES = {
     "pm_read_bwd_dM": [_c_p] * 5 + [_c_i] * 6 + [_c_p],
     "pm_read_planes": [],
     "pm_read_fwd_planes": [_c_p] * 8 + [_c_i] * 6 + [_c_p],
-    "pm_read_bwd_planes": [_c_p] * 9 + [_c_i] * 6 + [_c_p],
+    "pm_read_bwd_planes": [_c_p] * 10 + [_c_i] * 6 + [_c_p],
     "pm_fold_weight_fwd": [_c_p] * 3 + [_c_i] * 3 + [_c_p],
     "pm_fold_weight_bwd": [_c_p] * 3 + [_c_i] * 3 + [_c_p],
     "pm_score_nhwc": [_c_p] * 3 + [_c_i] * 3 + [_c_p],
@@ -181,7 +181,7 @@ def score_stride(K):
 # with CUDA events on the launching stream to get per-kernel durations live.
 
 LAUNCHES = 0
-_KERNELS_PER_CALL = {"pm_colsoftmax": 3, "pm_colsoftmax_apply": 2, "pm_read_bwd": 2, "pm_read_bwd_planes": 2, "pm_conv1x1_wgrad": 2}
+_KERNELS_PER_CALL = {"pm_colsoftmax": 3, "pm_colsoftmax_apply": 1, "pm_read_bwd": 2, "pm_read_bwd_planes": 2, "pm_conv1x1_wgrad": 2}
 PLANES = 32  # PM_PLANES: score planes appended to q in the score-plane read
 _timing = None  # name -> list of (start_event, end_event) when enabled
 
@@ -255,10 +255,17 @@ def readloss_fwd(s, labels, temperature, B, h, w, K, ds_rl, ws, out):
                                   _ptr(ws), _ptr(out), _stream())
 
 
-def read_bwd(du, x, M, score_m, ds_rl, g_loss, rl_out, dx, ds, K, planes=False):
+def read_bwd(du, x, M, score_m, ds_rl, g_loss, rl_out, dx, ds, K, planes=False, dx_add=None):
+    """``dx_add`` (score-plane read only): a second gradient of x summed into dx by the kernel."""
     B, C, h, w = x.shape
-    _call("pm_read_bwd_planes" if planes else "pm_read_bwd", _ptr(du), _ptr(x), _ptr(M), _ptr(score_m), _ptr(ds_rl), _ptr(g_loss), _ptr(rl_out),
-                              _ptr(dx), _ptr(ds), B, C, h, w, K, dtype_code(x), _stream())
+    if planes:
+        _call("pm_read_bwd_planes", _ptr(du), _ptr(x), _ptr(M), _ptr(score_m), _ptr(ds_rl), _ptr(g_loss), _ptr(rl_out),
+              _ptr(dx), _ptr(dx_add), _ptr(ds), B, C, h, w, K, dtype_code(x), _stream())
+        return
+    if dx_add is not None:
+        raise RuntimeError("pinmem_b200: dx_add is only supported by the score-plane read backward")
+    _call("pm_read_bwd", _ptr(du), _ptr(x), _ptr(M), _ptr(score_m), _ptr(ds_rl), _ptr(g_loss), _ptr(rl_out),
+          _ptr(dx), _ptr(ds), B, C, h, w, K, dtype_code(x), _stream())
 
 
 def read_bwd_dM(du, x, score_m, ds, dM, K):

@@ -333,14 +333,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 const float sc = ep_scale != nullptr ? __ldg(ep_scale + row0 + lane) : 1.f;
                 const float sh = ep_scale != nullptr ? __ldg(ep_shift + row0 + lane) : 0.f;
                 float ts = 0.f, tq = 0.f;
-#pragma unroll 1
-                for (int c = 0; c < NCH; ++c) {
-                    const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((a * MT + mt) * NT + c * PXC);
-                    uint4 out[8];
-                    if constexpr (sizeof(T) == 4) {
-                        uint32_t r[32];
-                        tmem_ld32(ta, r);
-                        tmem_ld_wait();
+                const uint32_t ta0 = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((a * MT + mt) * NT);
+                // stage one 32-row x 128-byte chunk in shared memory (swizzled) and hand it to the TMA unit
+                auto emit = [&](const uint4 (&out)[8], int c) {
+                    unsigned char* buf = mystg + bi * 4096;
+                    bi ^= 1;
+                    if (lane == 0) bulk_wait_read<1>();  // the store issued two chunks ago has left this buffer
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = out[j];
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (accumulate) tma_reduce_add_2d(&mapY, px0 + c * PXC, b * M + row0, buf);
+                        else tma_store_2d(&mapY, px0 + c * PXC, b * M + row0, buf);
+                        bulk_commit();
+                    }
+                };
+                if constexpr (sizeof(T) == 4) {
+                    // software pipeline over the chunks: the TMEM load of chunk c+1 is in flight while chunk c is reduced,
+                    // staged and stored (tcgen05.wait::ld waits for everything outstanding, so exactly one load is)
+                    auto process = [&](uint32_t (&r)[32], int c) {
                         if (ep_scale != nullptr) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
@@ -355,9 +369,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                             ts += v;
                             tq = fmaf(v, v, tq);
                         }
+                        uint4 out[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) out[j] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-                    } else {
+                        emit(out, c);
+                    };
+                    uint32_t ra[32], rb[32];
+                    tmem_ld32(ta0, ra);
+#pragma unroll 1
+                    for (int c = 0; c < NCH; c += 2) {
+                        tmem_ld_wait();
+                        if (c + 1 < NCH) tmem_ld32(ta0 + (uint32_t)((c + 1) * PXC), rb);
+                        process(ra, c);
+                        if (c + 1 < NCH) {
+                            tmem_ld_wait();
+                            if (c + 2 < NCH) tmem_ld32(ta0 + (uint32_t)((c + 2) * PXC), ra);
+                            process(rb, c + 1);
+                        }
+                    }
+                } else {
+#pragma unroll 1
+                    for (int c = 0; c < NCH; ++c) {
+                        const uint32_t ta = ta0 + (uint32_t)(c * PXC);
+                        uint4 out[8];
                         uint32_t r0[32], r1[32];
                         tmem_ld32(ta, r0);
                         tmem_ld32(ta + 32, r1);
@@ -383,20 +417,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                         }
 #pragma unroll
                         for (int j = 0; j < 8; ++j) out[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-                    }
-                    unsigned char* buf = mystg + bi * 4096;
-                    bi ^= 1;
-                    if (lane == 0) bulk_wait_read<1>();  // the store issued two chunks ago has left this buffer
-                    __syncwarp();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = out[j];
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (accumulate) tma_reduce_add_2d(&mapY, px0 + c * PXC, b * M + row0, buf);
-                        else tma_store_2d(&mapY, px0 + c * PXC, b * M + row0, buf);
-                        bulk_commit();
+                        emit(out, c);
                     }
                 }
                 sum[mt] += (double)ts;

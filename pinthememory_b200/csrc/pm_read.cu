@@ -565,7 +565,7 @@ extern "C" int pm_read_bwd(const void* du, const void* x, const float* M, const 
     if (int e = check_common(B, C, h, w, K, dtype)) return e;
     if (((uintptr_t)ds & 15) != 0 || ((uintptr_t)ds_rl & 15) != 0) return PM_ERR_ALIGN;
     if (ds != nullptr && pm::tiled_ok(du, x, dx, h * w, dtype))
-        return pm::read_bwd_tiled(du, x, M, score_m, ds_rl, g_loss, rl_out, dx, ds, B, C, h * w, K, dtype, 0,
+        return pm::read_bwd_tiled(du, x, M, score_m, ds_rl, g_loss, rl_out, dx, nullptr, ds, B, C, h * w, K, dtype, 0,
                                   (cudaStream_t)stream);
     PM_DISPATCH(PM_DISPATCH_CW, launch_read_bwd, du, x, M, score_m, ds_rl, g_loss, rl_out, dx, ds, B, h * w, K,
                 (cudaStream_t)stream);
@@ -584,13 +584,14 @@ extern "C" int pm_read_fwd_planes(const void* x, const float* M, const float* gu
 }
 
 extern "C" int pm_read_bwd_planes(const void* du, const void* x, const float* M, const float* score_m,
-                                  const float* ds_rl, const float* g_loss, const float* rl_out, void* dx, float* ds,
-                                  int B, int C, int h, int w, int K, int dtype, void* stream) {
+                                  const float* ds_rl, const float* g_loss, const float* rl_out, void* dx,
+                                  const void* dx_add, float* ds, int B, int C, int h, int w, int K, int dtype,
+                                  void* stream) {
     if (!du || !x || !M || !score_m || !dx || !ds) return PM_ERR_NULL;
     if (int e = check_common(B, C, h, w, K, dtype)) return e;
     if (((uintptr_t)ds & 15) != 0 || ((uintptr_t)ds_rl & 15) != 0 || !pm::tiled_ok(du, x, dx, h * w, dtype))
         return PM_ERR_ALIGN;
-    return pm::read_bwd_tiled(du, x, M, score_m, ds_rl, g_loss, rl_out, dx, ds, B, C, h * w, K, dtype, 1,
+    return pm::read_bwd_tiled(du, x, M, score_m, ds_rl, g_loss, rl_out, dx, dx_add, ds, B, C, h * w, K, dtype, 1,
                               (cudaStream_t)stream);
 }
 

@@ -597,9 +597,61 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
             colpart[(size_t)blockIdx.x * 64 + tid] = Mx;
             colpart[(size_t)blockIdx.x * 64 + 32 + tid] = L;
         }
-        if (blockIdx.x == 0) {  // rows of CTAs that do not exist
-            for (int i = gridDim.x * 64 + tid; i < PM_COLPART_ROWS * 64; i += TL_THREADS)
-                colpart[i] = ((i & 63) < 32) ? -INFINITY : 0.f;
+        // The last CTA to get here combines the gridDim.x partial rows into the final column maximum and 1/sum (row
+        // PM_COLPART_ROWS) -- what used to be a separate one-CTA launch between this kernel and the normalising pass.
+        // Ticket = first word of row PM_COLPART_ROWS + 1: zero on entry (caller), left zero.
+        __shared__ int s_last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            unsigned* ticket = reinterpret_cast<unsigned*>(colpart + (size_t)(PM_COLPART_ROWS + 1) * 64);
+            s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            // thread (k = tid % 32, r0 = tid / 32): rows r0, r0 + 8, ..; loads in batches of 8 independent L2 hits
+            const int k = tid & 31, r0 = tid >> 5;
+            float Mx = -INFINITY, L = 0.f;
+            const int G = (int)gridDim.x;
+            for (int rb = r0; rb < G; rb += 8 * 8) {
+                float pmx[8], pl[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int r = rb + 8 * j;
+                    pmx[j] = (r < G && k < K) ? __ldcg(colpart + (size_t)r * 64 + k) : -INFINITY;
+                    pl[j] = (r < G && k < K) ? __ldcg(colpart + (size_t)r * 64 + 32 + k) : 0.f;
+                }
+                float bm = Mx;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bm = fmaxf(bm, pmx[j]);
+                if (bm > -INFINITY) {
+                    L *= expf(Mx - bm);  // Mx = -inf: L is 0 and exp(-inf) = 0
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (pmx[j] > -INFINITY) L += pl[j] * expf(pmx[j] - bm);
+                    Mx = bm;
+                }
+            }
+            float* scr = part;  // [8][2][32]
+            __syncthreads();
+            scr[(r0 * 2 + 0) * 32 + k] = Mx;
+            scr[(r0 * 2 + 1) * 32 + k] = L;
+            __syncthreads();
+            if (tid < K) {
+                float Mt_ = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) Mt_ = fmaxf(Mt_, scr[(i * 2) * 32 + tid]);
+                float Ls = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float mi = scr[(i * 2) * 32 + tid];
+                    if (mi > -INFINITY) Ls += scr[(i * 2 + 1) * 32 + tid] * expf(mi - Mt_);
+                }
+                colpart[(size_t)PM_COLPART_ROWS * 64 + tid] = Mt_;
+                colpart[(size_t)PM_COLPART_ROWS * 64 + 32 + tid] = 1.f / Ls;
+            }
+            if (tid == 0) *reinterpret_cast<unsigned*>(colpart + (size_t)(PM_COLPART_ROWS + 1) * 64) = 0u;
         }
     }
 }
@@ -771,8 +823,8 @@ constexpr int DX_THREADS = 512, DX_WARPS = 16;
 template <typename T, int C, int KP, int NSTAGE>
 __global__ void __launch_bounds__(DX_THREADS, 1)
     read_bwd_dx_tiled_kernel(const T* __restrict__ du, const T* __restrict__ x, const float* __restrict__ M,
-                             const float* __restrict__ ds, T* __restrict__ dx, int hw, int K, int tiles_per_img,
-                             int ntiles, int UC) {  // UC: channels per image of du (2C, or C + PM_PLANES)
+                             const float* __restrict__ ds, T* __restrict__ dx, const T* __restrict__ dx_add, int hw, int K,
+                             int tiles_per_img, int ntiles, int UC) {  // UC: channels per image of du (2C, or C + PM_PLANES)
     constexpr int CW = C / DX_WARPS;
     extern __shared__ __align__(16) unsigned char smraw[];
     float* Mt = reinterpret_cast<float*>(smraw);        // [C][KP]
@@ -867,11 +919,24 @@ __global__ void __launch_bounds__(DX_THREADS, 1)
         for (int w = 0; w < DX_WARPS; ++w) dot += pd[w * TP + lane];
         if (nrm <= PM_NORM_EPS) dot = 0.f;  // F.normalize clamps the norm: no projection gradient below eps
         if (lane < nvalid) {
-            T* dxp = dx + ((size_t)b * C + wid * CW) * hw + px0 + lane;
+            const size_t o0 = ((size_t)b * C + wid * CW) * hw + px0 + lane;
+            T* dxp = dx + o0;
+            if (dx_add != nullptr) {  // a second gradient of x (the write branch's) summed here instead of by an add kernel
+                const T* ap = dx_add + o0;
+                float av[CW];
 #pragma unroll
-            for (int j = 0; j < CW; ++j) {
-                stf(dxp, (dq[j] - xv[j] * dot) * ir);
-                dxp += hw;
+                for (int j = 0; j < CW; ++j) av[j] = ldf(ap + (size_t)j * hw);
+#pragma unroll
+                for (int j = 0; j < CW; ++j) {
+                    stf(dxp, (dq[j] - xv[j] * dot) * ir + av[j]);
+                    dxp += hw;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < CW; ++j) {
+                    stf(dxp, (dq[j] - xv[j] * dot) * ir);
+                    dxp += hw;
+                }
             }
         }
         stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
@@ -889,8 +954,8 @@ __global__ void __launch_bounds__(DX_THREADS, 1)
 template <typename T, int C, int KP, int NSTAGE>
 __global__ void __launch_bounds__(DX_THREADS, 1)
     read_bwd_dx_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_du,
-                           const float* __restrict__ M, const float* __restrict__ ds, T* __restrict__ dx, int hw, int K,
-                           int tiles_per_img, int ntiles, int UC) {
+                           const float* __restrict__ M, const float* __restrict__ ds, T* __restrict__ dx,
+                           const T* __restrict__ dx_add, int hw, int K, int tiles_per_img, int ntiles, int UC) {
     constexpr int CW = C / DX_WARPS;
     extern __shared__ __align__(1024) unsigned char smraw_[];
     __shared__ __align__(8) uint64_t full[NSTAGE];
@@ -943,6 +1008,10 @@ __global__ void __launch_bounds__(DX_THREADS, 1)
         const int nvalid = min(TP, hw - px0);
         const T* xcol = xt + wid * CW * 32 + lane;
         const T* qcol = qt + wid * CW * 32 + lane;
+        const size_t o0 = ((size_t)b * C + wid * CW) * hw + px0 + lane;
+        float av[CW];  // a second gradient of x (the write branch's), summed here instead of by an add kernel
+#pragma unroll
+        for (int j = 0; j < CW; ++j) av[j] = (dx_add != nullptr && lane < nvalid) ? ldf(dx_add + o0 + (size_t)j * hw) : 0.f;
         float xv[CW], n2 = 0.f;
 #pragma unroll
         for (int j = 0; j < CW; ++j) {
@@ -995,10 +1064,10 @@ __global__ void __launch_bounds__(DX_THREADS, 1)
         for (int w = 0; w < DX_WARPS; ++w) dot += pd[w * TP + lane];
         if (nrm <= PM_NORM_EPS) dot = 0.f;
         if (lane < nvalid) {
-            T* dxp = dx + ((size_t)b * C + wid * CW) * hw + px0 + lane;
+            T* dxp = dx + o0;
 #pragma unroll
             for (int j = 0; j < CW; ++j) {
-                stf(dxp, (dq[j] - xv[j] * dot) * ir);
+                stf(dxp, (dq[j] - xv[j] * dot) * ir + av[j]);
                 dxp += hw;
             }
         }
@@ -1195,8 +1264,8 @@ __global__ void __launch_bounds__(DXB_THREADS, 2)
 
 template <typename T, int C, int KP>
 int launch_read_bwd_tiled(const void* du, const void* x, const float* M, const float* p, const float* ds_rl,
-                          const float* g_loss, const float* rl_out, void* dx, float* ds, int B, int hw, int K,
-                          int planes, cudaStream_t st) {
+                          const float* g_loss, const float* rl_out, void* dx, const void* dx_add, float* ds, int B, int hw,
+                          int K, int planes, cudaStream_t st) {
     constexpr int NSTAGE = 2;
     const int tiles = (hw + TP - 1) / TP, ntiles = B * tiles;
     const int UC = planes ? C + PM_PLANES : 2 * C;
@@ -1228,7 +1297,7 @@ int launch_read_bwd_tiled(const void* du, const void* x, const float* M, const f
         if constexpr (sizeof(T) == 2 && (C == 128 || C == 256)) {
             static const bool off = getenv("PM_BF16_MMA_OFF") != nullptr;  // A/B switch
             CUtensorMap tm_dx;
-            if (!off && tma_enabled() && make_map_2d<T>(&tm_x, x, (size_t)B * C, hw, C, TP, 3) &&
+            if (!off && dx_add == nullptr && tma_enabled() && make_map_2d<T>(&tm_x, x, (size_t)B * C, hw, C, TP, 3) &&
                 make_map_2d<T>(&tm_du, du, (size_t)B * UC, hw, C, TP, 3) && make_map_2d<T>(&tm_dx, dx, (size_t)B * C, hw, C, TP, 3)) {
                 constexpr int NS = 2;
                 const size_t sm = sizeof(T) * (size_t)NS * 2 * C * TP + sizeof(float) * ((size_t)NS * TP * KP + 2 * DXB_WARPS * TP) +
@@ -1248,12 +1317,12 @@ int launch_read_bwd_tiled(const void* du, const void* x, const float* M, const f
             auto kern = read_bwd_dx_tma_kernel<T, C, KP, NSTAGE>;
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024);
             if (e != cudaSuccess) return (int)e;
-            kern<<<grid, DX_THREADS, smem + 1024, st>>>(tm_x, tm_du, M, ds, (T*)dx, hw, K, tiles, ntiles, UC);
+            kern<<<grid, DX_THREADS, smem + 1024, st>>>(tm_x, tm_du, M, ds, (T*)dx, (const T*)dx_add, hw, K, tiles, ntiles, UC);
         } else {
             auto kern = read_bwd_dx_tiled_kernel<T, C, KP, NSTAGE>;
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
-            kern<<<grid, DX_THREADS, smem, st>>>((const T*)du, (const T*)x, M, ds, (T*)dx, hw, K, tiles, ntiles, UC);
+            kern<<<grid, DX_THREADS, smem, st>>>((const T*)du, (const T*)x, M, ds, (T*)dx, (const T*)dx_add, hw, K, tiles, ntiles, UC);
         }
         e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
@@ -1287,14 +1356,14 @@ int read_fwd_tiled(const void* x, const float* M, const float* gum_m, const floa
 }
 
 int read_bwd_tiled(const void* du, const void* x, const float* M, const float* p, const float* ds_rl,
-                   const float* g_loss, const float* rl_out, void* dx, float* ds, int B, int C, int hw, int K, int dtype,
-                   int planes, cudaStream_t st) {
+                   const float* g_loss, const float* rl_out, void* dx, const void* dx_add, float* ds, int B, int C, int hw,
+                   int K, int dtype, int planes, cudaStream_t st) {
     if (dtype == PM_F32) {
-        if (K <= 19) { PM_TILED_SWITCH_C(float, 20, launch_read_bwd_tiled, du, x, M, p, ds_rl, g_loss, rl_out, dx, ds, B, hw, K, planes, st) }
-        else { PM_TILED_SWITCH_C(float, 32, launch_read_bwd_tiled, du, x, M, p, ds_rl, g_loss, rl_out, dx, ds, B, hw, K, planes, st) }
+        if (K <= 19) { PM_TILED_SWITCH_C(float, 20, launch_read_bwd_tiled, du, x, M, p, ds_rl, g_loss, rl_out, dx, dx_add, ds, B, hw, K, planes, st) }
+        else { PM_TILED_SWITCH_C(float, 32, launch_read_bwd_tiled, du, x, M, p, ds_rl, g_loss, rl_out, dx, dx_add, ds, B, hw, K, planes, st) }
     } else {
-        if (K <= 19) { PM_TILED_SWITCH_C(__nv_bfloat16, 20, launch_read_bwd_tiled, du, x, M, p, ds_rl, g_loss, rl_out, dx, ds, B, hw, K, planes, st) }
-        else { PM_TILED_SWITCH_C(__nv_bfloat16, 32, launch_read_bwd_tiled, du, x, M, p, ds_rl, g_loss, rl_out, dx, ds, B, hw, K, planes, st) }
+        if (K <= 19) { PM_TILED_SWITCH_C(__nv_bfloat16, 20, launch_read_bwd_tiled, du, x, M, p, ds_rl, g_loss, rl_out, dx, dx_add, ds, B, hw, K, planes, st) }
+        else { PM_TILED_SWITCH_C(__nv_bfloat16, 32, launch_read_bwd_tiled, du, x, M, p, ds_rl, g_loss, rl_out, dx, dx_add, ds, B, hw, K, planes, st) }
     }
 }
 

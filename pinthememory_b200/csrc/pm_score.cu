@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) colsoftmax_stats_kernel(const float* __re
 // 1/sum, stored in row PM_COLPART_ROWS of the partials buffer ([0..32) max, [32..64) 1/sum). The apply kernel that follows
 // then runs on as many small CTAs as there are rows to normalise (the round-1 version re-combined the 296 x 64 partials
 // in every one of its <= 296 CTAs: 75 KB of L2 reads and a dependent latency chain per CTA, 18 us for 11 MB of work).
-__global__ void __launch_bounds__(256) colsoftmax_combine_kernel(float* __restrict__ partial, int K) {
+__global__ void __launch_bounds__(256) colsoftmax_combine_kernel(float* __restrict__ partial, int K) {  // all PM_COLPART_ROWS rows
     __shared__ float sm_m[256], sm_l[256];
     const int t = threadIdx.x, k = t % K, r0 = t / K, rstep = blockDim.x / K;
     constexpr int MAXJ = (CS_MAXG + 7) / 8;  // rstep >= 8 for K <= 31
@@ -123,13 +123,14 @@ __global__ void __launch_bounds__(256) rowsoftmax_kernel(const float* __restrict
 }  // namespace pm
 
 extern "C" int pm_score_stride(int K) { return K <= 19 ? 20 : 32; }
-extern "C" int pm_colsoftmax_workspace_floats(int K) { return (pm::CS_MAXG + 1) * 64; }  // + the combined row
+extern "C" int pm_colsoftmax_workspace_floats(int K) { return (pm::CS_MAXG + 2) * 64; }  // + the combined row + the ticket row
 
 namespace pm {
 int colsoftmax_stats(const float* s, const float* gumbel_q, float* partial, int N, int K, cudaStream_t st) {
     const int KP = pm_score_stride(K), tpb = K * (256 / K);
     const int rows_per_cta = (N + CS_MAXG - 1) / CS_MAXG;  // CTAs past the end write (-inf, 0)
     colsoftmax_stats_kernel<<<CS_MAXG, tpb, 0, st>>>(s, gumbel_q, partial, N, K, KP, rows_per_cta);
+    colsoftmax_combine_kernel<<<1, tpb, 0, st>>>(partial, K);  // -> row PM_COLPART_ROWS: column maximum, 1/sum
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }
@@ -141,8 +142,7 @@ extern "C" int pm_colsoftmax_apply(const float* s, const float* gumbel_q, const 
     if (K < 1 || K > 31) return PM_ERR_SLOTS;
     if (N <= 0) return PM_ERR_SHAPE;
     const int KP = pm_score_stride(K), tpb = K * (256 / K), rstep = tpb / K;
-    // the partials are written by another kernel of this stream and only read here, except for the combined row
-    pm::colsoftmax_combine_kernel<<<1, tpb, 0, (cudaStream_t)stream>>>(const_cast<float*>(col_partials), K);
+    // the combined row (column maximum, 1/sum) was left by pm_read_fwd[_planes] / the statistics pass
     const int rows_per_cta = rstep * 5;   // 5 rows per thread: ~1100 small CTAs at cfg 2
     const int G = (N + rows_per_cta - 1) / rows_per_cta;
     pm::colsoftmax_apply_kernel<<<G, tpb, 0, (cudaStream_t)stream>>>(s, gumbel_q, col_partials, score_q, N, K, KP,

@@ -79,7 +79,10 @@ class _ReadFn(torch.autograd.Function):
     last_lab8 = None  # the packed uint8 class map that read produced (None when the first-generation kernel ran)
 
     @staticmethod
-    def forward(ctx, x, M, labels, g_query, g_memory, temperature, K, planes=False):
+    def forward(ctx, x, M, labels, g_query, g_memory, temperature, K, planes=False, tee=False):
+        """``tee=True`` appends x itself to the outputs: a caller that feeds the same features to a second branch (the
+        writing net) hands that branch the tee, so its gradient arrives HERE as an input of backward() and the dx kernel
+        sums it in (``dx_add``) -- instead of autograd adding two feature-sized gradients with an element-wise kernel."""
         B, C, h, w = x.shape
         N = B * h * w
         dev = x.device
@@ -90,15 +93,18 @@ class _ReadFn(torch.autograd.Function):
         score_m = torch.empty(N, K, dtype=torch.float32, device=dev)
         score_q = torch.empty(N, K, dtype=torch.float32, device=dev)
         M = M.contiguous()
-        col_partials = torch.empty(capi.colsoftmax_workspace_floats(K), dtype=torch.float32, device=dev)
+        # one zeroed allocation: [ds_rl (N*KP floats, with labels) | workspace (40 x 8 bytes) | out (4 floats) | column
+        # partials (their ticket row must be zero)]
+        n_rl = N * KP if labels is not None else 0
+        n_cp = capi.colsoftmax_workspace_floats(K)
+        buf = torch.zeros(n_rl + 2 * capi.WS_WORDS + 4 + n_cp, dtype=torch.float32, device=dev)
+        col_partials = buf[n_rl + 2 * capi.WS_WORDS + 4:]
         capi.read_fwd(x, M, g_memory, u, s, score_m, K, gumbel_q=g_query, col_partials=col_partials, planes=planes)
         capi.colsoftmax_apply(s, g_query, col_partials, score_q, N, K)
         if labels is not None:
-            # one zeroed allocation: [ds_rl (N*KP floats) | workspace (40 x 8 bytes) | out (2 floats)]
-            buf = torch.zeros(N * KP + 2 * capi.WS_WORDS + 4, dtype=torch.float32, device=dev)
             ds_rl = buf[: N * KP]
             ws = buf[N * KP: N * KP + 2 * capi.WS_WORDS]
-            rl_out = buf[N * KP + 2 * capi.WS_WORDS:]
+            rl_out = buf[N * KP + 2 * capi.WS_WORDS: N * KP + 2 * capi.WS_WORDS + 4]
             # one pass over the labels (packed uint8 classes + histogram + bad-label count), then the read loss on it
             _ReadFn.last_lab8 = capi.readloss(s, labels, temperature, B, h, w, K, ds_rl, ws, rl_out)
             readloss = rl_out[0]
@@ -113,10 +119,11 @@ class _ReadFn(torch.autograd.Function):
         ctx.set_materialize_grads(False)  # unused outputs (scores, histogram) arrive as None, not as zero fills
         ctx.save_for_backward(x, M, score_m, ds_rl, rl_out)
         ctx.mark_non_differentiable(score_q, score_m, hist)
-        return u, score_q.view(B, h, w, K), score_m.view(B, h, w, K), readloss, hist
+        outs = (u, score_q.view(B, h, w, K), score_m.view(B, h, w, K), readloss, hist)
+        return outs + (x,) if tee else outs
 
     @staticmethod
-    def backward(ctx, du, _g_sq, _g_sm, g_loss, _g_hist):
+    def backward(ctx, du, _g_sq, _g_sm, g_loss, _g_hist, g_tee=None):
         x, M, score_m, ds_rl, rl_out = ctx.saved_tensors
         B, C, h, w = x.shape
         K = ctx.K
@@ -130,13 +137,17 @@ class _ReadFn(torch.autograd.Function):
             g_loss = None
         dx = torch.empty_like(x)
         ds = torch.empty(B * h * w, capi.score_stride(K), dtype=torch.float32, device=x.device)
+        fused_add = g_tee is not None and ctx.planes and g_tee.dtype == x.dtype and g_tee.shape == x.shape
         capi.read_bwd(du, x, M, score_m, ds_rl if g_loss is not None else None, g_loss,
-                      rl_out if g_loss is not None else None, dx, ds, K, planes=ctx.planes)
+                      rl_out if g_loss is not None else None, dx, ds, K, planes=ctx.planes,
+                      dx_add=g_tee.contiguous() if fused_add else None)
+        if g_tee is not None and not fused_add:
+            dx = dx + g_tee.to(dx.dtype)
         dM = None
         if need_dM:
             dM = torch.zeros_like(M)
             capi.read_bwd_dM(None if ctx.planes else du, x, score_m, ds, dM, K)
-        return dx, dM, None, None, None, None, None, None
+        return dx, dM, None, None, None, None, None, None, None
 
 
 class _FoldWeightFn(torch.autograd.Function):
@@ -549,6 +560,8 @@ class Memory_sup(nn.Module):
         # extras (not in the reference)
         self.overlap_write = False     # run the write branch on a side stream next to the read (see forward)
         self.fold_memory_into_conv = True  # read hands [q ; score planes] to a convolution with the memory folded in
+        # the write branch's d/d(query) is summed inside the read's dx kernel (see read()); env switch for A/B runs
+        self.fuse_grad_sum = not os.environ.get("PINMEM_B200_NO_GRAD_SUM_FUSION")
         self.fold_min_pixels = 32768       # ... for feature maps of at least this many pixels per call
         self.shard_group = None        # set by sharding.enable_sharded_update()
         self.last_label_hist = None    # int64 [K+1] label histogram of the last read with labels
@@ -561,9 +574,10 @@ class Memory_sup(nn.Module):
     def forward(self, query, mask=None, memory_writing=True, writing_detach=True):
         if memory_writing and self.overlap_write and query.is_cuda:
             return self._forward_two_streams(query, mask, writing_detach)
-        updated_query, score_query, score_memory, readloss = self.read(query, mask, memory_writing)
+        updated_query, score_query, score_memory, readloss = self.read(query, mask, memory_writing, _tee=memory_writing)
         if memory_writing:
-            writeloss = self.write(query, mask, writing_detach)
+            tee, self._tee = getattr(self, "_tee", None), None
+            writeloss = self.write(query if tee is None else tee, mask, writing_detach)
         else:
             writeloss = [0, 0]
         return updated_query, score_query, score_memory, readloss, writeloss
@@ -579,11 +593,12 @@ class Memory_sup(nn.Module):
             side = _SIDE_STREAMS[query.device] = torch.cuda.Stream(device=query.device)
         side.wait_stream(cur)                     # fork: the write depends only on what precedes this call
         memory_in = self.m_items
-        updated_query, score_query, score_memory, readloss = self.read(query, mask, True)   # main stream
+        updated_query, score_query, score_memory, readloss = self.read(query, mask, True, _tee=True)   # main stream
         memory_after_read = self.m_items          # the detached view read() installed (memory.py:323-324)
+        tee, self._tee = getattr(self, "_tee", None), None
         with torch.cuda.stream(side):
             self.m_items = memory_after_read
-            writeloss = self.write(query, mask, writing_detach)
+            writeloss = self.write(query if tee is None else tee, mask, writing_detach)
             for t in (query, mask, memory_in, memory_after_read):
                 if torch.is_tensor(t):
                     t.record_stream(side)
@@ -624,7 +639,7 @@ class Memory_sup(nn.Module):
             raise RuntimeError(f"pinmem_b200: m_items must be [{self.memory_size},{self.feature_dim}]")
         return M
 
-    def read(self, query, mask, memory_writing):
+    def read(self, query, mask, memory_writing, _tee=False):
         """memory.py:317-336. Returns (updated_query, score_query, score_memory, readloss)."""
         query = _check_features(query, "query")
         B, C, h, w = query.shape
@@ -641,8 +656,13 @@ class Memory_sup(nn.Module):
         # pays once the GEMMs are big enough to be compute- rather than launch-bound (break-even ~ 3e4 pixels)
         planes = (plain and self.fold_memory_into_conv and B * h * w >= self.fold_min_pixels
                   and _foldable(self.output[0], C) and capi.planes_ok(query))
-        u, score_query, score_memory, readloss, hist = _ReadFn.apply(
-            query, M, labels, g_query, g_memory, float(self.temperature), self.memory_size, planes)
+        # fp32 score-plane read about to be followed by a write on the same features: tee the features through the read so
+        # that the write branch's gradient is summed inside the read's dx kernel (pm_read_bwd_planes, dx_add)
+        tee = (_tee and memory_writing and planes and self.fuse_grad_sum and torch.is_grad_enabled()
+               and query.requires_grad and query.dtype == torch.float32)
+        outs = _ReadFn.apply(query, M, labels, g_query, g_memory, float(self.temperature), self.memory_size, planes, tee)
+        u, score_query, score_memory, readloss, hist = outs[:5]
+        self._tee = outs[5] if tee else None
         if labels is None:
             readloss = 0  # memory.py:178
         else:
