@@ -232,6 +232,14 @@ int pm_bn_mask_words(int B, int C, int hw);
 int pm_bn_apply(const void* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
                 const void* residual, void* y, uint32_t* relu_mask, int relu, int B, int C, int hw, int dtype,
                 void* stream);
+/* The same with the statistics finalised in the kernel: `stats` = the fp64 [sum | sum of squares] per channel that
+ * pm_conv1x1_fwd's epilogue produced, `count` = B*h*w. Every CTA derives mean / invstd of its channel itself; mean_out /
+ * invstd_out [C] (for the backward) and the running statistics (momentum update, unbiased variance; may be NULL) are
+ * written once per channel. Replaces pm_bn_finalize + pm_bn_apply (one launch less between the GEMM and its consumer). */
+int pm_bn_apply_stats(const void* x, const double* stats, double count, float eps, const float* gamma, const float* beta,
+                      const void* residual, void* y, uint32_t* relu_mask, int relu, float* mean_out, float* invstd_out,
+                      float* running_mean, float* running_var, float momentum, int B, int C, int hw, int dtype,
+                      void* stream);
 int pm_bn_bwd_reduce(const void* dy, const void* y, const uint32_t* relu_mask, const void* x, const float* mean,
                      const float* invstd, int relu, float* dgamma, float* dbeta, int B, int C, int hw, int dtype,
                      void* stream);

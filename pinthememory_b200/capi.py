@@ -60,6 +60,7 @@ PROTOTYPES = {
     "pm_conv1x1_wgrad_workspace_floats": [_c_i] * 5,
     "pm_conv1x1_wgrad": [_c_p] * 4 + [_c_i] * 6 + [_c_p],
     "pm_bn_finalize": [_c_p, _c_i, _c_d, _c_f] + [_c_p] * 4 + [_c_f, _c_p],
+    "pm_bn_apply_stats": [_c_p, _c_p, _c_d, _c_f] + [_c_p] * 5 + [_c_i] + [_c_p] * 4 + [_c_f] + [_c_i] * 4 + [_c_p],
     "pm_write_reduce_fwd8": [_c_p] * 3 + [_c_i] * 8 + [_c_p],
     "pm_write_bwd8": [_c_p] * 4 + [_c_i] * 8 + [_c_p],
     "pm_peer_buffer_bytes": [],
@@ -425,6 +426,15 @@ def conv1x1_wgrad(dy, x, dW=None, accumulate=False):
     _call("pm_conv1x1_wgrad", _ptr(dy), _ptr(x), _ptr(ws), _ptr(dW), B, M, N, h * w, int(bool(accumulate)), dtype_code(x),
           _stream())
     return dW
+
+
+def bn_apply_stats(x, stats, count, eps, gamma, beta, residual, y, relu, mean_out, invstd_out, running_mean, running_var,
+                   momentum, relu_mask=None):
+    """Normalise pass with the batch statistics finalised in-kernel from the GEMM epilogue's fp64 sums."""
+    B, C, h, w = x.shape
+    _call("pm_bn_apply_stats", _ptr(x), _ptr(stats), float(count), float(eps), _ptr(gamma), _ptr(beta), _ptr(residual), _ptr(y),
+          _ptr(relu_mask), int(bool(relu)), _ptr(mean_out), _ptr(invstd_out), _ptr(running_mean), _ptr(running_var),
+          float(momentum), B, C, h * w, dtype_code(x), _stream())
 
 
 def bn_finalize(stats, C, count, eps, mean, invstd, running_mean, running_var, momentum):

@@ -109,14 +109,42 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const T* __restric
 }
 
 // one CTA per (b, c) row
+struct BnFinalize {  // stats == nullptr: mean / invstd are given
+    const double* stats;
+    double n;
+    float eps, momentum;
+    float *mean_out, *invstd_out, *running_mean, *running_var;
+};
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ mean,
                                                        const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, const T* __restrict__ residual,
                                                        T* __restrict__ y, unsigned* __restrict__ relu_mask, int relu,
-                                                       int C, int hw) {
+                                                       int C, int hw, BnFinalize fin) {
     const int row = blockIdx.x, c = row % C;
-    const float sc = invstd[c] * gamma[c], sh = beta[c] - mean[c] * sc;
+    float mu, is;
+    if (fin.stats != nullptr) {
+        // batch statistics straight from the convolution epilogue's fp64 (sum, sum of squares): every CTA finalises its
+        // own channel (two loads, a division and a square root) instead of waiting for a finalise launch; the CTAs of
+        // image 0 publish mean / invstd for the backward and update the running statistics
+        const double m = fin.stats[c] / fin.n;
+        double var = fin.stats[C + c] / fin.n - m * m;
+        if (var < 0.0) var = 0.0;
+        mu = (float)m;
+        is = (float)(1.0 / sqrt(var + (double)fin.eps));
+        if (row < C && threadIdx.x == 0) {
+            fin.mean_out[c] = mu;
+            fin.invstd_out[c] = is;
+            if (fin.running_mean != nullptr) {
+                const double unb = fin.n > 1.0 ? var * fin.n / (fin.n - 1.0) : var;
+                fin.running_mean[c] = (float)((1.0 - fin.momentum) * fin.running_mean[c] + fin.momentum * m);
+                fin.running_var[c] = (float)((1.0 - fin.momentum) * fin.running_var[c] + fin.momentum * unb);
+            }
+        }
+    } else {
+        mu = mean[c], is = invstd[c];
+    }
+    const float sc = is * gamma[c], sh = beta[c] - mu * sc;
     const size_t base = (size_t)row * hw;
     if (VEC) {
         // relu_mask (optional): 1 bit per element, bit = output > 0, 32 elements per word, rows padded to whole
@@ -371,21 +399,43 @@ extern "C" int pm_bn_stats(const void* x, int B, int C, int hw, int dtype, float
 
 extern "C" int pm_bn_mask_words(int B, int C, int hw) { return hw % 4 == 0 ? B * C * ((hw / 4 + 7) / 8) : 0; }
 
+static int bn_apply_impl(const void* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                         const void* residual, void* y, uint32_t* relu_mask, int relu, int B, int C, int hw, int dtype,
+                         pm::BnFinalize fin, void* stream);
+
 extern "C" int pm_bn_apply(const void* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
                            const void* residual, void* y, uint32_t* relu_mask, int relu, int B, int C, int hw, int dtype,
                            void* stream) {
-    if (!x || !mean || !invstd || !gamma || !beta || !y) return PM_ERR_NULL;
+    if (!mean || !invstd) return PM_ERR_NULL;
+    return bn_apply_impl(x, mean, invstd, gamma, beta, residual, y, relu_mask, relu, B, C, hw, dtype,
+                         pm::BnFinalize{nullptr, 0.0, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr}, stream);
+}
+
+extern "C" int pm_bn_apply_stats(const void* x, const double* stats, double count, float eps, const float* gamma,
+                                 const float* beta, const void* residual, void* y, uint32_t* relu_mask, int relu,
+                                 float* mean_out, float* invstd_out, float* running_mean, float* running_var, float momentum,
+                                 int B, int C, int hw, int dtype, void* stream) {
+    if (!stats || !mean_out || !invstd_out || ((running_mean == nullptr) != (running_var == nullptr))) return PM_ERR_NULL;
+    if (!(count > 0.0)) return PM_ERR_SHAPE;
+    return bn_apply_impl(x, nullptr, nullptr, gamma, beta, residual, y, relu_mask, relu, B, C, hw, dtype,
+                         pm::BnFinalize{stats, count, eps, momentum, mean_out, invstd_out, running_mean, running_var}, stream);
+}
+
+static int bn_apply_impl(const void* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                         const void* residual, void* y, uint32_t* relu_mask, int relu, int B, int C, int hw, int dtype,
+                         pm::BnFinalize fin, void* stream) {
+    if (!x || !gamma || !beta || !y) return PM_ERR_NULL;
     if (int e = bn_check(B, C, hw, dtype)) return e;
     const bool vec = pm::vec_ok(hw, x, residual, y, nullptr, nullptr, dtype);
     if (relu_mask != nullptr && !vec) return PM_ERR_ALIGN;  // the packed mask exists only on the vector path
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == PM_F32) {
-        if (vec) pm::bn_apply_kernel<float, true><<<B * C, 256, 0, st>>>((const float*)x, mean, invstd, gamma, beta, (const float*)residual, (float*)y, relu_mask, relu, C, hw);
-        else pm::bn_apply_kernel<float, false><<<B * C, 256, 0, st>>>((const float*)x, mean, invstd, gamma, beta, (const float*)residual, (float*)y, relu_mask, relu, C, hw);
+        if (vec) pm::bn_apply_kernel<float, true><<<B * C, 256, 0, st>>>((const float*)x, mean, invstd, gamma, beta, (const float*)residual, (float*)y, relu_mask, relu, C, hw, fin);
+        else pm::bn_apply_kernel<float, false><<<B * C, 256, 0, st>>>((const float*)x, mean, invstd, gamma, beta, (const float*)residual, (float*)y, relu_mask, relu, C, hw, fin);
     } else {
         typedef __nv_bfloat16 bf;
-        if (vec) pm::bn_apply_kernel<bf, true><<<B * C, 256, 0, st>>>((const bf*)x, mean, invstd, gamma, beta, (const bf*)residual, (bf*)y, relu_mask, relu, C, hw);
-        else pm::bn_apply_kernel<bf, false><<<B * C, 256, 0, st>>>((const bf*)x, mean, invstd, gamma, beta, (const bf*)residual, (bf*)y, relu_mask, relu, C, hw);
+        if (vec) pm::bn_apply_kernel<bf, true><<<B * C, 256, 0, st>>>((const bf*)x, mean, invstd, gamma, beta, (const bf*)residual, (bf*)y, relu_mask, relu, C, hw, fin);
+        else pm::bn_apply_kernel<bf, false><<<B * C, 256, 0, st>>>((const bf*)x, mean, invstd, gamma, beta, (const bf*)residual, (bf*)y, relu_mask, relu, C, hw, fin);
     }
     PM_CHECK_LAUNCH();
     return 0;

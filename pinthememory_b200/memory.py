@@ -343,7 +343,6 @@ class _ConvBnActFn(torch.autograd.Function):
             xc = capi.conv1x1_fwd(x, hi, lo, M, stats=stats)
             mean = torch.empty(M, dtype=torch.float32, device=dev)
             invstd = torch.empty(M, dtype=torch.float32, device=dev)
-            capi.bn_finalize(stats, M, B * h * w, eps, mean, invstd, running_mean, running_var, factor)
         else:
             xc = capi.conv1x1_fwd(x, hi, lo, M)
             mean = running_mean.to(torch.float32).contiguous()
@@ -353,7 +352,11 @@ class _ConvBnActFn(torch.autograd.Function):
         nwords = capi.bn_mask_words(B, M, h * w) if relu else 0
         vec_ok = nwords > 0 and all(t is None or t.data_ptr() % 16 == 0 for t in (xc, y, res))
         mask = torch.empty(nwords, dtype=torch.int32, device=dev) if vec_ok else None
-        capi.bn_apply(xc, mean, invstd, g32, b32, res, y, relu, relu_mask=mask)
+        if use_batch_stats:  # mean / invstd / running statistics are finalised inside the normalise pass
+            capi.bn_apply_stats(xc, stats, B * h * w, eps, g32, b32, res, y, relu, mean, invstd, running_mean, running_var,
+                                factor, relu_mask=mask)
+        else:
+            capi.bn_apply(xc, mean, invstd, g32, b32, res, y, relu, relu_mask=mask)
         ctx.relu, ctx.training, ctx.res_is_x, ctx.has_res = relu, use_batch_stats, res_is_x, res is not None
         ctx.use_mask = mask is not None
         ctx.wshape, ctx.wdtype = W.shape, W.dtype
