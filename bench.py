@@ -787,6 +787,7 @@ def main():
         # the fused BatchNorm passes run once per conv block (2 per step); bytes are the mean of the two calls
         "pm_bn_stats": N * C * esz,
         "pm_bn_apply": N * C * esz * 2.5,        # x (+ residual in one of the two blocks) -> y
+        "pm_bn_apply_stats": N * C * esz * 2.5,  # the same pass with the statistics finalised in-kernel
         "pm_bn_bwd_reduce": N * C * esz * 2,     # dy, x (+ the packed ReLU mask, 1/32)
         "pm_bn_bwd_apply": N * C * esz * 3.5,    # dy, x -> dx (+ dres in one of the two blocks)
     }

@@ -47,6 +47,37 @@ struct Vec4<__nv_bfloat16> {
     }
 };
 
+// 16-byte bf16 vector (8 elements): the width at which the bf16 passes move as many bytes per load as the fp32 ones
+struct Vec8bf {
+    uint4 v;
+    __device__ __forceinline__ void load(const __nv_bfloat16* p) { v = *reinterpret_cast<const uint4*>(p); }
+    __device__ __forceinline__ void store(__nv_bfloat16* p) const { *reinterpret_cast<uint4*>(p) = v; }
+    __device__ __forceinline__ float get(int i) const {
+        const unsigned w = (i >> 1) == 0 ? v.x : (i >> 1) == 1 ? v.y : (i >> 1) == 2 ? v.z : v.w;
+        return __uint_as_float((i & 1) ? (w & 0xffff0000u) : (w << 16));
+    }
+    __device__ __forceinline__ void set(int i, float f) {
+        const unsigned b = (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(f));
+        unsigned& w = (i >> 1) == 0 ? v.x : (i >> 1) == 1 ? v.y : (i >> 1) == 2 ? v.z : v.w;
+        w = (i & 1) ? ((w & 0x0000ffffu) | (b << 16)) : ((w & 0xffff0000u) | b);
+    }
+};
+// VN = elements per thread and load: 4 (float4 / 8-byte bf16) or 8 (16-byte bf16); 0 = scalar path
+template <typename T, int VN>
+struct VecSel {
+    typedef Vec4<T> type;
+};
+template <>
+struct VecSel<__nv_bfloat16, 8> {
+    typedef Vec8bf type;
+};
+// bits of the VN elements of vector j of a row out of the packed mask (1 bit per element, 32 per word)
+template <int VN>
+__device__ __forceinline__ unsigned mask_bits(const unsigned* __restrict__ words, int j) {
+    constexpr int LPW = 32 / VN;  // vectors per word
+    return (__ldg(words + j / LPW) >> (VN * (j % LPW))) & ((1u << VN) - 1u);
+}
+
 __device__ __forceinline__ double block_sum_double(double v, double* red) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
@@ -60,7 +91,7 @@ __device__ __forceinline__ double block_sum_double(double v, double* red) {
 }
 
 // one CTA per channel
-template <typename T, bool VEC>
+template <typename T, int VN>
 __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const T* __restrict__ x, int B, int C, int hw, float eps,
                                                               float* __restrict__ mean, float* __restrict__ invstd,
                                                               float* __restrict__ running_mean,
@@ -68,15 +99,15 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const T* __restric
     __shared__ double red[BN_THREADS / 32];
     const int c = blockIdx.x;
     float s = 0.f, q = 0.f;
-    if (VEC) {
-        const int nv = hw / 4, total = B * nv;
+    if constexpr (VN != 0) {
+        const int nv = hw / VN, total = B * nv;
 #pragma unroll 4
         for (int i = threadIdx.x; i < total; i += BN_THREADS) {
             const int b = i / nv, j = i - b * nv;
-            Vec4<T> v;
-            v.load(x + ((size_t)b * C + c) * hw + 4 * j);
+            typename VecSel<T, VN>::type v;
+            v.load(x + ((size_t)b * C + c) * hw + VN * j);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+            for (int e = 0; e < VN; ++e) {
                 const float f = v.get(e);
                 s += f;
                 q = fmaf(f, f, q);
@@ -115,7 +146,7 @@ struct BnFinalize {  // stats == nullptr: mean / invstd are given
     float eps, momentum;
     float *mean_out, *invstd_out, *running_mean, *running_var;
 };
-template <typename T, bool VEC>
+template <typename T, int VN>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ mean,
                                                        const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, const T* __restrict__ residual,
@@ -146,31 +177,32 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, 
     }
     const float sc = is * gamma[c], sh = beta[c] - mu * sc;
     const size_t base = (size_t)row * hw;
-    if (VEC) {
+    if constexpr (VN != 0) {
         // relu_mask (optional): 1 bit per element, bit = output > 0, 32 elements per word, rows padded to whole
         // words: the backward reads it instead of y (1/32 of the bytes). The loop is warp-uniform so that the
-        // eight lanes that share a word can OR their nibbles with one REDUX.
-        const int nv = hw / 4, wpr = (nv + 7) / 8, lane = threadIdx.x & 31;
-        const unsigned gmask = 0xffu << (lane & 24);
+        // 32 / VN lanes that share a word can OR their bit groups with one REDUX.
+        constexpr int LPW = 32 / VN;
+        const int nv = hw / VN, wpr = (nv + LPW - 1) / LPW, lane = threadIdx.x & 31;
+        const unsigned gmask = ((LPW == 32) ? 0xffffffffu : ((1u << LPW) - 1u)) << (lane & ~(LPW - 1));
         for (int j0 = 0; j0 < nv; j0 += 256) {
             const int j = j0 + threadIdx.x;
             unsigned nib = 0u;
             if (j < nv) {
-                Vec4<T> v, r, o;
-                v.load(x + base + 4 * j);
-                if (residual) r.load(residual + base + 4 * j);
+                typename VecSel<T, VN>::type v, r, o;
+                v.load(x + base + VN * j);
+                if (residual) r.load(residual + base + VN * j);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
+                for (int e = 0; e < VN; ++e) {
                     float f = fmaf(v.get(e), sc, sh);
                     if (residual) f += r.get(e);
                     nib |= (f > 0.f ? 1u : 0u) << e;
                     o.set(e, relu ? fmaxf(f, 0.f) : f);
                 }
-                o.store(y + base + 4 * j);
+                o.store(y + base + VN * j);
             }
             if (relu_mask != nullptr) {
-                const unsigned word = __reduce_or_sync(gmask, nib << (4 * (lane & 7)));
-                if ((lane & 7) == 0 && j < nv) relu_mask[(size_t)row * wpr + (j >> 3)] = word;
+                const unsigned word = __reduce_or_sync(gmask, nib << (VN * (lane & (LPW - 1))));
+                if ((lane & (LPW - 1)) == 0 && j < nv) relu_mask[(size_t)row * wpr + j / LPW] = word;
             }
         }
     } else {
@@ -183,7 +215,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, 
 }
 
 // one CTA per channel: dbeta = sum g, dgamma = sum g * xhat, g = dy * (y > 0 if relu)
-template <typename T, bool VEC>
+template <typename T, int VN>
 __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ y,
                                                                    const unsigned* __restrict__ relu_mask,
                                                                    const T* __restrict__ x, const float* __restrict__ mean,
@@ -198,28 +230,29 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const T* __re
     const int c = blockIdx.x, S = gridDim.y, sp = blockIdx.y;
     const float m = mean[c], is = invstd[c];
     float sg = 0.f, sgx = 0.f;
-    if (VEC) {
-        const int nv = hw / 4, total = B * nv, wpr = (nv + 7) / 8;
+    if constexpr (VN != 0) {
+        const int nv = hw / VN, total = B * nv, wpr = (nv + 32 / VN - 1) / (32 / VN);
         const int per = (total + S - 1) / S, i0 = sp * per, i1 = min(total, i0 + per);
 #pragma unroll 4
         for (int i = i0 + threadIdx.x; i < i1; i += BN_THREADS) {
             const int b = i / nv, j = i - b * nv;
-            const size_t off = ((size_t)b * C + c) * hw + 4 * j;
-            Vec4<T> g, yy, xx;
+            const size_t off = ((size_t)b * C + c) * hw + VN * j;
+            typename VecSel<T, VN>::type g, yy, xx;
             g.load(dy + off);
             xx.load(x + off);
-            unsigned bits = 0xfu;
+            unsigned bits = (1u << VN) - 1u;
             if (relu) {
                 if (relu_mask != nullptr) {
-                    bits = (__ldg(relu_mask + ((size_t)b * C + c) * wpr + (j >> 3)) >> (4 * (j & 7))) & 0xfu;
+                    bits = mask_bits<VN>(relu_mask + ((size_t)b * C + c) * wpr, j);
                 } else {
                     yy.load(y + off);
-                    bits = (yy.get(0) > 0.f ? 1u : 0u) | (yy.get(1) > 0.f ? 2u : 0u) | (yy.get(2) > 0.f ? 4u : 0u) |
-                           (yy.get(3) > 0.f ? 8u : 0u);
+                    bits = 0u;
+#pragma unroll
+                    for (int e = 0; e < VN; ++e) bits |= (yy.get(e) > 0.f ? 1u : 0u) << e;
                 }
             }
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+            for (int e = 0; e < VN; ++e) {
                 const float gv = ((bits >> e) & 1u) ? g.get(e) : 0.f;
                 sg += gv;
                 sgx = fmaf(gv, (xx.get(e) - m) * is, sgx);
@@ -265,7 +298,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const T* __re
 }
 
 // one CTA per (b, c) row: dx = gamma*invstd*(g - [training] (dbeta + xhat*dgamma)/n); dres = g
-template <typename T, bool VEC>
+template <typename T, int VN>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ y,
                                                            const unsigned* __restrict__ relu_mask,
                                                            const T* __restrict__ x, const float* __restrict__ mean,
@@ -277,31 +310,32 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
     const float m = mean[c], is = invstd[c], gi = gamma[c] * is;
     const float k1 = training ? dbeta[c] * inv_n : 0.f, k2 = training ? dgamma[c] * inv_n : 0.f;
     const size_t base = (size_t)row * hw;
-    if (VEC) {
-        const int wpr = (hw / 4 + 7) / 8;
-        for (int j = threadIdx.x; j < hw / 4; j += 256) {
-            Vec4<T> g, yy, xx, o, r;
-            g.load(dy + base + 4 * j);
-            xx.load(x + base + 4 * j);
-            unsigned bits = 0xfu;
+    if constexpr (VN != 0) {
+        const int nv = hw / VN, wpr = (nv + 32 / VN - 1) / (32 / VN);
+        for (int j = threadIdx.x; j < nv; j += 256) {
+            typename VecSel<T, VN>::type g, yy, xx, o, r;
+            g.load(dy + base + VN * j);
+            xx.load(x + base + VN * j);
+            unsigned bits = (1u << VN) - 1u;
             if (relu) {
                 if (relu_mask != nullptr) {
-                    bits = (__ldg(relu_mask + (size_t)row * wpr + (j >> 3)) >> (4 * (j & 7))) & 0xfu;
+                    bits = mask_bits<VN>(relu_mask + (size_t)row * wpr, j);
                 } else {
-                    yy.load(y + base + 4 * j);
-                    bits = (yy.get(0) > 0.f ? 1u : 0u) | (yy.get(1) > 0.f ? 2u : 0u) | (yy.get(2) > 0.f ? 4u : 0u) |
-                           (yy.get(3) > 0.f ? 8u : 0u);
+                    yy.load(y + base + VN * j);
+                    bits = 0u;
+#pragma unroll
+                    for (int e = 0; e < VN; ++e) bits |= (yy.get(e) > 0.f ? 1u : 0u) << e;
                 }
             }
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+            for (int e = 0; e < VN; ++e) {
                 const float gv = ((bits >> e) & 1u) ? g.get(e) : 0.f;
                 const float xh = (xx.get(e) - m) * is;
                 o.set(e, gi * (gv - k1 - xh * k2));
                 r.set(e, gv);
             }
-            o.store(dx + base + 4 * j);
-            if (dres) r.store(dres + base + 4 * j);
+            o.store(dx + base + VN * j);
+            if (dres) r.store(dres + base + VN * j);
         }
     } else {
         for (int j = threadIdx.x; j < hw; j += 256) {
@@ -313,9 +347,12 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
     }
 }
 
-static bool vec_ok(int hw, const void* a, const void* b, const void* c, const void* d, const void* e, int dtype) {
+// vector width of the streaming loops: 4 (fp32: 16-byte rows; bf16: 8-byte), 8 (bf16, 16-byte rows), 0 = scalar
+static int vec_ok(int hw, const void* a, const void* b, const void* c, const void* d, const void* e, int dtype) {
+    const uintptr_t all = (uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d | (uintptr_t)e;
+    if (dtype != PM_F32 && hw % 8 == 0 && (all & 15) == 0) return 8;
     const uintptr_t m = dtype == PM_F32 ? 15 : 7;
-    return hw % 4 == 0 && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d | (uintptr_t)e) & m) == 0;
+    return (hw % 4 == 0 && (all & m) == 0) ? 4 : 0;
 }
 
 // mean / invstd / running statistics from the fp64 (sum, sum of squares) pairs the convolution epilogue produced
@@ -383,14 +420,15 @@ extern "C" int pm_bn_stats(const void* x, int B, int C, int hw, int dtype, float
                            float* running_mean, float* running_var, float momentum, void* stream) {
     if (!x || !mean || !invstd || ((running_mean == nullptr) != (running_var == nullptr))) return PM_ERR_NULL;
     if (int e = bn_check(B, C, hw, dtype)) return e;
-    const bool vec = pm::vec_ok(hw, x, nullptr, nullptr, nullptr, nullptr, dtype);
+    const int vec = pm::vec_ok(hw, x, nullptr, nullptr, nullptr, nullptr, dtype);
 #define X_(T) (const T*)x
     if (dtype == PM_F32) {
-        if (vec) pm::bn_stats_kernel<float, true><<<C, pm::BN_THREADS, 0, (cudaStream_t)stream>>>(X_(float), B, C, hw, eps, mean, invstd, running_mean, running_var, momentum);
-        else pm::bn_stats_kernel<float, false><<<C, pm::BN_THREADS, 0, (cudaStream_t)stream>>>(X_(float), B, C, hw, eps, mean, invstd, running_mean, running_var, momentum);
+        if (vec) pm::bn_stats_kernel<float, 4><<<C, pm::BN_THREADS, 0, (cudaStream_t)stream>>>(X_(float), B, C, hw, eps, mean, invstd, running_mean, running_var, momentum);
+        else pm::bn_stats_kernel<float, 0><<<C, pm::BN_THREADS, 0, (cudaStream_t)stream>>>(X_(float), B, C, hw, eps, mean, invstd, running_mean, running_var, momentum);
     } else {
-        if (vec) pm::bn_stats_kernel<__nv_bfloat16, true><<<C, pm::BN_THREADS, 0, (cudaStream_t)stream>>>(X_(__nv_bfloat16), B, C, hw, eps, mean, invstd, running_mean, running_var, momentum);
-        else pm::bn_stats_kernel<__nv_bfloat16, false><<<C, pm::BN_THREADS, 0, (cudaStream_t)stream>>>(X_(__nv_bfloat16), B, C, hw, eps, mean, invstd, running_mean, running_var, momentum);
+        if (vec == 8) pm::bn_stats_kernel<__nv_bfloat16, 8><<<C, pm::BN_THREADS, 0, (cudaStream_t)stream>>>(X_(__nv_bfloat16), B, C, hw, eps, mean, invstd, running_mean, running_var, momentum);
+        else if (vec) pm::bn_stats_kernel<__nv_bfloat16, 4><<<C, pm::BN_THREADS, 0, (cudaStream_t)stream>>>(X_(__nv_bfloat16), B, C, hw, eps, mean, invstd, running_mean, running_var, momentum);
+        else pm::bn_stats_kernel<__nv_bfloat16, 0><<<C, pm::BN_THREADS, 0, (cudaStream_t)stream>>>(X_(__nv_bfloat16), B, C, hw, eps, mean, invstd, running_mean, running_var, momentum);
     }
 #undef X_
     PM_CHECK_LAUNCH();
@@ -426,16 +464,17 @@ static int bn_apply_impl(const void* x, const float* mean, const float* invstd, 
                          pm::BnFinalize fin, void* stream) {
     if (!x || !gamma || !beta || !y) return PM_ERR_NULL;
     if (int e = bn_check(B, C, hw, dtype)) return e;
-    const bool vec = pm::vec_ok(hw, x, residual, y, nullptr, nullptr, dtype);
+    const int vec = pm::vec_ok(hw, x, residual, y, nullptr, nullptr, dtype);
     if (relu_mask != nullptr && !vec) return PM_ERR_ALIGN;  // the packed mask exists only on the vector path
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == PM_F32) {
-        if (vec) pm::bn_apply_kernel<float, true><<<B * C, 256, 0, st>>>((const float*)x, mean, invstd, gamma, beta, (const float*)residual, (float*)y, relu_mask, relu, C, hw, fin);
-        else pm::bn_apply_kernel<float, false><<<B * C, 256, 0, st>>>((const float*)x, mean, invstd, gamma, beta, (const float*)residual, (float*)y, relu_mask, relu, C, hw, fin);
+        if (vec) pm::bn_apply_kernel<float, 4><<<B * C, 256, 0, st>>>((const float*)x, mean, invstd, gamma, beta, (const float*)residual, (float*)y, relu_mask, relu, C, hw, fin);
+        else pm::bn_apply_kernel<float, 0><<<B * C, 256, 0, st>>>((const float*)x, mean, invstd, gamma, beta, (const float*)residual, (float*)y, relu_mask, relu, C, hw, fin);
     } else {
         typedef __nv_bfloat16 bf;
-        if (vec) pm::bn_apply_kernel<bf, true><<<B * C, 256, 0, st>>>((const bf*)x, mean, invstd, gamma, beta, (const bf*)residual, (bf*)y, relu_mask, relu, C, hw, fin);
-        else pm::bn_apply_kernel<bf, false><<<B * C, 256, 0, st>>>((const bf*)x, mean, invstd, gamma, beta, (const bf*)residual, (bf*)y, relu_mask, relu, C, hw, fin);
+        if (vec == 8) pm::bn_apply_kernel<bf, 8><<<B * C, 256, 0, st>>>((const bf*)x, mean, invstd, gamma, beta, (const bf*)residual, (bf*)y, relu_mask, relu, C, hw, fin);
+        else if (vec) pm::bn_apply_kernel<bf, 4><<<B * C, 256, 0, st>>>((const bf*)x, mean, invstd, gamma, beta, (const bf*)residual, (bf*)y, relu_mask, relu, C, hw, fin);
+        else pm::bn_apply_kernel<bf, 0><<<B * C, 256, 0, st>>>((const bf*)x, mean, invstd, gamma, beta, (const bf*)residual, (bf*)y, relu_mask, relu, C, hw, fin);
     }
     PM_CHECK_LAUNCH();
     return 0;
@@ -466,17 +505,18 @@ static int bn_bwd_reduce_impl(const void* dy, const void* y, const uint32_t* rel
                               double* scratch, void* stream) {
     if (!dy || !x || !mean || !invstd || !dgamma || !dbeta || (relu && !y && !relu_mask)) return PM_ERR_NULL;
     if (int e = bn_check(B, C, hw, dtype)) return e;
-    const bool vec = pm::vec_ok(hw, dy, y, x, nullptr, nullptr, dtype);
+    const int vec = pm::vec_ok(hw, dy, y, x, nullptr, nullptr, dtype);
     if (relu && !y && !vec) return PM_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     const dim3 grid(C, scratch != nullptr ? PM_BN_SPLITS : 1);
     if (dtype == PM_F32) {
-        if (vec) pm::bn_bwd_reduce_kernel<float, true><<<grid, pm::BN_THREADS, 0, st>>>((const float*)dy, (const float*)y, relu_mask, (const float*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw, scratch);
-        else pm::bn_bwd_reduce_kernel<float, false><<<grid, pm::BN_THREADS, 0, st>>>((const float*)dy, (const float*)y, relu_mask, (const float*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw, scratch);
+        if (vec) pm::bn_bwd_reduce_kernel<float, 4><<<grid, pm::BN_THREADS, 0, st>>>((const float*)dy, (const float*)y, relu_mask, (const float*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw, scratch);
+        else pm::bn_bwd_reduce_kernel<float, 0><<<grid, pm::BN_THREADS, 0, st>>>((const float*)dy, (const float*)y, relu_mask, (const float*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw, scratch);
     } else {
         typedef __nv_bfloat16 bf;
-        if (vec) pm::bn_bwd_reduce_kernel<bf, true><<<grid, pm::BN_THREADS, 0, st>>>((const bf*)dy, (const bf*)y, relu_mask, (const bf*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw, scratch);
-        else pm::bn_bwd_reduce_kernel<bf, false><<<grid, pm::BN_THREADS, 0, st>>>((const bf*)dy, (const bf*)y, relu_mask, (const bf*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw, scratch);
+        if (vec == 8) pm::bn_bwd_reduce_kernel<bf, 8><<<grid, pm::BN_THREADS, 0, st>>>((const bf*)dy, (const bf*)y, relu_mask, (const bf*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw, scratch);
+        else if (vec) pm::bn_bwd_reduce_kernel<bf, 4><<<grid, pm::BN_THREADS, 0, st>>>((const bf*)dy, (const bf*)y, relu_mask, (const bf*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw, scratch);
+        else pm::bn_bwd_reduce_kernel<bf, 0><<<grid, pm::BN_THREADS, 0, st>>>((const bf*)dy, (const bf*)y, relu_mask, (const bf*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw, scratch);
     }
     PM_CHECK_LAUNCH();
     return 0;
@@ -488,17 +528,18 @@ extern "C" int pm_bn_bwd_apply(const void* dy, const void* y, const uint32_t* re
     if (!dy || !x || !mean || !invstd || !gamma || !dgamma || !dbeta || !dx || (relu && !y && !relu_mask))
         return PM_ERR_NULL;
     if (int e = bn_check(B, C, hw, dtype)) return e;
-    const bool vec = pm::vec_ok(hw, dy, y, x, dx, dres, dtype);
+    const int vec = pm::vec_ok(hw, dy, y, x, dx, dres, dtype);
     if (relu && !y && !vec) return PM_ERR_ALIGN;
     const float inv_n = 1.f / ((float)B * (float)hw);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == PM_F32) {
-        if (vec) pm::bn_bwd_apply_kernel<float, true><<<B * C, 256, 0, st>>>((const float*)dy, (const float*)y, relu_mask, (const float*)x, mean, invstd, gamma, dgamma, dbeta, relu, training, inv_n, (float*)dx, (float*)dres, C, hw);
-        else pm::bn_bwd_apply_kernel<float, false><<<B * C, 256, 0, st>>>((const float*)dy, (const float*)y, relu_mask, (const float*)x, mean, invstd, gamma, dgamma, dbeta, relu, training, inv_n, (float*)dx, (float*)dres, C, hw);
+        if (vec) pm::bn_bwd_apply_kernel<float, 4><<<B * C, 256, 0, st>>>((const float*)dy, (const float*)y, relu_mask, (const float*)x, mean, invstd, gamma, dgamma, dbeta, relu, training, inv_n, (float*)dx, (float*)dres, C, hw);
+        else pm::bn_bwd_apply_kernel<float, 0><<<B * C, 256, 0, st>>>((const float*)dy, (const float*)y, relu_mask, (const float*)x, mean, invstd, gamma, dgamma, dbeta, relu, training, inv_n, (float*)dx, (float*)dres, C, hw);
     } else {
         typedef __nv_bfloat16 bf;
-        if (vec) pm::bn_bwd_apply_kernel<bf, true><<<B * C, 256, 0, st>>>((const bf*)dy, (const bf*)y, relu_mask, (const bf*)x, mean, invstd, gamma, dgamma, dbeta, relu, training, inv_n, (bf*)dx, (bf*)dres, C, hw);
-        else pm::bn_bwd_apply_kernel<bf, false><<<B * C, 256, 0, st>>>((const bf*)dy, (const bf*)y, relu_mask, (const bf*)x, mean, invstd, gamma, dgamma, dbeta, relu, training, inv_n, (bf*)dx, (bf*)dres, C, hw);
+        if (vec == 8) pm::bn_bwd_apply_kernel<bf, 8><<<B * C, 256, 0, st>>>((const bf*)dy, (const bf*)y, relu_mask, (const bf*)x, mean, invstd, gamma, dgamma, dbeta, relu, training, inv_n, (bf*)dx, (bf*)dres, C, hw);
+        else if (vec) pm::bn_bwd_apply_kernel<bf, 4><<<B * C, 256, 0, st>>>((const bf*)dy, (const bf*)y, relu_mask, (const bf*)x, mean, invstd, gamma, dgamma, dbeta, relu, training, inv_n, (bf*)dx, (bf*)dres, C, hw);
+        else pm::bn_bwd_apply_kernel<bf, 0><<<B * C, 256, 0, st>>>((const bf*)dy, (const bf*)y, relu_mask, (const bf*)x, mean, invstd, gamma, dgamma, dbeta, relu, training, inv_n, (bf*)dx, (bf*)dres, C, hw);
     }
     PM_CHECK_LAUNCH();
     return 0;
