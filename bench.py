@@ -853,7 +853,7 @@ def main():
     def traffic_of(k):
         if k.startswith("pm_readloss ("):
             return (tr.get("pm_labels_pack", 0.0) + tr.get("pm_readloss_fwd8", 0.0)) or None
-        for cand_k in (k, k.replace("_planes", ""), k.rstrip("8")):
+        for cand_k in (k, k.replace("_planes", ""), k.rstrip("8"), k.replace("_apply_stats", "_apply")):
             if cand_k in tr:
                 return tr[cand_k]
         return None
