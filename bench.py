@@ -306,7 +306,12 @@ def eval_read_main(args, wl):
     ms_eager, _ = run(eager_step, args.steps, args.warmup)
     capi.enable_kernel_timing(True)
     capi.reset_counters()
-    run(eager_step, 20, 2)
+
+    def eager_step_queued():   # behind a device-side sleep: the events bracket the kernels, not the Python between launches
+        torch.cuda._sleep(2_000_000)
+        eager_step()
+
+    run(eager_step_queued, 20, 2)
     ktimes = capi.kernel_timings_ms()
     launches_per_step = capi.LAUNCHES / 22.0
     capi.enable_kernel_timing(False)
@@ -763,7 +768,13 @@ def main():
             mem.overlap_write = bool(args.overlap_write) or world > 1
 
     # per-kernel durations measured live (events around every C-ABI launch) in a second timed region
-    ms_k, _, ktimes, _ = timed(lambda: module_step(x, labels), args.steps, 2, kernel_timing=True)
+    # (each step starts behind a ~3 ms device-side sleep so that the host has queued the whole step before the first kernel
+    # runs: the event pair around a launch then brackets the kernel alone, not the Python time between the two records)
+    def timed_kernels_step():
+        torch.cuda._sleep(6_000_000)
+        module_step(x, labels)
+
+    ms_k, _, ktimes, _ = timed(timed_kernels_step, args.steps, 2, kernel_timing=True)
     kavg = {k: sum(v) / len(v) for k, v in ktimes.items()}  # ms per call
     r = Hm * Wm / float(h * w)
     KP = 20

@@ -415,6 +415,41 @@ def test_memory_folded_into_the_output_convolution_is_the_same_function(writing,
             close(gb, ga, "grad " + n)
 
 
+@pytest.mark.parametrize("two_streams", [False, True])
+def test_write_branch_gradient_summed_inside_the_read_backward(two_streams):
+    """forward() tees the features through the read so that the writing net's d/d(query) arrives as an input of the
+    read's backward and is summed by the dx kernel (pm_read_bwd_planes, dx_add). Same gradients as letting autograd add
+    the two branches; also under retain_graph (second backward) and with the write branch on its side stream."""
+    from pinthememory_b200 import synth
+
+    B, C, h, w, Hm, Wm, K = 2, 64, 12, 16, 48, 64, 19
+    x0 = synth.make_features(B, C, h, w, seed=31, device="cuda")
+    lab = synth.make_labels(B, Hm, Wm, K, "blocky", seed=32).cuda()
+    G = synth.make_upstream_grad((B, C, h, w), seed=33, device="cuda")
+    res = []
+    for fuse in (False, True):
+        mem = _module(K, C)
+        mem.fold_min_pixels = 0
+        mem.fuse_grad_sum = fuse
+        mem.overlap_write = two_streams
+        x = x0.clone().requires_grad_(True)
+        uq, _, _, rl, wl = mem(x, lab, True, False)
+        loss = (uq * G).sum() + 0.02 * rl + 0.4 * wl[0] + 0.2 * wl[1]
+        loss.backward(retain_graph=True)
+        g1 = x.grad.clone()
+        x.grad = None
+        loss.backward()
+        torch.cuda.synchronize()
+        assert getattr(mem, "_tee", None) is None          # nothing left behind by forward()
+        res.append(dict(dx=g1, dx2=x.grad.clone(), gp=[p.grad.clone() for p in mem.parameters()], mem=mem.m_items.detach()))
+    a, b = res
+    assert_close(b["dx"], a["dx"], 2e-6, "dx (fused sum vs autograd add)")
+    assert_close(b["dx2"], b["dx"], 1e-6, "dx of the second backward")
+    assert_close(b["mem"], a["mem"], 1e-6, "memory")
+    for ga, gb in zip(a["gp"], b["gp"]):
+        assert_close(gb, ga, 2e-6, "parameter gradient")
+
+
 # --------------------------------------------------------- the reference's public loss methods, checkpoint key
 
 
