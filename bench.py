@@ -14,8 +14,8 @@ The metric is feature-map Mpixels/s. Prints ONE JSON line (rank 0).
 * ``core``       only the hand-written kernels (write feature f and upstream du given), with the aggregate
                  fraction of the HBM roofline for A_train bytes/pixel
 * ``roofline``   the dominant kernel: algorithmic bytes / its CUDA-event duration measured inside the timed region
-* ``cpu_baseline`` the CPU port of the reference (oracle/) timed on this host's cores on a bounded sample
-``--impl reference`` times that CPU port instead (all host threads, the workload's full batch) and prints the same
+* ``cpu_baseline`` the reference's own module (byte-compiled into oracle/_ref/, else the oracle/ port) timed on this host's cores on a bounded sample
+``--impl reference`` times that CPU arm instead (all host threads, the workload's full batch) and prints the same
 line shape. Timed regions are blocks of ``--steps`` steps repeated until >= 0.5 s; the median block is reported.
 Under torchrun (N>1) every rank runs its own batch (weak scaling); the write path all-reduces the class sums.
 """
@@ -170,15 +170,39 @@ def host_threads():
     return torch.get_num_threads()
 
 
+def reference_module(device, gumbel=False):
+    """The reference's OWN ``Memory_sup`` (unmodified, byte-compiled into oracle/_ref/ by oracle/build_ref.py, or loaded from
+    /root/reference where that is mounted) on ``device``; None when neither is there (the oracle port is used then)."""
+    try:
+        from oracle import ref_loader
+
+        if not (ref_loader.reference_available() or ref_loader.compiled_reference_available()):
+            return None
+        cpu = torch.device(device).type == "cpu"
+        m = ref_loader.build_reference_memory(K, C, 0.8, 1.0, gumbel, force_cpu=cpu)
+        if not cpu:
+            m = m.to(device)
+            m.m_items = m.m_items.to(device)
+            m.mem_cls = m.mem_cls.to(device)
+        return m
+    except Exception:
+        return None
+
+
 def cpu_reference_run(wl, kind, steps, warmup, sample_B=None, budget_s=120.0):
-    """The CPU port of the reference module (oracle/) on the workload's own batch (or a bounded sample of it), all
-    host threads; stops early when the time budget is spent (the step count actually timed is reported)."""
+    """The reference module on the host cores, on the workload's own batch (or a bounded sample of it), all host threads:
+    the reference's own ``network/memory.py`` when oracle/_ref holds it (``kind: "reference"``), else the oracle port
+    (``kind: "port"``). Stops early when the time budget is spent (the step count actually timed is reported)."""
     from oracle import memory_oracle as mo
+    from oracle import ref_loader
 
     cores = host_threads()
     torch.manual_seed(synth.SEED)
     B = wl["B"] if sample_B is None else min(sample_B, wl["B"])
-    mem = mo.OracleMemorySup(K, C, C, 0.8, 1.0, False)
+    mem = reference_module("cpu")
+    impl_kind = "reference" if mem is not None else "port"
+    if mem is None:
+        mem = mo.OracleMemorySup(K, C, C, 0.8, 1.0, False)
     mem.train()
     x = synth.make_features(B, C, wl["h"], wl["w"]).requires_grad_(True)
     labels = synth.make_labels(B, wl["Hm"], wl["Wm"], K, kind)
@@ -191,10 +215,11 @@ def cpu_reference_run(wl, kind, steps, warmup, sample_B=None, budget_s=120.0):
         x.grad = None
         mem.zero_grad(set_to_none=True)
         t0 = time.perf_counter()
-        uq, _, _, rl, wlss = mem(x, labels, True, False)
-        torch.autograd.backward([uq, rl, wlss[0], wlss[1]],
-                                [G, torch.tensor(LOSS_W["read"]), torch.tensor(LOSS_W["div"]),
-                                 torch.tensor(LOSS_W["cls"])])
+        with ref_loader.cuda_identity(force=True):   # the reference calls .cuda() inside write() (memory.py:246)
+            uq, _, _, rl, wlss = mem(x, labels, True, False)
+            torch.autograd.backward([uq, rl, wlss[0], wlss[1]],
+                                    [G, torch.tensor(LOSS_W["read"]), torch.tensor(LOSS_W["div"]),
+                                     torch.tensor(LOSS_W["cls"])])
         t1 = time.perf_counter()
         if i >= warmup:
             times.append(t1 - t0)
@@ -203,7 +228,7 @@ def cpu_reference_run(wl, kind, steps, warmup, sample_B=None, budget_s=120.0):
     px = B * wl["h"] * wl["w"]
     total = sum(times)
     return dict(value=px * len(times) / total / 1e6, ms_per_step=1e3 * total / len(times), cores=cores,
-                same_config=(B == wl["B"]),
+                same_config=(B == wl["B"]), kind=impl_kind,
                 sample="B=%d of the workload's %d images per step (%dx%d features, %dx%d labels), %d timed steps, %d threads" %
                        (B, wl["B"], wl["h"], wl["w"], wl["Hm"], wl["Wm"], len(times), cores))
 
@@ -231,12 +256,18 @@ def eval_read_main(args, wl):
             return
         from oracle import memory_oracle as mo
 
+        from oracle import ref_loader
+
         host_threads()
         torch.manual_seed(synth.SEED)
-        ora = mo.OracleMemorySup(K, C, C, 0.8, 1.0, True).eval()
+        ora = reference_module("cpu", gumbel=True)      # the reference's own module when oracle/_ref holds it
+        kind_ = "reference" if ora is not None else "port"
+        if ora is None:
+            ora = mo.OracleMemorySup(K, C, C, 0.8, 1.0, True)
+        ora.eval()
         x = synth.make_features(B, C, h, w)
         times = []
-        with torch.no_grad():
+        with torch.no_grad(), ref_loader.cuda_identity(force=True):
             for i in range(2 + args.steps):
                 t0 = time.perf_counter()
                 ora(x, None, False)
@@ -245,7 +276,7 @@ def eval_read_main(args, wl):
         v = N * len(times) / sum(times) / 1e6
         line.update({"impl": "reference", "value": v, "ms_per_step": 1e3 * sum(times) / len(times), "dtype": "f32",
                      "gpu_launches": 0,
-                     "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                     "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind_,
                                       "sample": "the full per-GPU step (B=%d), %d timed steps" % (B, len(times))},
                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         print(json.dumps(line))
@@ -353,18 +384,24 @@ def eval_read_main(args, wl):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import memory_oracle as mo
 
+        from oracle import ref_loader
+
         host_threads()
-        ora = mo.OracleMemorySup(K, C, C, 0.8, 1.0, True).eval()
+        ora = reference_module("cpu", gumbel=True)
+        kind_ = "reference" if ora is not None else "port"
+        if ora is None:
+            ora = mo.OracleMemorySup(K, C, C, 0.8, 1.0, True)
+        ora.eval()
         xc = x_host.float()
         times = []
-        with torch.no_grad():
+        with torch.no_grad(), ref_loader.cuda_identity(force=True):
             for i in range(5):
                 t0 = time.perf_counter()
                 ora(xc, None, False)
                 if i >= 2:
                     times.append(time.perf_counter() - t0)
         line["cpu_baseline"] = {"value": N * len(times) / sum(times) / 1e6, "unit": UNIT, "cores": torch.get_num_threads(),
-                                "kind": "port", "sample": "the full per-GPU step (B=%d), 3 timed steps" % B}
+                                "kind": kind_, "sample": "the full per-GPU step (B=%d), 3 timed steps" % B}
     if rank == 0:
         print(json.dumps(line), flush=True)
     gstep.release()
@@ -557,13 +594,15 @@ def main():
         line = dict(base)
         line.update({"impl": "reference", "value": r["value"], "ms_per_step": r["ms_per_step"], "n_gpus": args.gpus,
                      "dtype": "f32", "gpu_launches": 0, "same_config": r["same_config"],
-                     "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                     "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                                       "sample": r["sample"]},
                      "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                     "note": "reference's own CPU path = oracle/ port of network/memory.py (the reference is Python and "
-                             "/root/reference is not on this box); torch %s, %d threads; one rank's batch (the metric is "
-                             "per-pixel throughput, the CPU arm does not scale with --gpus)" %
-                             (torch.__version__, r["cores"])})
+                     "note": ("reference's own CPU path = %s; torch %s, %d threads; one rank's batch (the metric is "
+                              "per-pixel throughput, the CPU arm does not scale with --gpus)" %
+                              ("the reference's unmodified network/memory.py::Memory_sup, byte-compiled into oracle/_ref/ "
+                               "(oracle/build_ref.py)" if r["kind"] == "reference" else
+                               "oracle/ port of network/memory.py (oracle/_ref/ is not on this box)",
+                               torch.__version__, r["cores"]))})
         print(json.dumps(line))
         return
 
@@ -1089,9 +1128,31 @@ def main():
                                             if dt == torch.float32 else "oracle restatement under bf16 autocast (speed only)"}
         except Exception as e:  # the comparison is informative only
             line["torch_eager_same_gpu"] = {"error": str(e)[:200]}
+        if dt == torch.float32:
+            try:   # the reference's OWN module (unmodified, oracle/_ref), eagerly on this GPU
+                refm = reference_module(dev)
+                if refm is not None:
+                    refm.load_state_dict(mem.state_dict())
+                    refm.train()
+
+                    def ref_step():
+                        refm.m_items = M0
+                        x.grad = None
+                        refm.zero_grad(set_to_none=True)
+                        uq, _, _, rl, wlss = refm(x, labels, True, False)
+                        torch.autograd.backward([uq, rl, wlss[0], wlss[1]], [G.to(uq.dtype), gw[0], gw[1], gw[2]])
+
+                    ms_r, _, _, _ = timed(ref_step, 10, 3)
+                    line["reference_eager_same_gpu"] = {
+                        "value": N / (ms_r / 10 * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_r / 10,
+                        "what": "the reference's unmodified network/memory.py::Memory_sup (oracle/_ref), eager PyTorch on this "
+                                "GPU, fp32 with TF32 off (the parity configuration)"}
+                    del refm
+            except Exception as e:
+                line["reference_eager_same_gpu"] = {"error": str(e)[:200]}
         if not args.no_cpu_baseline:
             cb = cpu_reference_run(wl, args.labels, 6, 1, None, budget_s=25.0)
-            line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "port",
+            line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"],
                                     "sample": cb["sample"], "ms_per_step": cb["ms_per_step"], "same_config": cb["same_config"]}
     if rank == 0:
         print(json.dumps(line), flush=True)
