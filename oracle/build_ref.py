@@ -1,7 +1,7 @@
 """Byte-compile the reference's network/memory.py into oracle/_ref/ (build container only).
 
 TEST INFRASTRUCTURE. The reference is pure Python, so its "compiled from its own sources where they lie" form is a
-.pyc: ``py_compile`` of /root/reference/network/memory.py, unmodified, written to oracle/_ref/reference_memory.pyc
+.pyc: ``py_compile`` of /root/reference/network/memory.py, unmodified, written to oracle/_ref/reference_memory.bytecode
 together with a manifest (source path, SHA-256 of the source, interpreter). oracle/_ref/ is git-ignored (an output, like
 a built .so; no reference source text enters the repository) but not gpurun-ignored, so it travels to the GPU box, where
 ``bench.py --impl reference`` and ``cpu_baseline`` time THE REFERENCE'S OWN MODULE on the host cores instead of the
@@ -19,7 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REFERENCE_ROOT = os.environ.get("PINMEM_REFERENCE_ROOT", "/root/reference")
 SRC = os.path.join(REFERENCE_ROOT, "network", "memory.py")
 OUT_DIR = os.path.join(HERE, "_ref")
-OUT = os.path.join(OUT_DIR, "reference_memory.pyc")
+OUT = os.path.join(OUT_DIR, "reference_memory.bytecode")
 
 
 def build():

@@ -5,7 +5,7 @@ the GPU box, so this loader is used by ``oracle/make_golden.py`` (fixture genera
 and by the CPU tests that pin the oracle against the live reference; everything that
 runs on the GPU box uses the committed fixtures in ``tests/golden/`` instead -- except
 ``bench.py --impl reference`` / ``cpu_baseline``, which TIME the reference's own module from
-the byte-compiled ``oracle/_ref/reference_memory.pyc`` (oracle/build_ref.py) when it is there.
+the byte-compiled ``oracle/_ref/reference_memory.bytecode`` (oracle/build_ref.py) when it is there.
 
 Recipe: the reference file imports one unused foreign symbol
 (``transforms.transforms.HideAndSeek``, memory.py:7) and calls ``.cuda()``
@@ -26,7 +26,7 @@ _REF_FILE = os.path.join(REFERENCE_ROOT, "network", "memory.py")
 # Byte-compiled copy of the same file, made by oracle/build_ref.py where the reference tree is mounted (the build
 # container). Like a .so built from C sources it is an OUTPUT: git-ignored, never edited, no source text -- but it travels
 # to the GPU box with the snapshot, so `bench.py --impl reference` can time the reference's own module there.
-_REF_PYC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference_memory.pyc")
+_REF_PYC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference_memory.bytecode")
 
 
 def reference_available() -> bool:

@@ -1,4 +1,4 @@
-"""CPU: oracle/_ref/reference_memory.pyc -- the byte-compiled, unmodified reference module that `bench.py --impl
+"""CPU: oracle/_ref/reference_memory.bytecode -- the byte-compiled, unmodified reference module that `bench.py --impl
 reference` times on the GPU box (oracle/build_ref.py) -- loads without the reference tree and behaves like the oracle.
 
 Skipped when the file has not been built (a checkout that never saw /root/reference)."""
@@ -14,7 +14,7 @@ import torch
 from golden_util import assert_close
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PYC = os.path.join(ROOT, "oracle", "_ref", "reference_memory.pyc")
+PYC = os.path.join(ROOT, "oracle", "_ref", "reference_memory.bytecode")
 pytestmark = pytest.mark.skipif(not os.path.isfile(PYC), reason="oracle/_ref not built (reference tree never mounted)")
 
 
