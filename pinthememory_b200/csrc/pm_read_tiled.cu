@@ -98,7 +98,10 @@ __device__ __forceinline__ void tile_dots_mma(const float* xt, const float* Mt, 
         }
 #pragma unroll
         for (int n = 0; n < NT; ++n) {
-            const float b0 = mrow[8 * n], b1 = mrow[KP + 8 * n];
+            // slots >= KP of the last 8-slot step do not exist (their accumulators are never stored): read zeros instead
+            // of the next row's first slots -- past the end of Mt for the last channel
+            const bool in = (8 * n + 8 <= KP) || (8 * n + g < KP);
+            const float b0 = in ? mrow[8 * n] : 0.f, b1 = in ? mrow[KP + 8 * n] : 0.f;
             const unsigned b0h = tf32_hi(b0), b1h = tf32_hi(b1);
             const unsigned b0l = tf32_lo(b0), b1l = tf32_lo(b1);
 #pragma unroll
