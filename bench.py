@@ -441,7 +441,10 @@ def extra_configs(args, dev, dt, world, rank, mem0, timed):
         Bg = 64
         Bl = max(Bg // world, 1)
         w4 = synth.WORKLOADS["cfg4_dp_os16_b8"]
-        m = fresh(shard=True).train()
+        m = fresh(shard=True)
+        if world > 1:   # the reference's multi-GPU scripts pass --syncbn (train.py:95): batch statistics of the GLOBAL batch
+            m = torch.nn.SyncBatchNorm.convert_sync_batchnorm(m)
+        m = m.train()
         seed = synth.SEED + 100 * rank + 7
         x4 = synth.make_features(Bl, C, w4["h"], w4["w"], seed=seed, dtype=dt, device=dev)
         l4 = synth.make_labels(Bl, w4["Hm"], w4["Wm"], K, args.labels, seed=seed + 2, device=dev)
@@ -454,8 +457,11 @@ def extra_configs(args, dev, dt, world, rank, mem0, timed):
         out["cfg4_dp_os16_global_batch_64"] = {
             "ms_per_step": ms, "value": Bg * w4["h"] * w4["w"] / (ms * 1e-3) / 1e6, "unit": UNIT, "scaling": "strong",
             "per_gpu_batch": Bl, "what": "DR50V3P shape (48x48 features, 768x768 labels), global batch 64 split over %d "
-                                         "GPU(s), class sums|counts exchanged before the update (%s), CUDA graph "
-                                         "replay" % (world, exchange_name(m))}
+                                         "GPU(s), class sums|counts exchanged before the update (%s), %s, CUDA graph "
+                                         "replay" % (world, exchange_name(m),
+                                                     "SyncBatchNorm as under --syncbn (statistics all-reduced out of the GEMM "
+                                                     "epilogue, 4 small NCCL all-reduces per step)" if world > 1 else
+                                                     "BatchNorm2d")}
         gs.release()
         del gs, m, x4, l4, G4
     except Exception as e:

@@ -54,7 +54,7 @@ enum pm_readloss_ws_layout {
 #define PM_COLPART_ROWS 296
 
 /* Bumped with every prototype change; the binding refuses a library whose pm_version() differs. */
-#define PM_ABI_VERSION 201
+#define PM_ABI_VERSION 202
 int pm_version(void);
 const char* pm_status_string(int code);
 /* Row stride (floats) of the internal score buffers for K slots: 20 for K<=19, else 32. */
@@ -238,8 +238,11 @@ int pm_bn_apply(const void* x, const float* mean, const float* invstd, const flo
  * written once per channel. Replaces pm_bn_finalize + pm_bn_apply (one launch less between the GEMM and its consumer). */
 int pm_bn_apply_stats(const void* x, const double* stats, double count, float eps, const float* gamma, const float* beta,
                       const void* residual, void* y, uint32_t* relu_mask, int relu, float* mean_out, float* invstd_out,
-                      float* running_mean, float* running_var, float momentum, int B, int C, int hw, int dtype,
-                      void* stream);
+                      float* running_mean, float* running_var, float momentum, const double* count_dev, int B, int C,
+                      int hw, int dtype, void* stream);
+/*   count_dev  NULL, or the element count in device memory, used instead of `count`: SyncBatchNorm (the reference under
+ *              --syncbn, train.py:95) all-reduces [stats | count] over the ranks and normalises with the global statistics
+ *              without a device->host read. */
 int pm_bn_bwd_reduce(const void* dy, const void* y, const uint32_t* relu_mask, const void* x, const float* mean,
                      const float* invstd, int relu, float* dgamma, float* dbeta, int B, int C, int hw, int dtype,
                      void* stream);

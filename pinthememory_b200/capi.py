@@ -16,7 +16,7 @@ WS_WORDS = 40  # PM_WS_WORDS
 WS_HIST = 4    # PM_WS_HIST
 WS_BAD = 2     # PM_WS_BAD
 
-ABI_VERSION = 201  # PM_ABI_VERSION of include/pinmem_b200.h the argtypes below were written against
+ABI_VERSION = 202  # PM_ABI_VERSION of include/pinmem_b200.h the argtypes below were written against
 
 _c_p = ctypes.c_void_p
 _c_i = ctypes.c_int
@@ -60,7 +60,7 @@ PROTOTYPES = {
     "pm_conv1x1_wgrad_workspace_floats": [_c_i] * 5,
     "pm_conv1x1_wgrad": [_c_p] * 4 + [_c_i] * 6 + [_c_p],
     "pm_bn_finalize": [_c_p, _c_i, _c_d, _c_f] + [_c_p] * 4 + [_c_f, _c_p],
-    "pm_bn_apply_stats": [_c_p, _c_p, _c_d, _c_f] + [_c_p] * 5 + [_c_i] + [_c_p] * 4 + [_c_f] + [_c_i] * 4 + [_c_p],
+    "pm_bn_apply_stats": [_c_p, _c_p, _c_d, _c_f] + [_c_p] * 5 + [_c_i] + [_c_p] * 4 + [_c_f, _c_p] + [_c_i] * 4 + [_c_p],
     "pm_write_reduce_fwd8": [_c_p] * 3 + [_c_i] * 8 + [_c_p],
     "pm_write_bwd8": [_c_p] * 4 + [_c_i] * 8 + [_c_p],
     "pm_peer_buffer_bytes": [],
@@ -429,12 +429,13 @@ def conv1x1_wgrad(dy, x, dW=None, accumulate=False):
 
 
 def bn_apply_stats(x, stats, count, eps, gamma, beta, residual, y, relu, mean_out, invstd_out, running_mean, running_var,
-                   momentum, relu_mask=None):
-    """Normalise pass with the batch statistics finalised in-kernel from the GEMM epilogue's fp64 sums."""
+                   momentum, relu_mask=None, count_dev=None):
+    """Normalise pass with the batch statistics finalised in-kernel from the GEMM epilogue's fp64 sums (``count_dev``: a
+    float64 device scalar that replaces ``count`` -- the all-reduced global count of a SyncBatchNorm)."""
     B, C, h, w = x.shape
     _call("pm_bn_apply_stats", _ptr(x), _ptr(stats), float(count), float(eps), _ptr(gamma), _ptr(beta), _ptr(residual), _ptr(y),
           _ptr(relu_mask), int(bool(relu)), _ptr(mean_out), _ptr(invstd_out), _ptr(running_mean), _ptr(running_var),
-          float(momentum), B, C, h * w, dtype_code(x), _stream())
+          float(momentum), _ptr(count_dev), B, C, h * w, dtype_code(x), _stream())
 
 
 def bn_finalize(stats, C, count, eps, mean, invstd, running_mean, running_var, momentum):

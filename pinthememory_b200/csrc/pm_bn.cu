@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const T* __restric
 // one CTA per (b, c) row
 struct BnFinalize {  // stats == nullptr: mean / invstd are given
     const double* stats;
+    const double* n_dev;  // NULL, or the element count on the device (SyncBatchNorm: the all-reduced global count)
     double n;
     float eps, momentum;
     float *mean_out, *invstd_out, *running_mean, *running_var;
@@ -158,8 +159,9 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, 
         // batch statistics straight from the convolution epilogue's fp64 (sum, sum of squares): every CTA finalises its
         // own channel (two loads, a division and a square root) instead of waiting for a finalise launch; the CTAs of
         // image 0 publish mean / invstd for the backward and update the running statistics
-        const double m = fin.stats[c] / fin.n;
-        double var = fin.stats[C + c] / fin.n - m * m;
+        const double n = fin.n_dev != nullptr ? *fin.n_dev : fin.n;
+        const double m = fin.stats[c] / n;
+        double var = fin.stats[C + c] / n - m * m;
         if (var < 0.0) var = 0.0;
         mu = (float)m;
         is = (float)(1.0 / sqrt(var + (double)fin.eps));
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, 
             fin.mean_out[c] = mu;
             fin.invstd_out[c] = is;
             if (fin.running_mean != nullptr) {
-                const double unb = fin.n > 1.0 ? var * fin.n / (fin.n - 1.0) : var;
+                const double unb = n > 1.0 ? var * n / (n - 1.0) : var;
                 fin.running_mean[c] = (float)((1.0 - fin.momentum) * fin.running_mean[c] + fin.momentum * m);
                 fin.running_var[c] = (float)((1.0 - fin.momentum) * fin.running_var[c] + fin.momentum * unb);
             }
@@ -446,17 +448,18 @@ extern "C" int pm_bn_apply(const void* x, const float* mean, const float* invstd
                            void* stream) {
     if (!mean || !invstd) return PM_ERR_NULL;
     return bn_apply_impl(x, mean, invstd, gamma, beta, residual, y, relu_mask, relu, B, C, hw, dtype,
-                         pm::BnFinalize{nullptr, 0.0, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr}, stream);
+                         pm::BnFinalize{nullptr, nullptr, 0.0, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr}, stream);
 }
 
 extern "C" int pm_bn_apply_stats(const void* x, const double* stats, double count, float eps, const float* gamma,
                                  const float* beta, const void* residual, void* y, uint32_t* relu_mask, int relu,
                                  float* mean_out, float* invstd_out, float* running_mean, float* running_var, float momentum,
-                                 int B, int C, int hw, int dtype, void* stream) {
+                                 const double* count_dev, int B, int C, int hw, int dtype, void* stream) {
     if (!stats || !mean_out || !invstd_out || ((running_mean == nullptr) != (running_var == nullptr))) return PM_ERR_NULL;
     if (!(count > 0.0)) return PM_ERR_SHAPE;
     return bn_apply_impl(x, nullptr, nullptr, gamma, beta, residual, y, relu_mask, relu, B, C, hw, dtype,
-                         pm::BnFinalize{stats, count, eps, momentum, mean_out, invstd_out, running_mean, running_var}, stream);
+                         pm::BnFinalize{stats, count_dev, count, eps, momentum, mean_out, invstd_out, running_mean, running_var},
+                         stream);
 }
 
 static int bn_apply_impl(const void* x, const float* mean, const float* invstd, const float* gamma, const float* beta,

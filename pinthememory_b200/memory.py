@@ -330,7 +330,7 @@ class _ConvBnActFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, W, gamma, beta, residual, running_mean, running_var, use_batch_stats, factor, eps, relu,
-                res_is_x):
+                res_is_x, sync_group=None):
         B, K, h, w = x.shape
         M = W.shape[0]
         dev = x.device
@@ -339,8 +339,17 @@ class _ConvBnActFn(torch.autograd.Function):
         b32 = beta.detach().to(torch.float32).contiguous()
         hi, lo = capi.conv1x1_prep(W2, False, x.dtype)
         if use_batch_stats:
-            stats = torch.zeros(2 * M, dtype=torch.float64, device=dev)
+            # [sum | sum of squares | element count]: the GEMM epilogue fills the first 2M; with SyncBatchNorm the whole
+            # vector is summed over the ranks (fp64, one small all-reduce) and the normalise pass finalises GLOBAL statistics
+            stats = torch.zeros(2 * M + 1, dtype=torch.float64, device=dev)
             xc = capi.conv1x1_fwd(x, hi, lo, M, stats=stats)
+            count = None
+            if sync_group is not None:
+                import torch.distributed as dist
+
+                stats[2 * M] = float(B * h * w)
+                dist.all_reduce(stats, group=sync_group)
+                count = stats[2 * M:]
             mean = torch.empty(M, dtype=torch.float32, device=dev)
             invstd = torch.empty(M, dtype=torch.float32, device=dev)
         else:
@@ -354,18 +363,20 @@ class _ConvBnActFn(torch.autograd.Function):
         mask = torch.empty(nwords, dtype=torch.int32, device=dev) if vec_ok else None
         if use_batch_stats:  # mean / invstd / running statistics are finalised inside the normalise pass
             capi.bn_apply_stats(xc, stats, B * h * w, eps, g32, b32, res, y, relu, mean, invstd, running_mean, running_var,
-                                factor, relu_mask=mask)
+                                factor, relu_mask=mask, count_dev=count)
         else:
             capi.bn_apply(xc, mean, invstd, g32, b32, res, y, relu, relu_mask=mask)
         ctx.relu, ctx.training, ctx.res_is_x, ctx.has_res = relu, use_batch_stats, res_is_x, res is not None
         ctx.use_mask = mask is not None
         ctx.wshape, ctx.wdtype = W.shape, W.dtype
-        ctx.save_for_backward(x, W2, xc, mask if mask is not None else y, mean, invstd, g32)
+        ctx.sync_group = sync_group if use_batch_stats else None
+        ctx.save_for_backward(x, W2, xc, mask if mask is not None else y, mean, invstd, g32,
+                              count if (use_batch_stats and sync_group is not None) else None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, W2, xc, y_or_mask, mean, invstd, g32 = ctx.saved_tensors
+        x, W2, xc, y_or_mask, mean, invstd, g32, count = ctx.saved_tensors
         y, mask = (None, y_or_mask) if ctx.use_mask else (y_or_mask, None)
         M, K = W2.shape
         dy = dy.to(xc.dtype).contiguous()
@@ -378,7 +389,18 @@ class _ConvBnActFn(torch.autograd.Function):
         if mask is not None and any(t is not None and t.data_ptr() % 16 for t in (dy, dxc, dres)):
             raise RuntimeError("pinmem_b200: misaligned gradient buffer on the packed-mask BatchNorm path")
         capi.bn_bwd_reduce(dy, y, mask, xc, mean, invstd, ctx.relu, dgamma, dbeta)
-        capi.bn_bwd_apply(dy, y, mask, xc, mean, invstd, g32, dgamma, dbeta, ctx.relu, ctx.training, dxc, dres)
+        sg, sb = dgamma, dbeta
+        if ctx.sync_group is not None:
+            # SyncBatchNorm: the input gradient needs the sums over ALL ranks' pixels (the parameter gradients stay
+            # local, DDP averages them -- torch's own SyncBatchNorm does the same). One all-reduce of 2M floats; the
+            # kernel divides by the LOCAL pixel count, so the global sums are pre-scaled by local / global.
+            import torch.distributed as dist
+
+            sums = torch.cat([dgamma, dbeta])
+            dist.all_reduce(sums, group=ctx.sync_group)
+            sums = sums * (float(xc.shape[0] * xc.shape[2] * xc.shape[3]) / count).to(torch.float32)
+            sg, sb = sums[:M].contiguous(), sums[M:].contiguous()
+        capi.bn_bwd_apply(dy, y, mask, xc, mean, invstd, g32, sg, sb, ctx.relu, ctx.training, dxc, dres)
         dW = None
         if ctx.needs_input_grad[1]:
             dW = capi.conv1x1_wgrad(dxc, x).view(ctx.wshape).to(ctx.wdtype)
@@ -390,7 +412,7 @@ class _ConvBnActFn(torch.autograd.Function):
                 dres = None
             else:
                 dx = capi.conv1x1_fwd(dxc, hiT, loT, K)
-        return dx, dW, dgamma, dbeta, (None if ctx.res_is_x else dres), None, None, None, None, None, None, None
+        return dx, dW, dgamma, dbeta, (None if ctx.res_is_x else dres), None, None, None, None, None, None, None, None
 
 
 def _plain(m):
@@ -442,8 +464,22 @@ def _bn_args(bn):
 
 
 def _bn_fast(bn, xc):
-    return (type(bn) is nn.BatchNorm2d and bn.affine and _plain(bn) and xc.is_cuda and xc.dim() == 4
+    return (type(bn) in (nn.BatchNorm2d, nn.SyncBatchNorm) and bn.affine and _plain(bn) and xc.is_cuda and xc.dim() == 4
             and xc.dtype in (torch.float32, torch.bfloat16) and bn.weight.is_cuda)
+
+
+def _sync_group(bn):
+    """The process group whose ranks share this layer's batch statistics: ``nn.SyncBatchNorm`` in training mode with
+    more than one rank (what ``convert_sync_batchnorm`` makes of the module's two BatchNorm2d under ``--syncbn``,
+    train.py:95). Returns None when the layer behaves like a plain BatchNorm2d (eval mode, one rank, not initialised)."""
+    if type(bn) is not nn.SyncBatchNorm or not (bn.training or bn.running_mean is None):
+        return None
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return None
+    group = bn.process_group if bn.process_group is not None else dist.group.WORLD
+    return group if dist.get_world_size(group) > 1 else None
 
 
 def weight_bn_act(W, bn, x, residual, relu, name=None, prepared=None):
@@ -482,7 +518,7 @@ def _weight_bn_act(W, bn, x, residual, relu, prepared=None):
             residual = residual.to(x.dtype).contiguous()
         use_batch, rm, rv, factor = _bn_args(bn)
         return _ConvBnActFn.apply(x, W, bn.weight, bn.bias, None if res_is_x else residual, rm, rv, use_batch, factor,
-                                  float(bn.eps), relu, res_is_x)
+                                  float(bn.eps), relu, res_is_x, _sync_group(bn))
     _warn_once("libconv", "a 1x1 convolution fell back to the library GEMM (feature rows not 16-byte aligned, or an "
                           "unsupported channel count); the BatchNorm passes stay fused")
     return bn_act(F.conv2d(x, W.to(x.dtype)), bn, residual, relu)
@@ -500,7 +536,7 @@ def conv_bn_act(conv, bn, x, residual, relu, name=None):
 
 def bn_act(xc, bn, residual, relu):
     """BatchNorm2d (-> + residual) (-> ReLU) of an already convolved tensor (see conv_bn_act)."""
-    if not _bn_fast(bn, xc):
+    if not _bn_fast(bn, xc) or _sync_group(bn) is not None:   # (cross-rank statistics exist on the fused conv path only)
         y = bn(xc)
         if residual is not None:
             y = residual + y

@@ -134,3 +134,92 @@ def test_two_rank_nccl_sharded_module_equals_global_batch(exchange):
     for k, g in ref_grads.items():
         mean = sum(out[r]["grads"][k] for r in range(world)) / world  # what DDP's all-reduce(mean) produces
         assert_close(mean, g, 5e-5, k)
+
+
+# ------------------------------------------------------------------ SyncBatchNorm (the reference under --syncbn)
+
+
+def _worker_syncbn(rank, world, port, out):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.pop("PINMEM_B200_NCCL_EXCHANGE", None)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        from pinthememory_b200 import memory as pm_memory
+        from pinthememory_b200 import sharding
+        from pinthememory_b200.memory import Memory_sup
+
+        ora = _state(dev)
+        mem = Memory_sup(K, C, C, 0.8, 1.0, False).to(dev)
+        mem.load_state_dict(ora.state_dict())
+        mem.m_items = ora.m_items.clone()
+        mem = torch.nn.SyncBatchNorm.convert_sync_batchnorm(mem).train()      # train.py:95
+        assert type(mem.output[1]) is torch.nn.SyncBatchNorm and type(mem.writenet.writefeat[1]) is torch.nn.SyncBatchNorm
+        mem.fold_min_pixels = 0
+        sharding.enable_sharded_update(mem)
+        x, labels, G = _inputs(dev)
+        n = B // world
+        sl = slice(rank * n, (rank + 1) * n)
+        xr = x[sl].clone().requires_grad_(True)
+        pm_memory._warned.clear()
+        uq, _, _, rl, wl = mem(xr, labels[sl].contiguous(), True, False)
+        ((uq * G[sl]).sum() + LW["div"] * wl[0] + LW["cls"] * wl[1]).backward()
+        out[rank] = dict(m_items=mem.m_items.detach().cpu(), dx=xr.grad.cpu(), uq=uq.detach().cpu(),
+                         grads={k: p.grad.cpu() for k, p in mem.named_parameters() if p.grad is not None},
+                         rmean=mem.output[1].running_mean.cpu(), rvar=mem.writenet.writefeat[1].running_var.cpu(),
+                         fell_back="libconv" in pm_memory._warned)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_syncbatchnorm_module_equals_global_batch_batchnorm():
+    """``convert_sync_batchnorm`` turns the module's two BatchNorm2d into SyncBatchNorm (the reference's multi-GPU scripts
+    pass --syncbn). The fused conv+BN path must then normalise with the statistics of the GLOBAL batch: the GEMM
+    epilogue's fp64 sums (+ the pixel count) are all-reduced before the normalise pass, the two backward sums before the
+    input-gradient pass. Checker: the oracle with plain BatchNorm2d in training mode on the concatenated batch."""
+    import torch.multiprocessing as mp
+
+    from golden_util import assert_close
+    from oracle import memory_oracle as mo
+
+    world = 2
+    mgr = mp.get_context("spawn").Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_syncbn, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert not out[0]["fell_back"], "the SyncBatchNorm module must stay on the fused tcgen05 conv + BatchNorm path"
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = torch.device("cuda", 0)
+    ora = _state(dev).train()
+    x, labels, G = _inputs(dev)
+    xa = x.clone().requires_grad_(True)
+    M0 = ora.m_items.clone()
+    wr = mo.write(ora.writenet(xa), labels, M0, 0.8, ora.clsfier.weight, ora.clsfier.bias)   # BN over the whole batch
+    n = B // world
+    us = [mo.read(xa[r * n:(r + 1) * n], M0, None, 1.0)["u"] for r in range(world)]     # the read is per pixel
+    uq = ora.output(torch.cat(us))                                                        # BN over the whole batch
+    ((uq * G).sum() + LW["div"] * wr["div_loss"] + LW["cls"] * wr["cls_loss"]).backward()
+
+    assert torch.equal(out[0]["m_items"], out[1]["m_items"])
+    assert_close(out[0]["m_items"], wr["memory_new"].detach().cpu(), 1e-5, "m_items")
+    for r in range(world):
+        assert_close(out[r]["uq"], uq[r * n:(r + 1) * n].detach().cpu(), 1e-5, "updated_query rank %d" % r)
+        assert_close(out[r]["rmean"], ora.output[1].running_mean.cpu(), 1e-5, "running_mean (global statistics)")
+        assert_close(out[r]["rvar"], ora.writenet.writefeat[1].running_var.cpu(), 1e-5, "running_var (unbiased, global count)")
+    ref = {k: p.grad.cpu() for k, p in ora.named_parameters() if p.grad is not None}
+    for k, g in ref.items():
+        total = sum(out[r]["grads"][k] for r in range(world))
+        if k.startswith("output."):
+            # the read branch: <uq, G> is a sum over the rank's own pixels, so the ranks' gradients ADD UP to the global one
+            assert_close(total, g, 5e-5, k)
+        else:
+            # the write branch: div / cls are functions of the (global) memory, identical on every rank, and the backward
+            # all-reduces dS -- every rank holds its pixels' share of W times the global gradient: DDP's mean restores it
+            assert_close(total / world, g, 5e-5, k)
