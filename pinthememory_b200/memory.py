@@ -347,7 +347,7 @@ class _ConvBnActFn(torch.autograd.Function):
             if sync_group is not None:
                 import torch.distributed as dist
 
-                stats[2 * M] = float(B * h * w)
+                stats[2 * M:].fill_(float(B * h * w))   # (a fill kernel: capturable, unlike a scalar copy from the host)
                 dist.all_reduce(stats, group=sync_group)
                 count = stats[2 * M:]
             mean = torch.empty(M, dtype=torch.float32, device=dev)
