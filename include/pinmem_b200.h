@@ -54,7 +54,7 @@ enum pm_readloss_ws_layout {
 #define PM_COLPART_ROWS 296
 
 /* Bumped with every prototype change; the binding refuses a library whose pm_version() differs. */
-#define PM_ABI_VERSION 202
+#define PM_ABI_VERSION 203
 int pm_version(void);
 const char* pm_status_string(int code);
 /* Row stride (floats) of the internal score buffers for K slots: 20 for K<=19, else 32. */
@@ -285,6 +285,19 @@ int pm_conv1x1_fwd(const void* X, const void* A_hi, const void* A_lo, void* Y, d
  * the GEMM epilogue -- the inference read (BASELINE config 5) then has no separate normalise pass. scale, shift fp32 [M]. */
 int pm_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps,
                       int C, float* scale, float* shift, void* stream);
+/*
+ * Input gradient of conv1x1 -> BatchNorm (-> ReLU) with the BatchNorm backward in the GEMM's operand path (fp32, blocks
+ * WITHOUT a residual: self.output, memory.py:103-107): dX[b] = W^T . dz[b], dz = gamma*invstd*(g - dbeta/n - xhat*dgamma/n),
+ * g = dY*(y > 0). Replaces pm_bn_bwd_apply + pm_conv1x1_fwd on the transposed weight: the producer loads the dY tile and the
+ * tile of the saved convolution output Z, the operand-split warps form dz in place (the ReLU gate is recomputed from Z with
+ * the forward's expression) and the dz tiles are stored to dZ [B,K,hw] for the weight-gradient GEMM.
+ *   dY, Z, dZ [B,K,hw] fp32 (K = the convolution's OUTPUT channels)      A_hi/A_lo = pm_conv1x1_prep(W, transpose = 1)
+ *   dX [B,M,hw] fp32 (M = the convolution's INPUT channels)              mean/invstd/gamma/beta [K], dgamma/dbeta [K] =
+ *   the sums pm_bn_bwd_reduce produced; training = 0: eval-mode BatchNorm (dz = gamma*invstd*g); n = B*hw.
+ */
+int pm_conv1x1_dgrad_bnbwd(const void* dY, const void* Z, const void* A_hi, const void* A_lo, void* dX, void* dZ,
+                           const float* mean, const float* invstd, const float* gamma, const float* beta, const float* dgamma,
+                           const float* dbeta, int relu, int training, int B, int K, int M, int hw, int dtype, void* stream);
 int pm_conv1x1_fwd_affine(const void* X, const void* A_hi, const void* A_lo, void* Y, const float* scale, const float* shift,
                           int relu, int B, int K, int M, int hw, int dtype, void* stream);
 int pm_conv1x1_wgrad_workspace_floats(int B, int M, int N, int hw, int dtype);

@@ -16,7 +16,7 @@ WS_WORDS = 40  # PM_WS_WORDS
 WS_HIST = 4    # PM_WS_HIST
 WS_BAD = 2     # PM_WS_BAD
 
-ABI_VERSION = 202  # PM_ABI_VERSION of include/pinmem_b200.h the argtypes below were written against
+ABI_VERSION = 203  # PM_ABI_VERSION of include/pinmem_b200.h the argtypes below were written against
 
 _c_p = ctypes.c_void_p
 _c_i = ctypes.c_int
@@ -60,6 +60,7 @@ PROTOTYPES = {
     "pm_conv1x1_wgrad_workspace_floats": [_c_i] * 5,
     "pm_conv1x1_wgrad": [_c_p] * 4 + [_c_i] * 6 + [_c_p],
     "pm_bn_finalize": [_c_p, _c_i, _c_d, _c_f] + [_c_p] * 4 + [_c_f, _c_p],
+    "pm_conv1x1_dgrad_bnbwd": [_c_p] * 12 + [_c_i] * 7 + [_c_p],
     "pm_bn_apply_stats": [_c_p, _c_p, _c_d, _c_f] + [_c_p] * 5 + [_c_i] + [_c_p] * 4 + [_c_f, _c_p] + [_c_i] * 4 + [_c_p],
     "pm_write_reduce_fwd8": [_c_p] * 3 + [_c_i] * 8 + [_c_p],
     "pm_write_bwd8": [_c_p] * 4 + [_c_i] * 8 + [_c_p],
@@ -182,7 +183,7 @@ def score_stride(K):
 # with CUDA events on the launching stream to get per-kernel durations live.
 
 LAUNCHES = 0
-_KERNELS_PER_CALL = {"pm_colsoftmax": 3, "pm_colsoftmax_apply": 1, "pm_read_bwd": 2, "pm_read_bwd_planes": 2, "pm_conv1x1_wgrad": 2}
+_KERNELS_PER_CALL = {"pm_conv1x1_dgrad_bnbwd": 2, "pm_colsoftmax": 3, "pm_colsoftmax_apply": 1, "pm_read_bwd": 2, "pm_read_bwd_planes": 2, "pm_conv1x1_wgrad": 2}
 PLANES = 32  # PM_PLANES: score planes appended to q in the score-plane read
 _timing = None  # name -> list of (start_event, end_event) when enabled
 
@@ -394,6 +395,18 @@ def conv1x1_fwd(x, A_hi, A_lo, M, y=None, stats=None, accumulate=False):
     _call("pm_conv1x1_fwd", _ptr(x), _ptr(A_hi), _ptr(A_lo), _ptr(y), _ptr(stats), B, K, M, h * w, int(bool(accumulate)),
           dtype_code(x), _stream())
     return y
+
+
+def conv1x1_dgrad_bnbwd(dy, z, A_hi, A_lo, M, mean, invstd, gamma, dgamma, dbeta, beta, relu, training):
+    """(dx [B,M,h,w], dz [B,K,h,w]): input gradient of conv1x1 -> BatchNorm (-> ReLU) with the BatchNorm backward formed in
+    the GEMM's operand path; dz is stored for the weight-gradient GEMM (fp32 only)."""
+    B, K, h, w = dy.shape
+    dx = torch.empty(B, M, h, w, dtype=dy.dtype, device=dy.device)
+    dz = torch.empty_like(dy)
+    _call("pm_conv1x1_dgrad_bnbwd", _ptr(dy), _ptr(z), _ptr(A_hi), _ptr(A_lo), _ptr(dx), _ptr(dz), _ptr(mean), _ptr(invstd),
+          _ptr(gamma), _ptr(beta), _ptr(dgamma), _ptr(dbeta), int(bool(relu)), int(bool(training)), B, K, M, h * w,
+          dtype_code(dy), _stream())
+    return dx, dz
 
 
 def bn_eval_affine(gamma, beta, running_mean, running_var, eps):

@@ -141,6 +141,51 @@ __device__ __forceinline__ void split_tile(float4* __restrict__ raw, float4* __r
     }
 }
 
+// ---- BatchNorm backward in the operand path of the input-gradient GEMM (fp32) ---------------------------------------
+// The input gradient of conv -> BatchNorm (-> ReLU) is W^T . dz with dz = gamma*invstd*(g - dbeta/n - xhat*dgamma/n),
+// g = dy*(y > 0), xhat = (z - mean)*invstd: an element-wise function of the incoming gradient dy and the saved
+// convolution output z. Instead of a separate pass that reads both and writes dz (bn_bwd_apply, 42 us at cfg 2) the
+// producer loads the dy tile AND the z tile of a stage, the operand-split warps -- which touch every element anyway --
+// form dz in place (raw fp32 = the "hi" operand in the dy buffer, dz - trunc(dz) = "lo" in the z buffer) and one of
+// them hands the dz tile to the TMA unit as a store, because the weight-gradient GEMM needs it too. The ReLU gate is
+// recomputed from z with the forward's own expression (no mask load); only for blocks without a residual.
+struct BnBwdArgs {
+    const float *mean, *invstd, *gamma, *beta, *dgamma, *dbeta;  // per conv-output channel; mean == nullptr: off
+    float inv_n;
+    int training, relu;
+};
+
+template <int KB>
+__device__ __forceinline__ void bnbwd_tile(float4* __restrict__ dy_hi, float4* __restrict__ z_lo, int n4, int t, int nthreads,
+                                           int ch0, const BnBwdArgs& bn) {
+    // 8 float4 per 128-byte row, KB rows per 32-pixel chunk: float4 i belongs to row (i >> 3) % KB. With 128 threads and
+    // KB = 16 a thread stays on ONE row (t >> 3) for the whole tile: its channel's coefficients are loaded once.
+    constexpr bool FIXED = (KB == 16);
+    float is = 0.f, mu = 0.f, sc = 0.f, sh = 0.f, k1 = 0.f, k2 = 0.f;
+    auto coef = [&](int c) {
+        is = __ldg(bn.invstd + c), mu = __ldg(bn.mean + c);
+        sc = is * __ldg(bn.gamma + c), sh = __ldg(bn.beta + c) - mu * sc;  // the forward's affine (bn_apply_kernel), same expression
+        k1 = bn.training ? __ldg(bn.dbeta + c) * bn.inv_n : 0.f, k2 = bn.training ? __ldg(bn.dgamma + c) * bn.inv_n : 0.f;
+    };
+    if (FIXED) coef(ch0 + ((t >> 3) % KB));
+    for (int i = t; i < n4; i += nthreads) {
+        if (!FIXED) coef(ch0 + ((i >> 3) % KB));
+        const float4 g = dy_hi[i], z = z_lo[i];
+        float4 d, l;
+#define PM_BNBWD_ONE(f)                                                                  \
+        {                                                                                \
+            const float gv = (!bn.relu || fmaf(z.f, sc, sh) > 0.f) ? g.f : 0.f;          \
+            const float xh = (z.f - mu) * is;                                            \
+            d.f = sc * (gv - k1 - xh * k2);                                              \
+            l.f = d.f - __uint_as_float(__float_as_uint(d.f) & 0xffffe000u);             \
+        }
+        PM_BNBWD_ONE(x) PM_BNBWD_ONE(y) PM_BNBWD_ONE(z) PM_BNBWD_ONE(w)
+#undef PM_BNBWD_ONE
+        dy_hi[i] = d;
+        z_lo[i] = l;
+    }
+}
+
 // =================================================================================================================
 // Form 1: Y[b] = A . X[b]   (forward convolution and input gradient)
 //   mapX  : [B*K rows][hw] activations, box [KB rows][PXC pixels]           (MN-major B operand)
@@ -158,9 +203,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     conv1x1_nn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapAh,
                       const __grid_constant__ CUtensorMap mapAl, const __grid_constant__ CUtensorMap mapY, int K, int M,
                       int m_tile0, int tiles_per_img, int total_tiles, int accumulate, double* __restrict__ stats,
-                      const float* __restrict__ ep_scale, const float* __restrict__ ep_shift, int ep_relu, int dbg) {
+                      const float* __restrict__ ep_scale, const float* __restrict__ ep_shift, int ep_relu, int dbg,
+                      const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ CUtensorMap mapDZ, const BnBwdArgs bn) {
     using TR = GemmTraits<T>;
     constexpr int PXC = TR::PXC, UK = TR::UK, KSTEPS = KB / UK;
+    const bool bnbwd = TR::SPLIT && !MIX && bn.mean != nullptr;  // X = dy, Z = saved conv output: dz formed in the split stage
     constexpr int NCH = NT / PXC;                      // 128-byte pixel chunks per tile
     constexpr int XCHUNK = KB * 128;                   // bytes of one [KB rows][128 B] chunk
     constexpr int XBYTES = NCH * XCHUNK;               // = NT * KB * sizeof(T)
@@ -189,7 +236,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     uint64_t* xfull = bars + 2 * STAGES;   // [STAGES] lo parts written (fp32)
     uint64_t* accf = bars + 3 * STAGES;    // [ACC] accumulator complete
     uint64_t* acce = accf + ACC;           // [ACC] accumulator drained
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acce + ACC);
+    uint64_t* sfree = acce + ACC;          // [STAGES] the dz store of the stage has left shared memory (bnbwd only)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sfree + STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -197,6 +245,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], CL);
             mbar_init(&xfull[i], 4);  // one arrival per operand-split warp
+            mbar_init(&sfree[i], 1);
         }
         for (int i = 0; i < ACC; ++i) {
             mbar_init(&accf[i], 1);
@@ -230,10 +279,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
                     mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                    if (bnbwd) mbar_wait(&sfree[s], ((it / STAGES) & 1) ^ 1);
                     unsigned char* st = smem + s * STAGE;
-                    mbar_expect_tx(&full[s], TX);
+                    mbar_expect_tx(&full[s], TX + (bnbwd ? (uint32_t)XBYTES : 0u));
 #pragma unroll
                     for (int c = 0; c < NCH; ++c) tma_load_2d(st + c * XCHUNK, &mapX, px0 + c * PXC, b * K + kb * KB, &full[s]);
+                    if (bnbwd) {  // the saved convolution output of the same block lands where "lo" will be written
+#pragma unroll
+                        for (int c = 0; c < NCH; ++c)
+                            tma_load_2d(st + XBYTES + c * XCHUNK, &mapZ, px0 + c * PXC, b * K + kb * KB, &full[s]);
+                    }
                     unsigned char* sa = st + NOPA * XBYTES;
 #pragma unroll
                     for (int j = 0; j < NOPA * MT; ++j) {  // weight blocks: [hi of every row tile | lo of every row tile]
@@ -442,17 +497,36 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             const int t = threadIdx.x - 6 * 32;
             uint32_t it = 0;
             for (int g = g0; g < ngroups; g += gstride) {
+                int tile = g * CL + crank;
+                const bool real_tile = tile < total_tiles;
+                if (!real_tile) tile = total_tiles - 1;
+                const int b = tile / tiles_per_img, px0 = (tile - b * tiles_per_img) * NT;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
                     mbar_wait(&full[s], (it / STAGES) & 1);
                     unsigned char* st = smem + s * STAGE;
                     if (MIX) mix_tile_mn<KB, NT>(st, st + XBYTES, t, 128);
+                    else if (bnbwd) bnbwd_tile<KB>(reinterpret_cast<float4*>(st), reinterpret_cast<float4*>(st + XBYTES), XBYTES / 16, t, 128, kb * KB, bn);
                     else split_tile_trunc(reinterpret_cast<float4*>(st), reinterpret_cast<float4*>(st + XBYTES), XBYTES / 16, t, 128);
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&xfull[s]);
+                    if (bnbwd && t == 0) {
+                        // once all four split warps have arrived the dz tile is complete: this thread stores it (the
+                        // weight-gradient GEMM reads it later) while the MMAs consume the same buffers; the stage may be
+                        // refilled once the MMAs AND this store have read it
+                        mbar_wait(&xfull[s], (it / STAGES) & 1);
+                        if (real_tile) {
+#pragma unroll
+                            for (int c = 0; c < NCH; ++c) tma_store_2d(&mapDZ, px0 + c * PXC, b * K + kb * KB, st + c * XCHUNK);
+                        }
+                        bulk_commit();
+                        bulk_wait_read<1>();  // every store but the one just issued has left shared memory
+                        if (it > 0) mbar_arrive(&sfree[(it - 1) % STAGES]);
+                    }
                 }
             }
+            if (bnbwd && t == 0) bulk_wait<0>();  // the last dz tiles are in global memory before the kernel ends
         }
     }
     tc_fence_before();
@@ -516,13 +590,20 @@ static int gemm_cluster() {  // PM_GEMM_CLUSTER = 1 | 2 | 4 (default 1): CTAs sh
 template <typename T, int MT, int NT, int KB>
 static int launch_nn(const void* X, const void* Ah, const void* Al, void* Y, double* stats, int B, int K, int M, int Mpad,
                      int hw, int m_tile0, int accumulate, const float* ep_scale, const float* ep_shift, int ep_relu,
-                     cudaStream_t st) {
+                     cudaStream_t st, const void* Z = nullptr, void* DZ = nullptr, const BnBwdArgs* bnargs = nullptr) {
     using TR = GemmTraits<T>;
-    CUtensorMap mX, mAh, mAl, mY;
+    CUtensorMap mX, mAh, mAl, mY, mZ, mDZ;
+    BnBwdArgs bn{};
+    if (bnargs != nullptr && Z != nullptr && DZ != nullptr) {
+        if (!TR::SPLIT || K % KB != 0) return PM_ERR_SHAPE;
+        bn = *bnargs;
+        if (!make_map_2d<T>(&mZ, Z, (size_t)B * K, hw, KB, TR::PXC, 2)) return PM_ERR_ALIGN;
+        if (!make_map_2d<T>(&mDZ, DZ, (size_t)B * K, hw, KB, TR::PXC, 2)) return PM_ERR_ALIGN;
+    }
     constexpr int ASW = KB * (int)sizeof(T) == 128 ? 1 : 3;  // TMA swizzle of the weight boxes: 128-byte or 64-byte rows
     if (!make_map_2d<T>(&mX, X, (size_t)B * K, hw, KB, TR::PXC, sizeof(T) == 4 ? 2 : 1)) return PM_ERR_ALIGN;
     if (!make_map_2d<T>(&mAh, Ah, Mpad, K, 128, KB, ASW)) return PM_ERR_ALIGN;
-    const bool mix = TR::SPLIT && gemm_mix() && K % 16 == 0;
+    const bool mix = TR::SPLIT && gemm_mix() && K % 16 == 0 && bn.mean == nullptr;
     if (mix) {
         if (!make_map_2d<__nv_bfloat16>(&mAl, Al, Mpad, 2 * (size_t)K, 128, 2 * KB, ASW)) return PM_ERR_ALIGN;
     } else if (TR::SPLIT) {
@@ -531,6 +612,7 @@ static int launch_nn(const void* X, const void* Ah, const void* Al, void* Y, dou
         mAl = mAh;
     }
     if (!make_map_2d<T>(&mY, Y, (size_t)B * M, hw, 32, TR::PXC, true)) return PM_ERR_ALIGN;
+    if (bn.mean == nullptr) mZ = mX, mDZ = mX;  // unused
     const int tiles_per_img = (hw + NT - 1) / NT, total = B * tiles_per_img;
     const size_t smem = nn_smem_bytes<T, MT, NT, KB>();
     // clusters of CL CTAs share the weight blocks by TMA multicast; the NOPA*MT blocks of a stage must split evenly
@@ -558,7 +640,7 @@ static int launch_nn(const void* X, const void* Ah, const void* Al, void* Y, dou
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                       \
         if (e != cudaSuccess) return (int)e;                                                                          \
         e = cudaLaunchKernelEx(&cfg, kern, mX, mAh, mAl, mY, K, M, m_tile0, tiles_per_img, total, accumulate, stats,     \
-                               ep_scale, ep_shift, ep_relu, dbg);                                                \
+                               ep_scale, ep_shift, ep_relu, dbg, mZ, mDZ, bn);                                   \
     }
     if (cl == 4) {
         if constexpr (CLMAX >= 4) PM_NN_LAUNCH(4) else return PM_ERR_SHAPE;
@@ -866,7 +948,8 @@ int pm_conv1x1_prep(const float* W, int M, int K, int transpose, int dtype, void
 }
 
 static int conv1x1_fwd_impl(const void* X, const void* A_hi, const void* A_lo, void* Y, double* stats, int B, int K, int M, int hw,
-                            int accumulate, const float* ep_scale, const float* ep_shift, int ep_relu, int dtype, void* stream) {
+                            int accumulate, const float* ep_scale, const float* ep_shift, int ep_relu, int dtype, void* stream,
+                            const void* Z = nullptr, void* DZ = nullptr, const BnBwdArgs* bn = nullptr) {
     if (!X || !A_hi || !Y || (dtype == PM_F32 && !A_lo) || ((ep_scale == nullptr) != (ep_shift == nullptr))) return PM_ERR_NULL;
     if (dtype != PM_F32 && dtype != PM_BF16) return PM_ERR_DTYPE;
     const int esz = dtype == PM_F32 ? 4 : 2, uk = dtype == PM_F32 ? 8 : 16;
@@ -883,12 +966,19 @@ static int conv1x1_fwd_impl(const void* X, const void* A_hi, const void* A_lo, v
         // small maps keep 128-pixel tiles so that more than a handful of SMs get work
         const bool wide = (long long)B * ((hw + 255) / 256) >= 96;
         if (dtype == PM_F32) {
+            // fused BatchNorm backward: the FIRST launch forms dz from (X = dy, Z) in its operand path and stores it to DZ
+            // (every launch walks all K operand channels of its pixel tiles); the remaining row tiles read DZ
+            const bool first = bn != nullptr && t0 == 0;
+            const void* Xin = (bn != nullptr && t0 > 0) ? DZ : X;
+            const void* Zi = first ? Z : nullptr;
+            void* DZo = first ? DZ : nullptr;
+            const BnBwdArgs* bi = first ? bn : nullptr;
             if (wide && !gemm_narrow())
-                rc = mt == 2 ? launch_nn<float, 2, 256, 16>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, ep_scale, ep_shift, ep_relu, st)
-                             : launch_nn<float, 1, 256, 16>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, ep_scale, ep_shift, ep_relu, st);
+                rc = mt == 2 ? launch_nn<float, 2, 256, 16>(Xin, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, ep_scale, ep_shift, ep_relu, st, Zi, DZo, bi)
+                             : launch_nn<float, 1, 256, 16>(Xin, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, ep_scale, ep_shift, ep_relu, st, Zi, DZo, bi);
             else
-                rc = mt == 2 ? launch_nn<float, 2, 128, 32>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, ep_scale, ep_shift, ep_relu, st)
-                             : launch_nn<float, 1, 128, 32>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, ep_scale, ep_shift, ep_relu, st);
+                rc = mt == 2 ? launch_nn<float, 2, 128, 32>(Xin, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, ep_scale, ep_shift, ep_relu, st, Zi, DZo, bi)
+                             : launch_nn<float, 1, 128, 32>(Xin, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, ep_scale, ep_shift, ep_relu, st, Zi, DZo, bi);
         } else {
             rc = mt == 2 ? launch_nn<__nv_bfloat16, 2, 128, 64>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, ep_scale, ep_shift, ep_relu, st)
                          : launch_nn<__nv_bfloat16, 1, 128, 64>(X, A_hi, A_lo, Y, stats, B, K, M, Mpad, hw, t0, accumulate, ep_scale, ep_shift, ep_relu, st);
@@ -901,6 +991,16 @@ static int conv1x1_fwd_impl(const void* X, const void* A_hi, const void* A_lo, v
 int pm_conv1x1_fwd(const void* X, const void* A_hi, const void* A_lo, void* Y, double* stats, int B, int K, int M, int hw,
                    int accumulate, int dtype, void* stream) {
     return conv1x1_fwd_impl(X, A_hi, A_lo, Y, stats, B, K, M, hw, accumulate, nullptr, nullptr, 0, dtype, stream);
+}
+
+int pm_conv1x1_dgrad_bnbwd(const void* dY, const void* Z, const void* A_hi, const void* A_lo, void* dX, void* dZ,
+                           const float* mean, const float* invstd, const float* gamma, const float* beta, const float* dgamma,
+                           const float* dbeta, int relu, int training, int B, int K, int M, int hw, int dtype, void* stream) {
+    if (!Z || !dZ || !mean || !invstd || !gamma || !beta || !dgamma || !dbeta) return PM_ERR_NULL;
+    if (dtype != PM_F32) return PM_ERR_DTYPE;  // the operand path transforms fp32 tiles; bf16 keeps the separate pass
+    if (K % 32 || ((uintptr_t)Z | (uintptr_t)dZ) % 16) return PM_ERR_ALIGN;
+    BnBwdArgs bn{mean, invstd, gamma, beta, dgamma, dbeta, 1.f / ((float)B * (float)hw), training, relu};
+    return conv1x1_fwd_impl(dY, A_hi, A_lo, dX, nullptr, B, K, M, hw, 0, nullptr, nullptr, 0, dtype, stream, Z, dZ, &bn);
 }
 
 int pm_conv1x1_fwd_affine(const void* X, const void* A_hi, const void* A_lo, void* Y, const float* scale, const float* shift,

@@ -370,6 +370,7 @@ class _ConvBnActFn(torch.autograd.Function):
         ctx.use_mask = mask is not None
         ctx.wshape, ctx.wdtype = W.shape, W.dtype
         ctx.sync_group = sync_group if use_batch_stats else None
+        ctx.beta32 = b32   # (a detached fp32 copy: only the fused BatchNorm-backward GEMM reads it, to recompute the ReLU gate)
         ctx.save_for_backward(x, W2, xc, mask if mask is not None else y, mean, invstd, g32,
                               count if (use_batch_stats and sync_group is not None) else None)
         return y
@@ -400,6 +401,17 @@ class _ConvBnActFn(torch.autograd.Function):
             dist.all_reduce(sums, group=ctx.sync_group)
             sums = sums * (float(xc.shape[0] * xc.shape[2] * xc.shape[3]) / count).to(torch.float32)
             sg, sb = sums[:M].contiguous(), sums[M:].contiguous()
+        if (need_x and not ctx.has_res and xc.dtype == torch.float32 and M % 32 == 0 and ctx.beta32 is not None
+                and not os.environ.get("PINMEM_B200_NO_BNBWD_FUSION")):
+            # blocks without a residual (self.output): the BatchNorm backward rides in the operand path of the
+            # input-gradient GEMM, which also stores dz for the weight-gradient GEMM -- no bn_bwd_apply pass
+            hiT, loT = capi.conv1x1_prep(W2, True, x.dtype)
+            dx, dxc = capi.conv1x1_dgrad_bnbwd(dy, xc, hiT, loT, K, mean, invstd, g32, sg, sb, ctx.beta32, ctx.relu,
+                                               ctx.training)
+            dW = None
+            if ctx.needs_input_grad[1]:
+                dW = capi.conv1x1_wgrad(dxc, x).view(ctx.wshape).to(ctx.wdtype)
+            return dx, dW, dgamma, dbeta, None, None, None, None, None, None, None, None, None
         capi.bn_bwd_apply(dy, y, mask, xc, mean, invstd, g32, sg, sb, ctx.relu, ctx.training, dxc, dres)
         dW = None
         if ctx.needs_input_grad[1]:

@@ -450,6 +450,37 @@ def test_write_branch_gradient_summed_inside_the_read_backward(two_streams):
         assert_close(gb, ga, 2e-6, "parameter gradient")
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 96, 12, 16), (3, 256, 288, 24, 24), (8, 256, 288, 48, 48)], ids=str)
+@pytest.mark.parametrize("training", [True, False], ids=["train", "eval"])
+def test_batchnorm_backward_in_the_gemm_operand_path(shape, training):
+    """pm_conv1x1_dgrad_bnbwd (dz formed by the operand-split warps from dy and the saved conv output, stored for the weight
+    gradient) against the two-kernel path pm_bn_bwd_apply -> pm_conv1x1_fwd on the transposed weight."""
+    from pinthememory_b200 import capi
+
+    B, Kc, Mc, h, w = shape     # Kc = conv output channels (operand rows), Mc = conv input channels (output rows)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    rnd = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    z, dy = rnd(B, Kc, h, w), rnd(B, Kc, h, w)
+    W = rnd(Kc, Mc) * 0.1
+    gamma, beta = 1 + 0.1 * rnd(Kc), 0.1 * rnd(Kc)
+    mean, invstd = z.mean((0, 2, 3)).contiguous(), (z.var((0, 2, 3), unbiased=False) + 1e-5).rsqrt().contiguous()
+    y = torch.empty_like(z)
+    mask = torch.empty(capi.bn_mask_words(B, Kc, h * w), dtype=torch.int32, device="cuda")
+    capi.bn_apply(z, mean, invstd, gamma, beta, None, y, True, relu_mask=mask)
+    dgamma, dbeta = torch.empty(Kc, device="cuda"), torch.empty(Kc, device="cuda")
+    capi.bn_bwd_reduce(dy, None, mask, z, mean, invstd, True, dgamma, dbeta)
+    dz_ref = torch.empty_like(z)
+    capi.bn_bwd_apply(dy, None, mask, z, mean, invstd, gamma, dgamma, dbeta, True, training, dz_ref, None)
+    hiT, loT = capi.conv1x1_prep(W.contiguous(), True, torch.float32)
+    dx_ref = capi.conv1x1_fwd(dz_ref, hiT, loT, Mc)
+    dx, dz = capi.conv1x1_dgrad_bnbwd(dy, z, hiT, loT, Mc, mean, invstd, gamma, dgamma, dbeta, beta, True, training)
+    torch.cuda.synchronize()
+    assert_close(dz, dz_ref, 1e-6, "dz")
+    assert_close(dx, dx_ref, 2e-6, "dx")
+    exact = torch.einsum("km,bkhw->bmhw", W.double(), dz_ref.double()).float()
+    assert_close(dx, exact, 1e-5, "dx vs fp64 product")
+
+
 # --------------------------------------------------------- the reference's public loss methods, checkpoint key
 
 
