@@ -22,6 +22,7 @@
 // loss and ds_rl stay below 3e-6 (tests/test_gpu_parity.py). The weights lambda_x / lambda_y themselves are computed
 // exactly as PyTorch does (fp32 `scale * dst`, floor, clamp).
 #include "pm_common.cuh"
+#include <cstdlib>
 
 namespace pm {
 
@@ -395,12 +396,28 @@ __global__ void __launch_bounds__(RL8_THREADS, 2)
 
 }  // namespace pm
 
+// third-generation kernel (pm_readloss9.cu): 0 = launched, -1 = shape outside its fixed-point range
+int pm_readloss_rows_launch(const float* s, const uint8_t* lab8, float temperature, int B, int h, int w, int Hm, int Wm, int K,
+                            float* ds_rl, void* ws, float* out, cudaStream_t st);
+static int readloss_gen2() {  // PINMEM_B200_READLOSS_GEN2=1: keep the one-thread-per-cell kernel (A/B switch for the profiles)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PINMEM_B200_READLOSS_GEN2");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v;
+}
+
 extern "C" int pm_readloss_fwd8(const float* s, const uint8_t* lab8, float temperature, int B, int h, int w, int Hm, int Wm,
                                 int K, float* ds_rl, void* ws, float* out, void* stream) {
     if (!s || !lab8 || !ds_rl || !ws || !out) return PM_ERR_NULL;
     if (K < 1 || K > 19) return PM_ERR_SLOTS;
     if (B <= 0 || h <= 0 || w <= 0 || Hm <= 0 || Wm <= 0 || !(temperature > 0.f)) return PM_ERR_SHAPE;
     if (((uintptr_t)s & 15) || ((uintptr_t)ds_rl & 15) || ((uintptr_t)ws & 7)) return PM_ERR_ALIGN;
+    if (!readloss_gen2()) {
+        const int rc = pm_readloss_rows_launch(s, lab8, temperature, B, h, w, Hm, Wm, K, ds_rl, ws, out, (cudaStream_t)stream);
+        if (rc >= 0) return rc;
+    }
     using namespace pm;
     // PyTorch's align_corners scale: (in-1)/(out-1) in fp32, 0 when out == 1
     const float sy = Hm > 1 ? (float)(h - 1) / (float)(Hm - 1) : 0.f;

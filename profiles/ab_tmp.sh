@@ -1,9 +1,8 @@
-timeout 300 python -m pytest tests -m gpu -q -x -k "operand_path" 2>&1 | tail -12; timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -6
-for i in 1 2; do
-for v in "" "PINMEM_B200_NO_BNBWD_FUSION=1"; do
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
+for v in "" "PINMEM_B200_READLOSS_GEN2=1"; do
 env $v timeout 200 python bench.py --no-extra --no-cpu-baseline --steps 50 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('$v', round(d['ms_per_step'],4), d['timing']['value']['block_ms_min'], d['timing']['value']['block_ms_max'], {k:(v.get('ms'), v.get('launches_per_step')) for k,v in d['kernels'].items() if 'conv1x1' in k or 'bn_bwd' in k})
+print('$v', 'step', round(d['ms_per_step'],4), 'core', round(d['core']['ms_per_step'],4), {k:(v.get('ms')) for k,v in d['kernels'].items() if 'readloss' in k or 'labels' in k})
 "
-done; done
+done
