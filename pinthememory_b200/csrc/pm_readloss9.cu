@@ -22,12 +22,17 @@
 namespace pm {
 namespace rw {
 
+constexpr int TX_ = 32;
+#ifndef PM_RL_MINB
+#define PM_RL_MINB 2
+#endif
 #ifndef PM_RL_THREADS
 #define PM_RL_THREADS 256
 #endif
 constexpr int THREADS = PM_RL_THREADS, WARPS = THREADS / 32, TX = 32, KP = 20, NH = KP / 2;
 constexpr int TPC = THREADS / TX;  // threads per cell in the y-weighting step
-constexpr int REC = 44;      // floats per (row slot, cell) record: 2 x 20 row sums, padded so that STS.128 is conflict-free
+constexpr int REC = 44;      // floats per (tile row, cell) in the tap tiles: 2 x 20 sums, padded so that 128-bit accesses are conflict-free
+constexpr int SLOTF = TX_ * 40 + (TX_ / 4) * 4;   // floats per row slot of the records: cell c at c*40 + (c/4)*4 (conflict-free too)
 constexpr int OSTR = 21;     // words per feature pixel in the one-hot tile (odd: neighbouring cells hit distinct banks)
 constexpr int TCOLS = TX + 1;
 constexpr int CHUNK = 3;     // label pixels per unrolled group
@@ -173,7 +178,7 @@ __device__ __forceinline__ void row_pixels(const float2 (&A)[NH], const float2 (
     flush();
 }
 
-__global__ void __launch_bounds__(THREADS, 512 / THREADS)
+__global__ void __launch_bounds__(THREADS, PM_RL_MINB)
     readloss_rows_kernel(const float* __restrict__ s, const unsigned char* __restrict__ lab8, float inv_T, float temperature, int h,
                          int w, int Hm, int Wm, int K, float sy, float sx, int CR, int slots, int tiles_x, int bands, float fscale,
                          float* __restrict__ ds_rl, unsigned long long* __restrict__ ws, float* __restrict__ out) {
@@ -183,8 +188,8 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS)
     float* s_tile = smem;                                // [TR][33][KP] similarities (clamped at the map's edge)
     float* lr_tile = s_tile + TR * TCOLS * KP;           // [TR][32][REC] tap sums: floats 0..19 left tap, 20..39 right tap
     unsigned* o_tile = reinterpret_cast<unsigned*>(lr_tile + TR * TX * REC);  // [TR][33][OSTR] fixed-point one-hot weights
-    float* rec = reinterpret_cast<float*>(o_tile + TR * TCOLS * OSTR + 3 - (TR * TCOLS * OSTR + 3) % 4);  // [slots][32][REC]
-    float* lamy_s = rec + (size_t)slots * TX * REC;      // [slots]
+    float* rec = reinterpret_cast<float*>(o_tile + TR * TCOLS * OSTR + 3 - (TR * TCOLS * OSTR + 3) % 4);  // [slots][SLOTF]
+    float* lamy_s = rec + (size_t)slots * SLOTF;      // [slots]
     int* geo = reinterpret_cast<int*>(lamy_s + slots);   // [0..33] Xa of the tile's cells (+1), [40..40+CR] Ya of the band's cell rows
     float* red = reinterpret_cast<float*>(geo + 48);     // [16]
 
@@ -273,7 +278,7 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS)
             const unsigned char* lrow = lab_b + (size_t)Y * Wm + Xa;
             if (!exact) row_pixels<false>(A, Bc, sx, cxf, Xa, ncols, nc_max, lrow, K, hy, lamy, o_top, TCOLS * OSTR, fscale, R0, R1, lossacc);
             else row_pixels<true>(A, Bc, sx, cxf, Xa, ncols, nc_max, lrow, K, hy, lamy, o_top, TCOLS * OSTR, fscale, R0, R1, lossacc);
-            float4* dst = reinterpret_cast<float4*>(rec + ((size_t)(Y - base) * TX + lane) * REC);
+            float4* dst = reinterpret_cast<float4*>(rec + (size_t)(Y - base) * SLOTF + lane * 40 + (lane >> 2) * 4);
 #pragma unroll
             for (int q = 0; q < NH / 2; ++q) {
                 dst[q] = make_float4(R0[2 * q].x, R0[2 * q].y, R0[2 * q + 1].x, R0[2 * q + 1].y);
@@ -293,8 +298,8 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS)
 #pragma unroll
                 for (int idx = j; idx < KP / 2; idx += TPC) {
                     float2 ta = make_float2(0.f, 0.f), tb = ta, ba = ta, bb = ta;
-                    const float4* r = reinterpret_cast<const float4*>(rec + ((size_t)(ra - base) * TX + cell) * REC) + idx;
-                    for (int Y = ra; Y < rb; ++Y, r += TX * REC / 4) {
+                    const float4* r = reinterpret_cast<const float4*>(rec + (size_t)(ra - base) * SLOTF + cell * 40 + (cell >> 2) * 4) + idx;
+                    for (int Y = ra; Y < rb; ++Y, r += SLOTF / 4) {
                         const float ly = lamy_s[Y - base];
                         const float2 ly2 = make_float2(ly, ly), hy2 = make_float2(1.f - ly, 1.f - ly);
                         const float4 v = *r;
@@ -386,13 +391,12 @@ int pm_readloss_rows_launch(const float* s, const uint8_t* lab8, float temperatu
     while (CR < MAX_CR && (CR + 1) * rtyp <= WARPS && CR < h) ++CR;
     if (const char* e = getenv("PM_RL_CR")) CR = atoi(e) < 1 ? 1 : (atoi(e) > MAX_CR ? MAX_CR : atoi(e));  // tuning switch
     int slots = CR * rmax;
-    slots = ((slots + WARPS - 1) / WARPS) * WARPS;
     if (slots > 16) slots = 16;
     const int TR = CR + 1;
     const int tiles_x = (w + TX - 1) / TX, bands = (h + CR - 1) / CR;
     const int o_words = TR * TCOLS * OSTR;
     const size_t smem = sizeof(float) * ((size_t)TR * TCOLS * KP + (size_t)TR * TX * REC + (o_words + 3 - (o_words + 3) % 4) +
-                                         (size_t)slots * TX * REC + slots + 48 + 16);
+                                         (size_t)slots * SLOTF + slots + 48 + 16);
     const long long grid = (long long)B * tiles_x * bands;
     if (grid > 0x7fffffffLL) return -1;
     cudaError_t e = cudaFuncSetAttribute(readloss_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
