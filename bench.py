@@ -845,6 +845,7 @@ def main():
         "pm_bn_apply": N * C * esz * 2.5,        # x (+ residual in one of the two blocks) -> y
         "pm_bn_apply_stats": N * C * esz * 2.5,  # the same pass with the statistics finalised in-kernel
         "pm_bn_bwd_reduce": N * C * esz * 2,     # dy, x (+ the packed ReLU mask, 1/32)
+        "pm_bn_bwd_reduce_rows": N * C * esz * 2,
         "pm_bn_bwd_apply": N * C * esz * 3.5,    # dy, x -> dx (+ dres in one of the two blocks)
     }
     if "pm_labels_pack" in kavg and "pm_readloss_fwd8" in kavg:
@@ -852,9 +853,9 @@ def main():
     bound_note = {
         "pm_readloss (pm_labels_pack + pm_readloss_fwd8)":
             "two launches reported as one logical kernel (time and bytes are their sums; bytes as SURVEY 8d counts them: "
-            "int64 labels read once). Not HBM-bound by nature: ~65 instructions per LABEL pixel (64 label pixels per "
-            "feature pixel) in one thread per bilinear cell at 8 warps per SM -- latency-bound, see DESIGN.md 6; DRAM "
-            "traffic = algorithmic bytes (no re-reads)",
+            "int64 labels read once). Not HBM-bound by nature: ~90 instructions per LABEL pixel (64 label pixels per "
+            "feature pixel) plus the per-row exp2 set-up, one thread per label row of a bilinear cell, 16 warps per SM -- "
+            "issue/latency-bound, see DESIGN.md 6; DRAM traffic = algorithmic bytes (no re-reads)",
         "pm_readloss_fwd": "not HBM-bound by nature: ~19 ex2 + ~60 FMA per LABEL pixel (64 label pixels per feature "
                            "pixel) make it FP32/MUFU-issue bound; the HBM fraction is reported because the contract asks "
                            "for it, see DESIGN.md 4/6",

@@ -54,7 +54,7 @@ enum pm_readloss_ws_layout {
 #define PM_COLPART_ROWS 296
 
 /* Bumped with every prototype change; the binding refuses a library whose pm_version() differs. */
-#define PM_ABI_VERSION 203
+#define PM_ABI_VERSION 204
 int pm_version(void);
 const char* pm_status_string(int code);
 /* Row stride (floats) of the internal score buffers for K slots: 20 for K<=19, else 32. */
@@ -252,6 +252,14 @@ int pm_bn_bwd_scratch_bytes(int C);
 int pm_bn_bwd_reduce_split(const void* dy, const void* y, const uint32_t* relu_mask, const void* x, const float* mean,
                            const float* invstd, int relu, float* dgamma, float* dbeta, int B, int C, int hw, int dtype,
                            void* scratch, void* stream);
+/* pm_bn_bwd_reduce with one CTA per (image, channel) row -- bn_bwd_apply's access pattern, ~1.6x the bandwidth of one CTA
+ * per channel. scratch: pm_bn_bwd_rows_scratch_bytes(B, C) bytes, 8-byte aligned, zeroed ONCE when allocated (the kernel
+ * leaves its arrival counters at zero); the B row partials of a channel are added in image order (deterministic). Use one
+ * scratch per stream that may run this entry concurrently. */
+int pm_bn_bwd_rows_scratch_bytes(int B, int C);
+int pm_bn_bwd_reduce_rows(const void* dy, const void* y, const uint32_t* relu_mask, const void* x, const float* mean,
+                          const float* invstd, int relu, float* dgamma, float* dbeta, int B, int C, int hw, int dtype,
+                          void* scratch, void* stream);
 int pm_bn_bwd_apply(const void* dy, const void* y, const uint32_t* relu_mask, const void* x, const float* mean,
                     const float* invstd, const float* gamma, const float* dgamma, const float* dbeta, int relu,
                     int training, void* dx, void* dres, int B, int C, int hw, int dtype, void* stream);

@@ -16,7 +16,7 @@ WS_WORDS = 40  # PM_WS_WORDS
 WS_HIST = 4    # PM_WS_HIST
 WS_BAD = 2     # PM_WS_BAD
 
-ABI_VERSION = 203  # PM_ABI_VERSION of include/pinmem_b200.h the argtypes below were written against
+ABI_VERSION = 204  # PM_ABI_VERSION of include/pinmem_b200.h the argtypes below were written against
 
 _c_p = ctypes.c_void_p
 _c_i = ctypes.c_int
@@ -52,6 +52,8 @@ PROTOTYPES = {
     "pm_bn_bwd_reduce": [_c_p] * 6 + [_c_i] + [_c_p] * 2 + [_c_i] * 4 + [_c_p],
     "pm_bn_bwd_scratch_bytes": [_c_i],
     "pm_bn_bwd_reduce_split": [_c_p] * 6 + [_c_i] + [_c_p] * 2 + [_c_i] * 4 + [_c_p] * 2,
+    "pm_bn_bwd_rows_scratch_bytes": [_c_i] * 2,
+    "pm_bn_bwd_reduce_rows": [_c_p] * 6 + [_c_i] + [_c_p] * 2 + [_c_i] * 4 + [_c_p] * 2,
     "pm_bn_bwd_apply": [_c_p] * 9 + [_c_i] * 2 + [_c_p] * 2 + [_c_i] * 4 + [_c_p],
     "pm_conv1x1_prep": [_c_p] + [_c_i] * 4 + [_c_p] * 3,
     "pm_conv1x1_fwd": [_c_p] * 5 + [_c_i] * 6 + [_c_p],
@@ -344,8 +346,27 @@ def bn_apply(x, mean, invstd, gamma, beta, residual, y, relu, relu_mask=None):
           _ptr(relu_mask), int(relu), B, C, h * w, dtype_code(x), _stream())
 
 
+_BN_ROWS_SCRATCH = {}  # (device, stream, B, C) -> zero-initialised scratch of pm_bn_bwd_reduce_rows (self-cleaning counters)
+
+
+def _bn_rows_scratch(x, B, C):
+    st = torch.cuda.current_stream(x.device)
+    key = (x.device.index, st.cuda_stream, B, C)
+    buf = _BN_ROWS_SCRATCH.get(key)
+    if buf is None:
+        # (allocated inside a graph capture the fill becomes a memset node that re-zeroes on every replay: harmless, and this
+        # cache keeps the buffer alive as long as the graph)
+        buf = torch.zeros(load().pm_bn_bwd_rows_scratch_bytes(B, C) // 8 + 1, dtype=torch.float64, device=x.device)
+        _BN_ROWS_SCRATCH[key] = buf
+    return buf
+
+
 def bn_bwd_reduce(dy, y, relu_mask, x, mean, invstd, relu, dgamma, dbeta):
     B, C, h, w = x.shape
+    if not os.environ.get("PINMEM_B200_BN_REDUCE_PER_CHANNEL"):  # one CTA per (image, channel) row: 48 -> ~30 us at cfg 2
+        _call("pm_bn_bwd_reduce_rows", _ptr(dy), _ptr(y), _ptr(relu_mask), _ptr(x), _ptr(mean), _ptr(invstd), int(relu),
+              _ptr(dgamma), _ptr(dbeta), B, C, h * w, dtype_code(x), _ptr(_bn_rows_scratch(x, B, C)), _stream())
+        return
     if os.environ.get("PINMEM_B200_BN_SPLIT"):   # measured 55.7 us vs 51 us unsplit at cfg 2: off by default (A/B switch)
         scratch = torch.zeros(load().pm_bn_bwd_scratch_bytes(C) // 8 + 1, dtype=torch.float64, device=x.device)
         _call("pm_bn_bwd_reduce_split", _ptr(dy), _ptr(y), _ptr(relu_mask), _ptr(x), _ptr(mean), _ptr(invstd), int(relu),

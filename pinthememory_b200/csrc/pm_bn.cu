@@ -299,6 +299,86 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const T* __re
     }
 }
 
+// The same sums with one CTA per (b, c) ROW -- the access pattern of bn_bwd_apply, which streams at ~90 % of the copy peak
+// where one CTA per channel reaches ~50 %: 8 x as many CTAs, each reading two contiguous rows front to back. A row's two
+// partial sums go to `partials` [B][C][2] (doubles); the CTA that completes a channel (per-channel arrival counter) adds
+// the B partials in image order -- deterministic -- and RESETS the counter, so the scratch only has to be zeroed when it is
+// allocated, not per call.
+template <typename T, int VN>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_rows_kernel(const T* __restrict__ dy, const T* __restrict__ y,
+                                                                 const unsigned* __restrict__ relu_mask,
+                                                                 const T* __restrict__ x, const float* __restrict__ mean,
+                                                                 const float* __restrict__ invstd, int relu,
+                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta, int B,
+                                                                 int C, int hw, double* __restrict__ partials,
+                                                                 unsigned* __restrict__ counters) {
+    __shared__ double red[16];
+    const int row = blockIdx.x, c = row % C;
+    const float m = mean[c], is = invstd[c];
+    const size_t base = (size_t)row * hw;
+    float sg = 0.f, sgx = 0.f;
+    if constexpr (VN != 0) {
+        const int nv = hw / VN, wpr = (nv + 32 / VN - 1) / (32 / VN);
+#pragma unroll 3
+        for (int j = threadIdx.x; j < nv; j += 256) {
+            typename VecSel<T, VN>::type g, yy, xx;
+            g.load(dy + base + VN * j);
+            xx.load(x + base + VN * j);
+            unsigned bits = (1u << VN) - 1u;
+            if (relu) {
+                if (relu_mask != nullptr) {
+                    bits = mask_bits<VN>(relu_mask + (size_t)row * wpr, j);
+                } else {
+                    yy.load(y + base + VN * j);
+                    bits = 0u;
+#pragma unroll
+                    for (int e = 0; e < VN; ++e) bits |= (yy.get(e) > 0.f ? 1u : 0u) << e;
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < VN; ++e) {
+                const float gv = ((bits >> e) & 1u) ? g.get(e) : 0.f;
+                sg += gv;
+                sgx = fmaf(gv, (xx.get(e) - m) * is, sgx);
+            }
+        }
+    } else {
+        for (int j = threadIdx.x; j < hw; j += 256) {
+            const float gv = (!relu || ldf(y + base + j) > 0.f) ? ldf(dy + base + j) : 0.f;
+            sg += gv;
+            sgx = fmaf(gv, (ldf(x + base + j) - m) * is, sgx);
+        }
+    }
+    // block sums (256 threads = 8 warps): both values in one round
+    double a = (double)sg, q = (double)sgx;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) red[wid] = a, red[8 + wid] = q;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a = q = 0.0;
+        for (int i = 0; i < 8; ++i) a += red[i], q += red[8 + i];
+        partials[(size_t)row * 2] = a;
+        partials[(size_t)row * 2 + 1] = q;
+        __threadfence();
+        if (atomicAdd(counters + c, 1u) == (unsigned)B - 1) {
+            __threadfence();
+            a = q = 0.0;
+            for (int b = 0; b < B; ++b) {
+                a += __ldcg(partials + ((size_t)b * C + c) * 2);
+                q += __ldcg(partials + ((size_t)b * C + c) * 2 + 1);
+            }
+            dbeta[c] = (float)a;
+            dgamma[c] = (float)q;
+            counters[c] = 0u;  // ready for the next call on this scratch
+        }
+    }
+}
+
 // one CTA per (b, c) row: dx = gamma*invstd*(g - [training] (dbeta + xhat*dgamma)/n); dres = g
 template <typename T, int VN>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ y,
@@ -520,6 +600,35 @@ static int bn_bwd_reduce_impl(const void* dy, const void* y, const uint32_t* rel
         if (vec == 8) pm::bn_bwd_reduce_kernel<bf, 8><<<grid, pm::BN_THREADS, 0, st>>>((const bf*)dy, (const bf*)y, relu_mask, (const bf*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw, scratch);
         else if (vec) pm::bn_bwd_reduce_kernel<bf, 4><<<grid, pm::BN_THREADS, 0, st>>>((const bf*)dy, (const bf*)y, relu_mask, (const bf*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw, scratch);
         else pm::bn_bwd_reduce_kernel<bf, 0><<<grid, pm::BN_THREADS, 0, st>>>((const bf*)dy, (const bf*)y, relu_mask, (const bf*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw, scratch);
+    }
+    PM_CHECK_LAUNCH();
+    return 0;
+}
+
+/* pm_bn_bwd_reduce with one CTA per (image, channel) row (csrc/pm_bn.cu: bn_bwd_reduce_rows_kernel). scratch:
+ * pm_bn_bwd_rows_scratch_bytes(B, C) bytes, 8-byte aligned, zeroed ONCE when allocated (the kernel leaves its arrival
+ * counters at zero); one scratch per stream that may run this concurrently. */
+extern "C" int pm_bn_bwd_rows_scratch_bytes(int B, int C) { return (B > 0 && C > 0) ? B * C * 2 * 8 + C * 4 : 0; }
+extern "C" int pm_bn_bwd_reduce_rows(const void* dy, const void* y, const uint32_t* relu_mask, const void* x, const float* mean,
+                                     const float* invstd, int relu, float* dgamma, float* dbeta, int B, int C, int hw, int dtype,
+                                     void* scratch, void* stream) {
+    if (!dy || !x || !mean || !invstd || !dgamma || !dbeta || (relu && !y && !relu_mask)) return PM_ERR_NULL;
+    if (!scratch || ((uintptr_t)scratch & 7)) return PM_ERR_NULL;
+    if (int e = bn_check(B, C, hw, dtype)) return e;
+    const int vec = pm::vec_ok(hw, dy, y, x, nullptr, nullptr, dtype);
+    if (relu && !y && !vec) return PM_ERR_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    double* partials = (double*)scratch;
+    unsigned* counters = (unsigned*)(partials + (size_t)B * C * 2);
+    const int grid = B * C;
+    if (dtype == PM_F32) {
+        if (vec) pm::bn_bwd_reduce_rows_kernel<float, 4><<<grid, 256, 0, st>>>((const float*)dy, (const float*)y, relu_mask, (const float*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw, partials, counters);
+        else pm::bn_bwd_reduce_rows_kernel<float, 0><<<grid, 256, 0, st>>>((const float*)dy, (const float*)y, relu_mask, (const float*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw, partials, counters);
+    } else {
+        typedef __nv_bfloat16 bf;
+        if (vec == 8) pm::bn_bwd_reduce_rows_kernel<bf, 8><<<grid, 256, 0, st>>>((const bf*)dy, (const bf*)y, relu_mask, (const bf*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw, partials, counters);
+        else if (vec) pm::bn_bwd_reduce_rows_kernel<bf, 4><<<grid, 256, 0, st>>>((const bf*)dy, (const bf*)y, relu_mask, (const bf*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw, partials, counters);
+        else pm::bn_bwd_reduce_rows_kernel<bf, 0><<<grid, 256, 0, st>>>((const bf*)dy, (const bf*)y, relu_mask, (const bf*)x, mean, invstd, relu, dgamma, dbeta, B, C, hw, partials, counters);
     }
     PM_CHECK_LAUNCH();
     return 0;
