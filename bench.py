@@ -871,6 +871,11 @@ def main():
     calls = {k: len(v) / float(args.steps) for k, v in ktimes.items()}          # launches per step
     kstep = {k: sum(v) / float(args.steps) for k, v in ktimes.items()}          # ms per step
     conv_flops_step = {"pm_conv1x1_fwd": 2.0 * N * C * (4 * C + 64), "pm_conv1x1_wgrad": 2.0 * N * C * (2 * C + 32)}
+    if "pm_conv1x1_dgrad_bnbwd" in kstep:
+        # the input gradient of the output block (C+32 rows) runs inside pm_conv1x1_dgrad_bnbwd (BatchNorm backward in the
+        # GEMM's operand path): its flops leave the pm_conv1x1_fwd budget
+        conv_flops_step["pm_conv1x1_dgrad_bnbwd"] = 2.0 * N * C * (C + 32)
+        conv_flops_step["pm_conv1x1_fwd"] -= conv_flops_step["pm_conv1x1_dgrad_bnbwd"]
     tpeak, tpeak_src = tensor_peak(dt)
     kernels = {}
     for k, t_ms in kavg.items():

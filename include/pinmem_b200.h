@@ -54,7 +54,7 @@ enum pm_readloss_ws_layout {
 #define PM_COLPART_ROWS 296
 
 /* Bumped with every prototype change; the binding refuses a library whose pm_version() differs. */
-#define PM_ABI_VERSION 204
+#define PM_ABI_VERSION 205
 int pm_version(void);
 const char* pm_status_string(int code);
 /* Row stride (floats) of the internal score buffers for K slots: 20 for K<=19, else 32. */
@@ -286,6 +286,9 @@ int pm_bn_bwd_apply(const void* dy, const void* y, const uint32_t* relu_mask, co
  *                     count = B*hw. Same arithmetic as pm_bn_stats.
  */
 int pm_conv1x1_prep(const float* W, int M, int K, int transpose, int dtype, void* A_hi, void* A_lo, void* stream);
+/* pm_conv1x1_prep for BOTH operand layouts of one weight W [R,S] in one launch: (A_hi, A_lo) = W (M = R, K = S), the forward
+ * operand, and (At_hi, At_lo) = W^T (M = S, K = R), the operand of the input-gradient GEMM. */
+int pm_conv1x1_prep_both(const float* W, int R, int S, int dtype, void* A_hi, void* A_lo, void* At_hi, void* At_lo, void* stream);
 int pm_conv1x1_fwd(const void* X, const void* A_hi, const void* A_lo, void* Y, double* stats, int B, int K, int M,
                    int hw, int accumulate, int dtype, void* stream);
 /* Y[b] = [relu](scale[m] * (A . X[b]) + shift[m]): the convolution with the eval-mode BatchNorm2d (+ ReLU) that follows it

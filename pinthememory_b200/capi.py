@@ -16,7 +16,7 @@ WS_WORDS = 40  # PM_WS_WORDS
 WS_HIST = 4    # PM_WS_HIST
 WS_BAD = 2     # PM_WS_BAD
 
-ABI_VERSION = 204  # PM_ABI_VERSION of include/pinmem_b200.h the argtypes below were written against
+ABI_VERSION = 205  # PM_ABI_VERSION of include/pinmem_b200.h the argtypes below were written against
 
 _c_p = ctypes.c_void_p
 _c_i = ctypes.c_int
@@ -56,6 +56,7 @@ PROTOTYPES = {
     "pm_bn_bwd_reduce_rows": [_c_p] * 6 + [_c_i] + [_c_p] * 2 + [_c_i] * 4 + [_c_p] * 2,
     "pm_bn_bwd_apply": [_c_p] * 9 + [_c_i] * 2 + [_c_p] * 2 + [_c_i] * 4 + [_c_p],
     "pm_conv1x1_prep": [_c_p] + [_c_i] * 4 + [_c_p] * 3,
+    "pm_conv1x1_prep_both": [_c_p, _c_i, _c_i, _c_i] + [_c_p] * 5,
     "pm_conv1x1_fwd": [_c_p] * 5 + [_c_i] * 6 + [_c_p],
     "pm_bn_eval_affine": [_c_p] * 4 + [_c_f, _c_i] + [_c_p] * 3,
     "pm_conv1x1_fwd_affine": [_c_p] * 6 + [_c_i] * 6 + [_c_p],
@@ -398,6 +399,19 @@ def conv1x1_prep(W2d, transpose, dtype):
     _call("pm_conv1x1_prep", _ptr(W2d), M, K, int(bool(transpose)), PM_F32 if dtype == torch.float32 else PM_BF16,
           _ptr(hi), _ptr(lo), _stream())
     return hi, lo
+
+
+def conv1x1_prep_both(W2d, dtype):
+    """((A_hi, A_lo), (At_hi, At_lo)): conv1x1_prep(W2d, False) and conv1x1_prep(W2d, True) from one launch."""
+    R, S = W2d.shape
+    W2d = _f32c(W2d, "weight")
+    f32 = dtype == torch.float32
+    hi = torch.empty((R + 127) // 128 * 128, S, dtype=dtype, device=W2d.device)
+    lo = torch.empty_like(hi) if f32 else None
+    hiT = torch.empty((S + 127) // 128 * 128, R, dtype=dtype, device=W2d.device)
+    loT = torch.empty_like(hiT) if f32 else None
+    _call("pm_conv1x1_prep_both", _ptr(W2d), R, S, PM_F32 if f32 else PM_BF16, _ptr(hi), _ptr(lo), _ptr(hiT), _ptr(loT), _stream())
+    return (hi, lo), (hiT, loT)
 
 
 def conv1x1_ok(x, M, K):

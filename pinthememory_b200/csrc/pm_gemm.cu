@@ -926,11 +926,54 @@ __global__ void conv1x1_prep_kernel(const float* __restrict__ W, int M, int K, i
     }
 }
 
+// both operand layouts of one weight in ONE launch (blockIdx.y = 0: A = W, 1: A = W^T): the transposed operand of the
+// input-gradient GEMM is produced next to the forward one instead of by a second launch in the backward pass
+template <typename T>
+__global__ void conv1x1_prep_both_kernel(const float* __restrict__ W, int R, int S, T* __restrict__ hi, T* __restrict__ lo,
+                                         T* __restrict__ hiT, T* __restrict__ loT, int mix) {
+    const int tr = blockIdx.y;
+    const int M = tr ? S : R, K = tr ? R : S, Mpad = (M + 127) / 128 * 128;
+    T* h_out = tr ? hiT : hi;
+    T* l_out = tr ? loT : lo;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Mpad * K) return;
+    const int m = i / K, k = i - m * K;
+    const float v = m < M ? (tr ? W[(size_t)k * M + m] : W[(size_t)m * K + k]) : 0.f;
+    if constexpr (sizeof(T) == 4) {
+        const float h = tf32_rn(v);
+        h_out[i] = h;
+        if (mix && K % 16 == 0) {
+            __nv_bfloat16* lb = reinterpret_cast<__nv_bfloat16*>(l_out) + (size_t)m * 2 * K + ((k >> 4) << 5) + (k & 15);
+            lb[0] = __float2bfloat16_rn(v - h);
+            lb[16] = __float2bfloat16_rn(h);
+        } else {
+            l_out[i] = v - h;
+        }
+    } else {
+        h_out[i] = __float2bfloat16_rn(v);
+    }
+}
+
 }  // namespace pm
 
 using namespace pm;
 
 extern "C" {
+
+int pm_conv1x1_prep_both(const float* W, int R, int S, int dtype, void* A_hi, void* A_lo, void* At_hi, void* At_lo, void* stream) {
+    if (!W || !A_hi || !At_hi || (dtype == PM_F32 && (!A_lo || !At_lo))) return PM_ERR_NULL;
+    if (dtype != PM_F32 && dtype != PM_BF16) return PM_ERR_DTYPE;
+    if (R <= 0 || S <= 0) return PM_ERR_SHAPE;
+    const int n0 = (R + 127) / 128 * 128 * S, n1 = (S + 127) / 128 * 128 * R, n = n0 > n1 ? n0 : n1;
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid((n + 255) / 256, 2);
+    if (dtype == PM_F32)
+        conv1x1_prep_both_kernel<float><<<grid, 256, 0, st>>>(W, R, S, (float*)A_hi, (float*)A_lo, (float*)At_hi, (float*)At_lo, gemm_mix());
+    else
+        conv1x1_prep_both_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(W, R, S, (__nv_bfloat16*)A_hi, nullptr, (__nv_bfloat16*)At_hi, nullptr, 0);
+    PM_CHECK_LAUNCH();
+    return 0;
+}
 
 int pm_conv1x1_prep(const float* W, int M, int K, int transpose, int dtype, void* A_hi, void* A_lo, void* stream) {
     if (!W || !A_hi || (dtype == PM_F32 && !A_lo)) return PM_ERR_NULL;

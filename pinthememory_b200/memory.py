@@ -337,7 +337,11 @@ class _ConvBnActFn(torch.autograd.Function):
         W2 = W.detach().reshape(M, K).to(torch.float32).contiguous()
         g32 = gamma.detach().to(torch.float32).contiguous()
         b32 = beta.detach().to(torch.float32).contiguous()
-        hi, lo = capi.conv1x1_prep(W2, False, x.dtype)
+        ctx.preT = None
+        if ctx.needs_input_grad[0]:   # the input-gradient GEMM's operand W^T comes out of the same launch
+            (hi, lo), ctx.preT = capi.conv1x1_prep_both(W2, x.dtype)
+        else:
+            hi, lo = capi.conv1x1_prep(W2, False, x.dtype)
         if use_batch_stats:
             # [sum | sum of squares | element count]: the GEMM epilogue fills the first 2M; with SyncBatchNorm the whole
             # vector is summed over the ranks (fp64, one small all-reduce) and the normalise pass finalises GLOBAL statistics
@@ -405,7 +409,7 @@ class _ConvBnActFn(torch.autograd.Function):
                 and not os.environ.get("PINMEM_B200_NO_BNBWD_FUSION")):
             # blocks without a residual (self.output): the BatchNorm backward rides in the operand path of the
             # input-gradient GEMM, which also stores dz for the weight-gradient GEMM -- no bn_bwd_apply pass
-            hiT, loT = capi.conv1x1_prep(W2, True, x.dtype)
+            hiT, loT = ctx.preT if ctx.preT is not None else capi.conv1x1_prep(W2, True, x.dtype)
             dx, dxc = capi.conv1x1_dgrad_bnbwd(dy, xc, hiT, loT, K, mean, invstd, g32, sg, sb, ctx.beta32, ctx.relu,
                                                ctx.training)
             dW = None
@@ -418,7 +422,7 @@ class _ConvBnActFn(torch.autograd.Function):
             dW = capi.conv1x1_wgrad(dxc, x).view(ctx.wshape).to(ctx.wdtype)
         dx = None
         if need_x:
-            hiT, loT = capi.conv1x1_prep(W2, True, x.dtype)
+            hiT, loT = ctx.preT if ctx.preT is not None else capi.conv1x1_prep(W2, True, x.dtype)
             if ctx.res_is_x:
                 dx = capi.conv1x1_fwd(dxc, hiT, loT, K, y=dres, accumulate=True)   # dres += W^T . dxc
                 dres = None
@@ -494,14 +498,19 @@ def _sync_group(bn):
     return group if dist.get_world_size(group) > 1 else None
 
 
-def weight_bn_act(W, bn, x, residual, relu, name=None, prepared=None):
+def weight_bn_act(W, bn, x, residual, relu, name=None, prepared=None, affine=None):
     """[relu](BatchNorm2d(conv1x1(x, W)) [+ residual]) for a [M,K,1,1] weight: everything in this package's kernels
     (tcgen05 GEMM with the statistics in its epilogue + one normalise pass) when the shapes allow, else the library
     convolution followed by the fused BatchNorm passes."""
-    y = _weight_bn_act(W, bn, x, residual, relu, prepared)
+    y = _weight_bn_act(W, bn, x, residual, relu, prepared, affine)
     if GATE_LOG is not None and relu and name is not None:
         GATE_LOG.setdefault(name, []).append(y.detach() > 0)
     return y
+
+
+def _eval_affine(bn):
+    return capi.bn_eval_affine(bn.weight.detach().float().contiguous(), bn.bias.detach().float().contiguous(),
+                               bn.running_mean, bn.running_var, bn.eps)
 
 
 def _inference_block(bn, x, residual):
@@ -511,7 +520,7 @@ def _inference_block(bn, x, residual):
             and bn.running_var.dtype == torch.float32 and not os.environ.get("PINMEM_B200_LIBRARY_CONV"))
 
 
-def _weight_bn_act(W, bn, x, residual, relu, prepared=None):
+def _weight_bn_act(W, bn, x, residual, relu, prepared=None, affine=None):
     if torch.is_autocast_enabled("cuda"):  # the nn.Conv2d this replaces would run in the autocast dtype
         x = x.to(torch.get_autocast_dtype("cuda"))
     M, K = W.shape[0], W.shape[1]
@@ -521,8 +530,7 @@ def _weight_bn_act(W, bn, x, residual, relu, prepared=None):
             # inference read (BASELINE config 5): the eval-mode BatchNorm and the ReLU ride in the GEMM epilogue
             hi, lo = prepared if prepared is not None else capi.conv1x1_prep(
                 W.detach().reshape(M, K).to(torch.float32).contiguous(), False, x.dtype)
-            scale, shift = capi.bn_eval_affine(bn.weight.detach().float().contiguous(), bn.bias.detach().float().contiguous(),
-                                               bn.running_mean, bn.running_var, bn.eps)
+            scale, shift = affine if affine is not None else _eval_affine(bn)
             return capi.conv1x1_fwd_affine(x, hi, lo, M, scale, shift, relu)
         res_is_x = residual is x or (residual is not None and residual.data_ptr() == x.data_ptr()
                                      and residual.shape == x.shape and residual.dtype == x.dtype)
@@ -711,8 +719,26 @@ class Memory_sup(nn.Module):
         # that the write branch's gradient is summed inside the read's dx kernel (pm_read_bwd_planes, dx_add)
         tee = (_tee and memory_writing and planes and self.fuse_grad_sum and torch.is_grad_enabled()
                and query.requires_grad and query.dtype == torch.float32)
+        # Inference read (BASELINE config 5): the folded + split weight and the BatchNorm affine depend on parameters only, so
+        # their three small kernels run on a side stream -- a parallel branch of a captured graph -- under the read kernels
+        # instead of between them and the convolution (27 us of a 108 us step at one 1024x2048 image per GPU)
+        pre = None
+        if (planes and _inference_block(self.output[1], query, None) and query.dtype in (torch.float32, torch.bfloat16)
+                and not os.environ.get("PINMEM_B200_NO_INFER_BRANCH")):
+            cur = torch.cuda.current_stream(query.device)
+            side = _SIDE_STREAMS.get(query.device)
+            if side is None:
+                side = _SIDE_STREAMS[query.device] = torch.cuda.Stream(device=query.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                pre = (self._inference_weights(M, query), _eval_affine(self.output[1]))
+            for t in (*pre[0], *pre[1]):
+                if torch.is_tensor(t):
+                    t.record_stream(cur)
         outs = _ReadFn.apply(query, M, labels, g_query, g_memory, float(self.temperature), self.memory_size, planes, tee)
         u, score_query, score_memory, readloss, hist = outs[:5]
+        if pre is not None:
+            torch.cuda.current_stream(query.device).wait_stream(_SIDE_STREAMS[query.device])
         self._tee = outs[5] if tee else None
         if labels is None:
             readloss = 0  # memory.py:178
@@ -727,11 +753,12 @@ class Memory_sup(nn.Module):
         if planes:
             # conv(W, [q ; p.M]) = W1.q + (W2.M^T).p : the memory is folded into the weight (a [C_out, 32] block) and
             # the convolution runs on [q ; score planes] -- C+32 input channels instead of 2C
-            prepared = (self._inference_weights(M, u)
-                        if (_inference_block(self.output[1], u, None)
-                            and capi.conv1x1_ok(u, self.output[0].weight.shape[0], C + capi.PLANES)) else None)
+            infer = (_inference_block(self.output[1], u, None)
+                     and capi.conv1x1_ok(u, self.output[0].weight.shape[0], C + capi.PLANES))
+            prepared = (pre[0] if pre is not None else self._inference_weights(M, u)) if infer else None
             Wp = self._folded_shape if prepared is not None else _FoldWeightFn.apply(self.output[0].weight, M)
-            updated_query = weight_bn_act(Wp, self.output[1], u, None, True, "output", prepared)  # Wp [C_out, C+32, 1, 1]
+            updated_query = weight_bn_act(Wp, self.output[1], u, None, True, "output", prepared,   # Wp [C_out, C+32, 1, 1]
+                                          pre[1] if (pre is not None and infer) else None)
         elif plain:
             updated_query = conv_bn_act(self.output[0], self.output[1], u, None, True, "output")
         else:
