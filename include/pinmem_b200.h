@@ -54,7 +54,7 @@ enum pm_readloss_ws_layout {
 #define PM_COLPART_ROWS 296
 
 /* Bumped with every prototype change; the binding refuses a library whose pm_version() differs. */
-#define PM_ABI_VERSION 205
+#define PM_ABI_VERSION 206
 int pm_version(void);
 const char* pm_status_string(int code);
 /* Row stride (floats) of the internal score buffers for K slots: 20 for K<=19, else 32. */
@@ -238,9 +238,11 @@ int pm_bn_apply(const void* x, const float* mean, const float* invstd, const flo
  * written once per channel. Replaces pm_bn_finalize + pm_bn_apply (one launch less between the GEMM and its consumer). */
 int pm_bn_apply_stats(const void* x, const double* stats, double count, float eps, const float* gamma, const float* beta,
                       const void* residual, void* y, uint32_t* relu_mask, int relu, float* mean_out, float* invstd_out,
-                      float* running_mean, float* running_var, float momentum, const double* count_dev, int B, int C,
-                      int hw, int dtype, void* stream);
-/*   count_dev  NULL, or the element count in device memory, used instead of `count`: SyncBatchNorm (the reference under
+                      float* running_mean, float* running_var, float momentum, const double* count_dev,
+                      long long* num_batches_tracked, int B, int C, int hw, int dtype, void* stream);
+/*   num_batches_tracked  NULL, or nn.BatchNorm2d's int64 counter: incremented by one by this launch (the module's own side
+ *              effect, torch/nn/modules/batchnorm.py) instead of by an element-wise kernel of its own.
+ *   count_dev  NULL, or the element count in device memory, used instead of `count`: SyncBatchNorm (the reference under
  *              --syncbn, train.py:95) all-reduces [stats | count] over the ranks and normalises with the global statistics
  *              without a device->host read. */
 int pm_bn_bwd_reduce(const void* dy, const void* y, const uint32_t* relu_mask, const void* x, const float* mean,
@@ -287,8 +289,10 @@ int pm_bn_bwd_apply(const void* dy, const void* y, const uint32_t* relu_mask, co
  */
 int pm_conv1x1_prep(const float* W, int M, int K, int transpose, int dtype, void* A_hi, void* A_lo, void* stream);
 /* pm_conv1x1_prep for BOTH operand layouts of one weight W [R,S] in one launch: (A_hi, A_lo) = W (M = R, K = S), the forward
- * operand, and (At_hi, At_lo) = W^T (M = S, K = R), the operand of the input-gradient GEMM. */
-int pm_conv1x1_prep_both(const float* W, int R, int S, int dtype, void* A_hi, void* A_lo, void* At_hi, void* At_lo, void* stream);
+ * operand, and (At_hi, At_lo) = W^T (M = S, K = R), the operand of the input-gradient GEMM. zero / zero_n: optional
+ * double buffer cleared by the same launch (the statistics buffer pm_conv1x1_fwd's epilogue adds into). */
+int pm_conv1x1_prep_both(const float* W, int R, int S, int dtype, void* A_hi, void* A_lo, void* At_hi, void* At_lo, double* zero,
+                         int zero_n, void* stream);
 int pm_conv1x1_fwd(const void* X, const void* A_hi, const void* A_lo, void* Y, double* stats, int B, int K, int M,
                    int hw, int accumulate, int dtype, void* stream);
 /* Y[b] = [relu](scale[m] * (A . X[b]) + shift[m]): the convolution with the eval-mode BatchNorm2d (+ ReLU) that follows it

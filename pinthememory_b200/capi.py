@@ -16,7 +16,7 @@ WS_WORDS = 40  # PM_WS_WORDS
 WS_HIST = 4    # PM_WS_HIST
 WS_BAD = 2     # PM_WS_BAD
 
-ABI_VERSION = 205  # PM_ABI_VERSION of include/pinmem_b200.h the argtypes below were written against
+ABI_VERSION = 206  # PM_ABI_VERSION of include/pinmem_b200.h the argtypes below were written against
 
 _c_p = ctypes.c_void_p
 _c_i = ctypes.c_int
@@ -56,7 +56,7 @@ PROTOTYPES = {
     "pm_bn_bwd_reduce_rows": [_c_p] * 6 + [_c_i] + [_c_p] * 2 + [_c_i] * 4 + [_c_p] * 2,
     "pm_bn_bwd_apply": [_c_p] * 9 + [_c_i] * 2 + [_c_p] * 2 + [_c_i] * 4 + [_c_p],
     "pm_conv1x1_prep": [_c_p] + [_c_i] * 4 + [_c_p] * 3,
-    "pm_conv1x1_prep_both": [_c_p, _c_i, _c_i, _c_i] + [_c_p] * 5,
+    "pm_conv1x1_prep_both": [_c_p, _c_i, _c_i, _c_i] + [_c_p] * 5 + [_c_i, _c_p],
     "pm_conv1x1_fwd": [_c_p] * 5 + [_c_i] * 6 + [_c_p],
     "pm_bn_eval_affine": [_c_p] * 4 + [_c_f, _c_i] + [_c_p] * 3,
     "pm_conv1x1_fwd_affine": [_c_p] * 6 + [_c_i] * 6 + [_c_p],
@@ -64,7 +64,7 @@ PROTOTYPES = {
     "pm_conv1x1_wgrad": [_c_p] * 4 + [_c_i] * 6 + [_c_p],
     "pm_bn_finalize": [_c_p, _c_i, _c_d, _c_f] + [_c_p] * 4 + [_c_f, _c_p],
     "pm_conv1x1_dgrad_bnbwd": [_c_p] * 12 + [_c_i] * 7 + [_c_p],
-    "pm_bn_apply_stats": [_c_p, _c_p, _c_d, _c_f] + [_c_p] * 5 + [_c_i] + [_c_p] * 4 + [_c_f, _c_p] + [_c_i] * 4 + [_c_p],
+    "pm_bn_apply_stats": [_c_p, _c_p, _c_d, _c_f] + [_c_p] * 5 + [_c_i] + [_c_p] * 4 + [_c_f, _c_p, _c_p] + [_c_i] * 4 + [_c_p],
     "pm_write_reduce_fwd8": [_c_p] * 3 + [_c_i] * 8 + [_c_p],
     "pm_write_bwd8": [_c_p] * 4 + [_c_i] * 8 + [_c_p],
     "pm_peer_buffer_bytes": [],
@@ -401,8 +401,9 @@ def conv1x1_prep(W2d, transpose, dtype):
     return hi, lo
 
 
-def conv1x1_prep_both(W2d, dtype):
-    """((A_hi, A_lo), (At_hi, At_lo)): conv1x1_prep(W2d, False) and conv1x1_prep(W2d, True) from one launch."""
+def conv1x1_prep_both(W2d, dtype, zero=None):
+    """((A_hi, A_lo), (At_hi, At_lo)): conv1x1_prep(W2d, False) and conv1x1_prep(W2d, True) from one launch, which also
+    clears the float64 buffer ``zero`` (the BatchNorm statistics the forward GEMM's epilogue adds into)."""
     R, S = W2d.shape
     W2d = _f32c(W2d, "weight")
     f32 = dtype == torch.float32
@@ -410,7 +411,10 @@ def conv1x1_prep_both(W2d, dtype):
     lo = torch.empty_like(hi) if f32 else None
     hiT = torch.empty((S + 127) // 128 * 128, R, dtype=dtype, device=W2d.device)
     loT = torch.empty_like(hiT) if f32 else None
-    _call("pm_conv1x1_prep_both", _ptr(W2d), R, S, PM_F32 if f32 else PM_BF16, _ptr(hi), _ptr(lo), _ptr(hiT), _ptr(loT), _stream())
+    if zero is not None and (zero.dtype != torch.float64 or not zero.is_contiguous()):
+        raise ValueError("conv1x1_prep_both: `zero` must be a contiguous float64 tensor")
+    _call("pm_conv1x1_prep_both", _ptr(W2d), R, S, PM_F32 if f32 else PM_BF16, _ptr(hi), _ptr(lo), _ptr(hiT), _ptr(loT),
+          _ptr(zero), 0 if zero is None else zero.numel(), _stream())
     return (hi, lo), (hiT, loT)
 
 
@@ -477,13 +481,13 @@ def conv1x1_wgrad(dy, x, dW=None, accumulate=False):
 
 
 def bn_apply_stats(x, stats, count, eps, gamma, beta, residual, y, relu, mean_out, invstd_out, running_mean, running_var,
-                   momentum, relu_mask=None, count_dev=None):
+                   momentum, relu_mask=None, count_dev=None, num_batches_tracked=None):
     """Normalise pass with the batch statistics finalised in-kernel from the GEMM epilogue's fp64 sums (``count_dev``: a
     float64 device scalar that replaces ``count`` -- the all-reduced global count of a SyncBatchNorm)."""
     B, C, h, w = x.shape
     _call("pm_bn_apply_stats", _ptr(x), _ptr(stats), float(count), float(eps), _ptr(gamma), _ptr(beta), _ptr(residual), _ptr(y),
           _ptr(relu_mask), int(bool(relu)), _ptr(mean_out), _ptr(invstd_out), _ptr(running_mean), _ptr(running_var),
-          float(momentum), _ptr(count_dev), B, C, h * w, dtype_code(x), _stream())
+          float(momentum), _ptr(count_dev), _ptr(num_batches_tracked), B, C, h * w, dtype_code(x), _stream())
 
 
 def bn_finalize(stats, C, count, eps, mean, invstd, running_mean, running_var, momentum):

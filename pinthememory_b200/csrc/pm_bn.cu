@@ -146,6 +146,7 @@ struct BnFinalize {  // stats == nullptr: mean / invstd are given
     double n;
     float eps, momentum;
     float *mean_out, *invstd_out, *running_mean, *running_var;
+    long long* num_batches_tracked;  // NULL, or nn.BatchNorm2d's counter: bumped here instead of by a torch add kernel
 };
 template <typename T, int VN>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ mean,
@@ -165,6 +166,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, 
         if (var < 0.0) var = 0.0;
         mu = (float)m;
         is = (float)(1.0 / sqrt(var + (double)fin.eps));
+        if (row == 0 && threadIdx.x == 0 && fin.num_batches_tracked != nullptr) *fin.num_batches_tracked += 1;
         if (row < C && threadIdx.x == 0) {
             fin.mean_out[c] = mu;
             fin.invstd_out[c] = is;
@@ -528,17 +530,18 @@ extern "C" int pm_bn_apply(const void* x, const float* mean, const float* invstd
                            void* stream) {
     if (!mean || !invstd) return PM_ERR_NULL;
     return bn_apply_impl(x, mean, invstd, gamma, beta, residual, y, relu_mask, relu, B, C, hw, dtype,
-                         pm::BnFinalize{nullptr, nullptr, 0.0, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr}, stream);
+                         pm::BnFinalize{nullptr, nullptr, 0.0, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr, nullptr}, stream);
 }
 
 extern "C" int pm_bn_apply_stats(const void* x, const double* stats, double count, float eps, const float* gamma,
                                  const float* beta, const void* residual, void* y, uint32_t* relu_mask, int relu,
                                  float* mean_out, float* invstd_out, float* running_mean, float* running_var, float momentum,
-                                 const double* count_dev, int B, int C, int hw, int dtype, void* stream) {
+                                 const double* count_dev, long long* num_batches_tracked, int B, int C, int hw, int dtype,
+                                 void* stream) {
     if (!stats || !mean_out || !invstd_out || ((running_mean == nullptr) != (running_var == nullptr))) return PM_ERR_NULL;
     if (!(count > 0.0)) return PM_ERR_SHAPE;
     return bn_apply_impl(x, nullptr, nullptr, gamma, beta, residual, y, relu_mask, relu, B, C, hw, dtype,
-                         pm::BnFinalize{stats, count_dev, count, eps, momentum, mean_out, invstd_out, running_mean, running_var},
+                         pm::BnFinalize{stats, count_dev, count, eps, momentum, mean_out, invstd_out, running_mean, running_var, num_batches_tracked},
                          stream);
 }
 

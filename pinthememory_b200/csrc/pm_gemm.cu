@@ -930,7 +930,12 @@ __global__ void conv1x1_prep_kernel(const float* __restrict__ W, int M, int K, i
 // input-gradient GEMM is produced next to the forward one instead of by a second launch in the backward pass
 template <typename T>
 __global__ void conv1x1_prep_both_kernel(const float* __restrict__ W, int R, int S, T* __restrict__ hi, T* __restrict__ lo,
-                                         T* __restrict__ hiT, T* __restrict__ loT, int mix) {
+                                         T* __restrict__ hiT, T* __restrict__ loT, int mix, double* __restrict__ zero,
+                                         int zero_n) {
+    // the statistics buffer of the BatchNorm that follows the forward GEMM is zeroed here (this launch precedes the GEMM
+    // on the same stream) instead of by a fill kernel of its own
+    if (blockIdx.x == 0 && blockIdx.y == 0)
+        for (int z = threadIdx.x; z < zero_n; z += blockDim.x) zero[z] = 0.0;
     const int tr = blockIdx.y;
     const int M = tr ? S : R, K = tr ? R : S, Mpad = (M + 127) / 128 * 128;
     T* h_out = tr ? hiT : hi;
@@ -960,17 +965,18 @@ using namespace pm;
 
 extern "C" {
 
-int pm_conv1x1_prep_both(const float* W, int R, int S, int dtype, void* A_hi, void* A_lo, void* At_hi, void* At_lo, void* stream) {
+int pm_conv1x1_prep_both(const float* W, int R, int S, int dtype, void* A_hi, void* A_lo, void* At_hi, void* At_lo, double* zero,
+                         int zero_n, void* stream) {
     if (!W || !A_hi || !At_hi || (dtype == PM_F32 && (!A_lo || !At_lo))) return PM_ERR_NULL;
     if (dtype != PM_F32 && dtype != PM_BF16) return PM_ERR_DTYPE;
-    if (R <= 0 || S <= 0) return PM_ERR_SHAPE;
+    if (R <= 0 || S <= 0 || zero_n < 0 || (zero_n > 0 && !zero)) return PM_ERR_SHAPE;
     const int n0 = (R + 127) / 128 * 128 * S, n1 = (S + 127) / 128 * 128 * R, n = n0 > n1 ? n0 : n1;
     cudaStream_t st = (cudaStream_t)stream;
     const dim3 grid((n + 255) / 256, 2);
     if (dtype == PM_F32)
-        conv1x1_prep_both_kernel<float><<<grid, 256, 0, st>>>(W, R, S, (float*)A_hi, (float*)A_lo, (float*)At_hi, (float*)At_lo, gemm_mix());
+        conv1x1_prep_both_kernel<float><<<grid, 256, 0, st>>>(W, R, S, (float*)A_hi, (float*)A_lo, (float*)At_hi, (float*)At_lo, gemm_mix(), zero, zero_n);
     else
-        conv1x1_prep_both_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(W, R, S, (__nv_bfloat16*)A_hi, nullptr, (__nv_bfloat16*)At_hi, nullptr, 0);
+        conv1x1_prep_both_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(W, R, S, (__nv_bfloat16*)A_hi, nullptr, (__nv_bfloat16*)At_hi, nullptr, 0, zero, zero_n);
     PM_CHECK_LAUNCH();
     return 0;
 }

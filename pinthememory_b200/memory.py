@@ -330,7 +330,7 @@ class _ConvBnActFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, W, gamma, beta, residual, running_mean, running_var, use_batch_stats, factor, eps, relu,
-                res_is_x, sync_group=None):
+                res_is_x, sync_group=None, num_batches_tracked=None):
         B, K, h, w = x.shape
         M = W.shape[0]
         dev = x.device
@@ -338,14 +338,18 @@ class _ConvBnActFn(torch.autograd.Function):
         g32 = gamma.detach().to(torch.float32).contiguous()
         b32 = beta.detach().to(torch.float32).contiguous()
         ctx.preT = None
-        if ctx.needs_input_grad[0]:   # the input-gradient GEMM's operand W^T comes out of the same launch
-            (hi, lo), ctx.preT = capi.conv1x1_prep_both(W2, x.dtype)
+        stats = None
+        if ctx.needs_input_grad[0]:   # the input-gradient GEMM's operand W^T comes out of the same launch ...
+            if use_batch_stats:       # ... which also clears the statistics buffer (no fill kernel)
+                stats = torch.empty(2 * M + 1, dtype=torch.float64, device=dev)
+            (hi, lo), ctx.preT = capi.conv1x1_prep_both(W2, x.dtype, zero=stats)
         else:
             hi, lo = capi.conv1x1_prep(W2, False, x.dtype)
         if use_batch_stats:
             # [sum | sum of squares | element count]: the GEMM epilogue fills the first 2M; with SyncBatchNorm the whole
             # vector is summed over the ranks (fp64, one small all-reduce) and the normalise pass finalises GLOBAL statistics
-            stats = torch.zeros(2 * M + 1, dtype=torch.float64, device=dev)
+            if stats is None:
+                stats = torch.zeros(2 * M + 1, dtype=torch.float64, device=dev)
             xc = capi.conv1x1_fwd(x, hi, lo, M, stats=stats)
             count = None
             if sync_group is not None:
@@ -367,8 +371,10 @@ class _ConvBnActFn(torch.autograd.Function):
         mask = torch.empty(nwords, dtype=torch.int32, device=dev) if vec_ok else None
         if use_batch_stats:  # mean / invstd / running statistics are finalised inside the normalise pass
             capi.bn_apply_stats(xc, stats, B * h * w, eps, g32, b32, res, y, relu, mean, invstd, running_mean, running_var,
-                                factor, relu_mask=mask, count_dev=count)
+                                factor, relu_mask=mask, count_dev=count, num_batches_tracked=num_batches_tracked)
         else:
+            if num_batches_tracked is not None:
+                num_batches_tracked.add_(1)
             capi.bn_apply(xc, mean, invstd, g32, b32, res, y, relu, relu_mask=mask)
         ctx.relu, ctx.training, ctx.res_is_x, ctx.has_res = relu, use_batch_stats, res_is_x, res is not None
         ctx.use_mask = mask is not None
@@ -415,7 +421,7 @@ class _ConvBnActFn(torch.autograd.Function):
             dW = None
             if ctx.needs_input_grad[1]:
                 dW = capi.conv1x1_wgrad(dxc, x).view(ctx.wshape).to(ctx.wdtype)
-            return dx, dW, dgamma, dbeta, None, None, None, None, None, None, None, None, None
+            return dx, dW, dgamma, dbeta, None, None, None, None, None, None, None, None, None, None
         capi.bn_bwd_apply(dy, y, mask, xc, mean, invstd, g32, sg, sb, ctx.relu, ctx.training, dxc, dres)
         dW = None
         if ctx.needs_input_grad[1]:
@@ -428,7 +434,7 @@ class _ConvBnActFn(torch.autograd.Function):
                 dres = None
             else:
                 dx = capi.conv1x1_fwd(dxc, hiT, loT, K)
-        return dx, dW, dgamma, dbeta, (None if ctx.res_is_x else dres), None, None, None, None, None, None, None, None
+        return dx, dW, dgamma, dbeta, (None if ctx.res_is_x else dres), None, None, None, None, None, None, None, None, None
 
 
 def _plain(m):
@@ -461,21 +467,30 @@ def _warn_once(key, msg):
         warnings.warn("pinmem_b200: " + msg, RuntimeWarning, stacklevel=3)
 
 
-def _bn_args(bn):
+def _bn_args(bn, defer_counter=False):
     """(use_batch_stats, running_mean, running_var, momentum factor) of one nn.BatchNorm2d call, with the module's
-    own side effect (num_batches_tracked += 1) applied."""
+    own side effect (num_batches_tracked += 1) applied -- or, with ``defer_counter``, left to the normalise kernel: then a
+    fifth element is returned, the counter tensor that launch must bump (None when there is nothing to bump)."""
+    nbt = None
     use_batch = bn.training or bn.running_mean is None
     factor = 0.0
     rm = rv = None
     if bn.training and bn.track_running_stats and bn.running_mean is not None:
         rm, rv = bn.running_mean, bn.running_var
         if bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
+            t = bn.num_batches_tracked
+            if (defer_counter and bn.momentum is not None and t.dtype == torch.int64 and t.is_cuda and t.is_contiguous()
+                    and rm.dtype == torch.float32 and rv.dtype == torch.float32):
+                nbt = t
+            else:
+                t.add_(1)
         factor = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
         if rm.dtype != torch.float32 or rv.dtype != torch.float32:
             rm = rv = None  # keep exotic buffer dtypes out of the kernel (statistics are still exact)
     elif not use_batch:
         rm, rv = bn.running_mean, bn.running_var
+    if defer_counter:
+        return use_batch, rm, rv, float(factor), nbt
     return use_batch, rm, rv, float(factor)
 
 
@@ -536,9 +551,9 @@ def _weight_bn_act(W, bn, x, residual, relu, prepared=None, affine=None):
                                      and residual.shape == x.shape and residual.dtype == x.dtype)
         if residual is not None and not res_is_x:
             residual = residual.to(x.dtype).contiguous()
-        use_batch, rm, rv, factor = _bn_args(bn)
+        use_batch, rm, rv, factor, nbt = _bn_args(bn, defer_counter=True)
         return _ConvBnActFn.apply(x, W, bn.weight, bn.bias, None if res_is_x else residual, rm, rv, use_batch, factor,
-                                  float(bn.eps), relu, res_is_x, _sync_group(bn))
+                                  float(bn.eps), relu, res_is_x, _sync_group(bn), nbt)
     _warn_once("libconv", "a 1x1 convolution fell back to the library GEMM (feature rows not 16-byte aligned, or an "
                           "unsupported channel count); the BatchNorm passes stay fused")
     return bn_act(F.conv2d(x, W.to(x.dtype)), bn, residual, relu)
