@@ -399,11 +399,18 @@ __global__ void __launch_bounds__(RL8_THREADS, 2)
 // third-generation kernel (pm_readloss9.cu): 0 = launched, -1 = shape outside its fixed-point range
 int pm_readloss_rows_launch(const float* s, const uint8_t* lab8, float temperature, int B, int h, int w, int Hm, int Wm, int K,
                             float* ds_rl, void* ws, float* out, cudaStream_t st);
-static int readloss_gen2() {  // PINMEM_B200_READLOSS_GEN2=1: keep the one-thread-per-cell kernel (A/B switch for the profiles)
+int pm_readloss_cells_launch(const float* s, const uint8_t* lab8, float temperature, int B, int h, int w, int Hm, int Wm, int K,
+                             float* ds_rl, void* ws, float* out, cudaStream_t st);
+// PINMEM_B200_READLOSS_GEN = 2 | 3 | 4 (default 4): which kernel generation runs (A/B switch for the profiles);
+// PINMEM_B200_READLOSS_GEN2=1 is the older spelling of GEN=2. Cells narrower than 6 label pixels always take generation 2.
+static int readloss_gen() {
     static int v = -1;
     if (v < 0) {
-        const char* e = getenv("PINMEM_B200_READLOSS_GEN2");
-        v = (e && e[0] == '1') ? 1 : 0;
+        const char* e = getenv("PINMEM_B200_READLOSS_GEN");
+        v = e ? atoi(e) : 4;
+        const char* e2 = getenv("PINMEM_B200_READLOSS_GEN2");
+        if (e2 && e2[0] == '1') v = 2;
+        if (v < 2 || v > 4) v = 4;
     }
     return v;
 }
@@ -414,7 +421,11 @@ extern "C" int pm_readloss_fwd8(const float* s, const uint8_t* lab8, float tempe
     if (K < 1 || K > 19) return PM_ERR_SLOTS;
     if (B <= 0 || h <= 0 || w <= 0 || Hm <= 0 || Wm <= 0 || !(temperature > 0.f)) return PM_ERR_SHAPE;
     if (((uintptr_t)s & 15) || ((uintptr_t)ds_rl & 15) || ((uintptr_t)ws & 7)) return PM_ERR_ALIGN;
-    if (!readloss_gen2()) {
+    if (readloss_gen() == 4 && w > 1 && (Wm - 1) / (w - 1) >= 6) {
+        const int rc = pm_readloss_cells_launch(s, lab8, temperature, B, h, w, Hm, Wm, K, ds_rl, ws, out, (cudaStream_t)stream);
+        if (rc >= 0) return rc;
+    }
+    if (readloss_gen() >= 3) {
         const int rc = pm_readloss_rows_launch(s, lab8, temperature, B, h, w, Hm, Wm, K, ds_rl, ws, out, (cudaStream_t)stream);
         if (rc >= 0) return rc;
     }
