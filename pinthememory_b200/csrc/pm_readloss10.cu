@@ -58,11 +58,15 @@ __device__ __forceinline__ float2 shfl_xor2(float2 v, int m) {
     return make_float2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
 }
 
+__device__ __forceinline__ void red_shared_add(unsigned addr, unsigned v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 struct RowCtx {
     float sx, cxf, hy, lamy, fscale;
     int Xa, ncols, nc_max, K, half;
     const unsigned char* lrow;
-    unsigned* o_cell;   // one-hot tile at (row 0, this cell's column)
+    unsigned o_cell;    // shared-memory byte address of the one-hot tile at (row 0, this cell's column)
 };
 
 // One label row of a cell for this lane's five slot pairs. A = stabilised logits at the cell's left edge, Bc = right - left.
@@ -147,11 +151,13 @@ __device__ __forceinline__ void row_pixels(const float2 (&A)[NJ], const float2 (
             for (int i = 0; i < CHUNK; ++i) {
                 const int cls = labs[g * CHUNK + i];
                 if (cls < c.K && ((X0 + i) & 1) == c.half) {
-                    unsigned* p = c.o_cell + cls;
-                    atomicAdd(p, __float2uint_rn(wt * hx[i]));
-                    atomicAdd(p + OSTR, __float2uint_rn(wt * lamx[i]));
-                    atomicAdd(p + TCOLS * OSTR, __float2uint_rn(wb * hx[i]));
-                    atomicAdd(p + TCOLS * OSTR + OSTR, __float2uint_rn(wb * lamx[i]));
+                    // (the address lives in ONE register: left to itself the compiler re-derives the tile pointer from the
+                    // CTA's shared window for every pixel, 12 integer instructions)
+                    const unsigned p = c.o_cell + 4u * (unsigned)cls;
+                    red_shared_add(p, __float2uint_rn(wt * hx[i]));
+                    red_shared_add(p + 4 * OSTR, __float2uint_rn(wt * lamx[i]));
+                    red_shared_add(p + 4 * TCOLS * OSTR, __float2uint_rn(wb * hx[i]));
+                    red_shared_add(p + 4 * (TCOLS * OSTR + OSTR), __float2uint_rn(wb * lamx[i]));
                 }
             }
         }
@@ -168,7 +174,7 @@ __device__ __forceinline__ void row_pixels(const float2 (&A)[NJ], const float2 (
 
 __global__ void __launch_bounds__(THREADS, 4)
     readloss_cells_kernel(const float* __restrict__ s, const unsigned char* __restrict__ lab8, float inv_T, float temperature, int h,
-                          int w, int Hm, int Wm, int K, float sy, float sx, int tiles_x, int nitems, float fscale,
+                          int w, int Hm, int Wm, int K, float sy, float sx, int tiles_x, int RS, int nitems, float fscale,
                           float* __restrict__ ds_rl, unsigned long long* __restrict__ ws, float* __restrict__ out) {
     __shared__ __align__(16) float s_tiles[WARPS][TILE_F];
     __shared__ __align__(16) unsigned o_tiles[WARPS][OTILE_W];
@@ -179,9 +185,12 @@ __global__ void __launch_bounds__(THREADS, 4)
     unsigned* o_tile = o_tiles[wid];
     float lossacc = 0.f;  // log2 units
 
-    const int item = blockIdx.x * WARPS + wid;   // (image, cell row, block of 16 cells)
+    const int item = blockIdx.x * WARPS + wid;   // (image, cell row, block of 16 cells, row split)
     if (item < nitems) {
-        const int tx_i = item % tiles_x, rest = item / tiles_x;
+        // RS > 1 (few cells: output stride 16, small batches): the label rows of a cell row are dealt round-robin to RS warps,
+        // each with its own tiles; their taps meet in the global REDs like those of neighbouring cells
+        const int rsp = item % RS, it2 = item / RS;
+        const int tx_i = it2 % tiles_x, rest = it2 / tiles_x;
         const int cy = rest % h, b = rest / h;
         const int fx0 = tx_i * CPW, cx = fx0 + cell;
         const float c2 = inv_T * 1.4426950408889634f;
@@ -243,12 +252,13 @@ __global__ void __launch_bounds__(THREADS, 4)
         for (int q = 0; q < NJ; ++q) G00[q] = G01[q] = G10[q] = G11[q] = make_float2(0.f, 0.f);
         RowCtx rc;
         rc.sx = sx, rc.cxf = (float)cx, rc.fscale = fscale, rc.Xa = Xa, rc.ncols = ncols, rc.nc_max = nc_max, rc.K = K, rc.half = half;
-        rc.o_cell = o_tile + cell * OSTR;
+        rc.o_cell = (unsigned)__cvta_generic_to_shared(o_tile + cell * OSTR);
+        asm volatile("mov.u32 %0, %0;" : "+r"(rc.o_cell));   // opaque: keeps the compiler from re-deriving it per pixel
         // this lane's slot pairs of the four taps: float2 index 2j + half of each 20-float pixel record
         const float2* t00 = reinterpret_cast<const float2*>(s_tile + cell * KP) + half;
         const float2 *t01 = t00 + KP / 2, *t10 = t00 + TCOLS * (KP / 2), *t11 = t10 + KP / 2;
         const unsigned char* lab_b = lab8 + (size_t)b * Hm * Wm + Xa;
-        for (int Y = Ya; Y < Yb; ++Y) {
+        for (int Y = Ya + rsp; Y < Yb; Y += RS) {
             const float lamy = fminf(fmaxf(sy * (float)Y - (float)cy, 0.f), 1.f);
             rc.lamy = lamy, rc.hy = 1.f - lamy;
             rc.lrow = lab_b + (size_t)Y * Wm;
@@ -370,11 +380,16 @@ int pm_readloss_cells_launch(const float* s, const uint8_t* lab8, float temperat
     if (bits < 16) return -1;
     const float fscale = (float)(1u << bits);
     const int tiles_x = (w + CPW - 1) / CPW;
-    const long long nitems = (long long)B * h * tiles_x;
+    long long nitems = (long long)B * h * tiles_x;
+    int RS = 1;   // row split: at least ~1.5 waves of 16 warps per SM
+    static int sms = 0;
+    if (sms == 0 && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0) != cudaSuccess) sms = 148;
+    while (RS < 4 && nitems * RS < 24LL * sms && 4 * (RS * 2) <= rmax - 1) RS *= 2;
+    nitems *= RS;
     if (nitems > 0x7fffffffLL) return -1;
     const int grid = (int)((nitems + WARPS - 1) / WARPS);
     readloss_cells_kernel<<<grid, THREADS, 0, st>>>(s, lab8, 1.f / temperature, temperature, h, w, Hm, Wm, K, sy, sx, tiles_x,
-                                                    (int)nitems, fscale, ds_rl, (unsigned long long*)ws, out);
+                                                    RS, (int)nitems, fscale, ds_rl, (unsigned long long*)ws, out);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }

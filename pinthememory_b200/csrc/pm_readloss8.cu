@@ -402,7 +402,8 @@ int pm_readloss_rows_launch(const float* s, const uint8_t* lab8, float temperatu
 int pm_readloss_cells_launch(const float* s, const uint8_t* lab8, float temperature, int B, int h, int w, int Hm, int Wm, int K,
                              float* ds_rl, void* ws, float* out, cudaStream_t st);
 // PINMEM_B200_READLOSS_GEN = 2 | 3 | 4 (default 4): which kernel generation runs (A/B switch for the profiles);
-// PINMEM_B200_READLOSS_GEN2=1 is the older spelling of GEN=2. Cells narrower than 6 label pixels always take generation 2.
+// PINMEM_B200_READLOSS_GEN2=1 is the older spelling of GEN=2. Generation 3 needs cells of >= 6 label pixels, generation 4
+// of >= 3 (PM_RL_MINRATIO); narrower cells take generation 2.
 static int readloss_gen() {
     static int v = -1;
     if (v < 0) {
@@ -421,7 +422,12 @@ extern "C" int pm_readloss_fwd8(const float* s, const uint8_t* lab8, float tempe
     if (K < 1 || K > 19) return PM_ERR_SLOTS;
     if (B <= 0 || h <= 0 || w <= 0 || Hm <= 0 || Wm <= 0 || !(temperature > 0.f)) return PM_ERR_SHAPE;
     if (((uintptr_t)s & 15) || ((uintptr_t)ds_rl & 15) || ((uintptr_t)ws & 7)) return PM_ERR_ALIGN;
-    if (readloss_gen() == 4 && w > 1 && (Wm - 1) / (w - 1) >= 6) {
+    static int minratio = -1;
+    if (minratio < 0) {
+        const char* e = getenv("PM_RL_MINRATIO");
+        minratio = e ? atoi(e) : 3;   // narrower cells (label map < 3x the feature map) keep the one-thread-per-cell kernel
+    }
+    if (readloss_gen() == 4 && w > 1 && (Wm - 1) / (w - 1) >= minratio) {
         const int rc = pm_readloss_cells_launch(s, lab8, temperature, B, h, w, Hm, Wm, K, ds_rl, ws, out, (cudaStream_t)stream);
         if (rc >= 0) return rc;
     }
