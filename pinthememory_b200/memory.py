@@ -65,6 +65,14 @@ def draw_gumbel_pair(N, K, device):
 
 
 _SIDE_STREAMS = {}  # device -> stream of the write branch (module-level: modules stay deep-copyable)
+_AUX_STREAMS = {}   # device -> second side stream (the column softmax of a branched read)
+
+
+def _stream_of(table, device):
+    st = table.get(device)
+    if st is None:
+        st = table[device] = torch.cuda.Stream(device=device)
+    return st
 
 
 class _ReadFn(torch.autograd.Function):
@@ -79,7 +87,7 @@ class _ReadFn(torch.autograd.Function):
     last_lab8 = None  # the packed uint8 class map that read produced (None when the first-generation kernel ran)
 
     @staticmethod
-    def forward(ctx, x, M, labels, g_query, g_memory, temperature, K, planes=False, tee=False):
+    def forward(ctx, x, M, labels, g_query, g_memory, temperature, K, planes=False, tee=False, branch=False):
         """``tee=True`` appends x itself to the outputs: a caller that feeds the same features to a second branch (the
         writing net) hands that branch the tee, so its gradient arrives HERE as an input of backward() and the dx kernel
         sums it in (``dx_add``) -- instead of autograd adding two feature-sized gradients with an element-wise kernel."""
@@ -99,14 +107,46 @@ class _ReadFn(torch.autograd.Function):
         n_cp = capi.colsoftmax_workspace_floats(K)
         buf = torch.zeros(n_rl + 2 * capi.WS_WORDS + 4 + n_cp, dtype=torch.float32, device=dev)
         col_partials = buf[n_rl + 2 * capi.WS_WORDS + 4:]
+        # ``branch`` (the module's two-stream mode): the label pass needs nothing from the read and nothing on the step's
+        # critical path needs the column softmax, so the pack runs on the write branch's stream UNDER read_fwd (which also
+        # orders it before the write kernels that consume the packed map) and the column softmax on a second side stream
+        # under the read loss: two small kernels (17 + 11 us at cfg 2) leave the main chain. Captured, they are parallel
+        # branches of the graph.
+        use_pack = labels is not None and K <= 19 and not os.environ.get("PINMEM_B200_READLOSS_V1")
+        branch = bool(branch) and x.is_cuda
+        lab8 = None
+        if branch:
+            cur = torch.cuda.current_stream(dev)
+            side, aux = _stream_of(_SIDE_STREAMS, dev), _stream_of(_AUX_STREAMS, dev)
+        if branch and use_pack:
+            ws = buf[N * KP: N * KP + 2 * capi.WS_WORDS]
+            side.wait_stream(cur)                      # (after the zero fill of the workspace)
+            with torch.cuda.stream(side):
+                lab8 = capi.labels_pack(labels, K, ws)
+            buf.record_stream(side)
+            labels.record_stream(side)
+            lab8.record_stream(cur)
         capi.read_fwd(x, M, g_memory, u, s, score_m, K, gumbel_q=g_query, col_partials=col_partials, planes=planes)
-        capi.colsoftmax_apply(s, g_query, col_partials, score_q, N, K)
+        if branch:
+            aux.wait_stream(cur)
+            with torch.cuda.stream(aux):
+                capi.colsoftmax_apply(s, g_query, col_partials, score_q, N, K)
+            for t in (s, g_query, buf, score_q):
+                if torch.is_tensor(t):
+                    t.record_stream(aux)
+        else:
+            capi.colsoftmax_apply(s, g_query, col_partials, score_q, N, K)
         if labels is not None:
             ds_rl = buf[: N * KP]
             ws = buf[N * KP: N * KP + 2 * capi.WS_WORDS]
             rl_out = buf[N * KP + 2 * capi.WS_WORDS: N * KP + 2 * capi.WS_WORDS + 4]
-            # one pass over the labels (packed uint8 classes + histogram + bad-label count), then the read loss on it
-            _ReadFn.last_lab8 = capi.readloss(s, labels, temperature, B, h, w, K, ds_rl, ws, rl_out)
+            if lab8 is not None:
+                cur.wait_stream(side)                  # the packed map and its histogram
+                capi.readloss_fwd8(s, lab8, temperature, B, h, w, K, ds_rl, ws, rl_out)
+                _ReadFn.last_lab8 = lab8
+            else:
+                # one pass over the labels (packed uint8 classes + histogram + bad-label count), then the read loss on it
+                _ReadFn.last_lab8 = capi.readloss(s, labels, temperature, B, h, w, K, ds_rl, ws, rl_out)
             readloss = rl_out[0]
             hist = ws.view(torch.int64)[capi.WS_HIST: capi.WS_HIST + K + 1]
             _ReadFn.last_bad = ws.view(torch.int64)[capi.WS_BAD]
@@ -119,6 +159,8 @@ class _ReadFn(torch.autograd.Function):
         ctx.set_materialize_grads(False)  # unused outputs (scores, histogram) arrive as None, not as zero fills
         ctx.save_for_backward(x, M, score_m, ds_rl, rl_out)
         ctx.mark_non_differentiable(score_q, score_m, hist)
+        if branch:
+            cur.wait_stream(aux)                       # join: score_query is ready for whoever reads it on this stream
         outs = (u, score_q.view(B, h, w, K), score_m.view(B, h, w, K), readloss, hist)
         return outs + (x,) if tee else outs
 
@@ -147,7 +189,7 @@ class _ReadFn(torch.autograd.Function):
         if need_dM:
             dM = torch.zeros_like(M)
             capi.read_bwd_dM(None if ctx.planes else du, x, score_m, ds, dM, K)
-        return dx, dM, None, None, None, None, None, None, None
+        return dx, dM, None, None, None, None, None, None, None, None
 
 
 class _FoldWeightFn(torch.autograd.Function):
@@ -667,7 +709,15 @@ class Memory_sup(nn.Module):
             side = _SIDE_STREAMS[query.device] = torch.cuda.Stream(device=query.device)
         side.wait_stream(cur)                     # fork: the write depends only on what precedes this call
         memory_in = self.m_items
-        updated_query, score_query, score_memory, readloss = self.read(query, mask, True, _tee=True)   # main stream
+        # the read's label pass runs on `side` too (before the write kernels that consume the packed map: stream order is
+        # the dependency), its column softmax on a second side stream
+        self._branch_read = not os.environ.get("PINMEM_B200_NO_READ_BRANCHES")
+        try:
+            updated_query, score_query, score_memory, readloss = self.read(query, mask, True, _tee=True)   # main stream
+        finally:
+            branched, self._branch_read = self._branch_read, False
+        if not branched and getattr(self, "_packed", None) is not None:
+            side.wait_stream(cur)   # the packed label map was produced on the main stream: the write must not start before it
         memory_after_read = self.m_items          # the detached view read() installed (memory.py:323-324)
         tee, self._tee = getattr(self, "_tee", None), None
         with torch.cuda.stream(side):
@@ -750,7 +800,8 @@ class Memory_sup(nn.Module):
             for t in (*pre[0], *pre[1]):
                 if torch.is_tensor(t):
                     t.record_stream(cur)
-        outs = _ReadFn.apply(query, M, labels, g_query, g_memory, float(self.temperature), self.memory_size, planes, tee)
+        outs = _ReadFn.apply(query, M, labels, g_query, g_memory, float(self.temperature), self.memory_size, planes, tee,
+                             bool(getattr(self, "_branch_read", False)))
         u, score_query, score_memory, readloss, hist = outs[:5]
         if pre is not None:
             torch.cuda.current_stream(query.device).wait_stream(_SIDE_STREAMS[query.device])
