@@ -23,6 +23,7 @@ for (B, C, h, w, Hm, Wm) in [(2, 256, 16, 16, 64, 64), (1, 64, 12, 20, 48, 80), 
         torch.manual_seed(3)
         mem = Memory_sup(19, C, C, 0.8, 1.0, False).cuda()
         mem.fold_min_pixels = 0
+        mem.overlap_write = (B == 2)   # the two-stream mode too (label pass / column softmax on side streams)
         x = synth.make_features(B, C, h, w, seed=1, device="cuda").requires_grad_(True)
         lab = synth.make_labels(B, Hm, Wm, 19, "blocky", seed=2).cuda()
         G = synth.make_upstream_grad((B, C, h, w), seed=3, device="cuda")
