@@ -853,9 +853,10 @@ def main():
     bound_note = {
         "pm_readloss (pm_labels_pack + pm_readloss_fwd8)":
             "two launches reported as one logical kernel (time and bytes are their sums; bytes as SURVEY 8d counts them: "
-            "int64 labels read once). Not HBM-bound by nature: ~90 instructions per LABEL pixel (64 label pixels per "
-            "feature pixel) plus the per-row exp2 set-up, one thread per label row of a bilinear cell, 16 warps per SM -- "
-            "issue/latency-bound, see DESIGN.md 6; DRAM traffic = algorithmic bytes (no re-reads)",
+            "int64 labels read once). Not HBM-bound by nature: ~2 x 55 instructions per LABEL pixel (64 label pixels per "
+            "feature pixel; a lane pair per bilinear cell, half of the 20 slots each) plus the per-row exp2 set-up, 16 "
+            "warps per SM -- instruction-issue bound (ncu: issue slots 61 % busy), see DESIGN.md 6; DRAM traffic = "
+            "algorithmic bytes (no re-reads)",
         "pm_readloss_fwd": "not HBM-bound by nature: ~19 ex2 + ~60 FMA per LABEL pixel (64 label pixels per feature "
                            "pixel) make it FP32/MUFU-issue bound; the HBM fraction is reported because the contract asks "
                            "for it, see DESIGN.md 4/6",
