@@ -372,7 +372,7 @@ class _ConvBnActFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, W, gamma, beta, residual, running_mean, running_var, use_batch_stats, factor, eps, relu,
-                res_is_x, sync_group=None, num_batches_tracked=None):
+                res_is_x, sync_group=None, num_batches_tracked=None, pre=None):
         B, K, h, w = x.shape
         M = W.shape[0]
         dev = x.device
@@ -381,7 +381,13 @@ class _ConvBnActFn(torch.autograd.Function):
         b32 = beta.detach().to(torch.float32).contiguous()
         ctx.preT = None
         stats = None
-        if ctx.needs_input_grad[0]:   # the input-gradient GEMM's operand W^T comes out of the same launch ...
+        if pre is not None and pre[0][0].dtype != x.dtype:
+            pre = None                # prepared for another compute dtype (autocast): redo it here
+        if pre is not None:           # operands (and the cleared statistics buffer) prepared ahead of time on a side stream
+            (hi, lo), ctx.preT, stats = pre
+            if not use_batch_stats:
+                stats = None
+        elif ctx.needs_input_grad[0]:   # the input-gradient GEMM's operand W^T comes out of the same launch ...
             if use_batch_stats:       # ... which also clears the statistics buffer (no fill kernel)
                 stats = torch.empty(2 * M + 1, dtype=torch.float64, device=dev)
             (hi, lo), ctx.preT = capi.conv1x1_prep_both(W2, x.dtype, zero=stats)
@@ -463,7 +469,7 @@ class _ConvBnActFn(torch.autograd.Function):
             dW = None
             if ctx.needs_input_grad[1]:
                 dW = capi.conv1x1_wgrad(dxc, x).view(ctx.wshape).to(ctx.wdtype)
-            return dx, dW, dgamma, dbeta, None, None, None, None, None, None, None, None, None, None
+            return dx, dW, dgamma, dbeta, None, None, None, None, None, None, None, None, None, None, None
         capi.bn_bwd_apply(dy, y, mask, xc, mean, invstd, g32, sg, sb, ctx.relu, ctx.training, dxc, dres)
         dW = None
         if ctx.needs_input_grad[1]:
@@ -476,7 +482,7 @@ class _ConvBnActFn(torch.autograd.Function):
                 dres = None
             else:
                 dx = capi.conv1x1_fwd(dxc, hiT, loT, K)
-        return dx, dW, dgamma, dbeta, (None if ctx.res_is_x else dres), None, None, None, None, None, None, None, None, None
+        return dx, dW, dgamma, dbeta, (None if ctx.res_is_x else dres), None, None, None, None, None, None, None, None, None, None
 
 
 def _plain(m):
@@ -555,11 +561,11 @@ def _sync_group(bn):
     return group if dist.get_world_size(group) > 1 else None
 
 
-def weight_bn_act(W, bn, x, residual, relu, name=None, prepared=None, affine=None):
+def weight_bn_act(W, bn, x, residual, relu, name=None, prepared=None, affine=None, pre=None):
     """[relu](BatchNorm2d(conv1x1(x, W)) [+ residual]) for a [M,K,1,1] weight: everything in this package's kernels
     (tcgen05 GEMM with the statistics in its epilogue + one normalise pass) when the shapes allow, else the library
     convolution followed by the fused BatchNorm passes."""
-    y = _weight_bn_act(W, bn, x, residual, relu, prepared, affine)
+    y = _weight_bn_act(W, bn, x, residual, relu, prepared, affine, pre)
     if GATE_LOG is not None and relu and name is not None:
         GATE_LOG.setdefault(name, []).append(y.detach() > 0)
     return y
@@ -577,7 +583,7 @@ def _inference_block(bn, x, residual):
             and bn.running_var.dtype == torch.float32 and not os.environ.get("PINMEM_B200_LIBRARY_CONV"))
 
 
-def _weight_bn_act(W, bn, x, residual, relu, prepared=None, affine=None):
+def _weight_bn_act(W, bn, x, residual, relu, prepared=None, affine=None, pre=None):
     if torch.is_autocast_enabled("cuda"):  # the nn.Conv2d this replaces would run in the autocast dtype
         x = x.to(torch.get_autocast_dtype("cuda"))
     M, K = W.shape[0], W.shape[1]
@@ -595,7 +601,7 @@ def _weight_bn_act(W, bn, x, residual, relu, prepared=None, affine=None):
             residual = residual.to(x.dtype).contiguous()
         use_batch, rm, rv, factor, nbt = _bn_args(bn, defer_counter=True)
         return _ConvBnActFn.apply(x, W, bn.weight, bn.bias, None if res_is_x else residual, rm, rv, use_batch, factor,
-                                  float(bn.eps), relu, res_is_x, _sync_group(bn), nbt)
+                                  float(bn.eps), relu, res_is_x, _sync_group(bn), nbt, pre)
     _warn_once("libconv", "a 1x1 convolution fell back to the library GEMM (feature rows not 16-byte aligned, or an "
                           "unsupported channel count); the BatchNorm passes stay fused")
     return bn_act(F.conv2d(x, W.to(x.dtype)), bn, residual, relu)
@@ -800,8 +806,33 @@ class Memory_sup(nn.Module):
             for t in (*pre[0], *pre[1]):
                 if torch.is_tensor(t):
                     t.record_stream(cur)
+        # Two-stream mode, training: the output convolution's weight work (fold the memory in, split both operand layouts,
+        # clear the statistics buffer: two small launches) depends on parameters only -- it runs on the second side stream
+        # under read_fwd instead of between the read loss and the convolution
+        wpre = None
+        branch = bool(getattr(self, "_branch_read", False))
+        if (branch and planes and pre is None and torch.is_grad_enabled() and self.output[1].training
+                and _bn_fast(self.output[1], query) and query.dtype in (torch.float32, torch.bfloat16)
+                and capi.conv1x1_ok(query, self.output[0].weight.shape[0], C + capi.PLANES)
+                and not os.environ.get("PINMEM_B200_LIBRARY_CONV")):
+            cur = torch.cuda.current_stream(query.device)
+            aux = _stream_of(_AUX_STREAMS, query.device)
+            aux.wait_stream(cur)
+            with torch.cuda.stream(aux):
+                Wp_early = _FoldWeightFn.apply(self.output[0].weight, M)
+                Co = Wp_early.shape[0]
+                stats = torch.empty(2 * Co + 1, dtype=torch.float64, device=query.device)
+                cdt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else query.dtype
+                ops, opsT = capi.conv1x1_prep_both(Wp_early.detach().reshape(Co, C + capi.PLANES).to(torch.float32).contiguous(),
+                                                   cdt, zero=stats)
+            wpre = (Wp_early, (ops, opsT, stats))
+            for t in (Wp_early, stats, *ops, *opsT):
+                if torch.is_tensor(t):
+                    t.record_stream(cur)
         outs = _ReadFn.apply(query, M, labels, g_query, g_memory, float(self.temperature), self.memory_size, planes, tee,
-                             bool(getattr(self, "_branch_read", False)))
+                             branch)
+        if wpre is not None:   # (a branched _ReadFn joins the aux stream itself; this covers the read without labels / K > 19)
+            torch.cuda.current_stream(query.device).wait_stream(_stream_of(_AUX_STREAMS, query.device))
         u, score_query, score_memory, readloss, hist = outs[:5]
         if pre is not None:
             torch.cuda.current_stream(query.device).wait_stream(_SIDE_STREAMS[query.device])
@@ -822,9 +853,15 @@ class Memory_sup(nn.Module):
             infer = (_inference_block(self.output[1], u, None)
                      and capi.conv1x1_ok(u, self.output[0].weight.shape[0], C + capi.PLANES))
             prepared = (pre[0] if pre is not None else self._inference_weights(M, u)) if infer else None
-            Wp = self._folded_shape if prepared is not None else _FoldWeightFn.apply(self.output[0].weight, M)
+            if prepared is not None:
+                Wp = self._folded_shape
+            elif wpre is not None:
+                Wp = wpre[0]
+            else:
+                Wp = _FoldWeightFn.apply(self.output[0].weight, M)
             updated_query = weight_bn_act(Wp, self.output[1], u, None, True, "output", prepared,   # Wp [C_out, C+32, 1, 1]
-                                          pre[1] if (pre is not None and infer) else None)
+                                          pre[1] if (pre is not None and infer) else None,
+                                          wpre[1] if (wpre is not None and prepared is None) else None)
         elif plain:
             updated_query = conv_bn_act(self.output[0], self.output[1], u, None, True, "output")
         else:
