@@ -404,15 +404,12 @@ int pm_readloss_cells_launch(const float* s, const uint8_t* lab8, float temperat
 // PINMEM_B200_READLOSS_GEN = 2 | 3 | 4 (default 4): which kernel generation runs (A/B switch for the profiles);
 // PINMEM_B200_READLOSS_GEN2=1 is the older spelling of GEN=2. Generation 3 needs cells of >= 6 label pixels, generation 4
 // of >= 3 (PM_RL_MINRATIO); narrower cells take generation 2.
-static int readloss_gen() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("PINMEM_B200_READLOSS_GEN");
-        v = e ? atoi(e) : 4;
-        const char* e2 = getenv("PINMEM_B200_READLOSS_GEN2");
-        if (e2 && e2[0] == '1') v = 2;
-        if (v < 2 || v > 4) v = 4;
-    }
+static int readloss_gen() {   // read on every call (a getenv): tests flip it inside one process
+    const char* e = getenv("PINMEM_B200_READLOSS_GEN");
+    int v = e ? atoi(e) : 4;
+    const char* e2 = getenv("PINMEM_B200_READLOSS_GEN2");
+    if (e2 && e2[0] == '1') v = 2;
+    if (v < 2 || v > 4) v = 4;
     return v;
 }
 
@@ -422,11 +419,7 @@ extern "C" int pm_readloss_fwd8(const float* s, const uint8_t* lab8, float tempe
     if (K < 1 || K > 19) return PM_ERR_SLOTS;
     if (B <= 0 || h <= 0 || w <= 0 || Hm <= 0 || Wm <= 0 || !(temperature > 0.f)) return PM_ERR_SHAPE;
     if (((uintptr_t)s & 15) || ((uintptr_t)ds_rl & 15) || ((uintptr_t)ws & 7)) return PM_ERR_ALIGN;
-    static int minratio = -1;
-    if (minratio < 0) {
-        const char* e = getenv("PM_RL_MINRATIO");
-        minratio = e ? atoi(e) : 3;   // narrower cells (label map < 3x the feature map) keep the one-thread-per-cell kernel
-    }
+    const int minratio = 3;   // narrower cells (label map < 3x the feature map) keep the one-thread-per-cell kernel
     if (readloss_gen() == 4 && w > 1 && (Wm - 1) / (w - 1) >= minratio) {
         const int rc = pm_readloss_cells_launch(s, lab8, temperature, B, h, w, Hm, Wm, K, ds_rl, ws, out, (cudaStream_t)stream);
         if (rc >= 0) return rc;
