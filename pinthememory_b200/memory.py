@@ -85,6 +85,8 @@ class _ReadFn(torch.autograd.Function):
 
     last_bad = None   # device int64 scalar: label values outside [0,K) u {255} seen by the last read with labels
     last_lab8 = None  # the packed uint8 class map that read produced (None when the first-generation kernel ran)
+    pack_event = None  # recorded behind the label pass when it ran on the read's own stream and want_pack_event is set
+    want_pack_event = False
 
     @staticmethod
     def forward(ctx, x, M, labels, g_query, g_memory, temperature, K, planes=False, tee=False, branch=False):
@@ -144,8 +146,16 @@ class _ReadFn(torch.autograd.Function):
                 cur.wait_stream(side)                  # the packed map and its histogram
                 capi.readloss_fwd8(s, lab8, temperature, B, h, w, K, ds_rl, ws, rl_out)
                 _ReadFn.last_lab8 = lab8
+            elif use_pack and x.is_cuda:
+                # one pass over the labels (packed uint8 classes + histogram + bad-label count), then the read loss on it; the
+                # event lets a write branch on another stream wait for exactly the pack (Memory_sup._forward_two_streams)
+                lab8 = capi.labels_pack(labels, K, ws)
+                if _ReadFn.want_pack_event:
+                    _ReadFn.pack_event = torch.cuda.Event()
+                    _ReadFn.pack_event.record(torch.cuda.current_stream(dev))
+                capi.readloss_fwd8(s, lab8, temperature, B, h, w, K, ds_rl, ws, rl_out)
+                _ReadFn.last_lab8 = lab8
             else:
-                # one pass over the labels (packed uint8 classes + histogram + bad-label count), then the read loss on it
                 _ReadFn.last_lab8 = capi.readloss(s, labels, temperature, B, h, w, K, ds_rl, ws, rl_out)
             readloss = rl_out[0]
             hist = ws.view(torch.int64)[capi.WS_HIST: capi.WS_HIST + K + 1]
@@ -718,12 +728,16 @@ class Memory_sup(nn.Module):
         # the read's label pass runs on `side` too (before the write kernels that consume the packed map: stream order is
         # the dependency), its column softmax on a second side stream
         self._branch_read = not os.environ.get("PINMEM_B200_NO_READ_BRANCHES")
+        _ReadFn.want_pack_event, _ReadFn.pack_event = not self._branch_read, None
         try:
             updated_query, score_query, score_memory, readloss = self.read(query, mask, True, _tee=True)   # main stream
         finally:
             branched, self._branch_read = self._branch_read, False
-        if not branched and getattr(self, "_packed", None) is not None:
-            side.wait_stream(cur)   # the packed label map was produced on the main stream: the write must not start before it
+            _ReadFn.want_pack_event = False
+        # (not branched: the packed label map is produced on the main stream; the write kernels that read it wait for the
+        # event recorded behind the pass -- see write())
+        self._pack_event = None if branched else _ReadFn.pack_event
+        _ReadFn.pack_event = None
         memory_after_read = self.m_items          # the detached view read() installed (memory.py:323-324)
         tee, self._tee = getattr(self, "_tee", None), None
         with torch.cuda.stream(side):
@@ -881,6 +895,9 @@ class Memory_sup(nn.Module):
         self._packed = None
         f = self.writenet(query)
         f = _check_features(f, "write feature")
+        ev, self._pack_event = getattr(self, "_pack_event", None), None
+        if ev is not None and labels.dtype == torch.uint8 and packed is not None:
+            torch.cuda.current_stream(query.device).wait_event(ev)   # two-stream mode: the packed map comes from the read's stream
         M_old = self._memory_for_kernels(query.device)
         if M_old.requires_grad and torch.is_grad_enabled():
             # memory.py:236 blends the NON-detached self.m_items[slot]; forward() never gets here with a grad-carrying
