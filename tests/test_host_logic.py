@@ -107,3 +107,26 @@ def test_attribute_surface_matches_the_live_reference():
 
     assert list(inspect.signature(ref.forward).parameters) == list(inspect.signature(mem.forward).parameters)
     assert list(inspect.signature(type(ref).__init__).parameters) == list(inspect.signature(type(mem).__init__).parameters)[:-1]
+
+
+def test_bn_args_counter_is_bumped_once_and_only_deferred_for_cuda_buffers():
+    """_bn_args applies nn.BatchNorm2d's own side effect (num_batches_tracked += 1) itself unless the normalise kernel can
+    do it (CUDA int64 counter, fixed momentum): on CPU buffers it must never defer."""
+    import torch
+    import torch.nn as nn
+
+    from pinthememory_b200.memory import _bn_args
+
+    bn = nn.BatchNorm2d(8)
+    bn.train()
+    use_batch, rm, rv, factor, nbt = _bn_args(bn, defer_counter=True)
+    assert use_batch and nbt is None and int(bn.num_batches_tracked) == 1 and factor == bn.momentum
+    assert rm is bn.running_mean and rv is bn.running_var
+    use_batch, rm, rv, factor = _bn_args(bn)
+    assert int(bn.num_batches_tracked) == 2
+    bn.momentum = None                       # cumulative average: the factor needs the bumped counter on the host
+    *_, factor, nbt = _bn_args(bn, defer_counter=True)
+    assert nbt is None and int(bn.num_batches_tracked) == 3 and abs(factor - 1.0 / 3.0) < 1e-12
+    bn.eval()
+    use_batch, rm, rv, factor, nbt = _bn_args(bn, defer_counter=True)
+    assert not use_batch and nbt is None and int(bn.num_batches_tracked) == 3 and rm is bn.running_mean
