@@ -393,6 +393,7 @@ class _ConvBnActFn(torch.autograd.Function):
         stats = None
         if pre is not None and pre[0][0].dtype != x.dtype:
             pre = None                # prepared for another compute dtype (autocast): redo it here
+        ctx.w_on_aux = pre is not None and not os.environ.get("PINMEM_B200_NO_WGRAD_BRANCH")
         if pre is not None:           # operands (and the cleared statistics buffer) prepared ahead of time on a side stream
             (hi, lo), ctx.preT, stats = pre
             if not use_batch_stats:
@@ -478,7 +479,19 @@ class _ConvBnActFn(torch.autograd.Function):
                                                ctx.training)
             dW = None
             if ctx.needs_input_grad[1]:
-                dW = capi.conv1x1_wgrad(dxc, x).view(ctx.wshape).to(ctx.wdtype)
+                if getattr(ctx, "w_on_aux", False):
+                    # two-stream mode: the weight came from the second side stream (folded there, so its backward runs there):
+                    # the weight-gradient GEMM goes to that stream too -- the read's backward, next on this stream, only
+                    # needs dx
+                    cur = torch.cuda.current_stream(x.device)
+                    aux = _stream_of(_AUX_STREAMS, x.device)
+                    aux.wait_stream(cur)
+                    with torch.cuda.stream(aux):
+                        dW = capi.conv1x1_wgrad(dxc, x).view(ctx.wshape).to(ctx.wdtype)
+                    dxc.record_stream(aux)
+                    x.record_stream(aux)
+                else:
+                    dW = capi.conv1x1_wgrad(dxc, x).view(ctx.wshape).to(ctx.wdtype)
             return dx, dW, dgamma, dbeta, None, None, None, None, None, None, None, None, None, None, None
         capi.bn_bwd_apply(dy, y, mask, xc, mean, invstd, g32, sg, sb, ctx.relu, ctx.training, dxc, dres)
         dW = None
