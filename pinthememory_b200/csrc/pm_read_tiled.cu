@@ -338,6 +338,15 @@ __device__ __forceinline__ void store_partial(float* part, int wid, int lane, co
 
 // TMA = true: the x tiles arrive as tensor-map boxes (SWIZZLE_128B for the tensor-core layout, dense otherwise) on an
 // mbarrier ring; tm_x is unused with the cp.async ring.
+// exp(x) for x <= 0 (softmax terms after the maximum is subtracted): ex2.approx of x*log2(e) -- 2 instructions instead of
+// expf's ~10; the terms that matter have |x| of a few units, where the product's rounding is ~1e-7 relative (the read-loss
+// kernels have always computed their softmax this way)
+__device__ __forceinline__ float fexp_nonpos(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+}
+
 template <typename T, int C, int KP, int NSTAGE, bool TMA>
 __global__ void __launch_bounds__(TL_THREADS, 2)
     read_fwd_tiled_kernel(const __grid_constant__ CUtensorMap tm_x, const T* __restrict__ x,
@@ -453,7 +462,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
             float sum = 0.f;
 #pragma unroll
             for (int i = 0; i < NI; ++i) {
-                z[i] = (j + 8 * i < K) ? expf(z[i] - mx) : 0.f;
+                z[i] = (j + 8 * i < K) ? fexp_nonpos(z[i] - mx) : 0.f;
                 sum += z[i];
             }
             sum += __shfl_xor_sync(0xffffffffu, sum, 1);
@@ -471,10 +480,10 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
                     float zq = sv[i];
                     if (gum_q != nullptr) zq += __ldg(gum_q + (n0g + px) * K + k);
                     if (zq > cm[i]) {
-                        cl[i] = cl[i] * expf(cm[i] - zq) + 1.f;
+                        cl[i] = cl[i] * fexp_nonpos(cm[i] - zq) + 1.f;
                         cm[i] = zq;
                     } else {
-                        cl[i] += expf(zq - cm[i]);
+                        cl[i] += fexp_nonpos(zq - cm[i]);
                     }
                 }
             }
